@@ -1,0 +1,184 @@
+/*
+ * seg_b200.h — C ABI of the B200-native segmentation hot path.
+ *
+ * Drop-in boundary for the forward/backward hot path of yassouali/pytorch-segmentation
+ * (dilated-ResNet encoder -> ASPP / PSP head -> bilinear upsample -> per-pixel loss).  The reference is
+ * 100 % Python and dispatches every op below to ATen/cuDNN; each entry point here names the reference call
+ * site(s) whose ATen op it replaces (path:line relative to the reference tree).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; seg_last_error() gives the message
+ *     (thread-local).  Python wrappers turn a non-zero status into RuntimeError (the reference's convention is
+ *     Python exceptions, e.g. trainer.py:58-59).
+ *   - all pointers are BORROWED device pointers; the library allocates nothing the caller must free.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *   - activations are NHWC; `ld*` is the channel pitch (elements) of the buffer a tensor lives in, so a tensor
+ *     can be a channel slice of a wider concat buffer (replaces torch.cat, deeplabv3_plus.py:293,329).
+ *   - bf16 = raw uint16 storage of __nv_bfloat16.  dtype codes: 0 = bf16, 1 = fp32.
+ *   - packed conv weights: bf16 [R*S][K][C] (tap-major, then output channel, input channel contiguous).
+ *   - nothing here falls back to the CPU; a missing GPU / wrong arch is an error.
+ */
+#ifndef SEG_B200_H
+#define SEG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEG_DT_BF16 0
+#define SEG_DT_F32 1
+
+/* implementation selector for the conv entry points */
+#define SEG_IMPL_AUTO 0 /* tcgen05 where the shape allows, else SIMT */
+#define SEG_IMPL_SIMT 1 /* CUDA-core implicit GEMM (any shape) */
+#define SEG_IMPL_TC 2   /* tcgen05 + TMA implicit GEMM, error if shape unsupported */
+
+typedef struct seg_conv_desc {
+  int32_t N, H, W, C;   /* input  [N,H,W,C]  (C = input channels)                 */
+  int32_t K;            /* output channels                                           */
+  int32_t R, S;         /* filter taps                                               */
+  int32_t stride, pad, dil;
+  int32_t P, Q;         /* output spatial size                                       */
+  int32_t ldx;          /* channel pitch of the input buffer  (>= C, multiple of 8)  */
+  int32_t ldy;          /* channel pitch of the output buffer (>= K)                 */
+} seg_conv_desc;
+
+const char* seg_last_error(void);
+int seg_version(void);
+/* 0 if the current device is sm_100 and kernels can be launched */
+int seg_device_ok(void);
+/* number of kernel launches issued by this library since the last reset (gpu_launches in bench.py) */
+int64_t seg_launch_count(void);
+void seg_launch_count_reset(void);
+
+/* ---- convolution: replaces nn.Conv2d (models/deeplabv3_plus.py:21,256,268,306,312-319; torchvision
+ *      Bottleneck conv1/2/3 + downsample.0 mutated at deeplabv3_plus.py:35-53; models/resnet.py:43-48,80-86) ---- */
+/* y[N,P,Q,K] = conv(x, w) (+bias[K]);  y = beta*y + result.  y_dtype in {bf16, fp32}.
+ * stats (optional, fp32 [2*K], must be zeroed by caller): per-channel sum and sum of squares of the fp32 result
+ * accumulated atomically (feeds seg_bn_finalize; replaces the reduction half of nn.BatchNorm2d). */
+int seg_conv2d_fwd(const seg_conv_desc* d, const void* x, const void* w_packed, void* y, int y_dtype,
+                   const float* bias, float beta, float* stats, int impl, void* stream);
+/* dx[N,H,W,C] = beta*dx + conv_transpose(dy, w)   (autograd of the above w.r.t. x) */
+int seg_conv2d_dgrad(const seg_conv_desc* d, const void* dy, const void* w_packed, void* dx, float beta,
+                     int impl, void* stream);
+/* dw_packed (fp32 [R*S][K][C]) += dy^T * im2col(x)   (autograd w.r.t. the weight; caller zeroes dw first) */
+int seg_conv2d_wgrad(const seg_conv_desc* d, const void* dy, const void* x, float* dw_packed, int impl,
+                     void* stream);
+
+/* OIHW fp32 master weight -> packed bf16 [R*S][K][Cpad]; Cpad >= C zero padded */
+int seg_pack_weight(const float* w_oihw, void* w_packed, int K, int C, int R, int S, int Cpad, void* stream);
+/* packed fp32 grad [R*S][K][Cpad] -> OIHW fp32:  g = beta*g + packed */
+int seg_unpack_wgrad(const float* dw_packed, float* g_oihw, int K, int C, int R, int S, int Cpad, float beta,
+                     void* stream);
+/* explicit im2col for convs TMA cannot address (C % 8 != 0: the 7x7/3-channel stem, deeplabv3_plus.py:21):
+ * col[N*P*Q][Kpad] bf16, column order (r, s, c), zero padded to Kpad.  x is NCHW fp32 (x_nchw_f32=1) or NHWC bf16. */
+int seg_im2col(const seg_conv_desc* d, const void* x, int x_nchw_f32, void* col, int Kpad, void* stream);
+
+/* ---- batch norm (nn.BatchNorm2d everywhere on the path; sync_batchnorm/batchnorm.py:128-145 for the multi-GPU
+ *      variant): statistics, finalize, apply(+residual+ReLU+dropout), backward ---- */
+/* stats[0:C] += sum_x, stats[C:2C] += sum_x^2 over M rows of x[M][ldx] (bf16) */
+int seg_bn_stats(const void* x, int64_t M, int C, int ldx, float* stats, void* stream);
+/* mean/var from (possibly all-reduced) sums over `count` elements; writes scale_shift[0:C]=gamma*inv_std,
+ * [C:2C]=beta-mean*scale, save_mean_istd[0:C]=mean,[C:2C]=inv_std; updates running stats with momentum and the
+ * unbiased variance.  clamp_eps=0: inv_std=(var+eps)^-1/2 (F.batch_norm); 1: clamp(var,eps)^-1/2
+ * (sync_batchnorm/batchnorm.py:145). */
+int seg_bn_finalize(const float* stats, double count, int C, const float* gamma, const float* beta, float eps,
+                    float momentum, int clamp_eps, float* running_mean, float* running_var, float* scale_shift,
+                    float* save_mean_istd, void* stream);
+/* eval-mode: scale/shift from running stats */
+int seg_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const float* running_mean,
+                            const float* running_var, float eps, float* scale_shift, void* stream);
+/* out = dropout(relu?(x*scale+shift (+res)))  — x,res,out bf16 [M][ld*]; drop_p = 0 disables dropout
+ * (nn.ReLU(inplace) + residual add torchvision Bottleneck; nn.Dropout deeplabv3_plus.py:282,318) */
+int seg_bn_apply(const void* x, int ldx, const float* scale_shift, const void* res, int ldr, void* out, int ldo,
+                 int64_t M, int C, int relu, float drop_p, uint64_t seed, void* stream);
+/* backward, pass 1: sums[0:C] += sum(dz), sums[C:2C] += sum(dz*xhat), dz = dout * (out>0) * 1/(1-drop_p) if relu */
+int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx,
+                      const float* save_mean_istd, int64_t M, int C, int relu, float drop_p, float* sums,
+                      void* stream);
+/* backward, pass 2: dx = gamma*istd*(dz - sums0/count - xhat*sums1/count); dres = beta_res*dres + dz (optional).
+ * `sums` are the (possibly all-reduced) sums, `count` the matching element count. */
+int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx,
+                     const float* save_mean_istd, const float* gamma, const float* sums, double count, int64_t M,
+                     int C, int relu, float drop_p, void* dx, int lddx, void* dres, int lddres, float beta_res,
+                     void* stream);
+/* parameter grads from the LOCAL sums: dbeta (=|+=) sums[0:C], dgamma (=|+=) sums[C:2C] */
+int seg_bn_param_grad(const float* sums, int C, float* dgamma, float* dbeta, int accumulate, void* stream);
+
+/* ---- pooling ---- */
+/* nn.MaxPool2d(3, stride 2, pad 1) (deeplabv3_plus.py:24; resnet.py:151); idx (uint8) saves the arg-max tap */
+int seg_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, int C, int P, int Q,
+                         void* stream);
+int seg_maxpool3x3s2_bwd(const void* dy, const uint8_t* idx, void* dx, int N, int H, int W, int C, int P, int Q,
+                         void* stream);
+/* nn.AdaptiveAvgPool2d(bins) (deeplabv3_plus.py:274 bins=1; pspnet.py:26 bins 1,2,3,6): y[N,b,b,C] bf16 */
+int seg_adaptive_avgpool_fwd(const void* x, int ldx, void* y, int N, int H, int W, int C, int bins, void* stream);
+/* dx = beta*dx + scatter(dy) */
+int seg_adaptive_avgpool_bwd(const void* dy, void* dx, int lddx, int N, int H, int W, int C, int bins, float beta,
+                             void* stream);
+
+/* ---- bilinear resize, F.interpolate(mode='bilinear') (deeplabv3_plus.py:291,328,361; pspnet.py:35,86,91) ---- */
+/* NHWC bf16 -> NHWC bf16 (channel-slice output allowed) */
+int seg_bilinear_fwd(const void* x, int ldx, void* y, int ldy, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                     int align_corners, void* stream);
+/* dx = beta*dx + bilinear^T(dy) */
+int seg_bilinear_bwd(const void* dy, int lddy, void* dx, int lddx, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                     int align_corners, float beta, void* stream);
+/* final logits: NHWC fp32 [N,Hi,Wi,C] -> NCHW fp32 [N,C,Ho,Wo] (the tensor the reference returns, deeplabv3_plus.py:361) */
+int seg_bilinear_logits_fwd(const float* x, float* y_nchw, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                            int align_corners, void* stream);
+/* NCHW fp32 grad -> NHWC bf16 grad at the low resolution */
+int seg_bilinear_logits_bwd(const float* dy_nchw, void* dx, int lddx, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                            int align_corners, void* stream);
+
+/* ---- per-pixel loss ---- */
+/* CrossEntropyLoss2d (utils/losses.py:24-31): logits NCHW fp32, target int64 [N,H,W].
+ * accum[0] += sum of -log p[target] over valid pixels, accum[1] += number of valid pixels (both fp64). */
+int seg_ce_nchw_fwd(const float* logits, const int64_t* target, int N, int C, int H, int W, int64_t ignore_index,
+                    double* accum, void* stream);
+/* dlogits = (softmax - onehot) * gscale / accum[1] for valid pixels, 0 for ignored (gscale = upstream grad) */
+int seg_ce_nchw_bwd(const float* logits, const int64_t* target, int N, int C, int H, int W, int64_t ignore_index,
+                    const double* accum, const float* gscale, float* dlogits, void* stream);
+/* fused: bilinear upsample (low-res NHWC fp32 logits) + log-softmax + NLL, no full-res logits in HBM.
+ * Also emits the arg-max label map (int32 [N,Ho,Wo], lowest index wins ties) when argmax != NULL. */
+int seg_upsample_ce_fwd(const float* logits_lo, const int64_t* target, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                        int align_corners, int64_t ignore_index, double* accum, int32_t* argmax, void* stream);
+/* d(logits_lo) of mean CE: accumulated in fp32 scratch dlo_f32 [N,Hi,Wi,C] (zeroed here), then written as bf16
+ * NHWC with pitch lddx (channels C..lddx-1 zero) when dx != NULL; gscale = upstream grad (fp32 scalar on device) */
+int seg_upsample_ce_bwd(const float* logits_lo, const int64_t* target, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                        int align_corners, int64_t ignore_index, const double* accum, const float* gscale,
+                        float* dlo_f32, void* dx, int lddx, void* stream);
+/* loss = accum[0]/accum[1] (fp32 scalar) */
+int seg_ce_finalize(const double* accum, float* loss, void* stream);
+
+/* ---- misc ---- */
+int seg_nhwc_to_nchw_f32(const void* x, int ldx, int x_dtype, float* y, int N, int H, int W, int C, void* stream);
+/* y[M][ldy] (bf16) = beta*y + x[M][ldx] (bf16) */
+int seg_axpby_bf16(const void* x, int ldx, void* y, int ldy, int64_t M, int C, float beta, void* stream);
+/* multi-tensor SGD step (torch.optim.SGD semantics: wd, momentum, dampening 0, no nesterov;
+ * base/base_trainer.py:57): n tensors described by device arrays of pointers/sizes */
+int seg_sgd_step(float* const* params, float* const* grads, float* const* momentum_bufs, const int64_t* sizes,
+                 const float* lrs, int n, float momentum, float weight_decay, int first_step, float grad_scale,
+                 void* stream);
+/* ---- SyncBN one-shot exchange over NVLink peer memory (replaces ReduceAddCoalesced + Broadcast,
+ *      sync_batchnorm/batchnorm.py:117,120 and the thread pipes of sync_batchnorm/comm.py) ----
+ * Each rank owns a symmetric buffer of seg_comm_buffer_bytes(world, n_max) bytes (seg_comm_alloc, zeroed), exports it
+ * with seg_comm_ipc_get, opens its peers' with seg_comm_ipc_open, and passes the world's pointers (indexed by rank;
+ * its own pointer at [rank]) as a DEVICE array.  seg_syncbn_exchange(vals[n]) leaves the rank-ordered sum over all
+ * ranks in vals on every rank (bit-identical everywhere).  epoch must increase by 1 per call, starting at 1, and be
+ * the same on all ranks. */
+size_t seg_comm_buffer_bytes(int world, int n_max);
+int seg_comm_alloc(size_t bytes, void** ptr);
+int seg_comm_free(void* ptr);
+int seg_comm_ipc_get(void* ptr, void* handle64);
+int seg_comm_ipc_open(const void* handle64, void** ptr);
+int seg_comm_ipc_close(void* ptr);
+int seg_syncbn_exchange(void* const* peer_bufs, int rank, int world, float* local_vals, int n, int n_max,
+                        uint32_t epoch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEG_B200_H */

@@ -1,0 +1,852 @@
+// seg_elementwise.cu — the HBM-bound kernels of the hot path: weight packing, explicit im2col (stem only),
+// BatchNorm statistics / finalize / apply(+residual+ReLU+dropout) / backward, max-pool, adaptive average pool,
+// bilinear resize (both align_corners modes) and layout conversion.  All activation kernels are NHWC bf16 and move
+// 16-byte (8-channel) vectors per thread; reductions use warp shuffles + one atomic per block-column.
+// Reference call sites are cited next to each entry point in include/seg_b200.h.
+#include "seg_common.cuh"
+
+namespace seg {
+
+static inline int grid_for(int64_t work_items, int threads, int max_blocks_per_sm = 8) {
+  int64_t b = ceil_div64(work_items, threads);
+  int64_t cap = (int64_t)num_sms() * max_blocks_per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------ weights
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int K, int C, int R,
+                                   int S, int Cpad) {
+  const int64_t total = (int64_t)R * S * K * Cpad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cpad);
+    const int64_t t1 = i / Cpad;
+    const int k = (int)(t1 % K);
+    const int tap = (int)(t1 / K);
+    const int r = tap / S, s = tap - r * S;
+    float v = 0.f;
+    if (c < C) v = w[(((int64_t)k * C + c) * R + r) * S + s];
+    out[i] = f2bf(v);
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ g, int K, int C, int R, int S,
+                                    int Cpad, float beta) {
+  const int64_t total = (int64_t)K * C * R * S;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i % S);
+    int64_t t = i / S;
+    const int r = (int)(t % R);
+    t /= R;
+    const int c = (int)(t % C);
+    const int k = (int)(t / C);
+    const float v = dw[((int64_t)(r * S + s) * K + k) * Cpad + c];
+    g[i] = (beta != 0.f) ? beta * g[i] + v : v;
+  }
+}
+
+__global__ void im2col_kernel(seg_conv_desc d, const void* __restrict__ x, int x_nchw_f32,
+                              __nv_bfloat16* __restrict__ col, int Kpad) {
+  const int64_t M = (int64_t)d.N * d.P * d.Q;
+  const int64_t total = M * Kpad;
+  const int Kreal = d.R * d.S * d.C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % Kpad);
+    const int64_t m = i / Kpad;
+    float v = 0.f;
+    if (kk < Kreal) {
+      const int c = kk % d.C;
+      const int tap = kk / d.C;
+      const int r = tap / d.S, s = tap - r * d.S;
+      const int n = (int)(m / (d.P * d.Q));
+      const int rem = (int)(m - (int64_t)n * d.P * d.Q);
+      const int op = rem / d.Q, oq = rem - op * d.Q;
+      const int ih = op * d.stride - d.pad + r * d.dil, iw = oq * d.stride - d.pad + s * d.dil;
+      if (ih >= 0 && ih < d.H && iw >= 0 && iw < d.W) {
+        if (x_nchw_f32)
+          v = reinterpret_cast<const float*>(x)[(((int64_t)n * d.C + c) * d.H + ih) * d.W + iw];
+        else
+          v = bf2f(reinterpret_cast<const __nv_bfloat16*>(x)[(((int64_t)n * d.H + ih) * d.W + iw) * d.ldx + c]);
+      }
+    }
+    col[i] = f2bf(v);
+  }
+}
+
+// ------------------------------------------------------------------ BatchNorm
+// Column-reduction skeleton shared by bn_stats and bn_bwd_reduce: a 256-thread block owns GB = min(G,256) channel
+// groups (8 channels each) and 256/GB row lanes; rows are grid-strided.
+template <int NACC, class F>
+__device__ __forceinline__ void column_reduce(int64_t M, int C, float* out /*[NACC][C]*/, F f) {
+  const int G = C >> 3;
+  const int GB = min(G, 256);
+  const int rows_par = 256 / GB;
+  const int gl = threadIdx.x % GB;
+  const int rl = threadIdx.x / GB;
+  const int g = blockIdx.y * GB + gl;
+  float acc[NACC][8];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
+  if (g < G && rl < rows_par) {
+    for (int64_t row = (int64_t)blockIdx.x * rows_par + rl; row < M; row += (int64_t)gridDim.x * rows_par)
+      f(row, g, acc);
+  }
+  __shared__ float red[256 * 8];
+  for (int a = 0; a < NACC; ++a) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[a][i];
+    __syncthreads();
+    if (rl == 0 && g < G) {
+      float s[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] = 0.f;
+      for (int r = 0; r < rows_par; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += red[(r * GB + gl) * 8 + i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(out + (size_t)a * C + g * 8 + i, s[i]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t M, int C, int ldx,
+                                                       float* __restrict__ stats) {
+  column_reduce<2>(M, C, stats, [&](int64_t row, int g, float(*acc)[8]) {
+    const bf16x8 v = *reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8);
+    float f[8];
+    unpack8(v, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[0][i] += f[i];
+      acc[1][i] += f[i] * f[i];
+    }
+  });
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, double count, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, int clamp_eps,
+                                   float* running_mean, float* running_var, float* __restrict__ scale_shift,
+                                   float* __restrict__ save) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = (double)stats[c] / count;
+  double var = (double)stats[C + c] / count - mean * mean;
+  if (var < 0) var = 0;
+  const double istd = clamp_eps ? 1.0 / sqrt(var < (double)eps ? (double)eps : var) : 1.0 / sqrt(var + (double)eps);
+  if (running_mean) {
+    const double unbiased = count > 1 ? var * count / (count - 1) : var;
+    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+  }
+  const float sc = (float)(gamma[c] * istd);
+  scale_shift[c] = sc;
+  scale_shift[C + c] = (float)(beta[c] - mean * gamma[c] * istd);
+  save[c] = (float)mean;
+  save[C + c] = (float)istd;
+}
+
+__global__ void bn_eval_kernel(int C, const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                               float* scale_shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float istd = rsqrtf(rv[c] + eps);
+  const float sc = gamma[c] * istd;
+  scale_shift[c] = sc;
+  scale_shift[C + c] = beta[c] - rm[c] * sc;
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                       const float* __restrict__ ss, const __nv_bfloat16* __restrict__ res,
+                                                       int ldr, __nv_bfloat16* __restrict__ out, int ldo, int64_t M, int C,
+                                                       int relu, float drop_p, uint64_t seed) {
+  const int G = C >> 3;
+  const int64_t total = M * G;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const int64_t row = i / G;
+    float f[8], sc[8], sh[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8), f);
+    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(ss + g * 8));
+    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(ss + g * 8 + 4));
+    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(ss + C + g * 8));
+    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(ss + C + g * 8 + 4));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+    if (res) {
+      float r[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(res + row * ldr + g * 8), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (drop_p > 0.f) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float u = hash_uniform(seed, (uint64_t)(row * C + g * 8 + j));
+        f[j] = (u >= drop_p) ? f[j] * keep_scale : 0.f;
+      }
+    }
+    *reinterpret_cast<bf16x8*>(out + row * ldo + g * 8) = pack8(f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ out, int ldo,
+                         const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save, int64_t M, int C,
+                         int relu, float drop_p, float* __restrict__ sums) {
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  column_reduce<2>(M, C, sums, [&](int64_t row, int g, float(*acc)[8]) {
+    float dz[8], xv[8], mean[8], istd[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(dout + row * lddo + g * 8), dz);
+    unpack8(*reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8), xv);
+    if (relu) {
+      float o[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(out + row * ldo + g * 8), o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dz[i] = (o[i] > 0.f) ? dz[i] * keep_scale : 0.f;
+    }
+    *reinterpret_cast<float4*>(mean) = __ldg(reinterpret_cast<const float4*>(save + g * 8));
+    *reinterpret_cast<float4*>(mean + 4) = __ldg(reinterpret_cast<const float4*>(save + g * 8 + 4));
+    *reinterpret_cast<float4*>(istd) = __ldg(reinterpret_cast<const float4*>(save + C + g * 8));
+    *reinterpret_cast<float4*>(istd + 4) = __ldg(reinterpret_cast<const float4*>(save + C + g * 8 + 4));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[0][i] += dz[i];
+      acc[1][i] += dz[i] * (xv[i] - mean[i]) * istd[i];
+    }
+  });
+}
+
+__global__ void __launch_bounds__(256)
+    bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ out, int ldo,
+                        const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save,
+                        const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count, int64_t M, int C,
+                        int relu, float drop_p, __nv_bfloat16* __restrict__ dx, int lddx, __nv_bfloat16* dres, int lddres,
+                        float beta_res) {
+  const int G = C >> 3;
+  const int64_t total = M * G;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const int64_t row = i / G;
+    float dz[8], xv[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(dout + row * lddo + g * 8), dz);
+    unpack8(*reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8), xv);
+    if (relu) {
+      float o[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(out + row * ldo + g * 8), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dz[j] = (o[j] > 0.f) ? dz[j] * keep_scale : 0.f;
+    }
+    if (dres) {
+      float r[8];
+      if (beta_res != 0.f) {
+        unpack8(*reinterpret_cast<const bf16x8*>(dres + row * lddres + g * 8), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = beta_res * r[j] + dz[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = dz[j];
+      }
+      *reinterpret_cast<bf16x8*>(dres + row * lddres + g * 8) = pack8(r);
+    }
+    float o8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      const float mean = __ldg(save + c), istd = __ldg(save + C + c);
+      const float xhat = (xv[j] - mean) * istd;
+      const float s0 = __ldg(sums + c) * inv_count, s1 = __ldg(sums + C + c) * inv_count;
+      o8[j] = __ldg(gamma + c) * istd * (dz[j] - s0 - xhat * s1);
+    }
+    *reinterpret_cast<bf16x8*>(dx + row * lddx + g * 8) = pack8(o8);
+  }
+}
+
+__global__ void bn_param_grad_kernel(const float* __restrict__ sums, int C, float* dgamma, float* dbeta, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + sums[c] : sums[c];
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + sums[C + c] : sums[C + c];
+}
+
+// ------------------------------------------------------------------ pooling
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                          uint8_t* __restrict__ idx, int N, int H, int W, int C, int P, int Q) {
+  const int G = C >> 3;
+  const int64_t total = (int64_t)N * P * Q * G;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    int64_t t = i / G;
+    const int q = (int)(t % Q);
+    t /= Q;
+    const int p = (int)(t % P);
+    const int n = (int)(t / P);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -INFINITY;
+      bi[j] = 0;
+    }
+    bool first = true;
+    for (int r = 0; r < 3; ++r) {
+      const int ih = 2 * p - 1 + r;
+      if (ih < 0 || ih >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int iw = 2 * q - 1 + s;
+        if (iw < 0 || iw >= W) continue;
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(x + (((int64_t)n * H + ih) * W + iw) * C + g * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (first || f[j] > best[j]) {  // first maximum wins (matches ATen max_pool2d index selection)
+            best[j] = f[j];
+            bi[j] = r * 3 + s;
+          }
+        first = false;
+      }
+    }
+    const int64_t o = (((int64_t)n * P + p) * Q + q) * C + g * 8;
+    *reinterpret_cast<bf16x8*>(y + o) = pack8(best);
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      lo |= (uint32_t)bi[j] << (8 * j);
+      hi |= (uint32_t)bi[j + 4] << (8 * j);
+    }
+    *reinterpret_cast<uint2*>(idx + o) = make_uint2(lo, hi);
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                                          __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int P,
+                                                          int Q) {
+  const int G = C >> 3;
+  const int64_t total = (int64_t)N * H * W * G;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    int64_t t = i / G;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int r = 0; r < 3; ++r) {
+      const int th = h + 1 - r;
+      if (th < 0 || (th & 1)) continue;
+      const int p = th >> 1;
+      if (p >= P) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int tw = w + 1 - s;
+        if (tw < 0 || (tw & 1)) continue;
+        const int q = tw >> 1;
+        if (q >= Q) continue;
+        const int64_t o = (((int64_t)n * P + p) * Q + q) * C + g * 8;
+        const uint2 id = *reinterpret_cast<const uint2*>(idx + o);
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(dy + o), f);
+        const int code = r * 3 + s;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if ((int)((id.x >> (8 * j)) & 0xff) == code) acc[j] += f[j];
+          if ((int)((id.y >> (8 * j)) & 0xff) == code) acc[j + 4] += f[j + 4];
+        }
+      }
+    }
+    *reinterpret_cast<bf16x8*>(dx + (((int64_t)n * H + h) * W + w) * C + g * 8) = pack8(acc);
+  }
+}
+
+__device__ __forceinline__ int bin_lo(int i, int L, int b) { return (i * L) / b; }
+__device__ __forceinline__ int bin_hi(int i, int L, int b) { return ((i + 1) * L + b - 1) / b; }
+
+// grid (N*bins*bins, ceil(G/32)); block 256 = 32 channel groups x 8 pixel lanes
+__global__ void __launch_bounds__(256) adaptive_avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                                   __nv_bfloat16* __restrict__ y, int N, int H, int W, int C,
+                                                                   int bins) {
+  const int G = C >> 3;
+  const int gl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int g = blockIdx.y * 32 + gl;
+  int t = blockIdx.x;
+  const int j = t % bins;
+  t /= bins;
+  const int i = t % bins;
+  const int n = t / bins;
+  const int h0 = bin_lo(i, H, bins), h1 = bin_hi(i, H, bins), w0 = bin_lo(j, W, bins), w1 = bin_hi(j, W, bins);
+  const int bw = w1 - w0, cnt = (h1 - h0) * bw;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (g < G) {
+    for (int e = pl; e < cnt; e += 8) {
+      const int h = h0 + e / bw, w = w0 + e % bw;
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + (((int64_t)n * H + h) * W + w) * ldx + g * 8), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += f[k];
+    }
+  }
+  __shared__ float red[8][32][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[pl][gl][k] = acc[k];
+  __syncthreads();
+  if (pl == 0 && g < G) {
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s[k] = 0.f;
+      for (int l = 0; l < 8; ++l) s[k] += red[l][gl][k];
+      s[k] /= (float)cnt;
+    }
+    *reinterpret_cast<bf16x8*>(y + (((int64_t)n * bins + i) * bins + j) * C + g * 8) = pack8(s);
+  }
+}
+
+__global__ void __launch_bounds__(256) adaptive_avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                   __nv_bfloat16* __restrict__ dx, int lddx, int N, int H,
+                                                                   int W, int C, int bins, float beta) {
+  const int G = C >> 3;
+  const int64_t total = (int64_t)N * H * W * G;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    int64_t t = idx / G;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int i = 0; i < bins; ++i) {
+      const int h0 = bin_lo(i, H, bins), h1 = bin_hi(i, H, bins);
+      if (h < h0 || h >= h1) continue;
+      for (int j = 0; j < bins; ++j) {
+        const int w0 = bin_lo(j, W, bins), w1 = bin_hi(j, W, bins);
+        if (w < w0 || w >= w1) continue;
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(dy + (((int64_t)n * bins + i) * bins + j) * C + g * 8), f);
+        const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += f[k] * inv;
+      }
+    }
+    __nv_bfloat16* o = dx + (((int64_t)n * H + h) * W + w) * lddx + g * 8;
+    if (beta != 0.f) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(o), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += beta * f[k];
+    }
+    *reinterpret_cast<bf16x8*>(o) = pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------ bilinear
+// Source index exactly as ATen's area_pixel_compute_source_index (float arithmetic).
+struct Lerp {
+  int i0, i1;
+  float l1;
+};
+__device__ __forceinline__ Lerp src_index(int dst, float scale, int in_size, int align_corners) {
+  float s;
+  if (align_corners) {
+    s = scale * (float)dst;
+  } else {
+    s = scale * ((float)dst + 0.5f) - 0.5f;
+    if (s < 0.f) s = 0.f;
+  }
+  Lerp r;
+  r.i0 = (int)s;
+  if (r.i0 > in_size - 1) r.i0 = in_size - 1;
+  r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
+  r.l1 = s - (float)r.i0;
+  return r;
+}
+static inline float resize_scale(int in_size, int out_size, int align_corners) {
+  if (align_corners) return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+  return (float)in_size / (float)out_size;
+}
+// candidate output range whose source support may touch input index y
+__device__ __forceinline__ void dst_range(int y, float scale, int out_size, int align_corners, int& lo, int& hi) {
+  if (scale <= 0.f) {
+    lo = 0;
+    hi = out_size - 1;
+    return;
+  }
+  float a, b;
+  if (align_corners) {
+    a = ((float)y - 1.f) / scale;
+    b = ((float)y + 1.f) / scale;
+  } else {
+    a = ((float)y - 0.5f) / scale - 0.5f;
+    b = ((float)y + 1.5f) / scale - 0.5f;
+  }
+  lo = max(0, (int)floorf(a) - 1);
+  hi = min(out_size - 1, (int)ceilf(b) + 1);
+}
+
+__global__ void __launch_bounds__(256) bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                           __nv_bfloat16* __restrict__ y, int ldy, int N, int Hi, int Wi,
+                                                           int Ho, int Wo, int C, int ac, float sh, float sw) {
+  const int G = C >> 3;
+  const int64_t total = (int64_t)N * Ho * Wo * G;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    int64_t t = i / G;
+    const int ox = (int)(t % Wo);
+    t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const Lerp ly = src_index(oy, sh, Hi, ac), lx = src_index(ox, sw, Wi, ac);
+    const __nv_bfloat16* base = x + (int64_t)n * Hi * Wi * ldx + g * 8;
+    float a[8], b[8], c[8], d[8], o[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(base + ((int64_t)ly.i0 * Wi + lx.i0) * ldx), a);
+    unpack8(*reinterpret_cast<const bf16x8*>(base + ((int64_t)ly.i0 * Wi + lx.i1) * ldx), b);
+    unpack8(*reinterpret_cast<const bf16x8*>(base + ((int64_t)ly.i1 * Wi + lx.i0) * ldx), c);
+    unpack8(*reinterpret_cast<const bf16x8*>(base + ((int64_t)ly.i1 * Wi + lx.i1) * ldx), d);
+    const float h1 = ly.l1, h0 = 1.f - h1, w1 = lx.l1, w0 = 1.f - w1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = h0 * (w0 * a[k] + w1 * b[k]) + h1 * (w0 * c[k] + w1 * d[k]);
+    *reinterpret_cast<bf16x8*>(y + (((int64_t)n * Ho + oy) * Wo + ox) * ldy + g * 8) = pack8(o);
+  }
+}
+
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy,
+                                                           __nv_bfloat16* __restrict__ dx, int lddx, int N, int Hi, int Wi,
+                                                           int Ho, int Wo, int C, int ac, float sh, float sw, float beta) {
+  const int G = C >> 3;
+  const int64_t total = (int64_t)N * Hi * Wi * G;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    int64_t t = i / G;
+    const int x = (int)(t % Wi);
+    t /= Wi;
+    const int y = (int)(t % Hi);
+    const int n = (int)(t / Hi);
+    int oy0, oy1, ox0, ox1;
+    dst_range(y, sh, Ho, ac, oy0, oy1);
+    dst_range(x, sw, Wo, ac, ox0, ox1);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int oy = oy0; oy <= oy1; ++oy) {
+      const Lerp ly = src_index(oy, sh, Hi, ac);
+      float wy = 0.f;
+      if (ly.i0 == y) wy += 1.f - ly.l1;
+      if (ly.i1 == y) wy += ly.l1;
+      if (wy == 0.f) continue;
+      for (int ox = ox0; ox <= ox1; ++ox) {
+        const Lerp lx = src_index(ox, sw, Wi, ac);
+        float wx = 0.f;
+        if (lx.i0 == x) wx += 1.f - lx.l1;
+        if (lx.i1 == x) wx += lx.l1;
+        if (wx == 0.f) continue;
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(dy + (((int64_t)n * Ho + oy) * Wo + ox) * lddy + g * 8), f);
+        const float wgt = wy * wx;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += wgt * f[k];
+      }
+    }
+    __nv_bfloat16* o = dx + (((int64_t)n * Hi + y) * Wi + x) * lddx + g * 8;
+    if (beta != 0.f) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(o), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += beta * f[k];
+    }
+    *reinterpret_cast<bf16x8*>(o) = pack8(acc);
+  }
+}
+
+// low-res NHWC fp32 logits -> full-res NCHW fp32 logits; threads run along ox for coalesced NCHW stores
+__global__ void __launch_bounds__(256) bilinear_logits_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N,
+                                                                  int Hi, int Wi, int Ho, int Wo, int C, int ac, float sh,
+                                                                  float sw) {
+  const int64_t total = (int64_t)N * Ho * Wo;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Wo);
+    int64_t t = i / Wo;
+    const int oy = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const Lerp ly = src_index(oy, sh, Hi, ac), lx = src_index(ox, sw, Wi, ac);
+    const float* base = x + (int64_t)n * Hi * Wi * C;
+    const float* pa = base + ((int64_t)ly.i0 * Wi + lx.i0) * C;
+    const float* pb = base + ((int64_t)ly.i0 * Wi + lx.i1) * C;
+    const float* pc = base + ((int64_t)ly.i1 * Wi + lx.i0) * C;
+    const float* pd = base + ((int64_t)ly.i1 * Wi + lx.i1) * C;
+    const float h1 = ly.l1, h0 = 1.f - h1, w1 = lx.l1, w0 = 1.f - w1;
+    float* o = y + (int64_t)n * C * Ho * Wo + (int64_t)oy * Wo + ox;
+    for (int c = 0; c < C; ++c)
+      o[(int64_t)c * Ho * Wo] = h0 * (w0 * pa[c] + w1 * pb[c]) + h1 * (w0 * pc[c] + w1 * pd[c]);
+  }
+}
+
+// NCHW fp32 grad -> low-res NHWC bf16 grad (pitch lddx, channels >= C zero-filled up to lddx)
+__global__ void __launch_bounds__(128) bilinear_logits_bwd_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
+                                                                  int lddx, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                                                                  int ac, float sh, float sw) {
+  const int64_t total = (int64_t)N * Hi * Wi;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wi);
+    int64_t t = i / Wi;
+    const int y = (int)(t % Hi);
+    const int n = (int)(t / Hi);
+    int oy0, oy1, ox0, ox1;
+    dst_range(y, sh, Ho, ac, oy0, oy1);
+    dst_range(x, sw, Wo, ac, ox0, ox1);
+    __nv_bfloat16* o = dx + (((int64_t)n * Hi + y) * Wi + x) * lddx;
+    for (int c = 0; c < C; ++c) {
+      const float* src = dy + ((int64_t)n * C + c) * Ho * Wo;
+      float acc = 0.f;
+      for (int oy = oy0; oy <= oy1; ++oy) {
+        const Lerp ly = src_index(oy, sh, Hi, ac);
+        float wy = 0.f;
+        if (ly.i0 == y) wy += 1.f - ly.l1;
+        if (ly.i1 == y) wy += ly.l1;
+        if (wy == 0.f) continue;
+        for (int ox = ox0; ox <= ox1; ++ox) {
+          const Lerp lx = src_index(ox, sw, Wi, ac);
+          float wx = 0.f;
+          if (lx.i0 == x) wx += 1.f - lx.l1;
+          if (lx.i1 == x) wx += lx.l1;
+          if (wx != 0.f) acc += wy * wx * src[(int64_t)oy * Wo + ox];
+        }
+      }
+      o[c] = f2bf(acc);
+    }
+    for (int c = C; c < lddx; ++c) o[c] = f2bf(0.f);
+  }
+}
+
+// ------------------------------------------------------------------ misc
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int ldx, int x_dtype, float* __restrict__ y, int N, int H,
+                                    int W, int C) {
+  const int64_t total = (int64_t)N * C * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    int64_t t = i / W;
+    const int h = (int)(t % H);
+    t /= H;
+    const int c = (int)(t % C);
+    const int n = (int)(t / C);
+    const int64_t src = (((int64_t)n * H + h) * W + w) * ldx + c;
+    y[i] = x_dtype == SEG_DT_BF16 ? bf2f(reinterpret_cast<const __nv_bfloat16*>(x)[src])
+                                  : reinterpret_cast<const float*>(x)[src];
+  }
+}
+
+__global__ void axpby_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy, int64_t M,
+                             int C, float beta) {
+  const int G = C >> 3;
+  const int64_t total = M * G;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const int64_t row = i / G;
+    float a[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8), a);
+    if (beta != 0.f) {
+      float b[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(y + row * ldy + g * 8), b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += beta * b[k];
+    }
+    *reinterpret_cast<bf16x8*>(y + row * ldy + g * 8) = pack8(a);
+  }
+}
+
+struct SgdChunkArgs {
+  float* const* params;
+  float* const* grads;
+  float* const* bufs;
+  const int64_t* sizes;
+  const float* lrs;
+};
+// one block-row (blockIdx.y) per tensor, grid-stride inside
+__global__ void sgd_kernel(SgdChunkArgs a, float momentum, float wd, int first_step, float grad_scale) {
+  const int t = blockIdx.y;
+  float* p = a.params[t];
+  const float* g = a.grads[t];
+  float* b = a.bufs[t];
+  const int64_t n = a.sizes[t];
+  const float lr = a.lrs[t];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float d = g[i] * grad_scale + wd * p[i];
+    if (momentum != 0.f) {
+      const float m = first_step ? d : momentum * b[i] + d;
+      b[i] = m;
+      d = m;
+    }
+    p[i] -= lr * d;
+  }
+}
+
+}  // namespace seg
+
+// =================================================================== C ABI
+using namespace seg;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" {
+
+int seg_pack_weight(const float* w, void* out, int K, int C, int R, int S, int Cpad, void* stream) {
+  const int64_t total = (int64_t)R * S * K * Cpad;
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(w, BF(out), K, C, R, S, Cpad);
+  return check_launch("pack_weight");
+}
+int seg_unpack_wgrad(const float* dw, float* g, int K, int C, int R, int S, int Cpad, float beta, void* stream) {
+  const int64_t total = (int64_t)K * C * R * S;
+  unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(dw, g, K, C, R, S, Cpad, beta);
+  return check_launch("unpack_wgrad");
+}
+int seg_im2col(const seg_conv_desc* d, const void* x, int x_nchw_f32, void* col, int Kpad, void* stream) {
+  SEG_REQUIRE(Kpad >= d->R * d->S * d->C, "im2col: Kpad too small");
+  const int64_t total = (int64_t)d->N * d->P * d->Q * Kpad;
+  im2col_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(*d, x, x_nchw_f32, BF(col), Kpad);
+  return check_launch("im2col");
+}
+
+static dim3 colreduce_grid(int64_t M, int C) {
+  const int G = C / 8;
+  const int GB = G < 256 ? G : 256;
+  const int rows_par = 256 / GB;
+  const int gy = ceil_div(G, GB);
+  int64_t gx = ceil_div64(M, (int64_t)rows_par * 4);
+  const int64_t cap = (int64_t)num_sms() * 4 / gy + 1;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+
+int seg_bn_stats(const void* x, int64_t M, int C, int ldx, float* stats, void* stream) {
+  SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0, "bn_stats: C/ldx must be multiples of 8 (C=%d ldx=%d)", C, ldx);
+  bn_stats_kernel<<<colreduce_grid(M, C), 256, 0, ST(stream)>>>(CBF(x), M, C, ldx, stats);
+  return check_launch("bn_stats");
+}
+int seg_bn_finalize(const float* stats, double count, int C, const float* gamma, const float* beta, float eps,
+                    float momentum, int clamp_eps, float* running_mean, float* running_var, float* scale_shift,
+                    float* save, void* stream) {
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(stats, count, C, gamma, beta, eps, momentum, clamp_eps,
+                                                                running_mean, running_var, scale_shift, save);
+  return check_launch("bn_finalize");
+}
+int seg_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                            float* scale_shift, void* stream) {
+  bn_eval_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(C, gamma, beta, rm, rv, eps, scale_shift);
+  return check_launch("bn_eval");
+}
+int seg_bn_apply(const void* x, int ldx, const float* ss, const void* res, int ldr, void* out, int ldo, int64_t M, int C,
+                 int relu, float drop_p, uint64_t seed, void* stream) {
+  SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldr % 8 == 0), "bn_apply: alignment");
+  bn_apply_kernel<<<grid_for(M * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(x), ldx, ss, CBF(res), ldr, BF(out), ldo, M, C,
+                                                                      relu, drop_p, seed);
+  return check_launch("bn_apply");
+}
+int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,
+                      int64_t M, int C, int relu, float drop_p, float* sums, void* stream) {
+  SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && (!relu || ldo % 8 == 0), "bn_bwd_reduce: alignment");
+  bn_bwd_reduce_kernel<<<colreduce_grid(M, C), 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M,
+                                                                     C, relu, drop_p, sums);
+  return check_launch("bn_bwd_reduce");
+}
+int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,
+                     const float* gamma, const float* sums, double count, int64_t M, int C, int relu, float drop_p,
+                     void* dx, int lddx, void* dres, int lddres, float beta_res, void* stream) {
+  SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0, "bn_bwd_apply: alignment");
+  bn_bwd_apply_kernel<<<grid_for(M * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save,
+                                                                          gamma, sums, (float)(1.0 / count), M, C, relu,
+                                                                          drop_p, BF(dx), lddx, BF(dres), lddres, beta_res);
+  return check_launch("bn_bwd_apply");
+}
+int seg_bn_param_grad(const float* sums, int C, float* dgamma, float* dbeta, int accumulate, void* stream) {
+  bn_param_grad_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(sums, C, dgamma, dbeta, accumulate);
+  return check_launch("bn_param_grad");
+}
+
+int seg_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, int C, int P, int Q, void* stream) {
+  SEG_REQUIRE(C % 8 == 0, "maxpool: C %% 8");
+  maxpool_fwd_kernel<<<grid_for((int64_t)N * P * Q * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(x), BF(y), idx, N, H, W, C, P, Q);
+  return check_launch("maxpool_fwd");
+}
+int seg_maxpool3x3s2_bwd(const void* dy, const uint8_t* idx, void* dx, int N, int H, int W, int C, int P, int Q,
+                         void* stream) {
+  SEG_REQUIRE(C % 8 == 0, "maxpool: C %% 8");
+  maxpool_bwd_kernel<<<grid_for((int64_t)N * H * W * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(dy), idx, BF(dx), N, H, W, C, P, Q);
+  return check_launch("maxpool_bwd");
+}
+int seg_adaptive_avgpool_fwd(const void* x, int ldx, void* y, int N, int H, int W, int C, int bins, void* stream) {
+  SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0, "avgpool: alignment");
+  dim3 grid((unsigned)(N * bins * bins), (unsigned)ceil_div(C / 8, 32), 1);
+  adaptive_avgpool_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(x), ldx, BF(y), N, H, W, C, bins);
+  return check_launch("adaptive_avgpool_fwd");
+}
+int seg_adaptive_avgpool_bwd(const void* dy, void* dx, int lddx, int N, int H, int W, int C, int bins, float beta,
+                             void* stream) {
+  SEG_REQUIRE(C % 8 == 0 && lddx % 8 == 0, "avgpool: alignment");
+  adaptive_avgpool_bwd_kernel<<<grid_for((int64_t)N * H * W * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(dy), BF(dx), lddx, N, H,
+                                                                                                   W, C, bins, beta);
+  return check_launch("adaptive_avgpool_bwd");
+}
+
+int seg_bilinear_fwd(const void* x, int ldx, void* y, int ldy, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                     int align_corners, void* stream) {
+  SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "bilinear: alignment");
+  bilinear_fwd_kernel<<<grid_for((int64_t)N * Ho * Wo * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(x), ldx, BF(y), ldy, N, Hi, Wi, Ho, Wo, C, align_corners, resize_scale(Hi, Ho, align_corners),
+      resize_scale(Wi, Wo, align_corners));
+  return check_launch("bilinear_fwd");
+}
+int seg_bilinear_bwd(const void* dy, int lddy, void* dx, int lddx, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                     int align_corners, float beta, void* stream) {
+  SEG_REQUIRE(C % 8 == 0 && lddx % 8 == 0 && lddy % 8 == 0, "bilinear: alignment");
+  bilinear_bwd_kernel<<<grid_for((int64_t)N * Hi * Wi * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(dy), lddy, BF(dx), lddx, N, Hi, Wi, Ho, Wo, C, align_corners, resize_scale(Hi, Ho, align_corners),
+      resize_scale(Wi, Wo, align_corners), beta);
+  return check_launch("bilinear_bwd");
+}
+int seg_bilinear_logits_fwd(const float* x, float* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int align_corners,
+                            void* stream) {
+  bilinear_logits_fwd_kernel<<<grid_for((int64_t)N * Ho * Wo, 256), 256, 0, ST(stream)>>>(
+      x, y, N, Hi, Wi, Ho, Wo, C, align_corners, resize_scale(Hi, Ho, align_corners), resize_scale(Wi, Wo, align_corners));
+  return check_launch("bilinear_logits_fwd");
+}
+int seg_bilinear_logits_bwd(const float* dy, void* dx, int lddx, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                            int align_corners, void* stream) {
+  bilinear_logits_bwd_kernel<<<grid_for((int64_t)N * Hi * Wi, 128, 16), 128, 0, ST(stream)>>>(
+      dy, BF(dx), lddx, N, Hi, Wi, Ho, Wo, C, align_corners, resize_scale(Hi, Ho, align_corners),
+      resize_scale(Wi, Wo, align_corners));
+  return check_launch("bilinear_logits_bwd");
+}
+
+int seg_nhwc_to_nchw_f32(const void* x, int ldx, int x_dtype, float* y, int N, int H, int W, int C, void* stream) {
+  nhwc_to_nchw_kernel<<<grid_for((int64_t)N * C * H * W, 256), 256, 0, ST(stream)>>>(x, ldx, x_dtype, y, N, H, W, C);
+  return check_launch("nhwc_to_nchw");
+}
+int seg_axpby_bf16(const void* x, int ldx, void* y, int ldy, int64_t M, int C, float beta, void* stream) {
+  SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "axpby: alignment");
+  axpby_kernel<<<grid_for(M * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(x), ldx, BF(y), ldy, M, C, beta);
+  return check_launch("axpby");
+}
+int seg_sgd_step(float* const* params, float* const* grads, float* const* bufs, const int64_t* sizes, const float* lrs,
+                 int n, float momentum, float weight_decay, int first_step, float grad_scale, void* stream) {
+  if (n <= 0) return 0;
+  SgdChunkArgs a{params, grads, bufs, sizes, lrs};
+  dim3 grid(64, (unsigned)n, 1);
+  sgd_kernel<<<grid, 256, 0, ST(stream)>>>(a, momentum, weight_decay, first_step, grad_scale);
+  return check_launch("sgd_step");
+}
+
+}  // extern "C"

@@ -1,0 +1,299 @@
+"""Tensor-level wrappers over the C ABI (one Python function per ``seg_*`` entry point).
+
+Activations are NHWC ``torch.bfloat16`` tensors; a tensor may be a channel slice ``buf[..., a:b]`` of a wider
+buffer (that is how concatenation is expressed — no copy).  These wrappers only compute shapes / pitches and pass
+raw pointers; all arithmetic happens in the sm_100a kernels.
+"""
+import ctypes
+
+import torch
+
+from . import lib
+from .lib import DT_BF16, DT_F32, IMPL_AUTO, IMPL_SIMT, IMPL_TC, ConvDesc, call, make_conv_desc, ptr
+
+_IMPL_OVERRIDE = None
+
+
+def set_conv_impl(impl):
+    """Force a conv implementation (IMPL_AUTO / IMPL_SIMT / IMPL_TC) for every conv call; None restores per-call choice."""
+    global _IMPL_OVERRIDE
+    _IMPL_OVERRIDE = impl
+
+
+def _impl(impl):
+    return _IMPL_OVERRIDE if _IMPL_OVERRIDE is not None else impl
+
+
+def ld(t):
+    """Channel pitch of an NHWC (or [M, C]) tensor; checks the slice is addressable as rows of `ld` elements."""
+    assert t.stride(-1) == 1, "channel dim must be contiguous"
+    if t.dim() == 4:
+        n, h, w, c = t.shape
+        pitch = t.stride(2) if w > 1 else (t.stride(1) // w if h > 1 else (t.stride(0) // (h * w) if n > 1 else c))
+        assert w == 1 or t.stride(2) == pitch
+        assert h == 1 or t.stride(1) == w * pitch, "rows must be dense"
+        assert n == 1 or t.stride(0) == h * w * pitch, "images must be dense"
+        return pitch
+    return t.stride(-2) if t.shape[-2] > 1 else t.shape[-1]
+
+
+def rows(t):
+    m = 1
+    for s in t.shape[:-1]:
+        m *= s
+    return m
+
+
+# ---------------------------------------------------------------- conv
+def pack_weight(w_oihw, cpad=None):
+    K, C, R, S = w_oihw.shape
+    cpad = cpad or C
+    out = torch.empty((R * S, K, cpad), dtype=torch.bfloat16, device=w_oihw.device)
+    call("seg_pack_weight", ptr(w_oihw), ptr(out), K, C, R, S, cpad)
+    return out
+
+
+def unpack_wgrad(dw_packed, shape, beta=0.0, out=None):
+    K, C, R, S = shape
+    cpad = dw_packed.shape[-1]
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=dw_packed.device)
+        beta = 0.0
+    call("seg_unpack_wgrad", ptr(dw_packed), ptr(out), K, C, R, S, cpad, float(beta))
+    return out
+
+
+def conv_desc_for(x, K, R, S, stride, pad, dil, ldy=None):
+    N, H, W, C = x.shape
+    return make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil, ldx=ld(x), ldy=ldy)
+
+
+def conv2d_fwd(x, w_packed, K, R, S, stride=1, pad=0, dil=1, out=None, out_dtype=torch.bfloat16, bias=None, beta=0.0,
+               stats=None, impl=IMPL_AUTO):
+    N, H, W, C = x.shape
+    d = make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil, ldx=ld(x))
+    if out is None:
+        out = torch.empty((N, d.P, d.Q, K), dtype=out_dtype, device=x.device)
+    d.ldy = ld(out)
+    call("seg_conv2d_fwd", ctypes.byref(d), ptr(x), ptr(w_packed), ptr(out), DT_BF16 if out.dtype == torch.bfloat16 else DT_F32,
+         ptr(bias), float(beta), ptr(stats), _impl(impl))
+    return out
+
+
+def conv2d_dgrad(dy, w_packed, x_shape, R, S, stride=1, pad=0, dil=1, out=None, beta=0.0, impl=IMPL_AUTO):
+    N, H, W, C = x_shape
+    K = dy.shape[-1]
+    if out is None:
+        out = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=dy.device)
+        beta = 0.0
+    d = make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil, ldx=ld(out), ldy=ld(dy))
+    assert (d.P, d.Q) == (dy.shape[1], dy.shape[2])
+    call("seg_conv2d_dgrad", ctypes.byref(d), ptr(dy), ptr(w_packed), ptr(out), float(beta), _impl(impl))
+    return out
+
+
+def conv2d_wgrad(dy, x, R, S, stride=1, pad=0, dil=1, out=None, impl=IMPL_AUTO):
+    """Returns / accumulates into fp32 packed grad [R*S][K][C]."""
+    N, H, W, C = x.shape
+    K = dy.shape[-1]
+    if out is None:
+        out = torch.zeros((R * S, K, C), dtype=torch.float32, device=x.device)
+    d = make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil, ldx=ld(x), ldy=ld(dy))
+    assert (d.P, d.Q) == (dy.shape[1], dy.shape[2])
+    call("seg_conv2d_wgrad", ctypes.byref(d), ptr(dy), ptr(x), ptr(out), _impl(impl))
+    return out
+
+
+def im2col(x, R, S, stride, pad, dil, kpad, nchw_f32):
+    if nchw_f32:
+        N, C, H, W = x.shape
+        ldx = C
+    else:
+        N, H, W, C = x.shape
+        ldx = ld(x)
+    d = make_conv_desc(N, H, W, C, 1, R, S, stride, pad, dil, ldx=ldx, ldy=1)
+    col = torch.empty((N, d.P, d.Q, kpad), dtype=torch.bfloat16, device=x.device)
+    call("seg_im2col", ctypes.byref(d), ptr(x), 1 if nchw_f32 else 0, ptr(col), kpad)
+    return col
+
+
+# ---------------------------------------------------------------- batch norm
+def bn_stats(x, stats=None):
+    C = x.shape[-1]
+    if stats is None:
+        stats = torch.zeros(2 * C, dtype=torch.float32, device=x.device)
+    call("seg_bn_stats", ptr(x), rows(x), C, ld(x), ptr(stats))
+    return stats
+
+
+def bn_finalize(stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var):
+    C = gamma.numel()
+    ss = torch.empty(2 * C, dtype=torch.float32, device=stats.device)
+    save = torch.empty(2 * C, dtype=torch.float32, device=stats.device)
+    call("seg_bn_finalize", ptr(stats), float(count), C, ptr(gamma), ptr(beta), float(eps), float(momentum), int(clamp_eps),
+         ptr(running_mean), ptr(running_var), ptr(ss), ptr(save))
+    return ss, save
+
+
+def bn_eval_scale_shift(gamma, beta, rm, rv, eps):
+    C = gamma.numel()
+    ss = torch.empty(2 * C, dtype=torch.float32, device=gamma.device)
+    call("seg_bn_eval_scale_shift", C, ptr(gamma), ptr(beta), ptr(rm), ptr(rv), float(eps), ptr(ss))
+    return ss
+
+
+def bn_apply(x, scale_shift, res=None, out=None, relu=True, drop_p=0.0, seed=0):
+    C = x.shape[-1]
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    call("seg_bn_apply", ptr(x), ld(x), ptr(scale_shift), ptr(res), ld(res) if res is not None else 0, ptr(out), ld(out),
+         rows(x), C, int(relu), float(drop_p), int(seed))
+    return out
+
+
+def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, sums=None):
+    C = x.shape[-1]
+    if sums is None:
+        sums = torch.zeros(2 * C, dtype=torch.float32, device=x.device)
+    call("seg_bn_bwd_reduce", ptr(dout), ld(dout), ptr(out), ld(out) if out is not None else 0, ptr(x), ld(x), ptr(save),
+         rows(x), C, int(relu), float(drop_p), ptr(sums))
+    return sums
+
+
+def bn_bwd_apply(dout, out, x, save, gamma, sums, count, relu=True, drop_p=0.0, dx=None, dres=None, beta_res=0.0):
+    C = x.shape[-1]
+    if dx is None:
+        dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    call("seg_bn_bwd_apply", ptr(dout), ld(dout), ptr(out), ld(out) if out is not None else 0, ptr(x), ld(x), ptr(save),
+         ptr(gamma), ptr(sums), float(count), rows(x), C, int(relu), float(drop_p), ptr(dx), ld(dx), ptr(dres),
+         ld(dres) if dres is not None else 0, float(beta_res))
+    return dx
+
+
+def bn_param_grad(sums, dgamma, dbeta, accumulate=False):
+    C = sums.numel() // 2
+    call("seg_bn_param_grad", ptr(sums), C, ptr(dgamma), ptr(dbeta), int(accumulate))
+
+
+# ---------------------------------------------------------------- pooling / resize
+def maxpool3x3s2_fwd(x):
+    N, H, W, C = x.shape
+    P, Q = lib.conv_out_size(H, 3, 2, 1, 1), lib.conv_out_size(W, 3, 2, 1, 1)
+    assert x.is_contiguous()
+    y = torch.empty((N, P, Q, C), dtype=torch.bfloat16, device=x.device)
+    idx = torch.empty((N, P, Q, C), dtype=torch.uint8, device=x.device)
+    call("seg_maxpool3x3s2_fwd", ptr(x), ptr(y), ptr(idx), N, H, W, C, P, Q)
+    return y, idx
+
+
+def maxpool3x3s2_bwd(dy, idx, x_shape):
+    N, H, W, C = x_shape
+    P, Q = dy.shape[1], dy.shape[2]
+    assert dy.is_contiguous()
+    dx = torch.empty(x_shape, dtype=torch.bfloat16, device=dy.device)
+    call("seg_maxpool3x3s2_bwd", ptr(dy), ptr(idx), ptr(dx), N, H, W, C, P, Q)
+    return dx
+
+
+def adaptive_avgpool_fwd(x, bins):
+    N, H, W, C = x.shape
+    y = torch.empty((N, bins, bins, C), dtype=torch.bfloat16, device=x.device)
+    call("seg_adaptive_avgpool_fwd", ptr(x), ld(x), ptr(y), N, H, W, C, bins)
+    return y
+
+
+def adaptive_avgpool_bwd(dy, x_shape, bins, dx=None, beta=0.0):
+    N, H, W, C = x_shape
+    assert dy.is_contiguous()
+    if dx is None:
+        dx = torch.empty(x_shape, dtype=torch.bfloat16, device=dy.device)
+        beta = 0.0
+    call("seg_adaptive_avgpool_bwd", ptr(dy), ptr(dx), ld(dx), N, H, W, C, bins, float(beta))
+    return dx
+
+
+def bilinear_fwd(x, Ho, Wo, align_corners, out=None):
+    N, Hi, Wi, C = x.shape
+    if out is None:
+        out = torch.empty((N, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
+    call("seg_bilinear_fwd", ptr(x), ld(x), ptr(out), ld(out), N, Hi, Wi, Ho, Wo, C, int(align_corners))
+    return out
+
+
+def bilinear_bwd(dy, Hi, Wi, align_corners, dx=None, beta=0.0):
+    N, Ho, Wo, C = dy.shape
+    if dx is None:
+        dx = torch.empty((N, Hi, Wi, C), dtype=torch.bfloat16, device=dy.device)
+        beta = 0.0
+    call("seg_bilinear_bwd", ptr(dy), ld(dy), ptr(dx), ld(dx), N, Hi, Wi, Ho, Wo, C, int(align_corners), float(beta))
+    return dx
+
+
+def bilinear_logits_fwd(x_nhwc_f32, Ho, Wo, align_corners):
+    N, Hi, Wi, C = x_nhwc_f32.shape
+    assert x_nhwc_f32.is_contiguous() and x_nhwc_f32.dtype == torch.float32
+    y = torch.empty((N, C, Ho, Wo), dtype=torch.float32, device=x_nhwc_f32.device)
+    call("seg_bilinear_logits_fwd", ptr(x_nhwc_f32), ptr(y), N, Hi, Wi, Ho, Wo, C, int(align_corners))
+    return y
+
+
+def bilinear_logits_bwd(dy_nchw, Hi, Wi, align_corners, ldx):
+    N, C, Ho, Wo = dy_nchw.shape
+    assert dy_nchw.is_contiguous() and dy_nchw.dtype == torch.float32
+    dx = torch.empty((N, Hi, Wi, ldx), dtype=torch.bfloat16, device=dy_nchw.device)
+    call("seg_bilinear_logits_bwd", ptr(dy_nchw), ptr(dx), ldx, N, Hi, Wi, Ho, Wo, C, int(align_corners))
+    return dx
+
+
+# ---------------------------------------------------------------- loss
+def ce_nchw_fwd(logits, target, ignore_index):
+    N, C, H, W = logits.shape
+    assert logits.is_contiguous() and logits.dtype == torch.float32 and target.dtype == torch.int64 and target.is_contiguous()
+    accum = torch.zeros(2, dtype=torch.float64, device=logits.device)
+    call("seg_ce_nchw_fwd", ptr(logits), ptr(target), N, C, H, W, int(ignore_index), ptr(accum))
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    call("seg_ce_finalize", ptr(accum), ptr(loss))
+    return loss, accum
+
+
+def ce_nchw_bwd(logits, target, ignore_index, accum, gscale=None):
+    N, C, H, W = logits.shape
+    dl = torch.empty_like(logits)
+    call("seg_ce_nchw_bwd", ptr(logits), ptr(target), N, C, H, W, int(ignore_index), ptr(accum), ptr(gscale), ptr(dl))
+    return dl
+
+
+def upsample_ce_fwd(logits_lo, target, align_corners, ignore_index, want_argmax=False):
+    N, Hi, Wi, C = logits_lo.shape
+    _, Ho, Wo = target.shape
+    assert logits_lo.is_contiguous() and logits_lo.dtype == torch.float32 and target.is_contiguous()
+    accum = torch.zeros(2, dtype=torch.float64, device=logits_lo.device)
+    am = torch.empty((N, Ho, Wo), dtype=torch.int32, device=logits_lo.device) if want_argmax else None
+    call("seg_upsample_ce_fwd", ptr(logits_lo), ptr(target), N, Hi, Wi, Ho, Wo, C, int(align_corners), int(ignore_index),
+         ptr(accum), ptr(am))
+    loss = torch.empty((), dtype=torch.float32, device=logits_lo.device)
+    call("seg_ce_finalize", ptr(accum), ptr(loss))
+    return loss, accum, am
+
+
+def upsample_ce_bwd(logits_lo, target, align_corners, ignore_index, accum, ldx, gscale=None):
+    N, Hi, Wi, C = logits_lo.shape
+    _, Ho, Wo = target.shape
+    dlo = torch.empty((N, Hi, Wi, C), dtype=torch.float32, device=logits_lo.device)
+    dx = torch.empty((N, Hi, Wi, ldx), dtype=torch.bfloat16, device=logits_lo.device)
+    call("seg_upsample_ce_bwd", ptr(logits_lo), ptr(target), N, Hi, Wi, Ho, Wo, C, int(align_corners), int(ignore_index),
+         ptr(accum), ptr(gscale), ptr(dlo), ptr(dx), ldx)
+    return dx, dlo
+
+
+# ---------------------------------------------------------------- misc
+def nhwc_to_nchw_f32(x):
+    N, H, W, C = x.shape
+    y = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    call("seg_nhwc_to_nchw_f32", ptr(x), ld(x), DT_BF16 if x.dtype == torch.bfloat16 else DT_F32, ptr(y), N, H, W, C)
+    return y
+
+
+def axpby(x, y, beta):
+    call("seg_axpby_bf16", ptr(x), ld(x), ptr(y), ld(y), rows(x), x.shape[-1], float(beta))
+    return y
