@@ -87,9 +87,10 @@ int seg_bn_stats(const void* x, int64_t M, int C, int ldx, float* stats, void* s
 int seg_bn_finalize(const float* stats, double count, int C, const float* gamma, const float* beta, float eps,
                     float momentum, int clamp_eps, float* running_mean, float* running_var, float* scale_shift,
                     float* save_mean_istd, void* stream);
-/* eval-mode: scale/shift from running stats */
+/* eval-mode (or frozen, BaseModel.freeze_bn): scale/shift from running stats; optionally also (mean, inv_std) */
 int seg_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const float* running_mean,
-                            const float* running_var, float eps, float* scale_shift, void* stream);
+                            const float* running_var, float eps, float* scale_shift, float* save_mean_istd,
+                            void* stream);
 /* out = dropout(relu?(x*scale+shift (+res)))  — x,res,out bf16 [M][ld*]; drop_p = 0 disables dropout
  * (nn.ReLU(inplace) + residual add torchvision Bottleneck; nn.Dropout deeplabv3_plus.py:282,318) */
 int seg_bn_apply(const void* x, int ldx, const float* scale_shift, const void* res, int ldr, void* out, int ldo,

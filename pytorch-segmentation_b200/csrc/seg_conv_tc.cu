@@ -481,7 +481,7 @@ int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int 
 }
 
 int conv_dgrad(const seg_conv_desc* d, const void* dy, const void* w, void* dx, float beta, cudaStream_t stream) {
-  SEG_REQUIRE(supported(d) && d->stride == 1 && d->K % 8 == 0 && d->ldy % 8 == 0,
+  SEG_REQUIRE(supported(d) && d->stride == 1 && d->ldy % 8 == 0,
               "tcgen05 conv dgrad: unsupported shape (stride=%d K=%d ldy=%d)", d->stride, d->K, d->ldy);
   TcParams p;
   memset(&p, 0, sizeof(p));

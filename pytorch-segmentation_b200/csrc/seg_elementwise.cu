@@ -150,13 +150,17 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, double count
 }
 
 __global__ void bn_eval_kernel(int C, const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
-                               float* scale_shift) {
+                               float* scale_shift, float* save) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float istd = rsqrtf(rv[c] + eps);
   const float sc = gamma[c] * istd;
   scale_shift[c] = sc;
   scale_shift[C + c] = beta[c] - rm[c] * sc;
+  if (save) {
+    save[c] = rm[c];
+    save[C + c] = istd;
+  }
 }
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
@@ -744,8 +748,8 @@ int seg_bn_finalize(const float* stats, double count, int C, const float* gamma,
   return check_launch("bn_finalize");
 }
 int seg_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
-                            float* scale_shift, void* stream) {
-  bn_eval_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(C, gamma, beta, rm, rv, eps, scale_shift);
+                            float* scale_shift, float* save_mean_istd, void* stream) {
+  bn_eval_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(C, gamma, beta, rm, rv, eps, scale_shift, save_mean_istd);
   return check_launch("bn_eval");
 }
 int seg_bn_apply(const void* x, int ldx, const float* ss, const void* res, int ldr, void* out, int ldo, int64_t M, int C,

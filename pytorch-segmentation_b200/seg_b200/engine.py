@@ -1,0 +1,311 @@
+"""Forward/backward engine: a tape of hand-written-kernel ops over NHWC bf16 activations.
+
+The reference runs the hot path through torch.autograd over ATen ops (trainer.py:56,70).  Here the model's forward
+is a straight-line sequence of C-ABI kernel calls recorded on a `Tape`; `Tape.backward()` replays the recorded
+closures in reverse (dgrad / wgrad / BN-backward / resize-backward kernels).  torch is used for device memory only.
+
+Conventions
+  * `Act` = an activation: `.t` NHWC bf16 tensor (possibly a channel slice of a concat buffer), `.grad` its
+    gradient buffer (allocated on first write; later writers accumulate with beta = 1).
+  * BatchNorm (training) = statistics fused into the producing conv's epilogue -> `bn_finalize` -> one fused
+    apply(+residual +ReLU +dropout) pass.  Backward = one reduce pass + one apply pass.
+  * concatenation never copies: producers write into channel slices of one buffer (`Tape.concat`).
+"""
+import torch
+
+from . import ops
+from .lib import IMPL_AUTO
+
+BN_EPS = 1e-5
+BN_MOM = 0.1
+ACT_DTYPE = torch.bfloat16  # storage type of activations / activation gradients (the kernels are bf16-only;
+                            # tests/test_engine_cpu_emulated.py flips this to fp32 together with the ATen emulation)
+
+
+class Act:
+    __slots__ = ("t", "grad", "needs_grad", "_written")
+
+    def __init__(self, t, needs_grad=True):
+        self.t = t
+        self.grad = None
+        self.needs_grad = needs_grad
+        self._written = False
+
+    @property
+    def shape(self):
+        return self.t.shape
+
+    def grad_target(self):
+        """(buffer, beta): beta = 0 for the first writer of this gradient, 1 afterwards."""
+        if self.grad is None:
+            self.grad = torch.empty(self.t.shape, dtype=ACT_DTYPE, device=self.t.device)
+        if not self._written:
+            self._written = True
+            return self.grad, 0.0
+        return self.grad, 1.0
+
+
+class ConvSpec:
+    """Static description of one nn.Conv2d holder + its packed bf16 weight cache."""
+
+    def __init__(self, name, module, explicit_im2col=False):
+        self.name = name
+        self.m = module
+        w = module.weight
+        self.K, self.C, self.R, self.S = w.shape
+        assert module.stride[0] == module.stride[1] and module.padding[0] == module.padding[1]
+        assert module.dilation[0] == module.dilation[1] and module.groups == 1
+        self.explicit = explicit_im2col or (self.C % 8 != 0)
+        self.kpad = (self.R * self.S * self.C + 7) // 8 * 8 if self.explicit else None
+        self._packed = None
+        self._version = None
+
+    @property
+    def stride(self):
+        return self.m.stride[0]
+
+    @property
+    def pad(self):
+        return self.m.padding[0]
+
+    @property
+    def dil(self):
+        return self.m.dilation[0]
+
+    def packed(self):
+        w = self.m.weight
+        key = (w._version, w.data_ptr())
+        if self._packed is None or self._version != key:
+            if self.explicit:
+                # column order (r, s, c): OIHW -> O,(H,W,I) as a 1x1 weight over Kpad "channels"
+                w2 = w.detach().permute(0, 2, 3, 1).reshape(self.K, self.R * self.S * self.C, 1, 1).contiguous()
+                self._packed = ops.pack_weight(w2, cpad=self.kpad)
+            else:
+                self._packed = ops.pack_weight(w.detach())
+            self._version = key
+        return self._packed
+
+
+class Tape:
+    def __init__(self, training, record=None, grads=None, impl=IMPL_AUTO, dropout=True, seed=0, sync=None, clamp_eps=False):
+        self.training = training                                  # module.training semantics (batch stats, dropout)
+        self.record = training if record is None else record      # record backward closures
+        self.back = []
+        self.grads = grads if grads is not None else {}  # Parameter -> fp32 grad tensor (param layout)
+        self.impl = impl
+        self.dropout = dropout
+        self.seed = seed
+        self.sync = sync  # object with .allreduce_(fp32 vector) and .world ; None = local BN
+        self.clamp_eps = clamp_eps
+        self._drop_ctr = 0
+        self.bn_modules = []
+
+    # ------------------------------------------------------------------ helpers
+    def _param_grad(self, p, value_fn):
+        """Write (or accumulate into) the fp32 gradient of parameter p.  value_fn(out, beta) fills it."""
+        if not p.requires_grad:
+            return
+        if p in self.grads:
+            value_fn(self.grads[p], 1.0)
+        else:
+            g = torch.empty(p.shape, dtype=torch.float32, device=p.device)
+            value_fn(g, 0.0)
+            self.grads[p] = g
+
+    def backward(self):
+        for fn in reversed(self.back):
+            fn()
+        self.back = []
+
+    # ------------------------------------------------------------------ conv
+    def conv(self, x, spec, out=None, out_dtype=None, want_stats=False):
+        """x: Act (NHWC bf16) — or, for an explicit-im2col conv, a raw NCHW fp32 tensor (the network input)."""
+        wp = spec.packed()
+        bias = spec.m.bias
+        stats = None
+        if out_dtype is None:
+            out_dtype = ACT_DTYPE
+        if want_stats and self.training:
+            stats = torch.zeros(2 * spec.K, dtype=torch.float32, device=wp.device)
+        if spec.explicit:
+            nchw = not isinstance(x, Act)
+            src = x if nchw else x.t
+            col = ops.im2col(src, spec.R, spec.S, spec.stride, spec.pad, spec.dil, spec.kpad, nchw_f32=nchw)
+            y = ops.conv2d_fwd(col, wp, spec.K, 1, 1, out=out, out_dtype=out_dtype,
+                               bias=bias.detach() if bias is not None else None, stats=stats, impl=self.impl)
+            xin, geo = col, (1, 1, 1, 0, 1)
+        else:
+            y = ops.conv2d_fwd(x.t, wp, spec.K, spec.R, spec.S, spec.stride, spec.pad, spec.dil, out=out, out_dtype=out_dtype,
+                               bias=bias.detach() if bias is not None else None, stats=stats, impl=self.impl)
+            xin, geo = x.t, (spec.R, spec.S, spec.stride, spec.pad, spec.dil)
+        ya = Act(y)
+        if self.record:
+            def bwd():
+                dy = ya.grad
+                if dy is None:
+                    return
+                R, S, stride, pad, dil = geo
+                if spec.m.weight.requires_grad:
+                    dwp = ops.conv2d_wgrad(dy, xin, R, S, stride, pad, dil, impl=self.impl)
+                    if spec.explicit:
+                        def fill(g, beta):
+                            # packed [1][K][Kpad] -> [K][R,S,C] -> OIHW
+                            full = dwp[0, :, : spec.R * spec.S * spec.C].reshape(spec.K, spec.R, spec.S, spec.C).permute(0, 3, 1, 2)
+                            if beta:
+                                g.add_(full)
+                            else:
+                                g.copy_(full)
+                    else:
+                        def fill(g, beta):
+                            ops.unpack_wgrad(dwp, tuple(spec.m.weight.shape), beta=beta, out=g)
+                    self._param_grad(spec.m.weight, fill)
+                if bias is not None and bias.requires_grad:
+                    cpad = ops.ld(dy)
+                    wide = dy if dy.shape[-1] % 8 == 0 else dy.as_strided(dy.shape[:-1] + (cpad,), dy.stride(), dy.storage_offset())
+                    s = ops.bn_stats(wide)
+                    self._param_grad(bias, lambda g, beta: g.add_(s[: spec.K]) if beta else g.copy_(s[: spec.K]))
+                if (not spec.explicit) and isinstance(x, Act) and x.needs_grad:
+                    gx, beta = x.grad_target()
+                    ops.conv2d_dgrad(dy, wp, tuple(x.t.shape), R, S, stride, pad, dil, out=gx, beta=beta, impl=self.impl)
+                ya.grad = None
+            self.back.append(bwd)
+        return ya, stats
+
+    # ------------------------------------------------------------------ batch norm (+ residual, ReLU, dropout)
+    def bn_act(self, y, bn, stats=None, relu=True, res=None, out=None, drop_p=0.0):
+        """y: Act holding the raw conv output.  Returns the activated Act."""
+        C = y.t.shape[-1]
+        count_local = ops.rows(y.t)
+        use_batch_stats = self.training and bn.training
+        if self.training and not (self.dropout):
+            drop_p = 0.0
+        if not self.training:
+            drop_p = 0.0
+        seed = 0
+        if drop_p > 0.0:
+            self._drop_ctr += 1
+            seed = (self.seed * 1000003 + self._drop_ctr * 7919) & 0x7FFFFFFFFFFFFFFF
+        if use_batch_stats:
+            if stats is None:
+                stats = ops.bn_stats(y.t)
+            count = count_local
+            if self.sync is not None and self.sync.world > 1:
+                self.sync.allreduce_(stats)
+                count = count_local * self.sync.world
+            ss, save = ops.bn_finalize(stats, count, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum if bn.momentum is not None else BN_MOM,
+                                       1 if (self.clamp_eps and self.sync is not None and self.sync.world > 1) else 0,
+                                       bn.running_mean, bn.running_var)
+            self.bn_modules.append(bn)
+        else:
+            ss, save = ops.bn_eval_scale_shift(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps,
+                                               want_save=True)
+            count = count_local
+        a = ops.bn_apply(y.t, ss, res=res.t if res is not None else None, out=out, relu=relu, drop_p=drop_p, seed=seed)
+        aa = Act(a)
+        if self.record:
+            def bwd():
+                da = aa.grad
+                if da is None:
+                    return
+                sums = ops.bn_bwd_reduce(da, a, y.t, save, relu=relu, drop_p=drop_p)
+                gsums = sums
+                if not use_batch_stats:
+                    gsums = torch.zeros_like(sums)  # frozen BN (freeze_bn): dx = gamma * inv_std * dz
+                elif self.sync is not None and self.sync.world > 1:
+                    gsums = sums.clone()
+                    self.sync.allreduce_(gsums)
+                if bn.weight.requires_grad:
+                    dg = torch.empty(C, dtype=torch.float32, device=a.device)
+                    db = torch.empty(C, dtype=torch.float32, device=a.device)
+                    ops.bn_param_grad(sums, dg, db)
+                    self._param_grad(bn.weight, lambda g, beta: g.add_(dg) if beta else g.copy_(dg))
+                    self._param_grad(bn.bias, lambda g, beta: g.add_(db) if beta else g.copy_(db))
+                dy = torch.empty(y.t.shape, dtype=ACT_DTYPE, device=a.device)
+                dres, beta_res = (None, 0.0)
+                if res is not None and res.needs_grad:
+                    dres, beta_res = res.grad_target()
+                ops.bn_bwd_apply(da, a, y.t, save, bn.weight.detach(), gsums, count, relu=relu, drop_p=drop_p, dx=dy, dres=dres,
+                                 beta_res=beta_res)
+                y.grad = dy
+                aa.grad = None
+            self.back.append(bwd)
+        return aa
+
+    # ------------------------------------------------------------------ pooling / resize / concat
+    def maxpool(self, x):
+        y, idx = ops.maxpool3x3s2_fwd(x.t)
+        ya = Act(y)
+        if self.record:
+            def bwd():
+                if ya.grad is None or not x.needs_grad:
+                    return
+                assert x.grad is None, "maxpool input must have a single consumer"
+                x.grad = ops.maxpool3x3s2_bwd(ya.grad, idx, tuple(x.t.shape))
+                ya.grad = None
+            self.back.append(bwd)
+        return ya
+
+    def avgpool(self, x, bins):
+        y = ops.adaptive_avgpool_fwd(x.t, bins)
+        ya = Act(y)
+        if self.record:
+            def bwd():
+                if ya.grad is None or not x.needs_grad:
+                    return
+                gx, beta = x.grad_target()
+                ops.adaptive_avgpool_bwd(ya.grad, tuple(x.t.shape), bins, dx=gx, beta=beta)
+                ya.grad = None
+            self.back.append(bwd)
+        return ya
+
+    def bilinear(self, x, Ho, Wo, align_corners, out=None):
+        y = ops.bilinear_fwd(x.t, Ho, Wo, align_corners, out=out)
+        ya = Act(y)
+        if self.record:
+            def bwd():
+                if ya.grad is None or not x.needs_grad:
+                    return
+                gx, beta = x.grad_target()
+                ops.bilinear_bwd(ya.grad, x.t.shape[1], x.t.shape[2], align_corners, dx=gx, beta=beta)
+                ya.grad = None
+            self.back.append(bwd)
+        return ya
+
+    def copy_into(self, x, out):
+        """Copy an activation into a concat slice (used when the producer's tensor is also consumed elsewhere)."""
+        ops.axpby(x.t, out, 0.0)
+        ya = Act(out)
+        if self.record:
+            def bwd():
+                if ya.grad is None or not x.needs_grad:
+                    return
+                gx, beta = x.grad_target()
+                ops.axpby(ya.grad, gx, beta)
+                ya.grad = None
+            self.back.append(bwd)
+        return ya
+
+    def concat(self, N, H, W, channels, device):
+        """Allocate one NHWC buffer; returns (whole Act, [slice tensors]).  Producers pass a slice as `out=`; call
+        `bind_slices` with the producer Acts so their gradients alias slices of the whole gradient."""
+        total = sum(channels)
+        buf = torch.empty((N, H, W, total), dtype=ACT_DTYPE, device=device)
+        whole = Act(buf)
+        slices, off = [], 0
+        for c in channels:
+            slices.append(buf[..., off:off + c])
+            off += c
+        return whole, slices
+
+    def bind_slices(self, whole, acts):
+        """After the producers ran: make each producer Act's gradient a view of the concat gradient buffer."""
+        if not self.record:
+            return
+        g = torch.empty(whole.t.shape, dtype=ACT_DTYPE, device=whole.t.device)
+        whole.grad = g
+        off = 0
+        for a in acts:
+            c = a.t.shape[-1]
+            a.grad = g[..., off:off + c]
+            off += c
+        whole._written = False  # the consumer's dgrad overwrites (beta = 0) the pre-allocated buffer

@@ -47,7 +47,7 @@ _SIGS = {
     "seg_im2col": (c_int, [POINTER(ConvDesc), c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "seg_bn_stats": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "seg_bn_finalize": (c_int, [c_void_p, c_double, c_int, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "seg_bn_eval_scale_shift": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "seg_bn_eval_scale_shift": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
     "seg_bn_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int, c_float, c_uint64, c_void_p]),
     "seg_bn_bwd_reduce": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p]),
     "seg_bn_bwd_apply": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_double, c_int64, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_int, c_float, c_void_p]),

@@ -1,0 +1,408 @@
+"""B200-native drop-in models for the reference's plugin surface (models/__init__.py registry):
+
+    DeepLab(num_classes, in_channels=3, backbone='resnet101', pretrained=False, output_stride=16, freeze_bn=False, **_)
+    PSPNet (num_classes, in_channels=3, backbone='resnet50',  pretrained=False, use_aux=True,   freeze_bn=False, **_)
+
+Same constructor contract, same `state_dict()` keys and OIHW fp32 parameter layout, same `get_backbone_params /
+get_decoder_params / freeze_bn` methods and the same forward contract (fp32 NCHW logits at input resolution; PSPNet
+returns `(out, aux)` in training) as models/deeplabv3_plus.py:336-377 and models/pspnet.py:41-105 — so train.py,
+BaseTrainer (base/base_trainer.py:46-57), torch.optim.SGD, checkpoints and `convert_model` keep working.
+
+The nn.Conv2d / nn.BatchNorm2d children are PARAMETER HOLDERS only: forward never calls them.  `forward` runs the
+hand-written sm_100a kernels through `engine.Tape`; gradients reach the parameters through one autograd.Function.
+There is no CPU / eager path: a CPU input raises.
+"""
+import logging
+import math
+from itertools import chain
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .engine import Act, ConvSpec, Tape
+from .lib import IMPL_AUTO, require_device
+
+try:  # inside the reference tree: subclass its BaseModel so isinstance checks and logging behave identically
+    from base import BaseModel as _RefBaseModel  # type: ignore
+except Exception:  # standalone (tests, bench, GPU box): API-compatible stand-in for base/base_model.py:6-23
+    _RefBaseModel = None
+
+
+class BaseModel(nn.Module if _RefBaseModel is None else _RefBaseModel):
+    def __init__(self):
+        super().__init__()
+        if not hasattr(self, "logger"):
+            self.logger = logging.getLogger(self.__class__.__name__)
+
+    def _n_trainable(self):
+        return int(sum(np.prod(p.size()) for p in self.parameters() if p.requires_grad))
+
+    def summary(self):
+        self.logger.info(f"Nbr of trainable parameters: {self._n_trainable()}")
+
+    def __str__(self):
+        return nn.Module.__str__(self) + f"\nNbr of trainable parameters: {self._n_trainable()}"
+
+
+RESNET_BLOCKS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3), "resnet152": (3, 8, 36, 3)}
+
+
+# ----------------------------------------------------------------------------------------------- holders
+class _Holder(nn.Module):
+    """Named container of parameter-holding children; never executed."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("seg_b200 modules are parameter holders; call the top-level model")
+
+
+def _cbn(cin, cout, k, stride=1, dil=1, pad=None):
+    if pad is None:
+        pad = 0 if k == 1 else dil
+    return nn.Conv2d(cin, cout, k, stride=stride, padding=pad, dilation=dil, bias=False), nn.BatchNorm2d(cout)
+
+
+def _bottleneck(inplanes, planes, stride, dil, with_downsample):
+    b = _Holder()
+    b.conv1, b.bn1 = _cbn(inplanes, planes, 1)
+    b.conv2, b.bn2 = _cbn(planes, planes, 3, stride, dil)
+    b.conv3, b.bn3 = _cbn(planes, planes * 4, 1)
+    b.relu = nn.ReLU(inplace=True)
+    if with_downsample:
+        c, n = _cbn(inplanes, planes * 4, 1, stride)
+        b.downsample = nn.Sequential(c, n)
+    else:
+        b.downsample = None
+    return b
+
+
+def _res_layers(blocks, inplanes, plan):
+    """plan: per layer (first-block stride, first-block dilation, other-block dilation)."""
+    layers = []
+    for li, (n, planes) in enumerate(zip(blocks, (64, 128, 256, 512))):
+        stride, d0, d = plan[li]
+        seq = []
+        for b in range(n):
+            seq.append(_bottleneck(inplanes, planes, stride if b == 0 else 1, d0 if b == 0 else d, b == 0))
+            inplanes = planes * 4
+        layers.append(nn.Sequential(*seq))
+    return layers
+
+
+def _init_like_reference_head(*mods):
+    """utils/helpers.py:12-22 (initialize_weights): kaiming-normal convs (fan_in, relu), BN gamma=1, beta=1e-4."""
+    for mod in mods:
+        for m in mod.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight.data, nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1.0)
+                m.bias.data.fill_(1e-4)
+
+
+def _init_like_torchvision_trunk(*mods):
+    for mod in mods:
+        for m in mod.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+
+def _init_like_resnet_s(*mods):
+    """models/resnet.py:172-178: normal(0, sqrt(2/(k*k*cout))), BN 1/0."""
+    for mod in mods:
+        for m in mod.modules():
+            if isinstance(m, nn.Conv2d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2.0 / n))
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+
+
+# ----------------------------------------------------------------------------------------------- autograd bridge
+class _EngineFn(torch.autograd.Function):
+    """One autograd node for the whole model: forward = kernel tape, backward = tape replay."""
+
+    @staticmethod
+    def forward(ctx, model, record, x, *params):
+        outs, tape, heads = model._run(x, training=model.training, record=record)
+        ctx.tape, ctx.heads, ctx.params = tape, heads, params
+        return outs if len(outs) > 1 else outs[0]
+
+    @staticmethod
+    def backward(ctx, *douts):
+        tape = ctx.tape
+        if tape is None or not tape.record:
+            raise RuntimeError("backward through a forward that ran without gradient recording")
+        for (lo_act, Hl, Wl, ac), dout in zip(ctx.heads, douts):
+            if dout is None:
+                continue
+            C = dout.shape[1]
+            ldx = (C + 7) // 8 * 8
+            g = ops.bilinear_logits_bwd(dout.contiguous().float(), Hl, Wl, ac, ldx)
+            lo_act.grad = g[..., :C]
+        tape.backward()
+        grads = tape.grads
+        ctx.tape = None
+        return (None, None, None) + tuple(grads.get(p) for p in ctx.params)
+
+
+class _EngineModel(BaseModel):
+    """Shared plumbing: spec cache, engine options, forward entry."""
+
+    def __init__(self):
+        super().__init__()
+        self._specs = {}
+        self.conv_impl = IMPL_AUTO
+        self.engine_dropout = True    # set False to run train-mode parity with p = 0
+        self.engine_seed = 0
+        self.bn_sync = None           # seg_b200.comm.SyncBNGroup for multi-GPU SyncBN
+        self.syncbn_clamp_eps = True  # reproduce sync_batchnorm/batchnorm.py:145 when stats are synchronised
+        self._step = 0
+
+    def _spec(self, name, module):
+        s = self._specs.get(name)
+        if s is None or s.m is not module:
+            s = ConvSpec(name, module)
+            self._specs[name] = s
+        return s
+
+    def _new_tape(self, training, record):
+        self._step += 1
+        return Tape(training, record=record, impl=self.conv_impl, dropout=self.engine_dropout, seed=self.engine_seed * 7919 + self._step,
+                    sync=self.bn_sync, clamp_eps=self.syncbn_clamp_eps)
+
+    def _cbr(self, tape, x, name, conv, bn, relu=True, res=None, out=None, drop_p=0.0):
+        y, st = tape.conv(x, self._spec(name, conv), want_stats=True)
+        return tape.bn_act(y, bn, st, relu=relu, res=res, out=out, drop_p=drop_p)
+
+    def _block(self, tape, x, prefix, blk):
+        a = self._cbr(tape, x, prefix + "conv1", blk.conv1, blk.bn1)
+        a = self._cbr(tape, a, prefix + "conv2", blk.conv2, blk.bn2)
+        r = x
+        if blk.downsample is not None:
+            r = self._cbr(tape, x, prefix + "downsample.0", blk.downsample[0], blk.downsample[1], relu=False)
+        return self._cbr(tape, a, prefix + "conv3", blk.conv3, blk.bn3, relu=True, res=r)
+
+    def _finish(self, tape):
+        if tape.bn_modules:
+            torch._foreach_add_([m.num_batches_tracked for m in tape.bn_modules], 1)
+
+    def _check_input(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("seg_b200 models run on a B200 only; there is no CPU / eager fallback")
+        require_device()
+
+    def forward(self, x):
+        self._check_input(x)
+        params = [p for p in self.parameters()]
+        record = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _EngineFn.apply(self, record, x, *params)
+
+    def freeze_bn(self):
+        for module in self.modules():
+            if isinstance(module, nn.BatchNorm2d):
+                module.eval()
+
+
+# ----------------------------------------------------------------------------------------------- DeepLabV3+
+class DeepLab(_EngineModel):
+    """DeepLabV3+ with a (dilated) torchvision-style ResNet trunk — replaces models/deeplabv3_plus.py:336-377."""
+
+    def __init__(self, num_classes, in_channels=3, backbone="resnet101", pretrained=False, output_stride=16,
+                 freeze_bn=False, freeze_backbone=False, **_):
+        super().__init__()
+        if "resnet" not in backbone or backbone not in RESNET_BLOCKS:
+            raise NotImplementedError(f"seg_b200.DeepLab: backbone {backbone!r} not built yet (resnet50/101/152 are)")
+        if pretrained:
+            raise RuntimeError("pretrained weights need network access; load a state_dict instead")
+        assert output_stride in (8, 16)
+        self.num_classes, self.output_stride, self.backbone_name = num_classes, output_stride, backbone
+        # deeplabv3_plus.py:35-53: os16 -> layer3 stride 2, layer4 every conv2 d=2 ; os8 -> layer3 d=2, layer4 d=4
+        if output_stride == 16:
+            plan = [(1, 1, 1), (2, 1, 1), (2, 1, 1), (1, 2, 2)]
+        else:
+            plan = [(1, 1, 1), (2, 1, 1), (1, 2, 2), (1, 4, 4)]
+        bb = _Holder()
+        c0, b0 = nn.Conv2d(in_channels, 64, 7, stride=2, padding=3, bias=False), nn.BatchNorm2d(64)
+        bb.layer0 = nn.Sequential(c0, b0, nn.ReLU(inplace=True), nn.MaxPool2d(kernel_size=3, stride=2, padding=1))
+        bb.layer1, bb.layer2, bb.layer3, bb.layer4 = _res_layers(RESNET_BLOCKS[backbone], 64, plan)
+        self.backbone = bb
+        dil = (1, 6, 12, 18) if output_stride == 16 else (1, 12, 24, 36)
+        a = _Holder()
+        for i, k in zip((1, 2, 3, 4), (1, 3, 3, 3)):
+            c, n = _cbn(2048, 256, k, 1, dil[i - 1])
+            setattr(a, f"aspp{i}", nn.Sequential(c, n, nn.ReLU(inplace=True)))
+        c, n = _cbn(2048, 256, 1)
+        a.avg_pool = nn.Sequential(nn.AdaptiveAvgPool2d((1, 1)), c, n, nn.ReLU(inplace=True))
+        a.conv1, a.bn1 = _cbn(256 * 5, 256, 1)
+        a.relu, a.dropout = nn.ReLU(inplace=True), nn.Dropout(0.5)
+        self.ASSP = a
+        d = _Holder()
+        d.conv1, d.bn1 = _cbn(256, 48, 1)
+        d.relu = nn.ReLU(inplace=True)
+        c1, n1 = _cbn(48 + 256, 256, 3)
+        c2, n2 = _cbn(256, 256, 3)
+        d.output = nn.Sequential(c1, n1, nn.ReLU(inplace=True), c2, n2, nn.ReLU(inplace=True), nn.Dropout(0.1),
+                                 nn.Conv2d(256, num_classes, 1, stride=1))
+        self.decoder = d
+        _init_like_torchvision_trunk(bb.layer1, bb.layer2, bb.layer3, bb.layer4)
+        _init_like_reference_head(bb.layer0, self.ASSP, self.decoder)
+        if freeze_bn:
+            self.freeze_bn()
+        if freeze_backbone:
+            for p in self.backbone.parameters():
+                p.requires_grad = False
+
+    # ---- engine forward: returns the stride-4 fp32 logits Act (NHWC) ----
+    def _features(self, tape, x):
+        N = x.shape[0]
+        bb = self.backbone
+        a = self._cbr(tape, x, "backbone.layer0.0", bb.layer0[0], bb.layer0[1])
+        a = tape.maxpool(a)
+        low = None
+        for li in (1, 2, 3, 4):
+            layer = getattr(bb, f"layer{li}")
+            for bi, blk in enumerate(layer):
+                a = self._block(tape, a, f"backbone.layer{li}.{bi}.", blk)
+            if li == 1:
+                low = a
+        # ---- ASPP (deeplabv3_plus.py:286-297): five branches written straight into one 1280-channel buffer ----
+        Hf, Wf = a.t.shape[1], a.t.shape[2]
+        A = self.ASSP
+        cat, sl = tape.concat(N, Hf, Wf, [256] * 5, a.t.device)
+        br = []
+        for i in (1, 2, 3, 4):
+            seq = getattr(A, f"aspp{i}")
+            br.append(self._cbr(tape, a, f"ASSP.aspp{i}.0", seq[0], seq[1], out=sl[i - 1]))
+        g = tape.avgpool(a, 1)
+        g = self._cbr(tape, g, "ASSP.avg_pool.1", A.avg_pool[1], A.avg_pool[2])
+        br.append(tape.bilinear(g, Hf, Wf, True, out=sl[4]))
+        tape.bind_slices(cat, br)
+        f = self._cbr(tape, cat, "ASSP.conv1", A.conv1, A.bn1, drop_p=A.dropout.p)
+        # ---- decoder (deeplabv3_plus.py:323-330): concat order (low-level 48, upsampled 256) ----
+        D = self.decoder
+        Hl, Wl = low.t.shape[1], low.t.shape[2]
+        cat2, sl2 = tape.concat(N, Hl, Wl, [48, 256], a.t.device)
+        l48 = self._cbr(tape, low, "decoder.conv1", D.conv1, D.bn1, out=sl2[0])
+        up = tape.bilinear(f, Hl, Wl, True, out=sl2[1])
+        tape.bind_slices(cat2, [l48, up])
+        y = self._cbr(tape, cat2, "decoder.output.0", D.output[0], D.output[1])
+        y = self._cbr(tape, y, "decoder.output.3", D.output[3], D.output[4], drop_p=D.output[6].p)
+        lo, _ = tape.conv(y, self._spec("decoder.output.7", D.output[7]), out_dtype=torch.float32)
+        return lo
+
+    def _run(self, x, training, record):
+        x = x.contiguous().float()
+        H, W = x.shape[2], x.shape[3]
+        tape = self._new_tape(training, record)
+        lo = self._features(tape, x)
+        Hl, Wl = lo.t.shape[1], lo.t.shape[2]
+        out = ops.bilinear_logits_fwd(lo.t, H, W, True)  # deeplabv3_plus.py:361
+        self._finish(tape)
+        return (out,), tape, [(lo, Hl, Wl, True)]
+
+    def get_backbone_params(self):
+        return self.backbone.parameters()
+
+    def get_decoder_params(self):
+        return chain(self.ASSP.parameters(), self.decoder.parameters())
+
+
+# ----------------------------------------------------------------------------------------------- PSPNet
+class PSPNet(_EngineModel):
+    """PSPNet over the deep-stem dilated ResNet — replaces models/pspnet.py:41-105 + models/resnet.py:124-212."""
+
+    def __init__(self, num_classes, in_channels=3, backbone="resnet50", pretrained=False, use_aux=True, freeze_bn=False,
+                 freeze_backbone=False, **_):
+        super().__init__()
+        if backbone not in RESNET_BLOCKS:
+            raise NotImplementedError(f"seg_b200.PSPNet: backbone {backbone!r} not built")
+        if pretrained:
+            raise RuntimeError("pretrained weights need network access; load a state_dict instead")
+        if in_channels != 3:
+            raise NotImplementedError("in_channels != 3 swaps the deep stem for a 7x7 conv (pspnet.py:50-51); not built")
+        self.num_classes, self.use_aux = num_classes, use_aux
+        s1, n1 = _cbn(3, 64, 3, 2, 1)
+        s2, n2 = _cbn(64, 64, 3, 1, 1)
+        s3 = nn.Conv2d(64, 128, 3, stride=1, padding=1, bias=False)
+        stem = nn.Sequential(s1, n1, nn.ReLU(inplace=True), s2, n2, nn.ReLU(inplace=True), s3)
+        self.initial = nn.Sequential(stem, nn.BatchNorm2d(128), nn.ReLU(inplace=True), nn.MaxPool2d(kernel_size=3, stride=2, padding=1))
+        # resnet.py:154-163,190-210: layer3 = [d1, d2, ...], layer4 = [d2, d4, ...], all stride 1 (output stride 8)
+        plan = [(1, 1, 1), (2, 1, 1), (1, 1, 2), (1, 2, 4)]
+        self.layer1, self.layer2, self.layer3, self.layer4 = _res_layers(RESNET_BLOCKS[backbone], 128, plan)
+        m_out = 2048
+        psp = _Holder()
+        stages = []
+        for b in (1, 2, 3, 6):
+            c, n = _cbn(m_out, m_out // 4, 1)
+            stages.append(nn.Sequential(nn.AdaptiveAvgPool2d(output_size=b), c, n, nn.ReLU(inplace=True)))
+        psp.stages = nn.ModuleList(stages)
+        c, n = _cbn(m_out * 2, m_out // 4, 3)
+        psp.bottleneck = nn.Sequential(c, n, nn.ReLU(inplace=True), nn.Dropout2d(0.1))
+        self.master_branch = nn.Sequential(psp, nn.Conv2d(m_out // 4, num_classes, kernel_size=1))
+        c, n = _cbn(m_out // 2, m_out // 4, 3)
+        self.auxiliary_branch = nn.Sequential(c, n, nn.ReLU(inplace=True), nn.Dropout2d(0.1),
+                                              nn.Conv2d(m_out // 4, num_classes, kernel_size=1))
+        self.bins = (1, 2, 3, 6)
+        _init_like_resnet_s(self.initial, self.layer1, self.layer2, self.layer3, self.layer4)
+        _init_like_reference_head(self.master_branch, self.auxiliary_branch)
+        if freeze_bn:
+            self.freeze_bn()
+        if freeze_backbone:
+            for m in (self.initial, self.layer1, self.layer2, self.layer3, self.layer4):
+                for p in m.parameters():
+                    p.requires_grad = False
+
+    def _run(self, x, training, record):
+        x = x.contiguous().float()
+        N, _, H, W = x.shape
+        tape = self._new_tape(training, record)
+        stem = self.initial[0]
+        a = self._cbr(tape, x, "initial.0.0", stem[0], stem[1])
+        a = self._cbr(tape, a, "initial.0.3", stem[3], stem[4])
+        a = self._cbr(tape, a, "initial.0.6", stem[6], self.initial[1])
+        a = tape.maxpool(a)
+        x_aux = None
+        for li in (1, 2, 3, 4):
+            for bi, blk in enumerate(getattr(self, f"layer{li}")):
+                a = self._block(tape, a, f"layer{li}.{bi}.", blk)
+            if li == 3:
+                x_aux = a
+        Hf, Wf = a.t.shape[1], a.t.shape[2]
+        psp = self.master_branch[0]
+        # pspnet.py:31-38: cat([features, stage1..4]) -> 3x3 bottleneck.  The trunk output is copied into slice 0
+        # (it is also the residual-stream tensor, so it cannot simply be produced in place there).
+        cat, sl = tape.concat(N, Hf, Wf, [2048, 512, 512, 512, 512], a.t.device)
+        feats = tape.copy_into(a, sl[0])
+        br = [feats]
+        for i, b in enumerate(self.bins):
+            st = psp.stages[i]
+            p = tape.avgpool(a, b)
+            p = self._cbr(tape, p, f"master_branch.0.stages.{i}.1", st[1], st[2])
+            br.append(tape.bilinear(p, Hf, Wf, True, out=sl[i + 1]))
+        tape.bind_slices(cat, br)
+        # Dropout2d (channel-wise) is approximated per element only when dropout is enabled; parity runs use p = 0
+        y = self._cbr(tape, cat, "master_branch.0.bottleneck.0", psp.bottleneck[0], psp.bottleneck[1], drop_p=psp.bottleneck[3].p)
+        lo, _ = tape.conv(y, self._spec("master_branch.1", self.master_branch[1]), out_dtype=torch.float32)
+        out = ops.bilinear_logits_fwd(lo.t, H, W, False)  # pspnet.py:86 (align_corners default False); crop is a no-op
+        outs, heads = [out], [(lo, Hf, Wf, False)]
+        if self.training and self.use_aux:
+            ab = self.auxiliary_branch
+            ya = self._cbr(tape, x_aux, "auxiliary_branch.0", ab[0], ab[1], drop_p=ab[3].p)
+            la, _ = tape.conv(ya, self._spec("auxiliary_branch.4", ab[4]), out_dtype=torch.float32)
+            outs.append(ops.bilinear_logits_fwd(la.t, H, W, False))
+            heads.append((la, x_aux.t.shape[1], x_aux.t.shape[2], False))
+        self._finish(tape)
+        return tuple(outs), tape, heads
+
+    def get_backbone_params(self):
+        return chain(self.initial.parameters(), self.layer1.parameters(), self.layer2.parameters(), self.layer3.parameters(),
+                     self.layer4.parameters())
+
+    def get_decoder_params(self):
+        return chain(self.master_branch.parameters(), self.auxiliary_branch.parameters())

@@ -135,11 +135,12 @@ def bn_finalize(stats, count, gamma, beta, eps, momentum, clamp_eps, running_mea
     return ss, save
 
 
-def bn_eval_scale_shift(gamma, beta, rm, rv, eps):
+def bn_eval_scale_shift(gamma, beta, rm, rv, eps, want_save=False):
     C = gamma.numel()
     ss = torch.empty(2 * C, dtype=torch.float32, device=gamma.device)
-    call("seg_bn_eval_scale_shift", C, ptr(gamma), ptr(beta), ptr(rm), ptr(rv), float(eps), ptr(ss))
-    return ss
+    save = torch.empty(2 * C, dtype=torch.float32, device=gamma.device) if want_save else None
+    call("seg_bn_eval_scale_shift", C, ptr(gamma), ptr(beta), ptr(rm), ptr(rv), float(eps), ptr(ss), ptr(save))
+    return (ss, save) if want_save else ss
 
 
 def bn_apply(x, scale_shift, res=None, out=None, relu=True, drop_p=0.0, seed=0):
