@@ -2,9 +2,25 @@
 
 Host side mirrors the reference's plugin surface (models / losses registries); all arithmetic runs in the hand-written
 sm_100a kernels of ``libseg_b200.so`` (C ABI: include/seg_b200.h).  No CPU fallback.
-"""
-from . import lib  # noqa: F401
-from .losses import CrossEntropyLoss2d  # noqa: F401
-from .nets import DeepLab, PSPNet  # noqa: F401
 
-__all__ = ["DeepLab", "PSPNet", "CrossEntropyLoss2d", "lib"]
+Attributes are resolved lazily so that ``python -m seg_b200.launch`` can order sys.path (overlay before the reference
+tree) before anything imports the reference's ``base`` / ``utils`` packages.
+"""
+_LAZY = {
+    "DeepLab": ("nets", "DeepLab"),
+    "PSPNet": ("nets", "PSPNet"),
+    "CrossEntropyLoss2d": ("losses", "CrossEntropyLoss2d"),
+    "FusedTrainStep": ("train", "FusedTrainStep"),
+}
+
+__all__ = list(_LAZY) + ["lib", "ops", "nets", "losses", "engine", "comm", "train", "launch"]
+
+
+def __getattr__(name):
+    import importlib
+    if name in _LAZY:
+        mod, attr = _LAZY[name]
+        return getattr(importlib.import_module(f"{__name__}.{mod}"), attr)
+    if name in ("lib", "ops", "nets", "losses", "engine", "comm", "train", "launch"):
+        return importlib.import_module(f"{__name__}.{name}")
+    raise AttributeError(name)

@@ -1,0 +1,96 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed/NCCL for the gradient all-reduce, and the
+one-shot NVLink peer-memory exchange (`seg_syncbn_exchange`) for SyncBN statistics.
+
+Replaces the reference's single-process nn.DataParallel + threaded SyncBN (base/base_trainer.py:33-38,
+utils/sync_batchnorm/batchnorm.py:105-126, comm.py): batch-dim sharding stays, the per-step parameter broadcast and
+logit gather disappear, and the two small collectives per BN layer become one kernel.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import lib
+
+
+class SyncBNGroup:
+    """Symmetric peer buffers + epoch counter for `seg_syncbn_exchange`.  `allreduce_(vec)` sums an fp32 vector
+    (<= n_max floats) over all ranks in place, bit-identically on every rank."""
+
+    def __init__(self, n_max=8192, group=None):
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.n_max = n_max
+        self.epoch = 0
+        L = lib.load()
+        nbytes = L.seg_comm_buffer_bytes(self.world, n_max)
+        mine = ctypes.c_void_p()
+        if L.seg_comm_alloc(nbytes, ctypes.byref(mine)) != 0:
+            raise RuntimeError(lib.last_error())
+        self._mine = mine
+        handle = (ctypes.c_char * 64)()
+        if L.seg_comm_ipc_get(mine, handle) != 0:
+            raise RuntimeError(lib.last_error())
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        ptrs = []
+        self._opened = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(mine.value)
+                continue
+            p = ctypes.c_void_p()
+            buf = ctypes.create_string_buffer(h, 64)
+            if L.seg_comm_ipc_open(buf, ctypes.byref(p)) != 0:
+                raise RuntimeError(lib.last_error())
+            self._opened.append(p)
+            ptrs.append(p.value)
+        self.peers = torch.tensor(ptrs, dtype=torch.int64, device="cuda")
+        dist.barrier(group=group)
+
+    def allreduce_(self, vec):
+        assert vec.dtype == torch.float32 and vec.is_contiguous() and vec.numel() <= self.n_max
+        self.epoch += 1
+        lib.call("seg_syncbn_exchange", self.peers.data_ptr(), self.rank, self.world, vec.data_ptr(), vec.numel(), self.n_max,
+                 self.epoch & 0xFFFFFFFF or 1)
+        return vec
+
+    def close(self):
+        L = lib.load()
+        torch.cuda.synchronize()
+        for p in self._opened:
+            L.seg_comm_ipc_close(p)
+        L.seg_comm_free(self._mine)
+        self._opened = []
+
+
+class LocalLoopbackGroup:
+    """world == 1 stand-in with the same interface (used by single-GPU tests of the exchange kernel)."""
+
+    def __init__(self, n_max=8192):
+        self.rank, self.world, self.n_max, self.epoch = 0, 1, n_max, 0
+        L = lib.load()
+        mine = ctypes.c_void_p()
+        if L.seg_comm_alloc(L.seg_comm_buffer_bytes(1, n_max), ctypes.byref(mine)) != 0:
+            raise RuntimeError(lib.last_error())
+        self._mine = mine
+        self.peers = torch.tensor([mine.value], dtype=torch.int64, device="cuda")
+
+    def allreduce_(self, vec):
+        self.epoch += 1
+        lib.call("seg_syncbn_exchange", self.peers.data_ptr(), 0, 1, vec.data_ptr(), vec.numel(), self.n_max, self.epoch)
+        return vec
+
+
+def init_distributed():
+    """Initialise torch.distributed from the torchrun environment (no-op for a single process)."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1, 0
+    rank = int(os.environ["RANK"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local

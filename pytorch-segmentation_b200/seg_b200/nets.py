@@ -203,6 +203,15 @@ class _EngineModel(BaseModel):
         record = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         return _EngineFn.apply(self, record, x, *params)
 
+    def _run(self, x, training, record):
+        x = x.contiguous().float()
+        H, W = x.shape[2], x.shape[3]
+        tape = self._new_tape(training, record)
+        heads = self._forward_heads(tape, x)
+        outs = tuple(ops.bilinear_logits_fwd(lo.t, H, W, ac) for lo, ac in heads)
+        self._finish(tape)
+        return outs, tape, [(lo, lo.t.shape[1], lo.t.shape[2], ac) for lo, ac in heads]
+
     def freeze_bn(self):
         for module in self.modules():
             if isinstance(module, nn.BatchNorm2d):
@@ -296,15 +305,9 @@ class DeepLab(_EngineModel):
         lo, _ = tape.conv(y, self._spec("decoder.output.7", D.output[7]), out_dtype=torch.float32)
         return lo
 
-    def _run(self, x, training, record):
-        x = x.contiguous().float()
-        H, W = x.shape[2], x.shape[3]
-        tape = self._new_tape(training, record)
-        lo = self._features(tape, x)
-        Hl, Wl = lo.t.shape[1], lo.t.shape[2]
-        out = ops.bilinear_logits_fwd(lo.t, H, W, True)  # deeplabv3_plus.py:361
-        self._finish(tape)
-        return (out,), tape, [(lo, Hl, Wl, True)]
+    def _forward_heads(self, tape, x):
+        """[(stride-4 fp32 logits Act, align_corners of the final upsample)]  (deeplabv3_plus.py:361: True)"""
+        return [(self._features(tape, x), True)]
 
     def get_backbone_params(self):
         return self.backbone.parameters()
@@ -358,10 +361,8 @@ class PSPNet(_EngineModel):
                 for p in m.parameters():
                     p.requires_grad = False
 
-    def _run(self, x, training, record):
-        x = x.contiguous().float()
-        N, _, H, W = x.shape
-        tape = self._new_tape(training, record)
+    def _forward_heads(self, tape, x):
+        N = x.shape[0]
         stem = self.initial[0]
         a = self._cbr(tape, x, "initial.0.0", stem[0], stem[1])
         a = self._cbr(tape, a, "initial.0.3", stem[3], stem[4])
@@ -389,16 +390,13 @@ class PSPNet(_EngineModel):
         # Dropout2d (channel-wise) is approximated per element only when dropout is enabled; parity runs use p = 0
         y = self._cbr(tape, cat, "master_branch.0.bottleneck.0", psp.bottleneck[0], psp.bottleneck[1], drop_p=psp.bottleneck[3].p)
         lo, _ = tape.conv(y, self._spec("master_branch.1", self.master_branch[1]), out_dtype=torch.float32)
-        out = ops.bilinear_logits_fwd(lo.t, H, W, False)  # pspnet.py:86 (align_corners default False); crop is a no-op
-        outs, heads = [out], [(lo, Hf, Wf, False)]
+        heads = [(lo, False)]  # pspnet.py:86,91: F.interpolate default align_corners=False; the crop is a no-op
         if self.training and self.use_aux:
             ab = self.auxiliary_branch
             ya = self._cbr(tape, x_aux, "auxiliary_branch.0", ab[0], ab[1], drop_p=ab[3].p)
             la, _ = tape.conv(ya, self._spec("auxiliary_branch.4", ab[4]), out_dtype=torch.float32)
-            outs.append(ops.bilinear_logits_fwd(la.t, H, W, False))
-            heads.append((la, x_aux.t.shape[1], x_aux.t.shape[2], False))
-        self._finish(tape)
-        return tuple(outs), tape, heads
+            heads.append((la, False))
+        return heads
 
     def get_backbone_params(self):
         return chain(self.initial.parameters(), self.layer1.parameters(), self.layer2.parameters(), self.layer3.parameters(),

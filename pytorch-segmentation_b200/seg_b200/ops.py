@@ -12,6 +12,18 @@ from . import lib
 from .lib import DT_BF16, DT_F32, IMPL_AUTO, IMPL_SIMT, IMPL_TC, ConvDesc, call, make_conv_desc, ptr
 
 _IMPL_OVERRIDE = None
+PROFILE = None  # set to a list to record (kind, algorithmic flops, start event, end event) for every conv launch
+
+
+def _prof(kind, d):
+    """Context helper: CUDA events on the launching stream around one conv launch (bench.py's roofline leg)."""
+    if PROFILE is None:
+        return None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flops = 2.0 * d.N * d.P * d.Q * d.K * d.C * d.R * d.S
+    PROFILE.append((kind, flops, e0, e1))
+    e0.record()
+    return e1
 
 
 def set_conv_impl(impl):
@@ -75,8 +87,11 @@ def conv2d_fwd(x, w_packed, K, R, S, stride=1, pad=0, dil=1, out=None, out_dtype
     if out is None:
         out = torch.empty((N, d.P, d.Q, K), dtype=out_dtype, device=x.device)
     d.ldy = ld(out)
+    ev = _prof("fprop", d)
     call("seg_conv2d_fwd", ctypes.byref(d), ptr(x), ptr(w_packed), ptr(out), DT_BF16 if out.dtype == torch.bfloat16 else DT_F32,
          ptr(bias), float(beta), ptr(stats), _impl(impl))
+    if ev is not None:
+        ev.record()
     return out
 
 
@@ -88,7 +103,10 @@ def conv2d_dgrad(dy, w_packed, x_shape, R, S, stride=1, pad=0, dil=1, out=None, 
         beta = 0.0
     d = make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil, ldx=ld(out), ldy=ld(dy))
     assert (d.P, d.Q) == (dy.shape[1], dy.shape[2])
+    ev = _prof("dgrad", d)
     call("seg_conv2d_dgrad", ctypes.byref(d), ptr(dy), ptr(w_packed), ptr(out), float(beta), _impl(impl))
+    if ev is not None:
+        ev.record()
     return out
 
 
@@ -100,7 +118,10 @@ def conv2d_wgrad(dy, x, R, S, stride=1, pad=0, dil=1, out=None, impl=IMPL_AUTO):
         out = torch.zeros((R * S, K, C), dtype=torch.float32, device=x.device)
     d = make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil, ldx=ld(x), ldy=ld(dy))
     assert (d.P, d.Q) == (dy.shape[1], dy.shape[2])
+    ev = _prof("wgrad", d)
     call("seg_conv2d_wgrad", ctypes.byref(d), ptr(dy), ptr(x), ptr(out), _impl(impl))
+    if ev is not None:
+        ev.record()
     return out
 
 

@@ -1,0 +1,78 @@
+"""Fused training step for the engine models: forward -> fused upsample+CE (no full-resolution logits in HBM) ->
+backward -> (NCCL gradient all-reduce) -> fused multi-tensor SGD.  Same arithmetic as one iteration of the
+reference's Trainer._train_epoch (trainer.py:55-71) with torch.optim.SGD and differential learning rates
+(base/base_trainer.py:46-57), minus the host synchronisations.
+"""
+import torch
+import torch.distributed as dist
+
+from . import lib, ops
+from .engine import Tape
+
+
+class FusedTrainStep:
+    def __init__(self, model, ignore_index=255, lr=0.01, backbone_lr_scale=0.1, momentum=0.9, weight_decay=1e-4,
+                 aux_weight=0.4, world=1):
+        self.model = model
+        self.ignore_index = ignore_index
+        self.momentum, self.wd = momentum, weight_decay
+        self.aux_weight = aux_weight
+        self.world = world
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_mom = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad_views, self.mom_views = {}, []
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            self.grad_views[p] = self.flat_grad[off:off + n].view(p.shape)
+            self.mom_views.append(self.flat_mom[off:off + n].view(p.shape))
+            off += n
+        bb = set(id(p) for p in model.get_backbone_params())
+        lrs = [lr * backbone_lr_scale if id(p) in bb else lr for p in self.params]
+        self.base_lrs = torch.tensor(lrs, dtype=torch.float32, device=dev)
+        self.lrs = self.base_lrs.clone()
+        i64 = dict(dtype=torch.int64, device=dev)
+        self.p_ptrs = torch.tensor([p.data_ptr() for p in self.params], **i64)
+        self.g_ptrs = torch.tensor([self.grad_views[p].data_ptr() for p in self.params], **i64)
+        self.m_ptrs = torch.tensor([m.data_ptr() for m in self.mom_views], **i64)
+        self.sizes = torch.tensor([p.numel() for p in self.params], **i64)
+        self.steps = 0
+
+    def set_lr_scale(self, scale):
+        """Poly / OneCycle schedules multiply the base rates (utils/lr_scheduler.py); host scalar, one tiny op."""
+        torch.mul(self.base_lrs, float(scale), out=self.lrs)
+
+    def step(self, x, target):
+        m = self.model
+        self.flat_grad.zero_()
+        tape = m._new_tape(True, True)
+        tape.grads = dict(self.grad_views)  # pre-bound views: every parameter gradient lands in the flat buffer
+        heads = m._forward_heads(tape, x.contiguous().float())
+        total = None
+        for i, (lo, ac) in enumerate(heads):
+            C = lo.t.shape[-1]
+            loss, accum, _ = ops.upsample_ce_fwd(lo.t, target, ac, self.ignore_index)
+            w = 1.0 if i == 0 else self.aux_weight
+            g = None if w == 1.0 else torch.full((1,), w, dtype=torch.float32, device=lo.t.device)
+            dx, _ = ops.upsample_ce_bwd(lo.t, target, ac, self.ignore_index, accum, (C + 7) // 8 * 8, gscale=g)
+            lo.grad = dx[..., :C]
+            total = loss if total is None else total + w * loss
+        m._finish(tape)
+        tape.backward()
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad)
+        lib.call("seg_sgd_step", self.p_ptrs.data_ptr(), self.g_ptrs.data_ptr(), self.m_ptrs.data_ptr(), self.sizes.data_ptr(),
+                 self.lrs.data_ptr(), len(self.params), float(self.momentum), float(self.wd), 1 if self.steps == 0 else 0,
+                 1.0 / self.world)
+        self._invalidate_weight_caches()
+        self.steps += 1
+        return total
+
+    def _invalidate_weight_caches(self):
+        # the SGD kernel updates parameters in place without bumping their autograd version counters,
+        # so the packed-bf16 weight caches are invalidated explicitly
+        for s in self.model._specs.values():
+            s._version = None

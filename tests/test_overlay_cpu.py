@@ -1,0 +1,48 @@
+"""The drop-in overlay: with `seg_b200.launch` ordering sys.path as [overlay, reference root], the
+reference's own registries resolve DeepLab / PSPNet / CrossEntropyLoss2d to the B200-native classes and everything else
+to the reference's.  Needs the reference checkout (build container only; skipped on the GPU box)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+CODE = r"""
+import sys
+from seg_b200 import launch
+launch.setup_paths('/root/reference')
+import models, seg_b200
+from utils import losses, lr_scheduler, helpers
+assert models.DeepLab is seg_b200.DeepLab and models.PSPNet is seg_b200.PSPNet, (models.DeepLab, models.PSPNet)
+assert models.UNet.__module__.endswith('unet') and 'reference' in models.UNet.__init__.__code__.co_filename
+assert losses.CrossEntropyLoss2d is seg_b200.CrossEntropyLoss2d
+assert hasattr(losses, 'DiceLoss') and hasattr(losses, 'LovaszSoftmax') and hasattr(lr_scheduler, 'Poly')
+from base import BaseModel
+m = models.DeepLab(19, backbone='resnet50', pretrained=False, freeze_bn=False, freeze_backbone=False, output_stride=16)
+assert isinstance(m, BaseModel)
+# exactly what train.py:14-16,26,30 and base_trainer.py:46-57 do
+import json
+cfg = json.load(open('/root/reference/config.json'))
+cfg['arch']['args']['pretrained'] = False
+cfg['arch']['type'], cfg['arch']['args']['backbone'] = 'PSPNet', 'resnet50'
+model = getattr(models, cfg['arch']['type'])(21, **cfg['arch']['args'])
+loss = getattr(losses, cfg['loss'])(ignore_index=cfg['ignore_index'])
+groups = [{'params': model.get_decoder_params()}, {'params': model.get_backbone_params(), 'lr': 0.001}]
+import torch
+opt = torch.optim.SGD(groups, lr=0.01, momentum=0.9, weight_decay=1e-4)
+assert sum(len(g['params']) for g in opt.param_groups) == len(list(model.parameters()))
+print(str(model).splitlines()[-1])
+print('OVERLAY_OK')
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+def test_overlay_resolves_registries():
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.path.join(ROOT, "pytorch-segmentation_b200")
+    r = subprocess.run([sys.executable, "-W", "ignore", "-c", CODE], env=env, cwd=REF, capture_output=True, text=True, timeout=600)
+    assert "OVERLAY_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "Nbr of trainable parameters: 51446762" in r.stdout
