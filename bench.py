@@ -92,6 +92,15 @@ def synthetic_batch(B, seed):
     return synth.make_batch(B, SIZE, SIZE, NUM_CLASSES, IGNORE, seed=seed)
 
 
+def host_threads():
+    """Threads for the CPU arm: all cores up to 32 — ATen/oneDNN at batch 2 gets SLOWER beyond that on the 128-core
+    GPU hosts (measured: 0.09 img/s at 128 threads vs ~0.5 at 8-32); override with SEG_CPU_THREADS."""
+    env = os.environ.get("SEG_CPU_THREADS")
+    if env:
+        return int(env)
+    return min(os.cpu_count() or 1, 32)
+
+
 def cpu_port_step_time(batch, steps, warmup, threads):
     """Reference algorithm on the host cores: oracle model + CE + autograd backward + torch.optim.SGD (fp32)."""
     from oracle import losses as ol
@@ -122,7 +131,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     B = args.cpu_batch
     t = cpu_port_step_time(B, args.steps, args.warmup, threads)
     v = B / t
@@ -148,6 +157,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--backbone", default="resnet101")
+    ap.add_argument("--trace", default=None, help="after the timed runs, trace 2 steps per C-ABI call and write a table here")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -267,9 +277,35 @@ def main():
                "api": "seg_b200.DeepLab.forward -> seg_b200.CrossEntropyLoss2d -> backward -> torch.optim.SGD.step (train.py plugin surface)",
                "ms_per_step": ms_e2e / Ke}
 
+    if args.trace and rank == 0:
+        lib.TRACE = []
+        for _ in range(2):
+            stepper.step(x_dev, y_dev)
+        torch.cuda.synchronize()
+        tr, lib.TRACE = lib.TRACE, None
+        agg = {}
+        for name, meta, a, b in tr:
+            key = (name, meta[:8] if meta else None)
+            d = agg.setdefault(key, [0.0, 0, 0.0])
+            d[0] += a.elapsed_time(b) / 2
+            d[1] += 1
+            d[2] += (meta[8] if meta else 0.0) / 2
+        tot = sum(v[0] for v in agg.values())
+        by_name = {}
+        for (name, _), v in agg.items():
+            by_name[name] = by_name.get(name, 0.0) + v[0]
+        with open(args.trace, "w") as f:
+            f.write(f"# per-step totals over 2 traced steps; sum of call times {tot:.2f} ms\n")
+            for name, ms in sorted(by_name.items(), key=lambda kv: -kv[1]):
+                f.write(f"{name:28s} {ms:9.3f} ms  {100 * ms / tot:5.1f}%\n")
+            f.write("\n# name (N,H,W,C,K,R,stride,dil) ms/step calls/2steps TFLOP/s\n")
+            for (name, meta), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:70]:
+                tf = v[2] / (v[0] * 1e-3) / 1e12 if v[0] > 0 and v[2] > 0 else 0.0
+                f.write(f"{name:22s} {str(meta):48s} {v[0]:8.3f} {v[1]:4d} {tf:8.1f}\n")
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         t = cpu_port_step_time(args.cpu_batch, 2, 1, threads)
         cpu_baseline = {"value": args.cpu_batch / t, "unit": "images/sec", "cores": threads, "kind": "port",
                         "sample": f"2 timed steps (after 1 warm-up) of batch {args.cpu_batch} of the same 513x513 train step, fp32 oracle port, {threads} threads"}

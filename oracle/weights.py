@@ -35,7 +35,8 @@ class _Gen:
         self.sd[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
 
 
-RESNET_LAYERS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3), "resnet152": (3, 8, 36, 3)}
+RESNET_LAYERS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3), "resnet152": (3, 8, 36, 3),
+                 "resnet14": (1, 1, 1, 1)}  # resnet14: shallow test-only trunk (same Bottleneck code path)
 
 
 def _tv_bottleneck_layers(g, prefix, layers, inplanes=64):

@@ -81,7 +81,7 @@ int seg_conv2d_fwd(const seg_conv_desc* d, const void* x, const void* w_packed, 
 int seg_conv2d_dgrad(const seg_conv_desc* d, const void* dy, const void* w_packed, void* dx, float beta, int impl,
                      void* stream) {
   if (check_desc(d)) return 1;
-  const bool tc_ok = tc::supported(d) && d->stride == 1 && d->ldy % 8 == 0;
+  const bool tc_ok = tc::supported(d) && d->ldy % 8 == 0;
   if (impl == SEG_IMPL_TC || (impl == SEG_IMPL_AUTO && tc_ok))
     return tc::conv_dgrad(d, dy, w_packed, dx, beta, ST(stream));
   return simt::conv_dgrad(d, dy, w_packed, dx, beta, ST(stream));

@@ -6,22 +6,27 @@
 //
 // One CTA computes a 128 x BN fp32 tile held in TMEM.  Warp roles (192 threads):
 //   warp 0  : TMA producer.  The activation operand is fetched with an IM2COL-mode tensor map: one instruction
-//             brings 128 output pixels x 64 channels of one filter tap (tap*dilation passed as the im2col offset,
-//             padding = the bounding-box corners, out-of-image taps zero-filled by the TMA unit) straight into the
-//             128B-swizzled K-major layout tcgen05 consumes — the im2col gather happens in the copy engine, never
+//             brings 128 output pixels x 64 channels of one filter tap (tap displacement passed as the im2col
+//             offset, padding = the bounding-box corners, out-of-image taps zero-filled by the TMA unit) straight into
+//             the 128B-swizzled K-major layout tcgen05 consumes — the im2col gather happens in the copy engine, never
 //             in HBM.  Weights come through a tiled 2-D map over the packed [tap][K][C] matrix.
 //   warp 1  : TMEM allocator + single-thread tcgen05.mma issuer (4 x K=16 per 64-wide k-block).
-//   warps 2-5: epilogue; tcgen05.ld 32 lanes x 32 columns, optional bias / beta-accumulate / per-channel
-//             sum & sum-of-squares (BatchNorm statistics fused here), bf16 or fp32 stores.
-// Three operand-major combinations of the same pipeline:
+//   warps 2-5: epilogue; tcgen05.ld 32 lanes x 32 columns -> optional bias -> staged through (now idle) pipeline
+//             shared memory with an XOR swizzle -> fully coalesced 16-byte global stores (optionally beta-accumulate,
+//             optionally onto a strided sub-grid of the output) ; per-channel sum / sum-of-squares of the fp32
+//             accumulators (BatchNorm statistics) reduced per warp by a 31-shuffle transpose-reduce, then per CTA in
+//             shared memory, one atomicAdd per channel per CTA.
+// Operand-major variants of the same pipeline:
 //   KK (fprop) : A = activations (K-major),  B = weights  [tap*K + k][c]   (K-major)
-//   KM (dgrad) : A = dY im2col  (K-major),  B = weights  [tap*K + k][c]   (MN-major: c contiguous), taps flipped
+//   KM (dgrad) : A = dY im2col  (K-major),  B = weights  [tap*K + k][c]   (MN-major: c contiguous).  Stride 1: taps
+//                flipped.  Stride s > 1: the input pixels are split into s*s parity classes; each class is a stride-1
+//                gather over dY with only the taps whose parity matches, written to its strided sub-grid of dX —
+//                no wasted MACs on inserted zeros.
 //   MM (wgrad) : A = dY [pixel][k] (MN-major), B = X im2col [pixel][c] (MN-major), contraction over pixels,
 //                split-K over pixel blocks with fp32 atomics into dW[tap][k][c].
 #include <cuda.h>
 #include <mutex>
-#include <unordered_map>
-#include <string>
+#include <stdlib.h>
 #include "seg_common.cuh"
 #include "seg_ptx.cuh"
 
@@ -35,51 +40,58 @@ constexpr int BK = 64;  // elements per k-block = 128 bytes of bf16
 constexpr int A_BYTES = BM * 128;
 constexpr int KIND_KK = 0, KIND_KM = 1, KIND_MM = 2;
 constexpr int NTHREADS = 192;
+constexpr int MAXT = 49;
 
 struct TcParams {
   CUtensorMap mapA;  // KK/KM: activation-side operand ; MM: dY 2-D
   CUtensorMap mapB;  // KK/KM: packed weights 2-D      ; MM: X (im2col or 2-D)
   int M;             // valid output rows
   int Ncols;         // valid output cols
-  int taps, S;
+  int taps;          // entries of the tap table
   int kchunks;       // KK/KM: 64-wide channel chunks per tap
-  int dil, stride, lower;
+  int stride;        // traversal stride of the im2col map (row -> base coordinate)
+  int lower_h, lower_w;
   int PQ, Q;         // row index -> (n, p, q)
   int x_im2col;      // activation operand uses the im2col map
-  int flip;          // KM: weight tap = taps-1-tap
   int brows_per_tap; // weight-matrix rows per tap
+  short tap_wt[MAXT];  // weight tap index
+  short tap_oh[MAXT];  // im2col offset (h)
+  short tap_ow[MAXT];  // im2col offset (w)
   void* out;
   long long ldo;
   int out_dtype;
   float beta;
   const float* bias;
   float* stats;      // [2*Ncols] or null
+  // strided sub-grid output (stride>1 dgrad): row (n,i,j) -> pixel (n, i*osy+opy, j*osx+opx) of an out_H x out_W map
+  int out_strided, out_H, out_W, osy, osx, opy, opx;
   // MM only
   int kblocks_total, kblocks_per_split;
   float* dw;
   int dw_K, dw_C;
 };
 
-template <int BN>
+template <int BN, int STAGES_>
 struct Cfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int STAGES = STAGES_;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ void row_to_coords(int m, int PQ, int Q, int stride, int lower, int& n, int& h, int& w) {
+__device__ __forceinline__ void row_to_coords(int m, int PQ, int Q, int stride, int lower_h, int lower_w, int& n, int& h,
+                                              int& w) {
   n = m / PQ;
   int rem = m - n * PQ;
   int pp = rem / Q;
   int qq = rem - pp * Q;
-  h = lower + pp * stride;
-  w = lower + qq * stride;
+  h = lower_h + pp * stride;
+  w = lower_w + qq * stride;
 }
 
-template <int BN, int KIND>
+template <int BN, int STAGES, int KIND>
 __global__ void __launch_bounds__(NTHREADS) conv_gemm_tc(const __grid_constant__ TcParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t smem0 = (raw_addr + 1023u) & ~1023u;  // 1024-B alignment for SWIZZLE_128B atoms
@@ -134,11 +146,11 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_tc(const __grid_constant__
     if (lane == 0 && num_iters > 0) {
       if (KIND != KIND_MM) {
         int n_img = 0, h0 = 0, w0 = 0;
-        if (p.x_im2col) row_to_coords(m0, p.PQ, p.Q, p.stride, p.lower, n_img, h0, w0);
+        if (p.x_im2col) row_to_coords(m0, p.PQ, p.Q, p.stride, p.lower_h, p.lower_w, n_img, h0, w0);
         int it = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
-          const int r = tap / p.S, s = tap - r * p.S;
-          const int wtap = p.flip ? (p.taps - 1 - tap) : tap;
+          const int wtap = p.tap_wt[tap];
+          const uint16_t oh = (uint16_t)p.tap_oh[tap], ow = (uint16_t)p.tap_ow[tap];
           for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
             const int st = it % C::STAGES;
             const uint32_t ph = (it / C::STAGES) & 1;
@@ -147,8 +159,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_tc(const __grid_constant__
             const uint32_t b_dst = a_dst + A_BYTES;
             mbar_arrive_expect_tx(full_bar(st), C::STAGE_BYTES);
             if (p.x_im2col)
-              tma_load_im2col_4d(a_dst, &p.mapA, full_bar(st), kc * BK, w0, h0, n_img, (uint16_t)(s * p.dil),
-                                 (uint16_t)(r * p.dil));
+              tma_load_im2col_4d(a_dst, &p.mapA, full_bar(st), kc * BK, w0, h0, n_img, ow, oh);
             else
               tma_load_2d(a_dst, &p.mapA, full_bar(st), kc * BK, m0);
             if (KIND == KIND_KK) {
@@ -161,7 +172,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_tc(const __grid_constant__
           }
         }
       } else {
-        const int r = tap_mm / p.S, s = tap_mm - r * p.S;
+        const uint16_t oh = (uint16_t)p.tap_oh[tap_mm], ow = (uint16_t)p.tap_ow[tap_mm];
         int it = 0;
         for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
           const int st = it % C::STAGES;
@@ -175,11 +186,10 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_tc(const __grid_constant__
           tma_load_2d(a_dst + 8192, &p.mapA, full_bar(st), m0 + 64, pix0);
           if (p.x_im2col) {
             int n_img, h0, w0;
-            row_to_coords(pix0, p.PQ, p.Q, p.stride, p.lower, n_img, h0, w0);
+            row_to_coords(pix0, p.PQ, p.Q, p.stride, p.lower_h, p.lower_w, n_img, h0, w0);
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tma_load_im2col_4d(b_dst + j * 8192, &p.mapB, full_bar(st), n0 + j * 64, w0, h0, n_img,
-                                 (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
+              tma_load_im2col_4d(b_dst + j * 8192, &p.mapB, full_bar(st), n0 + j * 64, w0, h0, n_img, ow, oh);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &p.mapB, full_bar(st), n0 + j * 64, pix0);
@@ -217,100 +227,163 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_tc(const __grid_constant__
   } else {
     // =============================== epilogue (warps 2..5) ===============================
     const int lg = warp & 3;  // TMEM lane group this warp may access
-    const int row = m0 + lg * 32 + lane;
+    const int trow = lg * 32 + lane;
+    const int row = m0 + trow;
     if (num_iters > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
     float v[32];
-    for (int ch = 0; ch < BN / 32; ++ch) {
-      const int col0 = n0 + ch * 32;
-      if (col0 >= p.Ncols) break;  // warp-uniform
-      if (num_iters > 0) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
-      }
-      if (KIND == KIND_MM) {
-        if (row < p.M) {
-          float* dst = p.dw + ((size_t)tap_mm * p.dw_K + row) * p.dw_C + col0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.Ncols) atomicAdd(dst + i, v[i]);
-        }
-        continue;
-      }
-      const bool row_ok = row < p.M;
-      if (p.bias) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < p.Ncols) v[i] += __ldg(p.bias + col0 + i);
-      }
-      if (row_ok) {
-        const bool full = (col0 + 32 <= p.Ncols);
-        if (p.out_dtype == SEG_DT_BF16) {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0;
-          const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-          if (vec) {
-            if (p.beta != 0.f) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                bf16x8 o = reinterpret_cast<const bf16x8*>(dst)[g];
-                float f[8];
-                unpack8(o, f);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[g * 8 + i] += p.beta * f[i];
-              }
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) reinterpret_cast<bf16x8*>(dst)[g] = pack8(v + g * 8);
-          } else {
+    if (KIND == KIND_MM) {
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int col0 = n0 + ch * 32;
+        if (col0 >= p.Ncols) break;  // warp-uniform
+        if (num_iters > 0) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
+          tmem_ld_wait();
+          if (row < p.M) {
+            float* dst = p.dw + ((size_t)tap_mm * p.dw_K + row) * p.dw_C + col0;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.Ncols) {
-                float o = v[i];
-                if (p.beta != 0.f) o += p.beta * bf2f(dst[i]);
-                dst[i] = f2bf(o);
+              if (col0 + i < p.Ncols) atomicAdd(dst + i, v[i]);
+          }
+        }
+      }
+    } else {
+      // -------- phase 1: TMEM -> registers -> (bias, stats) -> swizzled staging tile in the idle pipeline smem ------
+      const bool out_bf16 = (p.out_dtype == SEG_DT_BF16);
+      const int esize = out_bf16 ? 2 : 4;
+      const int CPR = BN * esize / 16;  // 16-byte chunks per staged row
+      const int swz = (CPR >= 32 ? 31 : CPR - 1);
+      uint8_t* stage = smem_gen;  // 128 rows x BN*esize bytes
+      float* stat_sm = reinterpret_cast<float*>(smem_gen + BM * BN * esize);  // [4 warps][2][BN], right after the staging tile
+      const bool row_ok = row < p.M;
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int col0 = n0 + ch * 32;
+        if (col0 >= p.Ncols) break;  // warp-uniform
+        if (num_iters > 0) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 32), v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.Ncols) v[i] += __ldg(p.bias + col0 + i);
+        }
+        if (out_bf16) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c16 = ch * 4 + g;
+            *reinterpret_cast<bf16x8*>(stage + (size_t)trow * (BN * 2) + ((c16 ^ (trow & swz)) << 4)) = pack8(v + g * 8);
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int c16 = ch * 8 + g;
+            *reinterpret_cast<float4*>(stage + (size_t)trow * (BN * 4) + ((c16 ^ (trow & swz)) << 4)) =
+                make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          }
+        }
+        if (p.stats) {
+          // column sums over this warp's 32 rows: transpose-reduce, lane i ends with column (col0+i)
+          float s1[32], s2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = row_ok ? v[i] : 0.f;
+            s1[i] = x;
+            s2[i] = x * x;
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < off; ++j) {
+              const float send1 = up ? s1[j] : s1[j + off];
+              const float keep1 = up ? s1[j + off] : s1[j];
+              s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+              const float send2 = up ? s2[j] : s2[j + off];
+              const float keep2 = up ? s2[j + off] : s2[j];
+              s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+            }
+          }
+          stat_sm[(lg * 2 + 0) * BN + ch * 32 + lane] = s1[0];
+          stat_sm[(lg * 2 + 1) * BN + ch * 32 + lane] = s2[0];
+        }
+      }
+      __syncwarp();
+      // -------- phase 2: each warp streams ITS 32 rows out with coalesced 16-byte stores --------
+      const int ncols_tile = min(BN, p.Ncols - n0);           // valid columns of this tile
+      const int nchunks = (ncols_tile * esize + 15) >> 4;      // 16-byte chunks that hold valid data
+      const bool vec_ok = ((p.ldo * esize) & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.out) + (size_t)n0 * esize) & 15) == 0;
+      for (int idx = lane; idx < 32 * CPR; idx += 32) {
+        const int rr = idx / CPR;
+        const int c16 = idx - rr * CPR;
+        if (c16 >= nchunks) continue;
+        const int tr = lg * 32 + rr;
+        const int grow = m0 + tr;
+        if (grow >= p.M) continue;
+        long long pixel = grow;
+        if (p.out_strided) {
+          const int n = grow / p.PQ;
+          const int rem = grow - n * p.PQ;
+          const int i = rem / p.Q, j = rem - i * p.Q;
+          pixel = ((long long)n * p.out_H + (i * p.osy + p.opy)) * p.out_W + (j * p.osx + p.opx);
+        }
+        const uint8_t* src = stage + (size_t)tr * (BN * esize) + ((c16 ^ (tr & swz)) << 4);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + ((size_t)pixel * p.ldo + n0) * esize + ((size_t)c16 << 4);
+        const int first_col = (c16 << 4) / esize;
+        const bool full = first_col + 16 / esize <= ncols_tile;
+        if (out_bf16) {
+          bf16x8 val = *reinterpret_cast<const bf16x8*>(src);
+          if (vec_ok && full) {
+            if (p.beta != 0.f) {
+              float a[8], b[8];
+              unpack8(val, a);
+              unpack8(*reinterpret_cast<const bf16x8*>(dst), b);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) a[k] += p.beta * b[k];
+              val = pack8(a);
+            }
+            *reinterpret_cast<bf16x8*>(dst) = val;
+          } else {
+            float a[8];
+            unpack8(val, a);
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
+            for (int k = 0; k < 8; ++k)
+              if (first_col + k < ncols_tile) {
+                float o = a[k];
+                if (p.beta != 0.f) o += p.beta * bf2f(d[k]);
+                d[k] = f2bf(o);
               }
           }
         } else {
-          float* dst = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.Ncols) {
-              float o = v[i];
-              if (p.beta != 0.f) o += p.beta * dst[i];
-              dst[i] = o;
-            }
-        }
-      }
-      if (p.stats) {
-        // column sums over this warp's 32 rows: transpose-reduce, lane i ends with column (col0+i)
-        float s1[32], s2[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = row_ok ? v[i] : 0.f;
-          s1[i] = x;
-          s2[i] = x * x;
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-          const bool up = (lane & off) != 0;
-#pragma unroll
-          for (int j = 0; j < off; ++j) {
-            const float send1 = up ? s1[j] : s1[j + off];
-            const float keep1 = up ? s1[j + off] : s1[j];
-            s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
-            const float send2 = up ? s2[j] : s2[j + off];
-            const float keep2 = up ? s2[j + off] : s2[j];
-            s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+          const float4 val = *reinterpret_cast<const float4*>(src);
+          const float a[4] = {val.x, val.y, val.z, val.w};
+          float* d = reinterpret_cast<float*>(dst);
+          if (vec_ok && full && p.beta == 0.f) {
+            *reinterpret_cast<float4*>(d) = val;
+          } else {
+            for (int k = 0; k < 4; ++k)
+              if (first_col + k < ncols_tile) d[k] = (p.beta != 0.f) ? a[k] + p.beta * d[k] : a[k];
           }
         }
-        if (col0 + lane < p.Ncols) {
-          atomicAdd(p.stats + col0 + lane, s1[0]);
-          atomicAdd(p.stats + p.Ncols + col0 + lane, s2[0]);
+      }
+      // -------- phase 3: per-CTA reduction of the BN statistics, one atomic per channel --------
+      if (p.stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int e = (warp - 2) * 32 + lane;
+        for (int c = e; c < ncols_tile; c += 128) {
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            a += stat_sm[(w * 2 + 0) * BN + c];
+            b += stat_sm[(w * 2 + 1) * BN + c];
+          }
+          atomicAdd(p.stats + n0 + c, a);
+          atomicAdd(p.stats + p.Ncols + n0 + c, b);
         }
       }
     }
@@ -371,23 +444,26 @@ static int make_map_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t co
   return 0;
 }
 
-// NHWC bf16 tensor, im2col mode: `pixels` output positions x 64 channels per load
-static int make_map_im2col(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int64_t ld, int lower,
-                           int upper, int stride, int pixels) {
+// NHWC bf16 tensor, im2col mode: `pixels` base positions x 64 channels per load.  Corners per dimension (w, h).
+static int make_map_im2col(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int64_t ld, int lower_w,
+                           int lower_h, int upper_w, int upper_h, int stride, int pixels) {
   if (resolve_driver()) return 1;
   SEG_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA: base pointer not 16-byte aligned");
   SEG_REQUIRE(ld % 8 == 0, "TMA: channel pitch %lld not a multiple of 8", (long long)ld);
-  SEG_REQUIRE(lower >= -128 && upper >= -128 && lower <= 127 && upper <= 127, "im2col corner out of range");
+  SEG_REQUIRE(lower_w >= -128 && upper_w >= -128 && lower_w <= 127 && upper_w <= 127 && lower_h >= -128 &&
+                  upper_h >= -128 && lower_h <= 127 && upper_h <= 127,
+              "im2col corner out of range");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-  int lo[2] = {lower, lower};
-  int up[2] = {upper, upper};
+  int lo[2] = {lower_w, lower_h};
+  int up[2] = {upper_w, upper_h};
   cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lo, up,
                                64, (cuuint32_t)pixels, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  SEG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed (%d) N=%d H=%d W=%d C=%d ld=%lld lo=%d up=%d s=%d",
-              (int)r, N, H, W, C, (long long)ld, lower, upper, stride);
+  SEG_REQUIRE(r == CUDA_SUCCESS,
+              "cuTensorMapEncodeIm2col failed (%d) N=%d H=%d W=%d C=%d ld=%lld lo=(%d,%d) up=(%d,%d) s=%d", (int)r, N, H,
+              W, C, (long long)ld, lower_w, lower_h, upper_w, upper_h, stride);
   // Same workaround CUTLASS applies for drivers <= 13.1: small tensors (< 128 KiB) must clear bit 21 of word 1.
   if (g_driver_version <= 13010) {
     const uint64_t bytes = (uint64_t)N * H * W * ld * 2;
@@ -396,43 +472,54 @@ static int make_map_im2col(CUtensorMap* m, const void* ptr, int N, int H, int W,
   return 0;
 }
 
-template <int BN, int KIND>
+template <int BN, int STAGES, int KIND>
 static int launch_kernel(const TcParams& p, dim3 grid, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kfn = conv_gemm_tc<BN, KIND>;
+  auto kfn = conv_gemm_tc<BN, STAGES, KIND>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM);
-    SEG_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(smem=%d): %s", Cfg<BN>::SMEM, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, STAGES>::SMEM);
+    SEG_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(smem=%d): %s", Cfg<BN, STAGES>::SMEM, cudaGetErrorString(e));
     attr_set = true;
   }
-  kfn<<<grid, NTHREADS, Cfg<BN>::SMEM, stream>>>(p);
+  kfn<<<grid, NTHREADS, Cfg<BN, STAGES>::SMEM, stream>>>(p);
   return check_launch("conv_gemm_tc");
 }
 
+// Tile configurations: every one fits two CTAs per SM (<= 113 KB smem, <= 256 TMEM columns) so one CTA's epilogue
+// overlaps the other's main loop; the staging tile of the epilogue (128 x BN x esize) must fit in STAGES*STAGE_BYTES.
 template <int KIND>
 static int launch_bn(int bn, const TcParams& p, dim3 grid, cudaStream_t stream) {
   switch (bn) {
-    case 64: return launch_kernel<64, KIND>(p, grid, stream);
-    case 128: return launch_kernel<128, KIND>(p, grid, stream);
-    case 256: return launch_kernel<256, KIND>(p, grid, stream);
+    case 64: return launch_kernel<64, 4, KIND>(p, grid, stream);    // 4 x 24 KB
+    case 128: return launch_kernel<128, 3, KIND>(p, grid, stream);  // 3 x 32 KB
+    case 256: return launch_kernel<256, 2, KIND>(p, grid, stream);  // 2 x 48 KB
   }
   set_error("bad BN %d", bn);
   return 1;
 }
 
-static int pick_bn(int ncols, int64_t m_tiles) {
+static int env_bn() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SEG_TC_BN");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+static int pick_bn(int ncols, int out_dtype) {
   if (ncols <= 64) return 64;
-  if (ncols <= 128) return 128;
-  // prefer 256-wide tiles only when they still fill the machine
-  const int64_t tiles256 = m_tiles * ceil_div(ncols, 256);
-  if (ncols % 256 == 0 && tiles256 >= 2 * num_sms()) return 256;
+  if (out_dtype == SEG_DT_F32) return 64;  // fp32 staging tile: 128 x 64 x 4 B
+  const int forced = env_bn();
+  if (forced == 64 || forced == 128 || forced == 256) return forced;
   return 128;
 }
 
 bool supported(const seg_conv_desc* d) {
   if (d->C % 8 != 0 || d->ldx % 8 != 0) return false;
   if (d->R != d->S) return false;
-  if (d->pad > 127 || d->dil * (d->R - 1) - d->pad > 127 || d->dil * (d->R - 1) - d->pad < 0) return false;
+  if (d->R * d->S > MAXT) return false;
+  if (d->pad > 127 || d->dil * (d->R - 1) - d->pad > 127 || d->dil * (d->R - 1) - d->pad < -127) return false;
   if (d->stride > 8) return false;
   return true;
 }
@@ -450,14 +537,16 @@ int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int 
   p.M = (int)M;
   p.Ncols = d->K;
   p.taps = d->R * d->S;
-  p.S = d->S;
+  for (int t = 0; t < p.taps; ++t) {
+    p.tap_wt[t] = (short)t;
+    p.tap_oh[t] = (short)((t / d->S) * d->dil);
+    p.tap_ow[t] = (short)((t % d->S) * d->dil);
+  }
   p.kchunks = ceil_div(d->C, BK);
-  p.dil = d->dil;
   p.stride = d->stride;
-  p.lower = -d->pad;
+  p.lower_h = p.lower_w = -d->pad;
   p.PQ = d->P * d->Q;
   p.Q = d->Q;
-  p.flip = 0;
   p.brows_per_tap = d->K;
   p.out = y;
   p.ldo = d->ldy;
@@ -466,60 +555,102 @@ int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int 
   p.bias = bias;
   p.stats = stats;
   const int64_t m_tiles = ceil_div64(M, BM);
-  const int bn = pick_bn(d->K, m_tiles);
+  const int bn = pick_bn(d->K, y_dtype);
   if (is_pointwise(d)) {
     p.x_im2col = 0;
     if (make_map_2d(&p.mapA, x, M, d->C, d->ldx, BM)) return 1;
   } else {
     p.x_im2col = 1;
     const int upper = d->pad - (d->R - 1) * d->dil;
-    if (make_map_im2col(&p.mapA, x, d->N, d->H, d->W, d->C, d->ldx, -d->pad, upper, d->stride, BM)) return 1;
+    if (make_map_im2col(&p.mapA, x, d->N, d->H, d->W, d->C, d->ldx, -d->pad, -d->pad, upper, upper, d->stride, BM)) return 1;
   }
   if (make_map_2d(&p.mapB, w, (int64_t)p.taps * d->K, d->C, d->C, bn)) return 1;
   dim3 grid((unsigned)m_tiles, (unsigned)ceil_div(d->K, bn), 1);
   return launch_bn<KIND_KK>(bn, p, grid, stream);
 }
 
+static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
 int conv_dgrad(const seg_conv_desc* d, const void* dy, const void* w, void* dx, float beta, cudaStream_t stream) {
-  SEG_REQUIRE(supported(d) && d->stride == 1 && d->ldy % 8 == 0,
-              "tcgen05 conv dgrad: unsupported shape (stride=%d K=%d ldy=%d)", d->stride, d->K, d->ldy);
-  TcParams p;
-  memset(&p, 0, sizeof(p));
-  const int64_t M = (int64_t)d->N * d->H * d->W;  // rows = input pixels
-  SEG_REQUIRE(M < (1ll << 31), "M too large");
-  const int padp = d->dil * (d->R - 1) - d->pad;  // padding of the transposed conv
-  // the transposed conv must map P x Q back onto H x W
-  SEG_REQUIRE(d->P + 2 * padp - d->dil * (d->R - 1) == d->H && d->Q + 2 * padp - d->dil * (d->S - 1) == d->W,
-              "dgrad geometry mismatch");
-  p.M = (int)M;
-  p.Ncols = d->C;
-  p.taps = d->R * d->S;
-  p.S = d->S;
-  p.kchunks = ceil_div(d->K, BK);
-  p.dil = d->dil;
-  p.stride = 1;
-  p.lower = -padp;
-  p.PQ = d->H * d->W;
-  p.Q = d->W;
-  p.flip = 1;
-  p.brows_per_tap = d->K;
-  p.out = dx;
-  p.ldo = d->ldx;
-  p.out_dtype = SEG_DT_BF16;
-  p.beta = beta;
-  const int64_t m_tiles = ceil_div64(M, BM);
-  const int bn = pick_bn(d->C, m_tiles);
-  if (is_pointwise(d)) {
-    p.x_im2col = 0;
-    if (make_map_2d(&p.mapA, dy, M, d->K, d->ldy, BM)) return 1;
-  } else {
-    p.x_im2col = 1;
-    const int upper = padp - (d->R - 1) * d->dil;
-    if (make_map_im2col(&p.mapA, dy, d->N, d->P, d->Q, d->K, d->ldy, -padp, upper, 1, BM)) return 1;
+  SEG_REQUIRE(supported(d) && d->ldy % 8 == 0, "tcgen05 conv dgrad: unsupported shape (stride=%d K=%d ldy=%d)", d->stride,
+              d->K, d->ldy);
+  const int s = d->stride;
+  const int bn = pick_bn(d->C, SEG_DT_BF16);
+  // One launch per parity class (py, px) of the input pixels; stride 1 has the single class (0, 0).
+  for (int py = 0; py < s; ++py) {
+    for (int px = 0; px < s; ++px) {
+      const int Hs = (d->H - py + s - 1) / s, Ws = (d->W - px + s - 1) / s;
+      if (Hs <= 0 || Ws <= 0) continue;
+      TcParams p;
+      memset(&p, 0, sizeof(p));
+      // taps whose parity matches: y*1 + pad - r*dil must be a multiple of the stride; offset = that / stride
+      int rh[8], oh[8], nh = 0, rw[8], ow[8], nw = 0;
+      for (int r = 0; r < d->R; ++r) {
+        const int num = py + d->pad - r * d->dil;
+        if (((num % s) + s) % s == 0) { rh[nh] = r; oh[nh] = floordiv(num, s); ++nh; }
+      }
+      for (int q = 0; q < d->S; ++q) {
+        const int num = px + d->pad - q * d->dil;
+        if (((num % s) + s) % s == 0) { rw[nw] = q; ow[nw] = floordiv(num, s); ++nw; }
+      }
+      int min_oh = 0, min_ow = 0;
+      for (int i = 0; i < nh; ++i) min_oh = (i == 0) ? oh[i] : min(min_oh, oh[i]);
+      for (int i = 0; i < nw; ++i) min_ow = (i == 0) ? ow[i] : min(min_ow, ow[i]);
+      p.taps = nh * nw;
+      for (int i = 0; i < nh; ++i)
+        for (int j = 0; j < nw; ++j) {
+          const int t = i * nw + j;
+          p.tap_wt[t] = (short)(rh[i] * d->S + rw[j]);
+          p.tap_oh[t] = (short)(oh[i] - min_oh);
+          p.tap_ow[t] = (short)(ow[j] - min_ow);
+        }
+      const int64_t M = (int64_t)d->N * Hs * Ws;
+      SEG_REQUIRE(M < (1ll << 31), "M too large");
+      p.M = (int)M;
+      p.Ncols = d->C;
+      p.kchunks = ceil_div(d->K, BK);
+      p.stride = 1;
+      p.lower_h = min_oh;
+      p.lower_w = min_ow;
+      p.PQ = Hs * Ws;
+      p.Q = Ws;
+      p.brows_per_tap = d->K;
+      p.out = dx;
+      p.ldo = d->ldx;
+      p.out_dtype = SEG_DT_BF16;
+      p.beta = beta;
+      if (s > 1) {
+        p.out_strided = 1;
+        p.out_H = d->H;
+        p.out_W = d->W;
+        p.osy = p.osx = s;
+        p.opy = py;
+        p.opx = px;
+      }
+      const int64_t m_tiles = ceil_div64(M, BM);
+      if (p.taps > 0) {
+        const bool plain = (s == 1 && is_pointwise(d));
+        if (plain) {
+          p.x_im2col = 0;
+          if (make_map_2d(&p.mapA, dy, M, d->K, d->ldy, BM)) return 1;
+        } else {
+          p.x_im2col = 1;
+          // base positions per dimension must number Hs (Ws): box = [lower, dim + upper - 1]
+          const int upper_h = Hs - d->P + min_oh, upper_w = Ws - d->Q + min_ow;
+          if (make_map_im2col(&p.mapA, dy, d->N, d->P, d->Q, d->K, d->ldy, min_ow, min_oh, upper_w, upper_h, 1, BM)) return 1;
+        }
+        if (make_map_2d(&p.mapB, w, (int64_t)d->R * d->S * d->K, d->C, d->C, 64)) return 1;
+      } else {
+        if (beta != 0.f) continue;  // nothing to add to this class
+        // no tap reaches this class: the kernel writes zeros (num_iters == 0); maps unused but must be valid objects
+        if (make_map_2d(&p.mapA, w, (int64_t)d->R * d->S * d->K, d->C, d->C, BM)) return 1;
+        if (make_map_2d(&p.mapB, w, (int64_t)d->R * d->S * d->K, d->C, d->C, 64)) return 1;
+      }
+      dim3 grid((unsigned)m_tiles, (unsigned)ceil_div(d->C, bn), 1);
+      if (launch_bn<KIND_KM>(bn, p, grid, stream)) return 1;
+    }
   }
-  if (make_map_2d(&p.mapB, w, (int64_t)p.taps * d->K, d->C, d->C, 64)) return 1;
-  dim3 grid((unsigned)m_tiles, (unsigned)ceil_div(d->C, bn), 1);
-  return launch_bn<KIND_KM>(bn, p, grid, stream);
+  return 0;
 }
 
 int conv_wgrad(const seg_conv_desc* d, const void* dy, const void* x, float* dw, cudaStream_t stream) {
@@ -531,10 +662,13 @@ int conv_wgrad(const seg_conv_desc* d, const void* dy, const void* x, float* dw,
   p.M = d->K;
   p.Ncols = d->C;
   p.taps = d->R * d->S;
-  p.S = d->S;
-  p.dil = d->dil;
+  for (int t = 0; t < p.taps; ++t) {
+    p.tap_wt[t] = (short)t;
+    p.tap_oh[t] = (short)((t / d->S) * d->dil);
+    p.tap_ow[t] = (short)((t % d->S) * d->dil);
+  }
   p.stride = d->stride;
-  p.lower = -d->pad;
+  p.lower_h = p.lower_w = -d->pad;
   p.PQ = d->P * d->Q;
   p.Q = d->Q;
   p.dw = dw;
@@ -555,7 +689,7 @@ int conv_wgrad(const seg_conv_desc* d, const void* dy, const void* x, float* dw,
   } else {
     p.x_im2col = 1;
     const int upper = d->pad - (d->R - 1) * d->dil;
-    if (make_map_im2col(&p.mapB, x, d->N, d->H, d->W, d->C, d->ldx, -d->pad, upper, d->stride, 64)) return 1;
+    if (make_map_im2col(&p.mapB, x, d->N, d->H, d->W, d->C, d->ldx, -d->pad, -d->pad, upper, upper, d->stride, 64)) return 1;
   }
   SEG_REQUIRE((unsigned)(p.taps * splits) <= 65535u, "wgrad grid.z too large");
   dim3 grid((unsigned)ceil_div(d->K, BM), (unsigned)ceil_div(d->C, bn), (unsigned)(p.taps * splits));

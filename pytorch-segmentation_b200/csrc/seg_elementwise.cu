@@ -163,42 +163,76 @@ __global__ void bn_eval_kernel(int C, const float* gamma, const float* beta, con
   }
 }
 
+// Channel-group-stationary mapping shared by the three streaming BN kernels: a 256-thread block owns GB = min(G,256)
+// channel groups (8 channels = one 16-byte vector each) x 256/GB row lanes, so every thread keeps its per-channel
+// coefficients in registers for the whole grid-stride loop over rows (no per-element coefficient loads, no division).
+struct RowMap {
+  int g, rl, rows_par;
+  bool active;
+};
+__device__ __forceinline__ RowMap row_map(int C) {
+  const int G = C >> 3;
+  const int GB = min(G, 256);
+  RowMap r;
+  r.rows_par = 256 / GB;
+  r.rl = threadIdx.x / GB;
+  r.g = blockIdx.y * GB + (threadIdx.x % GB);
+  r.active = r.g < G && r.rl < r.rows_par;
+  return r;
+}
+__device__ __forceinline__ void ld8(const float* p, float* v) {
+  *reinterpret_cast<float4*>(v) = __ldg(reinterpret_cast<const float4*>(p));
+  *reinterpret_cast<float4*>(v + 4) = __ldg(reinterpret_cast<const float4*>(p + 4));
+}
+
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                        const float* __restrict__ ss, const __nv_bfloat16* __restrict__ res,
                                                        int ldr, __nv_bfloat16* __restrict__ out, int ldo, int64_t M, int C,
                                                        int relu, float drop_p, uint64_t seed) {
-  const int G = C >> 3;
-  const int64_t total = M * G;
+  const RowMap rm = row_map(C);
+  if (!rm.active) return;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % G);
-    const int64_t row = i / G;
-    float f[8], sc[8], sh[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8), f);
-    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(ss + g * 8));
-    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(ss + g * 8 + 4));
-    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(ss + C + g * 8));
-    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(ss + C + g * 8 + 4));
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+  float sc[8], sh[8];
+  ld8(ss + rm.g * 8, sc);
+  ld8(ss + C + rm.g * 8, sh);
+  const int64_t step = (int64_t)gridDim.x * rm.rows_par;
+  const int co = rm.g * 8;
+  for (int64_t row = (int64_t)blockIdx.x * rm.rows_par + rm.rl; row < M; row += 2 * step) {
+    const int64_t row2 = row + step;
+    const bool has2 = row2 < M;
+    bf16x8 xa = *reinterpret_cast<const bf16x8*>(x + row * ldx + co), xb, ra, rb;
+    if (has2) xb = *reinterpret_cast<const bf16x8*>(x + row2 * ldx + co);
     if (res) {
-      float r[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(res + row * ldr + g * 8), r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += r[j];
+      ra = *reinterpret_cast<const bf16x8*>(res + row * ldr + co);
+      if (has2) rb = *reinterpret_cast<const bf16x8*>(res + row2 * ldr + co);
     }
-    if (relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-    }
-    if (drop_p > 0.f) {
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !has2) break;
+      const int64_t r = u ? row2 : row;
+      float f[8];
+      unpack8(u ? xb : xa, f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float u = hash_uniform(seed, (uint64_t)(row * C + g * 8 + j));
-        f[j] = (u >= drop_p) ? f[j] * keep_scale : 0.f;
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (res) {
+        float q[8];
+        unpack8(u ? rb : ra, q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += q[j];
       }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      if (drop_p > 0.f) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float uu = hash_uniform(seed, (uint64_t)(r * C + co + j));
+          f[j] = (uu >= drop_p) ? f[j] * keep_scale : 0.f;
+        }
+      }
+      *reinterpret_cast<bf16x8*>(out + r * ldo + co) = pack8(f);
     }
-    *reinterpret_cast<bf16x8*>(out + row * ldo + g * 8) = pack8(f);
   }
 }
 
@@ -207,20 +241,24 @@ __global__ void __launch_bounds__(256)
                          const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save, int64_t M, int C,
                          int relu, float drop_p, float* __restrict__ sums) {
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const RowMap rm = row_map(C);
+  float mean[8], istd[8];
+  if (rm.active) {
+    ld8(save + rm.g * 8, mean);
+    ld8(save + C + rm.g * 8, istd);
+  }
   column_reduce<2>(M, C, sums, [&](int64_t row, int g, float(*acc)[8]) {
-    float dz[8], xv[8], mean[8], istd[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(dout + row * lddo + g * 8), dz);
-    unpack8(*reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8), xv);
+    float dz[8], xv[8];
+    const bf16x8 dv = *reinterpret_cast<const bf16x8*>(dout + row * lddo + g * 8);
+    const bf16x8 xx = *reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8);
+    unpack8(dv, dz);
+    unpack8(xx, xv);
     if (relu) {
       float o[8];
       unpack8(*reinterpret_cast<const bf16x8*>(out + row * ldo + g * 8), o);
 #pragma unroll
       for (int i = 0; i < 8; ++i) dz[i] = (o[i] > 0.f) ? dz[i] * keep_scale : 0.f;
     }
-    *reinterpret_cast<float4*>(mean) = __ldg(reinterpret_cast<const float4*>(save + g * 8));
-    *reinterpret_cast<float4*>(mean + 4) = __ldg(reinterpret_cast<const float4*>(save + g * 8 + 4));
-    *reinterpret_cast<float4*>(istd) = __ldg(reinterpret_cast<const float4*>(save + C + g * 8));
-    *reinterpret_cast<float4*>(istd + 4) = __ldg(reinterpret_cast<const float4*>(save + C + g * 8 + 4));
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       acc[0][i] += dz[i];
@@ -229,49 +267,62 @@ __global__ void __launch_bounds__(256)
   });
 }
 
+// dx = A*dz + B*x + Cc with A = gamma*istd, B = -gamma*istd^2*s1/count, Cc = -gamma*istd*s0/count + gamma*istd^2*mean*s1/count
 __global__ void __launch_bounds__(256)
     bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ out, int ldo,
                         const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save,
                         const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count, int64_t M, int C,
                         int relu, float drop_p, __nv_bfloat16* __restrict__ dx, int lddx, __nv_bfloat16* dres, int lddres,
                         float beta_res) {
-  const int G = C >> 3;
-  const int64_t total = M * G;
+  const RowMap rm = row_map(C);
+  if (!rm.active) return;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % G);
-    const int64_t row = i / G;
+  const int co = rm.g * 8;
+  float cA[8], cB[8], cC[8];
+  {
+    float mean[8], istd[8], gm[8], s0[8], s1[8];
+    ld8(save + co, mean);
+    ld8(save + C + co, istd);
+    ld8(gamma + co, gm);
+    ld8(sums + co, s0);
+    ld8(sums + C + co, s1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = gm[j] * istd[j];
+      cA[j] = a;
+      cB[j] = -a * istd[j] * s1[j] * inv_count;
+      cC[j] = -a * s0[j] * inv_count - cB[j] * mean[j];
+    }
+  }
+  const int64_t step = (int64_t)gridDim.x * rm.rows_par;
+  for (int64_t row = (int64_t)blockIdx.x * rm.rows_par + rm.rl; row < M; row += step) {
     float dz[8], xv[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(dout + row * lddo + g * 8), dz);
-    unpack8(*reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8), xv);
+    const bf16x8 dv = *reinterpret_cast<const bf16x8*>(dout + row * lddo + co);
+    const bf16x8 xx = *reinterpret_cast<const bf16x8*>(x + row * ldx + co);
+    unpack8(dv, dz);
+    unpack8(xx, xv);
     if (relu) {
       float o[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(out + row * ldo + g * 8), o);
+      unpack8(*reinterpret_cast<const bf16x8*>(out + row * ldo + co), o);
 #pragma unroll
       for (int j = 0; j < 8; ++j) dz[j] = (o[j] > 0.f) ? dz[j] * keep_scale : 0.f;
     }
     if (dres) {
       float r[8];
       if (beta_res != 0.f) {
-        unpack8(*reinterpret_cast<const bf16x8*>(dres + row * lddres + g * 8), r);
+        unpack8(*reinterpret_cast<const bf16x8*>(dres + row * lddres + co), r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = beta_res * r[j] + dz[j];
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = dz[j];
       }
-      *reinterpret_cast<bf16x8*>(dres + row * lddres + g * 8) = pack8(r);
+      *reinterpret_cast<bf16x8*>(dres + row * lddres + co) = pack8(r);
     }
     float o8[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      const float mean = __ldg(save + c), istd = __ldg(save + C + c);
-      const float xhat = (xv[j] - mean) * istd;
-      const float s0 = __ldg(sums + c) * inv_count, s1 = __ldg(sums + C + c) * inv_count;
-      o8[j] = __ldg(gamma + c) * istd * (dz[j] - s0 - xhat * s1);
-    }
-    *reinterpret_cast<bf16x8*>(dx + row * lddx + g * 8) = pack8(o8);
+    for (int j = 0; j < 8; ++j) o8[j] = fmaf(cA[j], dz[j], fmaf(cB[j], xv[j], cC[j]));
+    *reinterpret_cast<bf16x8*>(dx + row * lddx + co) = pack8(o8);
   }
 }
 
@@ -723,13 +774,26 @@ int seg_im2col(const seg_conv_desc* d, const void* x, int x_nchw_f32, void* col,
   return check_launch("im2col");
 }
 
+// grid for the channel-group-stationary streaming kernels: full occupancy (8 blocks of 256 threads per SM)
+static dim3 rowmap_grid(int64_t M, int C, int rows_per_iter) {
+  const int G = C / 8;
+  const int GB = G < 256 ? G : 256;
+  const int rows_par = 256 / GB;
+  const int gy = ceil_div(G, GB);
+  int64_t gx = ceil_div64(M, (int64_t)rows_par * rows_per_iter);
+  const int64_t cap = ((int64_t)num_sms() * 8 + gy - 1) / gy;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+
 static dim3 colreduce_grid(int64_t M, int C) {
   const int G = C / 8;
   const int GB = G < 256 ? G : 256;
   const int rows_par = 256 / GB;
   const int gy = ceil_div(G, GB);
   int64_t gx = ceil_div64(M, (int64_t)rows_par * 4);
-  const int64_t cap = (int64_t)num_sms() * 4 / gy + 1;
+  const int64_t cap = (int64_t)num_sms() * 8 / gy + 1;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   return dim3((unsigned)gx, (unsigned)gy, 1);
@@ -755,8 +819,8 @@ int seg_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const 
 int seg_bn_apply(const void* x, int ldx, const float* ss, const void* res, int ldr, void* out, int ldo, int64_t M, int C,
                  int relu, float drop_p, uint64_t seed, void* stream) {
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldr % 8 == 0), "bn_apply: alignment");
-  bn_apply_kernel<<<grid_for(M * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(x), ldx, ss, CBF(res), ldr, BF(out), ldo, M, C,
-                                                                      relu, drop_p, seed);
+  bn_apply_kernel<<<rowmap_grid(M, C, 2), 256, 0, ST(stream)>>>(CBF(x), ldx, ss, CBF(res), ldr, BF(out), ldo, M, C, relu,
+                                                                drop_p, seed);
   return check_launch("bn_apply");
 }
 int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,
@@ -770,9 +834,9 @@ int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const
                      const float* gamma, const float* sums, double count, int64_t M, int C, int relu, float drop_p,
                      void* dx, int lddx, void* dres, int lddres, float beta_res, void* stream) {
   SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0, "bn_bwd_apply: alignment");
-  bn_bwd_apply_kernel<<<grid_for(M * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save,
-                                                                          gamma, sums, (float)(1.0 / count), M, C, relu,
-                                                                          drop_p, BF(dx), lddx, BF(dres), lddres, beta_res);
+  bn_bwd_apply_kernel<<<rowmap_grid(M, C, 1), 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, gamma,
+                                                                    sums, (float)(1.0 / count), M, C, relu, drop_p, BF(dx),
+                                                                    lddx, BF(dres), lddres, beta_res);
   return check_launch("bn_bwd_apply");
 }
 int seg_bn_param_grad(const float* sums, int C, float* dgamma, float* dbeta, int accumulate, void* stream) {

@@ -114,10 +114,20 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name, *args):
+TRACE = None  # set to a list to record (entry point, meta, start event, end event) for every C-ABI call
+
+
+def call(name, *args, meta=None):
     """Call ``name`` with the current torch CUDA stream appended; raise RuntimeError on a non-zero status."""
     lib = load()
-    rc = getattr(lib, name)(*args, stream())
+    if TRACE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream())
+        e1.record()
+        TRACE.append((name, meta, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args, stream())
     if rc != 0:
         raise RuntimeError(f"{name} failed: {last_error()}")
 

@@ -46,7 +46,8 @@ class BaseModel(nn.Module if _RefBaseModel is None else _RefBaseModel):
         return nn.Module.__str__(self) + f"\nNbr of trainable parameters: {self._n_trainable()}"
 
 
-RESNET_BLOCKS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3), "resnet152": (3, 8, 36, 3)}
+RESNET_BLOCKS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3), "resnet152": (3, 8, 36, 3),
+                 "resnet14": (1, 1, 1, 1)}  # resnet14: shallow variant used by the batch-statistics parity test only
 
 
 # ----------------------------------------------------------------------------------------------- holders

@@ -15,6 +15,12 @@ _IMPL_OVERRIDE = None
 PROFILE = None  # set to a list to record (kind, algorithmic flops, start event, end event) for every conv launch
 
 
+def _meta(d):
+    if lib.TRACE is None:
+        return None
+    return (d.N, d.H, d.W, d.C, d.K, d.R, d.stride, d.dil, 2.0 * d.N * d.P * d.Q * d.K * d.C * d.R * d.S)
+
+
 def _prof(kind, d):
     """Context helper: CUDA events on the launching stream around one conv launch (bench.py's roofline leg)."""
     if PROFILE is None:
@@ -89,7 +95,7 @@ def conv2d_fwd(x, w_packed, K, R, S, stride=1, pad=0, dil=1, out=None, out_dtype
     d.ldy = ld(out)
     ev = _prof("fprop", d)
     call("seg_conv2d_fwd", ctypes.byref(d), ptr(x), ptr(w_packed), ptr(out), DT_BF16 if out.dtype == torch.bfloat16 else DT_F32,
-         ptr(bias), float(beta), ptr(stats), _impl(impl))
+         ptr(bias), float(beta), ptr(stats), _impl(impl), meta=_meta(d))
     if ev is not None:
         ev.record()
     return out
@@ -104,7 +110,7 @@ def conv2d_dgrad(dy, w_packed, x_shape, R, S, stride=1, pad=0, dil=1, out=None, 
     d = make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil, ldx=ld(out), ldy=ld(dy))
     assert (d.P, d.Q) == (dy.shape[1], dy.shape[2])
     ev = _prof("dgrad", d)
-    call("seg_conv2d_dgrad", ctypes.byref(d), ptr(dy), ptr(w_packed), ptr(out), float(beta), _impl(impl))
+    call("seg_conv2d_dgrad", ctypes.byref(d), ptr(dy), ptr(w_packed), ptr(out), float(beta), _impl(impl), meta=_meta(d))
     if ev is not None:
         ev.record()
     return out
@@ -119,7 +125,7 @@ def conv2d_wgrad(dy, x, R, S, stride=1, pad=0, dil=1, out=None, impl=IMPL_AUTO):
     d = make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil, ldx=ld(x), ldy=ld(dy))
     assert (d.P, d.Q) == (dy.shape[1], dy.shape[2])
     ev = _prof("wgrad", d)
-    call("seg_conv2d_wgrad", ctypes.byref(d), ptr(dy), ptr(x), ptr(out), _impl(impl))
+    call("seg_conv2d_wgrad", ctypes.byref(d), ptr(dy), ptr(x), ptr(out), _impl(impl), meta=_meta(d))
     if ev is not None:
         ev.record()
     return out

@@ -62,6 +62,8 @@ CONV_SHAPES = [
     (2, 33, 33, 128, 128, 3, 2, 1, 1),    # stride-2 3x3 (layer2.0.conv2)
     (2, 33, 33, 256, 512, 1, 2, 0, 1),    # stride-2 1x1 downsample
     (3, 9, 9, 2048, 512, 1, 1, 0, 1),     # deep K
+    (2, 34, 30, 64, 128, 3, 2, 1, 1),     # stride 2 on even maps (parity classes of unequal size)
+    (1, 129, 129, 64, 256, 1, 1, 0, 1),   # many M tiles, short K: epilogue-bound shape
 ]
 
 
@@ -98,8 +100,6 @@ def test_conv_fwd(shape, impl, gpu_out_dir):
 @pytest.mark.parametrize("shape", CONV_SHAPES, ids=lambda s: "x".join(map(str, s)))
 def test_conv_dgrad(shape, impl, gpu_out_dir):
     N, H, W, C, K, ks, stride, pad, dil = shape
-    if impl == IMPL_TC and stride != 1:
-        pytest.skip("tcgen05 dgrad is stride-1 only; stride-2 goes to the SIMT kernel")
     x, w = conv_inputs(shape)
     x.requires_grad_(True)
     y = F.conv2d(x, w, None, stride, pad, dil)
