@@ -94,11 +94,17 @@ int seg_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const 
 /* out = dropout(relu?(x*scale+shift (+res)))  — x,res,out bf16 [M][ld*]; drop_p = 0 disables dropout
  * (nn.ReLU(inplace) + residual add torchvision Bottleneck; nn.Dropout deeplabv3_plus.py:282,318) */
 int seg_bn_apply(const void* x, int ldx, const float* scale_shift, const void* res, int ldr, void* out, int ldo,
-                 int64_t M, int C, int relu, float drop_p, uint64_t seed, void* stream);
-/* backward, pass 1: sums[0:C] += sum(dz), sums[C:2C] += sum(dz*xhat), dz = dout * (out>0) * 1/(1-drop_p) if relu */
+                 int64_t M, int C, int relu, float drop_p, uint64_t seed, const uint64_t* step_ctr, void* stream);
+/* device-side step counter (*ctr += inc): mixed into dropout seeds and SyncBN epochs so a captured CUDA graph of the
+ * train step stays correct on every replay */
+int seg_counter_add(uint64_t* ctr, uint64_t inc, void* stream);
+/* backward, pass 1 (deterministic two-stage reduction, no atomics): sums[0:C] = sum(dz), sums[C:2C] = sum(dz*xhat),
+ * dz = dout * (out>0) * 1/(1-drop_p) if relu.  scratch: seg_bn_bwd_reduce_scratch_floats(M, C) floats.  If given,
+ * dbeta (=|+=) sums[0:C] and dgamma (=|+=) sums[C:2C] — the parameter gradients from the LOCAL sums. */
+int64_t seg_bn_bwd_reduce_scratch_floats(int64_t M, int C);
 int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx,
                       const float* save_mean_istd, int64_t M, int C, int relu, float drop_p, float* sums,
-                      void* stream);
+                      float* scratch, float* dgamma, float* dbeta, int accumulate, void* stream);
 /* backward, pass 2: dx = gamma*istd*(dz - sums0/count - xhat*sums1/count); dres = beta_res*dres + dz (optional).
  * `sums` are the (possibly all-reduced) sums, `count` the matching element count. */
 int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx,
@@ -168,8 +174,8 @@ int seg_sgd_step(float* const* params, float* const* grads, float* const* moment
  * Each rank owns a symmetric buffer of seg_comm_buffer_bytes(world, n_max) bytes (seg_comm_alloc, zeroed), exports it
  * with seg_comm_ipc_get, opens its peers' with seg_comm_ipc_open, and passes the world's pointers (indexed by rank;
  * its own pointer at [rank]) as a DEVICE array.  seg_syncbn_exchange(vals[n]) leaves the rank-ordered sum over all
- * ranks in vals on every rank (bit-identical everywhere).  epoch must increase by 1 per call, starting at 1, and be
- * the same on all ranks. */
+ * ranks in vals on every rank (bit-identical everywhere).  The effective epoch is epoch + (*step_ctr << 12) when
+ * step_ctr != NULL; it must differ from the previous call's, be non-zero and be the same on all ranks. */
 size_t seg_comm_buffer_bytes(int world, int n_max);
 int seg_comm_alloc(size_t bytes, void** ptr);
 int seg_comm_free(void* ptr);
@@ -177,7 +183,7 @@ int seg_comm_ipc_get(void* ptr, void* handle64);
 int seg_comm_ipc_open(const void* handle64, void** ptr);
 int seg_comm_ipc_close(void* ptr);
 int seg_syncbn_exchange(void* const* peer_bufs, int rank, int world, float* local_vals, int n, int n_max,
-                        uint32_t epoch, void* stream);
+                        uint32_t epoch, const uint64_t* step_ctr, void* stream);
 
 #ifdef __cplusplus
 }

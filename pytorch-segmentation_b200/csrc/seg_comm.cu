@@ -31,7 +31,8 @@ __host__ __device__ inline size_t flags_offset(int world, int n_max) {
 
 __global__ void __launch_bounds__(1024) syncbn_exchange_kernel(void* const* __restrict__ peers, int rank, int world,
                                                                float* __restrict__ vals, int n, int n_max,
-                                                               uint32_t epoch) {
+                                                               uint32_t epoch, const uint64_t* __restrict__ step_ctr) {
+  if (step_ctr) epoch += (uint32_t)(*step_ctr) << 12;  // device-side step counter (CUDA-graph replays): step*4096 + index
   const int slot = epoch & 1;
   const size_t foff = flags_offset(world, n_max);
   // 1. scatter my vector into slot[rank] of every peer (including myself)
@@ -108,13 +109,13 @@ int seg_comm_ipc_close(void* ptr) {
 }
 
 int seg_syncbn_exchange(void* const* peer_bufs, int rank, int world, float* local_vals, int n, int n_max, uint32_t epoch,
-                        void* stream) {
+                        const uint64_t* step_ctr, void* stream) {
   SEG_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "bad rank/world %d/%d", rank, world);
   SEG_REQUIRE(n > 0 && n <= n_max, "syncbn exchange: n=%d exceeds n_max=%d", n, n_max);
   SEG_REQUIRE(epoch != 0, "epoch must be non-zero (buffers are zero-initialised)");
   const int threads = n >= 1024 ? 1024 : ((n + 31) / 32 * 32 < 64 ? 64 : (n + 31) / 32 * 32);
   syncbn_exchange_kernel<<<1, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(peer_bufs, rank, world, local_vals, n,
-                                                                                     n_max, epoch);
+                                                                                     n_max, epoch, step_ctr);
   return check_launch("syncbn_exchange");
 }
 

@@ -677,7 +677,8 @@ int conv_wgrad(const seg_conv_desc* d, const void* dy, const void* x, float* dw,
   p.kblocks_total = (int)ceil_div64(npix, BK);
   const int bn = (d->C <= 64) ? 64 : 128;
   const int tiles = ceil_div(d->K, BM) * ceil_div(d->C, bn) * p.taps;
-  int splits = max(1, (2 * num_sms() + tiles - 1) / tiles);
+  // one wave: tiles * splits <= resident CTA slots (2 per SM), so no CTA waits for a second wave
+  int splits = max(1, (2 * num_sms()) / tiles);
   splits = min(splits, p.kblocks_total);
   splits = min(splits, 1024);
   p.kblocks_per_split = ceil_div(p.kblocks_total, splits);

@@ -46,39 +46,48 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restr
   }
 }
 
-__global__ void im2col_kernel(seg_conv_desc d, const void* __restrict__ x, int x_nchw_f32,
-                              __nv_bfloat16* __restrict__ col, int Kpad) {
+__global__ void __launch_bounds__(256) im2col_kernel(seg_conv_desc d, const void* __restrict__ x, int x_nchw_f32,
+                                                     __nv_bfloat16* __restrict__ col, int Kpad) {
+  // one thread = 8 consecutive columns of one output pixel -> a single 16-byte store
   const int64_t M = (int64_t)d.N * d.P * d.Q;
-  const int64_t total = M * Kpad;
+  const int KV = Kpad >> 3;
+  const int64_t total = M * KV;
   const int Kreal = d.R * d.S * d.C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int kk = (int)(i % Kpad);
-    const int64_t m = i / Kpad;
-    float v = 0.f;
-    if (kk < Kreal) {
-      const int c = kk % d.C;
-      const int tap = kk / d.C;
-      const int r = tap / d.S, s = tap - r * d.S;
-      const int n = (int)(m / (d.P * d.Q));
-      const int rem = (int)(m - (int64_t)n * d.P * d.Q);
-      const int op = rem / d.Q, oq = rem - op * d.Q;
-      const int ih = op * d.stride - d.pad + r * d.dil, iw = oq * d.stride - d.pad + s * d.dil;
-      if (ih >= 0 && ih < d.H && iw >= 0 && iw < d.W) {
-        if (x_nchw_f32)
-          v = reinterpret_cast<const float*>(x)[(((int64_t)n * d.C + c) * d.H + ih) * d.W + iw];
-        else
-          v = bf2f(reinterpret_cast<const __nv_bfloat16*>(x)[(((int64_t)n * d.H + ih) * d.W + iw) * d.ldx + c]);
+    const int kv = (int)(i % KV);
+    const int64_t m = i / KV;
+    const int n = (int)(m / (d.P * d.Q));
+    const int rem = (int)(m - (int64_t)n * d.P * d.Q);
+    const int op = rem / d.Q, oq = rem - op * d.Q;
+    const int ih0 = op * d.stride - d.pad, iw0 = oq * d.stride - d.pad;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kk = kv * 8 + j;
+      float val = 0.f;
+      if (kk < Kreal) {
+        const int tap = kk / d.C;
+        const int c = kk - tap * d.C;
+        const int r = tap / d.S, s = tap - r * d.S;
+        const int ih = ih0 + r * d.dil, iw = iw0 + s * d.dil;
+        if (ih >= 0 && ih < d.H && iw >= 0 && iw < d.W) {
+          if (x_nchw_f32)
+            val = __ldg(reinterpret_cast<const float*>(x) + (((int64_t)n * d.C + c) * d.H + ih) * d.W + iw);
+          else
+            val = bf2f(reinterpret_cast<const __nv_bfloat16*>(x)[(((int64_t)n * d.H + ih) * d.W + iw) * d.ldx + c]);
+        }
       }
+      v[j] = val;
     }
-    col[i] = f2bf(v);
+    *reinterpret_cast<bf16x8*>(col + m * Kpad + kv * 8) = pack8(v);
   }
 }
 
 // ------------------------------------------------------------------ BatchNorm
 // Column-reduction skeleton shared by bn_stats and bn_bwd_reduce: a 256-thread block owns GB = min(G,256) channel
 // groups (8 channels each) and 256/GB row lanes; rows are grid-strided.
-template <int NACC, class F>
-__device__ __forceinline__ void column_reduce(int64_t M, int C, float* out /*[NACC][C]*/, F f) {
+template <int NACC, bool PARTIAL = false, class F>
+__device__ __forceinline__ void column_reduce(int64_t M, int C, float* out /*[NACC][C]  (PARTIAL: [gridDim.x][NACC][C])*/, F f) {
   const int G = C >> 3;
   const int GB = min(G, 256);
   const int rows_par = 256 / GB;
@@ -107,8 +116,14 @@ __device__ __forceinline__ void column_reduce(int64_t M, int C, float* out /*[NA
       for (int r = 0; r < rows_par; ++r)
 #pragma unroll
         for (int i = 0; i < 8; ++i) s[i] += red[(r * GB + gl) * 8 + i];
+      if (PARTIAL) {  // deterministic two-stage reduction: plain stores of this block's partial sums
+        float* o = out + ((size_t)blockIdx.x * NACC + a) * C + g * 8;
+        *reinterpret_cast<float4*>(o) = make_float4(s[0], s[1], s[2], s[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(s[4], s[5], s[6], s[7]);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(out + (size_t)a * C + g * 8 + i, s[i]);
+        for (int i = 0; i < 8; ++i) atomicAdd(out + (size_t)a * C + g * 8 + i, s[i]);
+      }
     }
   }
 }
@@ -188,9 +203,11 @@ __device__ __forceinline__ void ld8(const float* p, float* v) {
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                        const float* __restrict__ ss, const __nv_bfloat16* __restrict__ res,
                                                        int ldr, __nv_bfloat16* __restrict__ out, int ldo, int64_t M, int C,
-                                                       int relu, float drop_p, uint64_t seed) {
+                                                       int relu, float drop_p, uint64_t seed,
+                                                       const uint64_t* __restrict__ step_ctr) {
   const RowMap rm = row_map(C);
   if (!rm.active) return;
+  if (step_ctr) seed += (*step_ctr) * 0x9E3779B97F4A7C15ull;  // device-side step counter keeps CUDA-graph replays fresh
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   float sc[8], sh[8];
   ld8(ss + rm.g * 8, sc);
@@ -247,7 +264,7 @@ __global__ void __launch_bounds__(256)
     ld8(save + rm.g * 8, mean);
     ld8(save + C + rm.g * 8, istd);
   }
-  column_reduce<2>(M, C, sums, [&](int64_t row, int g, float(*acc)[8]) {
+  column_reduce<2, true>(M, C, sums, [&](int64_t row, int g, float(*acc)[8]) {
     float dz[8], xv[8];
     const bf16x8 dv = *reinterpret_cast<const bf16x8*>(dout + row * lddo + g * 8);
     const bf16x8 xx = *reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8);
@@ -324,6 +341,31 @@ __global__ void __launch_bounds__(256)
     for (int j = 0; j < 8; ++j) o8[j] = fmaf(cA[j], dz[j], fmaf(cB[j], xv[j], cC[j]));
     *reinterpret_cast<bf16x8*>(dx + row * lddx + co) = pack8(o8);
   }
+}
+
+// stage 2 of the BN backward reduction: sums[a][c] = sum_b partial[b][a][c]; optionally the parameter gradients
+// (dbeta = sum dz, dgamma = sum dz*xhat) from these LOCAL sums.
+__global__ void bn_bwd_reduce_final_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ sums,
+                                           float* dgamma, float* dbeta, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  int b = 0;
+  for (; b + 1 < nblocks; b += 2) {
+    a0 += partial[((size_t)b * 2 + 0) * C + c];
+    b0 += partial[((size_t)b * 2 + 1) * C + c];
+    a1 += partial[((size_t)(b + 1) * 2 + 0) * C + c];
+    b1 += partial[((size_t)(b + 1) * 2 + 1) * C + c];
+  }
+  if (b < nblocks) {
+    a0 += partial[((size_t)b * 2 + 0) * C + c];
+    b0 += partial[((size_t)b * 2 + 1) * C + c];
+  }
+  const float s0 = a0 + a1, s1 = b0 + b1;
+  sums[c] = s0;
+  sums[C + c] = s1;
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + s0 : s0;
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + s1 : s1;
 }
 
 __global__ void bn_param_grad_kernel(const float* __restrict__ sums, int C, float* dgamma, float* dbeta, int accumulate) {
@@ -721,6 +763,10 @@ __global__ void axpby_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_
   }
 }
 
+__global__ void counter_add_kernel(uint64_t* ctr, uint64_t inc) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *ctr += inc;
+}
+
 struct SgdChunkArgs {
   float* const* params;
   float* const* grads;
@@ -769,7 +815,8 @@ int seg_unpack_wgrad(const float* dw, float* g, int K, int C, int R, int S, int 
 }
 int seg_im2col(const seg_conv_desc* d, const void* x, int x_nchw_f32, void* col, int Kpad, void* stream) {
   SEG_REQUIRE(Kpad >= d->R * d->S * d->C, "im2col: Kpad too small");
-  const int64_t total = (int64_t)d->N * d->P * d->Q * Kpad;
+  SEG_REQUIRE(Kpad % 8 == 0, "im2col: Kpad must be a multiple of 8");
+  const int64_t total = (int64_t)d->N * d->P * d->Q * (Kpad / 8);
   im2col_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(*d, x, x_nchw_f32, BF(col), Kpad);
   return check_launch("im2col");
 }
@@ -817,18 +864,36 @@ int seg_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const 
   return check_launch("bn_eval");
 }
 int seg_bn_apply(const void* x, int ldx, const float* ss, const void* res, int ldr, void* out, int ldo, int64_t M, int C,
-                 int relu, float drop_p, uint64_t seed, void* stream) {
+                 int relu, float drop_p, uint64_t seed, const uint64_t* step_ctr, void* stream) {
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldr % 8 == 0), "bn_apply: alignment");
   bn_apply_kernel<<<rowmap_grid(M, C, 2), 256, 0, ST(stream)>>>(CBF(x), ldx, ss, CBF(res), ldr, BF(out), ldo, M, C, relu,
-                                                                drop_p, seed);
+                                                                drop_p, seed, step_ctr);
   return check_launch("bn_apply");
 }
+static dim3 reduce2_grid(int64_t M, int C) {
+  const int G = C / 8;
+  const int GB = G < 256 ? G : 256;
+  const int rows_par = 256 / GB;
+  const int gy = ceil_div(G, GB);
+  int64_t gx = ceil_div64(M, (int64_t)rows_par * 8);
+  const int64_t cap = ((int64_t)num_sms() * 4 + gy - 1) / gy;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+int64_t seg_bn_bwd_reduce_scratch_floats(int64_t M, int C) { return (int64_t)reduce2_grid(M, C).x * 2 * C; }
+
 int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,
-                      int64_t M, int C, int relu, float drop_p, float* sums, void* stream) {
+                      int64_t M, int C, int relu, float drop_p, float* sums, float* scratch, float* dgamma, float* dbeta,
+                      int accumulate, void* stream) {
   SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && (!relu || ldo % 8 == 0), "bn_bwd_reduce: alignment");
-  bn_bwd_reduce_kernel<<<colreduce_grid(M, C), 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M,
-                                                                     C, relu, drop_p, sums);
-  return check_launch("bn_bwd_reduce");
+  SEG_REQUIRE(scratch != nullptr, "bn_bwd_reduce: scratch of seg_bn_bwd_reduce_scratch_floats(M, C) floats required");
+  const dim3 grid = reduce2_grid(M, C);
+  bn_bwd_reduce_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p,
+                                                     scratch);
+  if (check_launch("bn_bwd_reduce")) return 1;
+  bn_bwd_reduce_final_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(scratch, (int)grid.x, C, sums, dgamma, dbeta, accumulate);
+  return check_launch("bn_bwd_reduce_final");
 }
 int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,
                      const float* gamma, const float* sums, double count, int64_t M, int C, int relu, float drop_p,
@@ -907,6 +972,10 @@ int seg_axpby_bf16(const void* x, int ldx, void* y, int ldy, int64_t M, int C, f
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "axpby: alignment");
   axpby_kernel<<<grid_for(M * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(x), ldx, BF(y), ldy, M, C, beta);
   return check_launch("axpby");
+}
+int seg_counter_add(uint64_t* ctr, uint64_t inc, void* stream) {
+  counter_add_kernel<<<1, 32, 0, ST(stream)>>>(ctr, inc);
+  return check_launch("counter_add");
 }
 int seg_sgd_step(float* const* params, float* const* grads, float* const* bufs, const int64_t* sizes, const float* lrs,
                  int n, float momentum, float weight_decay, int first_step, float grad_scale, void* stream) {

@@ -48,11 +48,17 @@ class SyncBNGroup:
         self.peers = torch.tensor(ptrs, dtype=torch.int64, device="cuda")
         dist.barrier(group=group)
 
-    def allreduce_(self, vec):
+    def begin_step(self):
+        """Called at the start of every training forward: exchanges inside a step are numbered 1, 2, ... and the
+        device-side step counter supplies the high bits, so a captured CUDA graph replays with fresh epochs."""
+        self.epoch = 0
+
+    def allreduce_(self, vec, step_ctr=None):
         assert vec.dtype == torch.float32 and vec.is_contiguous() and vec.numel() <= self.n_max
         self.epoch += 1
+        assert self.epoch < 4096
         lib.call("seg_syncbn_exchange", self.peers.data_ptr(), self.rank, self.world, vec.data_ptr(), vec.numel(), self.n_max,
-                 self.epoch & 0xFFFFFFFF or 1)
+                 self.epoch, lib.ptr(step_ctr))
         return vec
 
     def close(self):
@@ -76,9 +82,13 @@ class LocalLoopbackGroup:
         self._mine = mine
         self.peers = torch.tensor([mine.value], dtype=torch.int64, device="cuda")
 
-    def allreduce_(self, vec):
+    def begin_step(self):
+        self.epoch = 0
+
+    def allreduce_(self, vec, step_ctr=None):
         self.epoch += 1
-        lib.call("seg_syncbn_exchange", self.peers.data_ptr(), 0, 1, vec.data_ptr(), vec.numel(), self.n_max, self.epoch)
+        lib.call("seg_syncbn_exchange", self.peers.data_ptr(), 0, 1, vec.data_ptr(), vec.numel(), self.n_max, self.epoch,
+                 lib.ptr(step_ctr))
         return vec
 
 

@@ -59,6 +59,7 @@ class ConvSpec:
         self.kpad = (self.R * self.S * self.C + 7) // 8 * 8 if self.explicit else None
         self._packed = None
         self._version = None
+        self.always_repack = False  # set while a CUDA graph of the train step is captured / replayed
 
     @property
     def stride(self):
@@ -75,7 +76,7 @@ class ConvSpec:
     def packed(self):
         w = self.m.weight
         key = (w._version, w.data_ptr())
-        if self._packed is None or self._version != key:
+        if self._packed is None or self._version != key or self.always_repack:
             if self.explicit:
                 # column order (r, s, c): OIHW -> O,(H,W,I) as a 1x1 weight over Kpad "channels"
                 w2 = w.detach().permute(0, 2, 3, 1).reshape(self.K, self.R * self.S * self.C, 1, 1).contiguous()
@@ -87,7 +88,8 @@ class ConvSpec:
 
 
 class Tape:
-    def __init__(self, training, record=None, grads=None, impl=IMPL_AUTO, dropout=True, seed=0, sync=None, clamp_eps=False):
+    def __init__(self, training, record=None, grads=None, impl=IMPL_AUTO, dropout=True, seed=0, sync=None, clamp_eps=False,
+                 step_ctr=None):
         self.training = training                                  # module.training semantics (batch stats, dropout)
         self.record = training if record is None else record      # record backward closures
         self.back = []
@@ -95,7 +97,8 @@ class Tape:
         self.impl = impl
         self.dropout = dropout
         self.seed = seed
-        self.sync = sync  # object with .allreduce_(fp32 vector) and .world ; None = local BN
+        self.sync = sync  # object with .allreduce_(fp32 vector, step_ctr) and .world ; None = local BN
+        self.step_ctr = step_ctr  # device int64 step counter mixed into dropout seeds / SyncBN epochs (graph-replay safe)
         self.clamp_eps = clamp_eps
         self._drop_ctr = 0
         self.bn_modules = []
@@ -184,13 +187,13 @@ class Tape:
         seed = 0
         if drop_p > 0.0:
             self._drop_ctr += 1
-            seed = (self.seed * 1000003 + self._drop_ctr * 7919) & 0x7FFFFFFFFFFFFFFF
+            seed = (self.seed * 1000003 + self._drop_ctr * 7919) & 0x7FFFFFFFFFFFFFFF  # + step counter on the device
         if use_batch_stats:
             if stats is None:
                 stats = ops.bn_stats(y.t)
             count = count_local
             if self.sync is not None and self.sync.world > 1:
-                self.sync.allreduce_(stats)
+                self.sync.allreduce_(stats, self.step_ctr)
                 count = count_local * self.sync.world
             ss, save = ops.bn_finalize(stats, count, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum if bn.momentum is not None else BN_MOM,
                                        1 if (self.clamp_eps and self.sync is not None and self.sync.world > 1) else 0,
@@ -200,26 +203,28 @@ class Tape:
             ss, save = ops.bn_eval_scale_shift(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps,
                                                want_save=True)
             count = count_local
-        a = ops.bn_apply(y.t, ss, res=res.t if res is not None else None, out=out, relu=relu, drop_p=drop_p, seed=seed)
+        a = ops.bn_apply(y.t, ss, res=res.t if res is not None else None, out=out, relu=relu, drop_p=drop_p, seed=seed,
+                         step_ctr=self.step_ctr if drop_p > 0.0 else None)
         aa = Act(a)
         if self.record:
             def bwd():
                 da = aa.grad
                 if da is None:
                     return
-                sums = ops.bn_bwd_reduce(da, a, y.t, save, relu=relu, drop_p=drop_p)
+                want_pg = bn.weight.requires_grad
+                acc_pg = want_pg and (bn.weight in self.grads)
+                if want_pg and not acc_pg:
+                    self.grads[bn.weight] = torch.empty(C, dtype=torch.float32, device=a.device)
+                    self.grads[bn.bias] = torch.empty(C, dtype=torch.float32, device=a.device)
+                sums = ops.bn_bwd_reduce(da, a, y.t, save, relu=relu, drop_p=drop_p,
+                                         dgamma=self.grads[bn.weight] if want_pg else None,
+                                         dbeta=self.grads[bn.bias] if want_pg else None, accumulate=acc_pg)
                 gsums = sums
                 if not use_batch_stats:
                     gsums = torch.zeros_like(sums)  # frozen BN (freeze_bn): dx = gamma * inv_std * dz
                 elif self.sync is not None and self.sync.world > 1:
                     gsums = sums.clone()
-                    self.sync.allreduce_(gsums)
-                if bn.weight.requires_grad:
-                    dg = torch.empty(C, dtype=torch.float32, device=a.device)
-                    db = torch.empty(C, dtype=torch.float32, device=a.device)
-                    ops.bn_param_grad(sums, dg, db)
-                    self._param_grad(bn.weight, lambda g, beta: g.add_(dg) if beta else g.copy_(dg))
-                    self._param_grad(bn.bias, lambda g, beta: g.add_(db) if beta else g.copy_(db))
+                    self.sync.allreduce_(gsums, self.step_ctr)
                 dy = torch.empty(y.t.shape, dtype=ACT_DTYPE, device=a.device)
                 dres, beta_res = (None, 0.0)
                 if res is not None and res.needs_grad:

@@ -163,7 +163,7 @@ class _EngineModel(BaseModel):
         self.engine_seed = 0
         self.bn_sync = None           # seg_b200.comm.SyncBNGroup for multi-GPU SyncBN
         self.syncbn_clamp_eps = True  # reproduce sync_batchnorm/batchnorm.py:145 when stats are synchronised
-        self._step = 0
+        self._step_ctr = None
 
     def _spec(self, name, module):
         s = self._specs.get(name)
@@ -173,9 +173,17 @@ class _EngineModel(BaseModel):
         return s
 
     def _new_tape(self, training, record):
-        self._step += 1
-        return Tape(training, record=record, impl=self.conv_impl, dropout=self.engine_dropout, seed=self.engine_seed * 7919 + self._step,
-                    sync=self.bn_sync, clamp_eps=self.syncbn_clamp_eps)
+        ctr = None
+        if training:
+            dev = next(self.parameters()).device
+            if self._step_ctr is None or self._step_ctr.device != dev:
+                self._step_ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+            ctr = self._step_ctr
+            ops.counter_add(ctr, 1)  # device-side: stays correct when the step is replayed from a CUDA graph
+            if self.bn_sync is not None:
+                self.bn_sync.begin_step()
+        return Tape(training, record=record, impl=self.conv_impl, dropout=self.engine_dropout, seed=self.engine_seed,
+                    sync=self.bn_sync, clamp_eps=self.syncbn_clamp_eps, step_ctr=ctr)
 
     def _cbr(self, tape, x, name, conv, bn, relu=True, res=None, out=None, drop_p=0.0):
         y, st = tape.conv(x, self._spec(name, conv), want_stats=True)

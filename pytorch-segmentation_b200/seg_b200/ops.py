@@ -170,21 +170,27 @@ def bn_eval_scale_shift(gamma, beta, rm, rv, eps, want_save=False):
     return (ss, save) if want_save else ss
 
 
-def bn_apply(x, scale_shift, res=None, out=None, relu=True, drop_p=0.0, seed=0):
+def bn_apply(x, scale_shift, res=None, out=None, relu=True, drop_p=0.0, seed=0, step_ctr=None):
     C = x.shape[-1]
     if out is None:
         out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     call("seg_bn_apply", ptr(x), ld(x), ptr(scale_shift), ptr(res), ld(res) if res is not None else 0, ptr(out), ld(out),
-         rows(x), C, int(relu), float(drop_p), int(seed))
+         rows(x), C, int(relu), float(drop_p), int(seed), ptr(step_ctr))
     return out
 
 
-def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, sums=None):
+def counter_add(ctr, inc=1):
+    call("seg_counter_add", ptr(ctr), int(inc))
+
+
+def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False):
+    """Returns sums [2C] = (sum dz, sum dz*xhat); optionally writes the parameter gradients from them."""
     C = x.shape[-1]
-    if sums is None:
-        sums = torch.zeros(2 * C, dtype=torch.float32, device=x.device)
+    M = rows(x)
+    sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(int(lib.load().seg_bn_bwd_reduce_scratch_floats(M, C)), dtype=torch.float32, device=x.device)
     call("seg_bn_bwd_reduce", ptr(dout), ld(dout), ptr(out), ld(out) if out is not None else 0, ptr(x), ld(x), ptr(save),
-         rows(x), C, int(relu), float(drop_p), ptr(sums))
+         M, C, int(relu), float(drop_p), ptr(sums), ptr(scratch), ptr(dgamma), ptr(dbeta), int(accumulate))
     return sums
 
 

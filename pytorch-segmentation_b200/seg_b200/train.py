@@ -12,7 +12,7 @@ from .engine import Tape
 
 class FusedTrainStep:
     def __init__(self, model, ignore_index=255, lr=0.01, backbone_lr_scale=0.1, momentum=0.9, weight_decay=1e-4,
-                 aux_weight=0.4, world=1):
+                 aux_weight=0.4, world=1, cuda_graph=False):
         self.model = model
         self.ignore_index = ignore_index
         self.momentum, self.wd = momentum, weight_decay
@@ -40,12 +40,46 @@ class FusedTrainStep:
         self.m_ptrs = torch.tensor([m.data_ptr() for m in self.mom_views], **i64)
         self.sizes = torch.tensor([p.numel() for p in self.params], **i64)
         self.steps = 0
+        # CUDA graph of the whole step (forward, loss, backward, all-reduce, SGD): ~1 200 kernel launches per step are
+        # replayed by the driver instead of being re-issued from Python.  Dropout seeds and SyncBN epochs come from a
+        # device-side step counter, so every replay is a fresh step.
+        self.cuda_graph = cuda_graph
+        self._graph = None
+        self._static = None
 
     def set_lr_scale(self, scale):
         """Poly / OneCycle schedules multiply the base rates (utils/lr_scheduler.py); host scalar, one tiny op."""
         torch.mul(self.base_lrs, float(scale), out=self.lrs)
 
     def step(self, x, target):
+        if not self.cuda_graph:
+            return self._step_impl(x, target)
+        if self._graph is None or self._static[0].shape != x.shape or self._static[1].shape != target.shape:
+            self._capture(x, target)
+        self._static[0].copy_(x, non_blocking=True)
+        self._static[1].copy_(target, non_blocking=True)
+        self._graph.replay()
+        self.steps += 1
+        return self._static[2]
+
+    def _capture(self, x, target):
+        xs, ys = x.clone(), target.clone()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):  # warm-up outside the capture: lazy one-time initialisation, allocator pools
+            for _ in range(2):
+                self._step_impl(xs, ys)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        for s in self.model._specs.values():
+            s.always_repack = True  # the pack kernels must be part of the graph (weights change every replay)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            loss = self._step_impl(xs, ys)
+        self._graph, self._static = g, (xs, ys, loss)
+
+    def _step_impl(self, x, target):
         m = self.model
         self.flat_grad.zero_()
         tape = m._new_tape(True, True)
@@ -65,8 +99,8 @@ class FusedTrainStep:
         if self.world > 1:
             dist.all_reduce(self.flat_grad)
         lib.call("seg_sgd_step", self.p_ptrs.data_ptr(), self.g_ptrs.data_ptr(), self.m_ptrs.data_ptr(), self.sizes.data_ptr(),
-                 self.lrs.data_ptr(), len(self.params), float(self.momentum), float(self.wd), 1 if self.steps == 0 else 0,
-                 1.0 / self.world)
+                 self.lrs.data_ptr(), len(self.params), float(self.momentum), float(self.wd), 0, 1.0 / self.world)
+        # (momentum buffers start at zero, so "first step: buf = d" of torch.optim.SGD is the general formula)
         self._invalidate_weight_caches()
         self.steps += 1
         return total

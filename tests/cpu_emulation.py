@@ -127,7 +127,7 @@ def bn_eval_scale_shift(gamma, beta, rm, rv, eps, want_save=False):
     return (ss, torch.cat([rm, istd])) if want_save else ss
 
 
-def bn_apply(x, ss, res=None, out=None, relu=True, drop_p=0.0, seed=0):
+def bn_apply(x, ss, res=None, out=None, relu=True, drop_p=0.0, seed=0, step_ctr=None):
     C = x.shape[-1]
     v = x.float() * ss[:C] + ss[C:]
     if res is not None:
@@ -147,14 +147,13 @@ def _dz(dout, out, relu, drop_p):
     return dz
 
 
-def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, sums=None):
+def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False):
     C = x.shape[-1]
     dz = _dz(dout, out, relu, drop_p).reshape(-1, C)
     xhat = ((x.float() - save[:C]) * save[C:]).reshape(-1, C)
-    if sums is None:
-        sums = torch.zeros(2 * C)
-    sums[:C] += dz.sum(0)
-    sums[C:] += (dz * xhat).sum(0)
+    sums = torch.cat([dz.sum(0), (dz * xhat).sum(0)])
+    if dgamma is not None:
+        bn_param_grad(sums, dgamma, dbeta, accumulate)
     return sums
 
 
@@ -253,6 +252,10 @@ def ce_nchw_bwd(logits, target, ignore_index, accum, gscale=None):
         l = logits.detach().clone().requires_grad_(True)
         F.cross_entropy(l, target, ignore_index=ignore_index, reduction="mean").backward()
     return l.grad * (gscale.reshape(()) if gscale is not None else 1.0)
+
+
+def counter_add(ctr, inc=1):
+    ctr += inc
 
 
 def axpby(x, y, beta):

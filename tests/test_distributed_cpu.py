@@ -19,7 +19,10 @@ class GlooSync:
     def __init__(self):
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
 
-    def allreduce_(self, vec):
+    def begin_step(self):
+        pass
+
+    def allreduce_(self, vec, step_ctr=None):
         dist.all_reduce(vec)
         return vec
 
