@@ -72,6 +72,13 @@ int seg_pack_weight(const float* w_oihw, void* w_packed, int K, int C, int R, in
 /* packed fp32 grad [R*S][K][Cpad] -> OIHW fp32:  g = beta*g + packed */
 int seg_unpack_wgrad(const float* dw_packed, float* g_oihw, int K, int C, int R, int S, int Cpad, float beta,
                      void* stream);
+/* Batched forms: one launch for every conv of a model.  `table` is a DEVICE array of n entries
+ *   struct { const float* oihw; void* packed; int32 K, C, R, S, Cpad, explicit_rsc; int64 start; }  (48 bytes,
+ *   seg_pack_entry_bytes()); `start` = prefix sum of work items (pack: packed elements; unpack: OIHW elements),
+ *   explicit_rsc = 1 for the stem-style single-tap [K][(r,s,c)->Cpad] matrix. */
+int seg_pack_entry_bytes(void);
+int seg_pack_weights_batched(const void* table, int n, int64_t total, void* stream);
+int seg_unpack_wgrads_batched(const void* table, int n, int64_t total, float beta, void* stream);
 /* explicit im2col for convs TMA cannot address (C % 8 != 0: the 7x7/3-channel stem, deeplabv3_plus.py:21):
  * col[N*P*Q][Kpad] bf16, column order (r, s, c), zero padded to Kpad.  x is NCHW fp32 (x_nchw_f32=1) or NHWC bf16. */
 int seg_im2col(const seg_conv_desc* d, const void* x, int x_nchw_f32, void* col, int Kpad, void* stream);

@@ -31,6 +31,73 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
+// ---- batched variants: ONE launch packs every conv weight of the model / unpacks every weight gradient ----
+struct PackEntry {
+  const float* oihw;      // fp32 master weight (pack: source) / fp32 OIHW grad (unpack: destination, as float*)
+  void* packed;           // bf16 packed weight (pack: destination) / fp32 packed grad (unpack: source)
+  int K, C, R, S, Cpad;
+  int explicit_rsc;       // 1: stem-style [K][(r,s,c) padded to Cpad] single-tap matrix
+  long long start;        // prefix sum of work items
+};
+
+__device__ __forceinline__ int find_entry(const PackEntry* __restrict__ tab, int n, long long i) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab[mid].start <= i) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackEntry* __restrict__ tab, int n, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const PackEntry e = tab[find_entry(tab, n, i)];
+    const long long j = i - e.start;  // index into the packed tensor
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.packed);
+    float v = 0.f;
+    if (e.explicit_rsc) {
+      const int kk = (int)(j % e.Cpad);
+      const int k = (int)(j / e.Cpad);
+      if (kk < e.R * e.S * e.C) {
+        const int c = kk % e.C, tap = kk / e.C;
+        const int r = tap / e.S, s = tap - r * e.S;
+        v = e.oihw[(((long long)k * e.C + c) * e.R + r) * e.S + s];
+      }
+    } else {
+      const int c = (int)(j % e.Cpad);
+      const long long t1 = j / e.Cpad;
+      const int k = (int)(t1 % e.K);
+      const int tap = (int)(t1 / e.K);
+      const int r = tap / e.S, s = tap - r * e.S;
+      if (c < e.C) v = e.oihw[(((long long)k * e.C + c) * e.R + r) * e.S + s];
+    }
+    out[j] = f2bf(v);
+  }
+}
+
+// OIHW fp32 grad (+)= packed fp32 grad.  Work items index the OIHW tensor.
+__global__ void __launch_bounds__(256) unpack_wgrads_batched_kernel(const PackEntry* __restrict__ tab, int n, long long total,
+                                                                    float beta) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const PackEntry e = tab[find_entry(tab, n, i)];
+    const long long j = i - e.start;  // index into the OIHW tensor
+    const int s = (int)(j % e.S);
+    long long t = j / e.S;
+    const int r = (int)(t % e.R);
+    t /= e.R;
+    const int c = (int)(t % e.C);
+    const int k = (int)(t / e.C);
+    const float* src = reinterpret_cast<const float*>(e.packed);
+    float v;
+    if (e.explicit_rsc)
+      v = src[(long long)k * e.Cpad + (r * e.S + s) * e.C + c];
+    else
+      v = src[((long long)(r * e.S + s) * e.K + k) * e.Cpad + c];
+    float* g = const_cast<float*>(e.oihw);
+    g[j] = (beta != 0.f) ? beta * g[j] + v : v;
+  }
+}
+
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ g, int K, int C, int R, int S,
                                     int Cpad, float beta) {
   const int64_t total = (int64_t)K * C * R * S;
@@ -813,6 +880,18 @@ int seg_unpack_wgrad(const float* dw, float* g, int K, int C, int R, int S, int 
   unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(dw, g, K, C, R, S, Cpad, beta);
   return check_launch("unpack_wgrad");
 }
+int seg_pack_weights_batched(const void* table, int n, int64_t total, void* stream) {
+  if (n <= 0) return 0;
+  pack_weights_batched_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const PackEntry*>(table), n, total);
+  return check_launch("pack_weights_batched");
+}
+int seg_unpack_wgrads_batched(const void* table, int n, int64_t total, float beta, void* stream) {
+  if (n <= 0) return 0;
+  unpack_wgrads_batched_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const PackEntry*>(table), n, total,
+                                                                              beta);
+  return check_launch("unpack_wgrads_batched");
+}
+int seg_pack_entry_bytes(void) { return (int)sizeof(PackEntry); }
 int seg_im2col(const seg_conv_desc* d, const void* x, int x_nchw_f32, void* col, int Kpad, void* stream) {
   SEG_REQUIRE(Kpad >= d->R * d->S * d->C, "im2col: Kpad too small");
   SEG_REQUIRE(Kpad % 8 == 0, "im2col: Kpad must be a multiple of 8");
@@ -875,8 +954,8 @@ static dim3 reduce2_grid(int64_t M, int C) {
   const int GB = G < 256 ? G : 256;
   const int rows_par = 256 / GB;
   const int gy = ceil_div(G, GB);
-  int64_t gx = ceil_div64(M, (int64_t)rows_par * 8);
-  const int64_t cap = ((int64_t)num_sms() * 4 + gy - 1) / gy;
+  int64_t gx = ceil_div64(M, (int64_t)rows_par * 2);
+  const int64_t cap = ((int64_t)num_sms() * 8 + gy - 1) / gy;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   return dim3((unsigned)gx, (unsigned)gy, 1);

@@ -60,6 +60,8 @@ class ConvSpec:
         self._packed = None
         self._version = None
         self.always_repack = False  # set while a CUDA graph of the train step is captured / replayed
+        self.external_pack = False  # FusedTrainStep packs every weight with ONE batched launch and owns `_packed`
+        self.dw_buffer = None       # persistent fp32 packed weight-gradient buffer (FusedTrainStep); None -> per-call
 
     @property
     def stride(self):
@@ -73,7 +75,12 @@ class ConvSpec:
     def dil(self):
         return self.m.dilation[0]
 
+    def packed_shape(self):
+        return (1, self.K, self.kpad) if self.explicit else (self.R * self.S, self.K, self.C)
+
     def packed(self):
+        if self.external_pack:
+            return self._packed
         w = self.m.weight
         key = (w._version, w.data_ptr())
         if self._packed is None or self._version != key or self.always_repack:
@@ -148,7 +155,10 @@ class Tape:
                 if dy is None:
                     return
                 R, S, stride, pad, dil = geo
-                if spec.m.weight.requires_grad:
+                if spec.m.weight.requires_grad and spec.dw_buffer is not None:
+                    # accumulate into the trainer's persistent packed-gradient buffer; unpacked once per step, batched
+                    ops.conv2d_wgrad(dy, xin, R, S, stride, pad, dil, out=spec.dw_buffer, impl=self.impl)
+                elif spec.m.weight.requires_grad:
                     dwp = ops.conv2d_wgrad(dy, xin, R, S, stride, pad, dil, impl=self.impl)
                     if spec.explicit:
                         def fill(g, beta):

@@ -172,6 +172,10 @@ class _EngineModel(BaseModel):
             self._specs[name] = s
         return s
 
+    def all_conv_specs(self):
+        """ConvSpec of every nn.Conv2d holder (names = module paths, as used by the forward code)."""
+        return [self._spec(n, m) for n, m in self.named_modules() if isinstance(m, nn.Conv2d)]
+
     def _new_tape(self, training, record):
         ctr = None
         if training:

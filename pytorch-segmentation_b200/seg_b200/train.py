@@ -3,6 +3,7 @@ backward -> (NCCL gradient all-reduce) -> fused multi-tensor SGD.  Same arithmet
 reference's Trainer._train_epoch (trainer.py:55-71) with torch.optim.SGD and differential learning rates
 (base/base_trainer.py:46-57), minus the host synchronisations.
 """
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -40,12 +41,44 @@ class FusedTrainStep:
         self.m_ptrs = torch.tensor([m.data_ptr() for m in self.mom_views], **i64)
         self.sizes = torch.tensor([p.numel() for p in self.params], **i64)
         self.steps = 0
+        self._build_weight_tables(dev)
         # CUDA graph of the whole step (forward, loss, backward, all-reduce, SGD): ~1 200 kernel launches per step are
         # replayed by the driver instead of being re-issued from Python.  Dropout seeds and SyncBN epochs come from a
         # device-side step counter, so every replay is a fresh step.
         self.cuda_graph = cuda_graph
         self._graph = None
         self._static = None
+
+    def _build_weight_tables(self, dev):
+        """Persistent packed-weight (bf16) and packed-gradient (fp32) buffers for every conv + the device tables that
+        let ONE launch pack all weights / unpack all weight gradients (instead of 2 x ~114 small launches)."""
+        specs = [s for s in self.model.all_conv_specs()]
+        self.specs = specs
+        dt = np.dtype([("oihw", "<u8"), ("packed", "<u8"), ("K", "<i4"), ("C", "<i4"), ("R", "<i4"), ("S", "<i4"),
+                       ("Cpad", "<i4"), ("explicit", "<i4"), ("start", "<i8")])
+        assert dt.itemsize == lib.load().seg_pack_entry_bytes()
+        n_dw = sum(int(np.prod(s.packed_shape())) for s in specs if s.m.weight.requires_grad)
+        self.flat_dwp = torch.zeros(n_dw, dtype=torch.float32, device=dev)
+        pack = np.zeros(len(specs), dtype=dt)
+        unp = []
+        p_start = u_start = off = 0
+        for i, s in enumerate(specs):
+            shape = s.packed_shape()
+            s._packed = torch.empty(shape, dtype=torch.bfloat16, device=dev)
+            s.external_pack = True
+            w = s.m.weight
+            pack[i] = (w.data_ptr(), s._packed.data_ptr(), s.K, s.C, s.R, s.S, shape[2], int(s.explicit), p_start)
+            p_start += int(np.prod(shape))
+            if w.requires_grad:
+                n = int(np.prod(shape))
+                s.dw_buffer = self.flat_dwp[off:off + n].view(shape)
+                off += n
+                unp.append((self.grad_views[w].data_ptr(), s.dw_buffer.data_ptr(), s.K, s.C, s.R, s.S, shape[2], int(s.explicit), u_start))
+                u_start += w.numel()
+        self.pack_total, self.unpack_total = p_start, u_start
+        self.pack_table = torch.from_numpy(pack.view(np.uint8).copy()).to(dev)
+        self.unpack_n = len(unp)
+        self.unpack_table = torch.from_numpy(np.array(unp, dtype=dt).view(np.uint8).copy()).to(dev)
 
     def set_lr_scale(self, scale):
         """Poly / OneCycle schedules multiply the base rates (utils/lr_scheduler.py); host scalar, one tiny op."""
@@ -72,8 +105,6 @@ class FusedTrainStep:
                 self._step_impl(xs, ys)
         cur.wait_stream(side)
         torch.cuda.synchronize()
-        for s in self.model._specs.values():
-            s.always_repack = True  # the pack kernels must be part of the graph (weights change every replay)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             loss = self._step_impl(xs, ys)
@@ -82,6 +113,8 @@ class FusedTrainStep:
     def _step_impl(self, x, target):
         m = self.model
         self.flat_grad.zero_()
+        self.flat_dwp.zero_()
+        lib.call("seg_pack_weights_batched", self.pack_table.data_ptr(), len(self.specs), self.pack_total)
         tape = m._new_tape(True, True)
         tape.grads = dict(self.grad_views)  # pre-bound views: every parameter gradient lands in the flat buffer
         heads = m._forward_heads(tape, x.contiguous().float())
@@ -96,17 +129,11 @@ class FusedTrainStep:
             total = loss if total is None else total + w * loss
         m._finish(tape)
         tape.backward()
+        lib.call("seg_unpack_wgrads_batched", self.unpack_table.data_ptr(), self.unpack_n, self.unpack_total, 0.0)
         if self.world > 1:
             dist.all_reduce(self.flat_grad)
         lib.call("seg_sgd_step", self.p_ptrs.data_ptr(), self.g_ptrs.data_ptr(), self.m_ptrs.data_ptr(), self.sizes.data_ptr(),
                  self.lrs.data_ptr(), len(self.params), float(self.momentum), float(self.wd), 0, 1.0 / self.world)
         # (momentum buffers start at zero, so "first step: buf = d" of torch.optim.SGD is the general formula)
-        self._invalidate_weight_caches()
         self.steps += 1
         return total
-
-    def _invalidate_weight_caches(self):
-        # the SGD kernel updates parameters in place without bumping their autograd version counters,
-        # so the packed-bf16 weight caches are invalidated explicitly
-        for s in self.model._specs.values():
-            s._version = None
