@@ -105,7 +105,7 @@ int seg_bn_apply(const void* x, int ldx, const float* scale_shift, const void* r
 /* device-side step counter (*ctr += inc): mixed into dropout seeds and SyncBN epochs so a captured CUDA graph of the
  * train step stays correct on every replay */
 int seg_counter_add(uint64_t* ctr, uint64_t inc, void* stream);
-/* backward, pass 1 (deterministic two-stage reduction, no atomics): sums[0:C] = sum(dz), sums[C:2C] = sum(dz*xhat),
+/* backward, pass 1 (two-stage reduction: slotted partial sums, then a finalising kernel): sums[0:C] = sum(dz), sums[C:2C] = sum(dz*xhat),
  * dz = dout * (out>0) * 1/(1-drop_p) if relu.  scratch: seg_bn_bwd_reduce_scratch_floats(M, C) floats.  If given,
  * dbeta (=|+=) sums[0:C] and dgamma (=|+=) sums[C:2C] — the parameter gradients from the LOCAL sums. */
 int64_t seg_bn_bwd_reduce_scratch_floats(int64_t M, int C);

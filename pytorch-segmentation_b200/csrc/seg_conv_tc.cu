@@ -498,6 +498,21 @@ static int launch_bn(int bn, const TcParams& p, dim3 grid, cudaStream_t stream) 
   return 1;
 }
 
+}  // namespace tc
+}  // namespace seg
+#include "seg_conv_tc2.cuh"
+namespace seg {
+namespace tc {
+
+static bool use_v2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SEG_TC_V2");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 static int env_bn() {
   static int v = -1;
   if (v < 0) {
@@ -555,7 +570,9 @@ int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int 
   p.bias = bias;
   p.stats = stats;
   const int64_t m_tiles = ceil_div64(M, BM);
-  const int bn = pick_bn(d->K, y_dtype);
+  // persistent double-buffered kernel for bf16 outputs wider than 64 channels; the one-tile-per-CTA kernel otherwise
+  const bool v2 = use_v2() && y_dtype == SEG_DT_BF16 && bias == nullptr && d->K > 64;
+  const int bn = v2 ? V2_BN : pick_bn(d->K, y_dtype);
   if (is_pointwise(d)) {
     p.x_im2col = 0;
     if (make_map_2d(&p.mapA, x, M, d->C, d->ldx, BM)) return 1;
@@ -565,6 +582,7 @@ int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int 
     if (make_map_im2col(&p.mapA, x, d->N, d->H, d->W, d->C, d->ldx, -d->pad, -d->pad, upper, upper, d->stride, BM)) return 1;
   }
   if (make_map_2d(&p.mapB, w, (int64_t)p.taps * d->K, d->C, d->C, bn)) return 1;
+  if (v2) return launch_v2<KIND_KK>(p, stream);
   dim3 grid((unsigned)m_tiles, (unsigned)ceil_div(d->K, bn), 1);
   return launch_bn<KIND_KK>(bn, p, grid, stream);
 }
@@ -575,7 +593,8 @@ int conv_dgrad(const seg_conv_desc* d, const void* dy, const void* w, void* dx, 
   SEG_REQUIRE(supported(d) && d->ldy % 8 == 0, "tcgen05 conv dgrad: unsupported shape (stride=%d K=%d ldy=%d)", d->stride,
               d->K, d->ldy);
   const int s = d->stride;
-  const int bn = pick_bn(d->C, SEG_DT_BF16);
+  const bool v2 = use_v2() && d->C > 64;
+  const int bn = v2 ? V2_BN : pick_bn(d->C, SEG_DT_BF16);
   // One launch per parity class (py, px) of the input pixels; stride 1 has the single class (0, 0).
   for (int py = 0; py < s; ++py) {
     for (int px = 0; px < s; ++px) {
@@ -646,8 +665,12 @@ int conv_dgrad(const seg_conv_desc* d, const void* dy, const void* w, void* dx, 
         if (make_map_2d(&p.mapA, w, (int64_t)d->R * d->S * d->K, d->C, d->C, BM)) return 1;
         if (make_map_2d(&p.mapB, w, (int64_t)d->R * d->S * d->K, d->C, d->C, 64)) return 1;
       }
-      dim3 grid((unsigned)m_tiles, (unsigned)ceil_div(d->C, bn), 1);
-      if (launch_bn<KIND_KM>(bn, p, grid, stream)) return 1;
+      if (v2 && p.taps > 0) {
+        if (launch_v2<KIND_KM>(p, stream)) return 1;
+        continue;
+      }
+      dim3 grid((unsigned)m_tiles, (unsigned)ceil_div(d->C, v2 ? 128 : bn), 1);
+      if (launch_bn<KIND_KM>(v2 ? 128 : bn, p, grid, stream)) return 1;
     }
   }
   return 0;

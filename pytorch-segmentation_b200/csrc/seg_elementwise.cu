@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(seg_conv_desc d, const void
 // ------------------------------------------------------------------ BatchNorm
 // Column-reduction skeleton shared by bn_stats and bn_bwd_reduce: a 256-thread block owns GB = min(G,256) channel
 // groups (8 channels each) and 256/GB row lanes; rows are grid-strided.
+constexpr int REDUCE_SLOTS = 16;
 template <int NACC, bool PARTIAL = false, class F>
 __device__ __forceinline__ void column_reduce(int64_t M, int C, float* out /*[NACC][C]  (PARTIAL: [gridDim.x][NACC][C])*/, F f) {
   const int G = C >> 3;
@@ -183,10 +184,11 @@ __device__ __forceinline__ void column_reduce(int64_t M, int C, float* out /*[NA
       for (int r = 0; r < rows_par; ++r)
 #pragma unroll
         for (int i = 0; i < 8; ++i) s[i] += red[(r * GB + gl) * 8 + i];
-      if (PARTIAL) {  // deterministic two-stage reduction: plain stores of this block's partial sums
-        float* o = out + ((size_t)blockIdx.x * NACC + a) * C + g * 8;
-        *reinterpret_cast<float4*>(o) = make_float4(s[0], s[1], s[2], s[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(s[4], s[5], s[6], s[7]);
+      if (PARTIAL) {  // two-stage: blocks spread their partial sums over REDUCE_SLOTS slot rows (low atomic contention,
+                      // ~gridDim.x/REDUCE_SLOTS adds per address); a tiny second kernel sums the slots
+        float* o = out + ((size_t)(blockIdx.x % REDUCE_SLOTS) * NACC + a) * C + g * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(o + i, s[i]);
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) atomicAdd(out + (size_t)a * C + g * 8 + i, s[i]);
@@ -960,7 +962,7 @@ static dim3 reduce2_grid(int64_t M, int C) {
   if (gx < 1) gx = 1;
   return dim3((unsigned)gx, (unsigned)gy, 1);
 }
-int64_t seg_bn_bwd_reduce_scratch_floats(int64_t M, int C) { return (int64_t)reduce2_grid(M, C).x * 2 * C; }
+int64_t seg_bn_bwd_reduce_scratch_floats(int64_t M, int C) { return (int64_t)REDUCE_SLOTS * 2 * C; }
 
 int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,
                       int64_t M, int C, int relu, float drop_p, float* sums, float* scratch, float* dgamma, float* dbeta,
@@ -968,10 +970,11 @@ int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, cons
   SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && (!relu || ldo % 8 == 0), "bn_bwd_reduce: alignment");
   SEG_REQUIRE(scratch != nullptr, "bn_bwd_reduce: scratch of seg_bn_bwd_reduce_scratch_floats(M, C) floats required");
   const dim3 grid = reduce2_grid(M, C);
+  cudaMemsetAsync(scratch, 0, (size_t)REDUCE_SLOTS * 2 * C * sizeof(float), ST(stream));
   bn_bwd_reduce_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p,
                                                      scratch);
   if (check_launch("bn_bwd_reduce")) return 1;
-  bn_bwd_reduce_final_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(scratch, (int)grid.x, C, sums, dgamma, dbeta, accumulate);
+  bn_bwd_reduce_final_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(scratch, REDUCE_SLOTS, C, sums, dgamma, dbeta, accumulate);
   return check_launch("bn_bwd_reduce_final");
 }
 int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,

@@ -64,6 +64,8 @@ CONV_SHAPES = [
     (3, 9, 9, 2048, 512, 1, 1, 0, 1),     # deep K
     (2, 34, 30, 64, 128, 3, 2, 1, 1),     # stride 2 on even maps (parity classes of unequal size)
     (1, 129, 129, 64, 256, 1, 1, 0, 1),   # many M tiles, short K: epilogue-bound shape
+    (4, 65, 65, 128, 1024, 1, 1, 0, 1),   # persistent kernel: 8 column blocks, several tiles per CTA
+    (2, 65, 65, 192, 320, 3, 1, 1, 1),    # persistent kernel: column-block tail (320 = 2.5 x 128), C tail
 ]
 
 
@@ -92,8 +94,11 @@ def test_conv_fwd(shape, impl, gpu_out_dir):
     check(f"conv_fwd[{impl}] {shape}", y.permute(0, 3, 1, 2), ref, 2e-3, gpu_out_dir)
     ref_s = torch.cat([ref.sum((0, 2, 3)), (ref * ref).sum((0, 2, 3))])
     check(f"conv_fwd_stats[{impl}] {shape}", stats, ref_s, 2e-3, gpu_out_dir)
-    yb = ops.conv2d_fwd(to_nhwc_dev(x), wp, K, ks, ks, stride, pad, dil, impl=impl)
+    stats_b = torch.zeros(2 * K, device=DEV)
+    yb = ops.conv2d_fwd(to_nhwc_dev(x), wp, K, ks, ks, stride, pad, dil, stats=stats_b, impl=impl)
+    torch.cuda.synchronize()
     check(f"conv_fwd_bf16[{impl}] {shape}", yb.permute(0, 3, 1, 2), ref, 1e-2, gpu_out_dir)
+    check(f"conv_fwd_bf16_stats[{impl}] {shape}", stats_b, ref_s, 2e-3, gpu_out_dir)
 
 
 @pytest.mark.parametrize("impl", [IMPL_SIMT, IMPL_TC], ids=["simt", "tc"])
