@@ -243,9 +243,18 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_tc(const __grid_constant__
           tmem_ld_wait();
           if (row < p.M) {
             float* dst = p.dw + ((size_t)tap_mm * p.dw_K + row) * p.dw_C + col0;
+            if (col0 + 32 <= p.Ncols && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+              // 128-bit vector reductions: 8 RED.F32x4 instead of 32 scalar atomics per thread
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.Ncols) atomicAdd(dst + i, v[i]);
+              for (int i = 0; i < 32; i += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]),
+                             "f"(v[i + 2]), "f"(v[i + 3])
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.Ncols) atomicAdd(dst + i, v[i]);
+            }
           }
         }
       }
@@ -571,7 +580,11 @@ int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int 
   p.stats = stats;
   const int64_t m_tiles = ceil_div64(M, BM);
   // persistent double-buffered kernel for bf16 outputs wider than 64 channels; the one-tile-per-CTA kernel otherwise
-  const bool v2 = use_v2() && y_dtype == SEG_DT_BF16 && bias == nullptr && d->K > 64;
+  // (measured: with <= 2 tiles per SM and a long k-loop, two co-resident one-tile CTAs interleave better than one
+  //  persistent CTA; everywhere else — short k-loops, many tiles — the persistent kernel wins by 1.3-1.8x)
+  const int64_t tiles128 = m_tiles * ceil_div(d->K, 128);
+  const bool long_k_few_tiles = tiles128 <= 2 * num_sms() && (int64_t)d->R * d->S * ceil_div(d->C, BK) >= 32;
+  const bool v2 = use_v2() && y_dtype == SEG_DT_BF16 && bias == nullptr && d->K > 64 && !long_k_few_tiles;
   const int bn = v2 ? V2_BN : pick_bn(d->K, y_dtype);
   if (is_pointwise(d)) {
     p.x_im2col = 0;
@@ -593,7 +606,9 @@ int conv_dgrad(const seg_conv_desc* d, const void* dy, const void* w, void* dx, 
   SEG_REQUIRE(supported(d) && d->ldy % 8 == 0, "tcgen05 conv dgrad: unsupported shape (stride=%d K=%d ldy=%d)", d->stride,
               d->K, d->ldy);
   const int s = d->stride;
-  const bool v2 = use_v2() && d->C > 64;
+  const int64_t tiles128 = ceil_div64((int64_t)d->N * d->H * d->W, BM) * ceil_div(d->C, 128) / (s * s);
+  const bool long_k_few_tiles = tiles128 <= 2 * num_sms() && (int64_t)d->R * d->S * ceil_div(d->K, BK) / (s * s) >= 32;
+  const bool v2 = use_v2() && d->C > 64 && !long_k_few_tiles;
   const int bn = v2 ? V2_BN : pick_bn(d->C, SEG_DT_BF16);
   // One launch per parity class (py, px) of the input pixels; stride 1 has the single class (0, 0).
   for (int py = 0; py < s; ++py) {

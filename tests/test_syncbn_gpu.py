@@ -1,0 +1,113 @@
+"""SyncBN one-shot exchange kernel (seg_syncbn_exchange): single-GPU loopback, two simulated ranks on one GPU (two
+streams, two symmetric buffers), and — when the box has >= 2 GPUs — a real 2-process run over CUDA IPC / NVLink peer
+memory checked against the single-process concatenated batch (the property of sync_batchnorm/batchnorm.py:160-167)."""
+import ctypes
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from seg_b200 import comm, lib
+
+
+def _alloc(world, n_max):
+    L = lib.load()
+    p = ctypes.c_void_p()
+    assert L.seg_comm_alloc(L.seg_comm_buffer_bytes(world, n_max), ctypes.byref(p)) == 0, lib.last_error()
+    return p
+
+
+def test_loopback_world1():
+    g = comm.LocalLoopbackGroup(n_max=4096)
+    ctr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for n in (96, 512, 4096):
+        v = torch.randn(n, device="cuda")
+        ref = v.clone()
+        g.begin_step()
+        for _ in range(3):  # repeated exchanges alternate the two slots
+            g.allreduce_(v, ctr)
+        torch.cuda.synchronize()
+        assert torch.equal(v, ref)
+        ctr += 1
+
+
+def test_two_simulated_ranks_on_one_gpu():
+    L = lib.load()
+    n_max = 4096
+    bufs = [_alloc(2, n_max), _alloc(2, n_max)]
+    peers = torch.tensor([b.value for b in bufs], dtype=torch.int64, device="cuda")
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for epoch, n in enumerate((128, 2048, 4096, 64), start=1):
+        vals = [torch.randn(n, device="cuda"), torch.randn(n, device="cuda")]
+        expect = vals[0] + vals[1]
+        torch.cuda.synchronize()
+        for r in (0, 1):
+            with torch.cuda.stream(streams[r]):
+                rc = L.seg_syncbn_exchange(peers.data_ptr(), r, 2, vals[r].data_ptr(), n, n_max, epoch, None,
+                                           streams[r].cuda_stream)
+                assert rc == 0, lib.last_error()
+        torch.cuda.synchronize()
+        assert torch.equal(vals[0], vals[1]), "ranks must end with bit-identical sums"
+        assert torch.allclose(vals[0], expect, rtol=0, atol=1e-6)
+    for b in bufs:
+        L.seg_comm_free(b)
+
+
+def _worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "pytorch-segmentation_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import seg_b200
+    from seg_b200 import comm as C
+    from seg_b200.train import FusedTrainStep
+    from oracle import synth, weights
+    sd = weights.deeplab_resnet_state_dict(7, "resnet14", seed=11, randomize_bn=True)
+    x, y = synth.make_batch(4, 65, 65, 7, 255, seed=31)
+    m = seg_b200.DeepLab(7, backbone="resnet14")
+    m.load_state_dict(sd)
+    m.engine_dropout = False
+    m = m.cuda().train()
+    m.bn_sync = C.SyncBNGroup()
+    half = slice(rank * 2, rank * 2 + 2)
+    st = FusedTrainStep(m, world=world)
+    loss = st.step(x[half].cuda(), y[half].cuda())
+    lt = loss.detach().clone()
+    dist.all_reduce(lt)
+    if rank == 0:
+        m1 = seg_b200.DeepLab(7, backbone="resnet14")
+        m1.load_state_dict(sd)
+        m1.engine_dropout = False
+        m1 = m1.cuda().train()
+        st1 = FusedTrainStep(m1, world=1)
+        loss1 = st1.step(x.cuda(), y.cuda())
+        upd2 = torch.cat([(p.detach().cpu() - sd[n]).reshape(-1) for n, p in m.named_parameters()])
+        upd1 = torch.cat([(p.detach().cpu() - sd[n]).reshape(-1) for n, p in m1.named_parameters()])
+        rs2 = torch.cat([b.detach().cpu().float().reshape(-1) for n, b in m.named_buffers() if "running_" in n])
+        rs1 = torch.cat([b.detach().cpu().float().reshape(-1) for n, b in m1.named_buffers() if "running_" in n])
+        torch.save({"loss2": (lt / world).item(), "loss1": loss1.item(),
+                    "cos": torch.nn.functional.cosine_similarity(upd2.double(), upd1.double(), dim=0).item(),
+                    "stats_rel": ((rs2 - rs1).abs().max() / rs1.abs().max()).item()}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_syncbn_train_step_equals_single_gpu_on_concatenated_batch(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "r.pt")
+    mp.spawn(_worker, args=(2, 29600 + os.getpid() % 1000, out), nprocs=2, join=True)
+    r = torch.load(out)
+    print(r)
+    assert abs(r["loss2"] - r["loss1"]) < 2e-2 * abs(r["loss1"])
+    assert r["stats_rel"] < 2e-2
+    assert r["cos"] > 0.95
