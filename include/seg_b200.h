@@ -67,6 +67,21 @@ int seg_conv2d_dgrad(const seg_conv_desc* d, const void* dy, const void* w_packe
 int seg_conv2d_wgrad(const seg_conv_desc* d, const void* dy, const void* x, float* dw_packed, int impl,
                      void* stream);
 
+/* ---- depthwise 3x3 (atrous) convolution: SeparableConv2d.conv1 of the Aligned-Xception backbone
+ *      (models/deeplabv3_plus.py:77-78, groups = C).  desc: K == C, R = S = 3.  Packed weights: fp32 [9][C]. ---- */
+int64_t seg_dwconv_scratch_floats(int C);
+/* y = dw(x); stats (optional, fp32 [2C], accumulated) = per-channel sum / sum of squares of y; scratch: 16*2*C floats */
+int seg_dwconv3x3_fwd(const seg_conv_desc* d, const void* x, const float* w9, void* y, float* stats, float* scratch,
+                      void* stream);
+/* dx = beta*dx + dw^T(dy) */
+int seg_dwconv3x3_bwd_data(const seg_conv_desc* d, const void* dy, const float* w9, void* dx, float beta, void* stream);
+/* dw9 (fp32 [9][C]) = beta*dw9 + sum_pixels dy * x_shifted; scratch: seg_dwconv_scratch_floats(C) floats */
+int seg_dwconv3x3_bwd_weight(const seg_conv_desc* d, const void* dy, const void* x, float* dw9, float beta,
+                             float* scratch, void* stream);
+/* [C][1][3][3] fp32 <-> [9][C] fp32 */
+int seg_dw_pack_weight(const float* w_c133, float* w9, int C, void* stream);
+int seg_dw_unpack_wgrad(const float* g9, float* g_c133, int C, float beta, void* stream);
+
 /* OIHW fp32 master weight -> packed bf16 [R*S][K][Cpad]; Cpad >= C zero padded */
 int seg_pack_weight(const float* w_oihw, void* w_packed, int K, int C, int R, int S, int Cpad, void* stream);
 /* packed fp32 grad [R*S][K][Cpad] -> OIHW fp32:  g = beta*g + packed */
@@ -155,6 +170,14 @@ int seg_ce_nchw_fwd(const float* logits, const int64_t* target, int N, int C, in
 /* dlogits = (softmax - onehot) * gscale / accum[1] for valid pixels, 0 for ignored (gscale = upstream grad) */
 int seg_ce_nchw_bwd(const float* logits, const int64_t* target, int N, int C, int H, int W, int64_t ignore_index,
                     const double* accum, const float* gscale, float* dlogits, void* stream);
+/* DiceLoss (utils/losses.py:33-50): softmax over C, intersection with the one-hot target, whole-batch ratio.
+ * accum (fp64 [2], zeroed by the caller) receives (sum p[target], #pixels); loss = 1 - (2I+s)/(2*#pixels+s).
+ * The caller applies the reference's in-place target fix-up (losses.py:40-42) before calling. */
+int seg_dice_nchw_fwd(const float* logits, const int64_t* target, int N, int C, int H, int W, float smooth,
+                      double* accum, float* loss, void* stream);
+/* dlogits = beta*dlogits + gscale * d(dice)/d(logits) */
+int seg_dice_nchw_bwd(const float* logits, const int64_t* target, int N, int C, int H, int W, const double* accum,
+                      float smooth, const float* gscale, float* dlogits, float beta, void* stream);
 /* fused: bilinear upsample (low-res NHWC fp32 logits) + log-softmax + NLL, no full-res logits in HBM.
  * Also emits the arg-max label map (int32 [N,Ho,Wo], lowest index wins ties) when argmax != NULL. */
 int seg_upsample_ce_fwd(const float* logits_lo, const int64_t* target, int N, int Hi, int Wi, int Ho, int Wo, int C,
@@ -168,6 +191,10 @@ int seg_upsample_ce_bwd(const float* logits_lo, const int64_t* target, int N, in
 int seg_ce_finalize(const double* accum, float* loss, void* stream);
 
 /* ---- misc ---- */
+/* standalone ReLU on NHWC bf16 (F.relu, deeplabv3_plus.py:210) and its backward dx = beta*dx + dy*(y>0) */
+int seg_relu_fwd(const void* x, int ldx, void* y, int ldy, int64_t M, int C, void* stream);
+int seg_relu_bwd(const void* dy, int lddy, const void* y, int ldy, void* dx, int lddx, int64_t M, int C, float beta,
+                 void* stream);
 int seg_nhwc_to_nchw_f32(const void* x, int ldx, int x_dtype, float* y, int N, int H, int W, int C, void* stream);
 /* y[M][ldy] (bf16) = beta*y + x[M][ldx] (bf16) */
 int seg_axpby_bf16(const void* x, int ldx, void* y, int ldy, int64_t M, int C, float beta, void* stream);

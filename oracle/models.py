@@ -60,6 +60,57 @@ def deeplab_resnet_trunk(sd, x, backbone="resnet101", output_stride=16, train=Tr
     return x, low
 
 
+def _sepconv(sd, name, x, stride, dil, train):
+    """SeparableConv2d.forward (deeplabv3_plus.py:82-86): depthwise 3x3 ("same" padding = dilation) -> BN -> pointwise."""
+    C = x.shape[1]
+    y = F.conv2d(x, sd[name + ".conv1.weight"], None, stride, dil, dil, groups=C)
+    y = _bn(sd, name + ".bn", y, train)
+    return F.conv2d(y, sd[name + ".pointwise.weight"])
+
+
+def _xblock(sd, p, x, stride, dil, train, exit_flow=False, use_1st_relu=True):
+    """Block.forward (deeplabv3_plus.py:123-132).  rep[0] is an IN-PLACE ReLU on the block input, so the skip branch
+    (and an identity skip) sees relu(x) — except in block1, built with use_1st_relu=False."""
+    if use_1st_relu:
+        x = F.relu(x)
+    idx = 0 if not use_1st_relu else 1
+    h = x
+    for u in range(3):
+        if u > 0:
+            h = F.relu(h)
+        s = stride if u == 2 else 1
+        h = _sepconv(sd, f"{p}rep.{idx}", h, s, dil, train)
+        h = _bn(sd, f"{p}rep.{idx + 1}", h, train)
+        idx += 3
+    if (p + "skip.weight") in sd:
+        skip = _bn(sd, p + "skipbn", F.conv2d(x, sd[p + "skip.weight"], None, stride), train)
+    else:
+        skip = x
+    return h + skip
+
+
+def deeplab_xception_trunk(sd, x, output_stride=16, train=True):
+    """Xception.forward (deeplabv3_plus.py:201-247): low_level_features = block1 output BEFORE the ReLU."""
+    if output_stride == 16:
+        b3_s, mf_d, ef_d = 2, 1, (1, 2)
+    else:
+        b3_s, mf_d, ef_d = 1, 2, (2, 4)
+    x = F.relu(_bn(sd, "backbone.bn1", F.conv2d(x, sd["backbone.conv1.weight"], None, 2, 1), train))
+    x = _bn(sd, "backbone.bn2", F.conv2d(x, sd["backbone.conv2.weight"], None, 1, 1), train)
+    x = _xblock(sd, "backbone.block1.", x, 2, 1, train, use_1st_relu=False)
+    low = x
+    x = F.relu(x)
+    x = _xblock(sd, "backbone.block2.", x, 2, 1, train)
+    x = _xblock(sd, "backbone.block3.", x, b3_s, 1, train)
+    for i in range(16):
+        x = _xblock(sd, f"backbone.block{i + 4}.", x, 1, mf_d, train)
+    x = _xblock(sd, "backbone.block20.", x, 1, ef_d[0], train, exit_flow=True)
+    x = F.relu(x)
+    for n in (3, 4, 5):
+        x = F.relu(_bn(sd, f"backbone.bn{n}", _sepconv(sd, f"backbone.conv{n}", x, 1, ef_d[1], train), train))
+    return x, low
+
+
 def aspp(sd, x, output_stride=16, train=True, dropout=False):
     """deeplabv3_plus.py:286-297."""
     d = (1, 6, 12, 18) if output_stride == 16 else (1, 12, 24, 36)
@@ -91,7 +142,10 @@ def decoder(sd, x, low, train=True, dropout=False):
 def deeplab_forward(sd, x, backbone="resnet101", output_stride=16, train=True, dropout=False, return_lowres=False):
     """deeplabv3_plus.py:356-362.  Returns fp32 logits [B, C, H, W] (and the stride-4 logits if asked)."""
     H, W = x.shape[2:]
-    f, low = deeplab_resnet_trunk(sd, x, backbone, output_stride, train)
+    if backbone == "xception":
+        f, low = deeplab_xception_trunk(sd, x, output_stride, train)
+    else:
+        f, low = deeplab_resnet_trunk(sd, x, backbone, output_stride, train)
     f = aspp(sd, f, output_stride, train, dropout)
     lo = decoder(sd, f, low, train, dropout)
     out = F.interpolate(lo, size=(H, W), mode="bilinear", align_corners=True)
@@ -135,17 +189,63 @@ def pspnet_forward(sd, x, backbone="resnet50", train=True, use_aux=True, dropout
     return out
 
 
+def upernet_forward(sd, x, backbone="resnet101", train=True, dropout=False):
+    """upernet.py:136-144 (UperNet.forward) with ResNet.forward :79-87 (output_stride 16: layer3 stride 2, layer4 every
+    conv2 d=2), PSPModule.forward :31-38 (bins 1,2,4,6), FPN_fuse.forward :103-117 and up_and_add :89-90.
+    `smooth_conv` is ONE conv applied three times (shared weights); the top-down path is NOT cumulative."""
+    size = x.shape[2:]
+    y = _conv(sd, "backbone.initial.0", x, 2, 3)
+    y = F.relu(_bn(sd, "backbone.initial.1", y, train))
+    y = F.max_pool2d(y, 3, 2, 1)
+    layers = RESNET_LAYERS[backbone]
+    cfg = {1: (1, 1), 2: (2, 1), 3: (2, 1), 4: (1, 2)}
+    feats = []
+    for li in (1, 2, 3, 4):
+        stride, dil = cfg[li]
+        for b in range(layers[li - 1]):
+            y = _bottleneck(sd, f"backbone.layer{li}.{b}.", y, stride if b == 0 else 1, dil, train)
+        feats.append(y)
+    f4 = feats[-1]
+    h, w = f4.shape[2:]
+    pyr = [f4]
+    for i, bins in enumerate((1, 2, 4, 6)):
+        p = F.adaptive_avg_pool2d(f4, bins)
+        p = F.relu(_bn(sd, f"PPN.stages.{i}.2", _conv(sd, f"PPN.stages.{i}.1", p), train))
+        pyr.append(F.interpolate(p, size=(h, w), mode="bilinear", align_corners=True))
+    y = F.relu(_bn(sd, "PPN.bottleneck.1", _conv(sd, "PPN.bottleneck.0", torch.cat(pyr, 1), 1, 1), train))
+    if dropout and train:
+        y = F.dropout2d(y, 0.1, True)
+    feats[-1] = y
+    # FPN_fuse: laterals (with bias) on features[1:], then up(f_i) + f_{i-1} from the ORIGINAL laterals
+    f = [feats[0]] + [_conv(sd, f"FPN.conv1x1.{i}", feats[i + 1]) for i in range(3)]
+    P = []
+    for i in (3, 2, 1):
+        up = F.interpolate(f[i], size=f[i - 1].shape[2:], mode="bilinear", align_corners=True) + f[i - 1]
+        P.append(_conv(sd, "FPN.smooth_conv.0", up, 1, 1))
+    P = list(reversed(P))
+    P.append(f[-1])
+    H, W = P[0].shape[2:]
+    P[1:] = [F.interpolate(q, size=(H, W), mode="bilinear", align_corners=True) for q in P[1:]]
+    y = F.relu(_bn(sd, "FPN.conv_fusion.1", _conv(sd, "FPN.conv_fusion.0", torch.cat(P, 1), 1, 1), train))
+    y = _conv(sd, "head", y, 1, 1)
+    return F.interpolate(y, size=size, mode="bilinear", align_corners=False)
+
+
 def param_names(sd):
     """Names of trainable tensors (everything except BN running statistics / counters)."""
     return [k for k in sd if not (k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"))]
 
 
 def clone_sd(sd, requires_grad=False):
-    out = {}
+    """Deep copy that preserves aliasing (UperNet's three smooth_conv entries are one tensor)."""
+    out, seen = {}, {}
     names = set(param_names(sd))
     for k, v in sd.items():
-        t = v.clone()
-        if requires_grad and k in names:
-            t.requires_grad_(True)
-        out[k] = t
+        key = id(v)
+        if key not in seen:
+            t = v.clone()
+            if requires_grad and k in names:
+                t.requires_grad_(True)
+            seen[key] = t
+        out[k] = seen[key]
     return out

@@ -836,6 +836,42 @@ __global__ void counter_add_kernel(uint64_t* ctr, uint64_t inc) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *ctr += inc;
 }
 
+// standalone ReLU (Xception: F.relu(low_level) before block2, deeplabv3_plus.py:210)
+__global__ void relu_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy, int64_t M, int C) {
+  const int G = C >> 3;
+  const int64_t total = M * G;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const int64_t row = i / G;
+    float a[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8), a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], 0.f);
+    *reinterpret_cast<bf16x8*>(y + row * ldy + g * 8) = pack8(a);
+  }
+}
+__global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ y, int ldy,
+                                __nv_bfloat16* __restrict__ dx, int lddx, int64_t M, int C, float beta) {
+  const int G = C >> 3;
+  const int64_t total = M * G;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const int64_t row = i / G;
+    float d[8], o[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(dy + row * lddy + g * 8), d);
+    unpack8(*reinterpret_cast<const bf16x8*>(y + row * ldy + g * 8), o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] = o[k] > 0.f ? d[k] : 0.f;
+    if (beta != 0.f) {
+      float b[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dx + row * lddx + g * 8), b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] += beta * b[k];
+    }
+    *reinterpret_cast<bf16x8*>(dx + row * lddx + g * 8) = pack8(d);
+  }
+}
+
 struct SgdChunkArgs {
   float* const* params;
   float* const* grads;
@@ -1054,6 +1090,17 @@ int seg_axpby_bf16(const void* x, int ldx, void* y, int ldy, int64_t M, int C, f
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "axpby: alignment");
   axpby_kernel<<<grid_for(M * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(x), ldx, BF(y), ldy, M, C, beta);
   return check_launch("axpby");
+}
+int seg_relu_fwd(const void* x, int ldx, void* y, int ldy, int64_t M, int C, void* stream) {
+  SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "relu: alignment");
+  relu_fwd_kernel<<<grid_for(M * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(x), ldx, BF(y), ldy, M, C);
+  return check_launch("relu_fwd");
+}
+int seg_relu_bwd(const void* dy, int lddy, const void* y, int ldy, void* dx, int lddx, int64_t M, int C, float beta,
+                 void* stream) {
+  SEG_REQUIRE(C % 8 == 0 && lddy % 8 == 0 && ldy % 8 == 0 && lddx % 8 == 0, "relu: alignment");
+  relu_bwd_kernel<<<grid_for(M * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(dy), lddy, CBF(y), ldy, BF(dx), lddx, M, C, beta);
+  return check_launch("relu_bwd");
 }
 int seg_counter_add(uint64_t* ctr, uint64_t inc, void* stream) {
   counter_add_kernel<<<1, 32, 0, ST(stream)>>>(ctr, inc);

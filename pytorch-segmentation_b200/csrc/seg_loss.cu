@@ -79,6 +79,67 @@ __global__ void __launch_bounds__(256) ce_nchw_bwd_kernel(const float* __restric
   }
 }
 
+// ---------------------------------------------------------------- Dice (utils/losses.py:33-50)
+// loss = 1 - (2*I + smooth) / (sum(softmax) + sum(onehot) + smooth),  I = sum_pixels softmax[target].
+// accum[0] += I, accum[1] += sum(softmax) (== #pixels up to rounding), accum[2] += #pixels (sum of the one-hot tensor).
+__global__ void __launch_bounds__(256) dice_nchw_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target,
+                                                            int N, int C, int H, int W, double* accum) {
+  const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
+  double inter = 0.0, psum = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = target[i];
+    const int n = (int)(i / HW);
+    const float* l = logits + (int64_t)n * C * HW + (i - (int64_t)n * HW);
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, l[(int64_t)c * HW]);
+    float se = 0.f, et = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float e = expf(l[(int64_t)c * HW] - mx);
+      se += e;
+      if (c == t) et = e;
+    }
+    inter += (double)(et / se);
+    psum += 1.0;
+  }
+  block_accum2(inter, psum, accum);
+}
+
+// d loss / d logit_c = -(2 / D) * p_t * (delta_ct - p_c),  D = accum[1] + accum[2] + smooth
+__global__ void __launch_bounds__(256) dice_nchw_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target,
+                                                            int N, int C, int H, int W, const double* __restrict__ accum,
+                                                            float smooth, const float* __restrict__ gscale,
+                                                            float* __restrict__ dl, float beta) {
+  const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
+  const double I = accum[0], P = accum[1], T = accum[1];
+  const double D = P + T + (double)smooth;
+  // d/dp_t of -(2I+s)/D with D depending on sum(p): the sum(p) term has zero gradient through softmax (rows sum to 1)
+  const float g = (gscale ? *gscale : 1.f) * (float)(-2.0 / D);
+  (void)I;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = target[i];
+    const int n = (int)(i / HW);
+    const int64_t off = (int64_t)n * C * HW + (i - (int64_t)n * HW);
+    const float* l = logits + off;
+    float* d = dl + off;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, l[(int64_t)c * HW]);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(l[(int64_t)c * HW] - mx);
+    const float inv = 1.f / se;
+    const float pt = (t >= 0 && t < C) ? expf(l[t * HW] - mx) * inv : 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float pc = expf(l[(int64_t)c * HW] - mx) * inv;
+      const float v = g * pt * ((c == t ? 1.f : 0.f) - pc);
+      d[(int64_t)c * HW] = (beta != 0.f) ? beta * d[(int64_t)c * HW] + v : v;
+    }
+  }
+}
+
+__global__ void dice_finalize_kernel(const double* accum, float smooth, float* loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    *loss = (float)(1.0 - (2.0 * accum[0] + smooth) / (accum[1] + accum[1] + smooth));
+}
+
 __global__ void ce_finalize_kernel(const double* accum, float* loss) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *loss = (float)(accum[0] / fmax(accum[1], 1.0));
 }
@@ -244,6 +305,22 @@ int seg_ce_nchw_bwd(const float* logits, const int64_t* target, int N, int C, in
   int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 8);
   ce_nchw_bwd_kernel<<<blocks, 256, 0, ST(stream)>>>(logits, target, N, C, H, W, ignore_index, accum, gscale, dlogits);
   return check_launch("ce_nchw_bwd");
+}
+int seg_dice_nchw_fwd(const float* logits, const int64_t* target, int N, int C, int H, int W, float smooth, double* accum,
+                      float* loss, void* stream) {
+  const int64_t total = (int64_t)N * H * W;
+  int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 8);
+  dice_nchw_fwd_kernel<<<blocks, 256, 0, ST(stream)>>>(logits, target, N, C, H, W, accum);
+  if (check_launch("dice_nchw_fwd")) return 1;
+  dice_finalize_kernel<<<1, 32, 0, ST(stream)>>>(accum, smooth, loss);
+  return check_launch("dice_finalize");
+}
+int seg_dice_nchw_bwd(const float* logits, const int64_t* target, int N, int C, int H, int W, const double* accum,
+                      float smooth, const float* gscale, float* dlogits, float beta, void* stream) {
+  const int64_t total = (int64_t)N * H * W;
+  int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 8);
+  dice_nchw_bwd_kernel<<<blocks, 256, 0, ST(stream)>>>(logits, target, N, C, H, W, accum, smooth, gscale, dlogits, beta);
+  return check_launch("dice_nchw_bwd");
 }
 int seg_ce_finalize(const double* accum, float* loss, void* stream) {
   ce_finalize_kernel<<<1, 32, 0, ST(stream)>>>(accum, loss);

@@ -27,7 +27,7 @@ _REF_MODELS = _find_reference_models()
 if _REF_MODELS is not None:
     __path__.append(_REF_MODELS)  # submodules not overridden here (fcn, unet, segnet, ...) load from the reference
     for _mod, _names in (("fcn", ["FCN8"]), ("unet", ["UNet", "UNetResnet"]), ("segnet", ["SegNet", "SegResNet"]), ("enet", ["ENet"]),
-                         ("gcn", ["GCN"]), ("duc_hdc", ["DeepLab_DUC_HDC"]), ("upernet", ["UperNet"]), ("pspnet", ["PSPDenseNet"])):
+                         ("gcn", ["GCN"]), ("duc_hdc", ["DeepLab_DUC_HDC"]), ("pspnet", ["PSPDenseNet"])):
         try:
             _m = importlib.import_module(f"{__name__}.{_mod}")
             for _n in _names:
@@ -35,4 +35,4 @@ if _REF_MODELS is not None:
         except Exception as _e:  # a reference model that cannot import here stays unavailable, as in the reference
             globals().setdefault("_import_errors", {})[_mod] = repr(_e)
 
-from seg_b200.nets import DeepLab, PSPNet  # noqa: E402,F401  B200-native replacements (same names, same contract)
+from seg_b200.nets import DeepLab, PSPNet, UperNet  # noqa: E402,F401  B200-native replacements (same names, same contract)

@@ -9,7 +9,10 @@ tree) before anything imports the reference's ``base`` / ``utils`` packages.
 _LAZY = {
     "DeepLab": ("nets", "DeepLab"),
     "PSPNet": ("nets", "PSPNet"),
+    "UperNet": ("nets", "UperNet"),
     "CrossEntropyLoss2d": ("losses", "CrossEntropyLoss2d"),
+    "DiceLoss": ("losses", "DiceLoss"),
+    "CE_DiceLoss": ("losses", "CE_DiceLoss"),
     "FusedTrainStep": ("train", "FusedTrainStep"),
 }
 

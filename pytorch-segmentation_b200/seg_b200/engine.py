@@ -94,6 +94,29 @@ class ConvSpec:
         return self._packed
 
 
+class DwSpec:
+    """Depthwise 3x3 conv holder (nn.Conv2d with groups == channels) + packed fp32 [9][C] weight cache."""
+
+    def __init__(self, name, module):
+        self.name, self.m = name, module
+        assert module.groups == module.in_channels == module.out_channels and module.kernel_size == (3, 3)
+        self.C = module.in_channels
+        self._packed, self._version = None, None
+        self.always_repack = False
+
+    stride = property(lambda self: self.m.stride[0])
+    pad = property(lambda self: self.m.padding[0])
+    dil = property(lambda self: self.m.dilation[0])
+
+    def packed(self):
+        w = self.m.weight
+        key = (w._version, w.data_ptr())
+        if self._packed is None or self._version != key or self.always_repack:
+            self._packed = ops.dw_pack_weight(w.detach())
+            self._version = key
+        return self._packed
+
+
 class Tape:
     def __init__(self, training, record=None, grads=None, impl=IMPL_AUTO, dropout=True, seed=0, sync=None, clamp_eps=False,
                  step_ctr=None):
@@ -183,6 +206,40 @@ class Tape:
                 ya.grad = None
             self.back.append(bwd)
         return ya, stats
+
+    def dwconv(self, x, spec, want_stats=False):
+        """Depthwise 3x3 (SeparableConv2d.conv1).  Returns (raw output Act, BN statistics or None)."""
+        w9 = spec.packed()
+        stats = torch.zeros(2 * spec.C, dtype=torch.float32, device=w9.device) if (want_stats and self.training) else None
+        y = ops.dwconv_fwd(x.t, w9, spec.stride, spec.pad, spec.dil, stats=stats)
+        ya = Act(y)
+        if self.record:
+            def bwd():
+                dy = ya.grad
+                if dy is None:
+                    return
+                if spec.m.weight.requires_grad:
+                    g9 = ops.dwconv_bwd_weight(dy, x.t, spec.stride, spec.pad, spec.dil)
+                    self._param_grad(spec.m.weight, lambda g, beta: ops.dw_unpack_wgrad(g9, g, beta))
+                if x.needs_grad:
+                    gx, beta = x.grad_target()
+                    ops.dwconv_bwd_data(dy, w9, tuple(x.t.shape), spec.stride, spec.pad, spec.dil, out=gx, beta=beta)
+                ya.grad = None
+            self.back.append(bwd)
+        return ya, stats
+
+    def relu(self, x):
+        y = ops.relu_fwd(x.t)
+        ya = Act(y)
+        if self.record:
+            def bwd():
+                if ya.grad is None or not x.needs_grad:
+                    return
+                gx, beta = x.grad_target()
+                ops.relu_bwd(ya.grad, y, gx, beta)
+                ya.grad = None
+            self.back.append(bwd)
+        return ya
 
     # ------------------------------------------------------------------ batch norm (+ residual, ReLU, dropout)
     def bn_act(self, y, bn, stats=None, relu=True, res=None, out=None, drop_p=0.0):
@@ -285,6 +342,27 @@ class Tape:
                 ya.grad = None
             self.back.append(bwd)
         return ya
+
+    def up_add(self, x, y):
+        """up_and_add of the reference's FPN (models/upernet.py:89-90): bilinear(x -> size of y, align_corners=True) + y."""
+        Hy, Wy = y.t.shape[1], y.t.shape[2]
+        u = ops.bilinear_fwd(x.t, Hy, Wy, True)
+        ops.axpby(y.t, u, 1.0)  # u += y
+        ua = Act(u)
+        if self.record:
+            def bwd():
+                g = ua.grad
+                if g is None:
+                    return
+                if y.needs_grad:
+                    gy, beta = y.grad_target()
+                    ops.axpby(g, gy, beta)
+                if x.needs_grad:
+                    gx, beta = x.grad_target()
+                    ops.bilinear_bwd(g, x.t.shape[1], x.t.shape[2], True, dx=gx, beta=beta)
+                ua.grad = None
+            self.back.append(bwd)
+        return ua
 
     def copy_into(self, x, out):
         """Copy an activation into a concat slice (used when the producer's tensor is also consumed elsewhere)."""

@@ -1,6 +1,8 @@
 """Drop-in losses for the reference's loss registry (`getattr(losses, config['loss'])(ignore_index=...)`, train.py:30).
 
     CrossEntropyLoss2d(weight=None, ignore_index=255, reduction='mean')   — utils/losses.py:24-31
+    DiceLoss(smooth=1., ignore_index=255)                                 — utils/losses.py:33-50
+    CE_DiceLoss(smooth=1, reduction='mean', ignore_index=255, weight=None) — utils/losses.py:67-77
 
 forward(output fp32 [B,C,H,W], target int64 [B,H,W]) -> 0-dim tensor with autograd, computed by the sm_100a kernels
 (`seg_ce_nchw_fwd/bwd`); `.item()` works as the trainer expects (trainer.py:72,81).  CUDA tensors only.
@@ -39,3 +41,56 @@ class CrossEntropyLoss2d(nn.Module):
         if not output.is_cuda:
             raise RuntimeError("seg_b200 losses run on a B200 only; there is no CPU fallback")
         return _CEFn.apply(output, target, self.ignore_index)
+
+
+class _DiceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, smooth):
+        logits = logits.contiguous().float()
+        loss, accum = ops.dice_nchw_fwd(logits, target, smooth)
+        ctx.save_for_backward(logits, target, accum)
+        ctx.smooth = smooth
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        logits, target, accum = ctx.saved_tensors
+        g = gout.detach().reshape(1).float().contiguous()
+        return ops.dice_nchw_bwd(logits, target, accum, ctx.smooth, gscale=g), None, None
+
+
+def _dice_fix_target_(target, ignore_index):
+    """The reference's label fix-up, reproduced including its in-place mutation of the caller's tensor and its
+    `range(min, max)` test (utils/losses.py:40-42): ignored pixels become target.min()."""
+    tmin, tmax = int(target.min()), int(target.max())
+    if ignore_index not in range(tmin, tmax):
+        if (target == ignore_index).sum() > 0:
+            target[target == ignore_index] = tmin
+    return target
+
+
+class DiceLoss(nn.Module):
+    def __init__(self, smooth=1.0, ignore_index=255):
+        super().__init__()
+        self.ignore_index = ignore_index
+        self.smooth = smooth
+
+    def forward(self, output, target):
+        if not output.is_cuda:
+            raise RuntimeError("seg_b200 losses run on a B200 only; there is no CPU fallback")
+        target = _dice_fix_target_(target, self.ignore_index)
+        return _DiceFn.apply(output, target.contiguous(), float(self.smooth))
+
+
+class CE_DiceLoss(nn.Module):
+    def __init__(self, smooth=1, reduction="mean", ignore_index=255, weight=None):
+        super().__init__()
+        if weight is not None or reduction != "mean":
+            raise NotImplementedError("seg_b200.CE_DiceLoss: only weight=None, reduction='mean'")
+        self.smooth = smooth
+        self.dice = DiceLoss()  # the reference builds it with the DEFAULT ignore_index (utils/losses.py:71)
+        self.ignore_index = ignore_index
+
+    def forward(self, output, target):
+        ce = _CEFn.apply(output, target, self.ignore_index)  # CE first: it sees the target before Dice mutates it
+        return ce + self.dice(output, target)

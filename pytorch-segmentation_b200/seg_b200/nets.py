@@ -2,6 +2,7 @@
 
     DeepLab(num_classes, in_channels=3, backbone='resnet101', pretrained=False, output_stride=16, freeze_bn=False, **_)
     PSPNet (num_classes, in_channels=3, backbone='resnet50',  pretrained=False, use_aux=True,   freeze_bn=False, **_)
+    UperNet(num_classes, in_channels=3, backbone='resnet101', pretrained=False, use_aux=True, fpn_out=256, freeze_bn=False, **_)
 
 Same constructor contract, same `state_dict()` keys and OIHW fp32 parameter layout, same `get_backbone_params /
 get_decoder_params / freeze_bn` methods and the same forward contract (fp32 NCHW logits at input resolution; PSPNet
@@ -21,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .engine import Act, ConvSpec, Tape
+from .engine import Act, ConvSpec, DwSpec, Tape
 from .lib import IMPL_AUTO, require_device
 
 try:  # inside the reference tree: subclass its BaseModel so isinstance checks and logging behave identically
@@ -91,6 +92,57 @@ def _res_layers(blocks, inplanes, plan):
     return layers
 
 
+def _sepconv(cin, cout, stride, dil):
+    """SeparableConv2d holder (deeplabv3_plus.py:70-86): depthwise 3x3 'same' conv -> BN -> pointwise 1x1."""
+    s = _Holder()
+    pad = dil if dil > 1 else 1
+    s.conv1 = nn.Conv2d(cin, cin, 3, stride, padding=pad, dilation=dil, groups=cin, bias=False)
+    s.bn = nn.BatchNorm2d(cin)
+    s.pointwise = nn.Conv2d(cin, cout, 1, 1, bias=False)
+    return s
+
+
+def _xception_block(cin, cout, stride=1, dil=1, exit_flow=False, use_1st_relu=True):
+    """Block holder (deeplabv3_plus.py:89-121) with the reference's child order / Sequential indices."""
+    b = _Holder()
+    if cin != cout or stride != 1:
+        b.skip = nn.Conv2d(cin, cout, 1, stride=stride, bias=False)
+        b.skipbn = nn.BatchNorm2d(cout)
+    else:
+        b.skip = None
+    b.relu = nn.ReLU(inplace=True)
+    units = [(cin, cin), (cin, cout), (cout, cout)] if exit_flow else [(cin, cout), (cout, cout), (cout, cout)]
+    rep = []
+    for i, (a, c) in enumerate(units):
+        rep += [b.relu, _sepconv(a, c, stride if i == 2 else 1, dil), nn.BatchNorm2d(c)]
+    if not use_1st_relu:
+        rep = rep[1:]
+    b.rep = nn.Sequential(*rep)
+    b.use_1st_relu = use_1st_relu
+    return b
+
+
+def _xception_trunk(output_stride):
+    """Aligned Xception holder (deeplabv3_plus.py:134-171)."""
+    b3_s, mf_d, ef_d = (2, 1, (1, 2)) if output_stride == 16 else (1, 2, (2, 4))
+    x = _Holder()
+    x.conv1 = nn.Conv2d(3, 32, 3, 2, padding=1, bias=False)
+    x.bn1 = nn.BatchNorm2d(32)
+    x.relu = nn.ReLU(inplace=True)
+    x.conv2 = nn.Conv2d(32, 64, 3, 1, padding=1, bias=False)
+    x.bn2 = nn.BatchNorm2d(64)
+    x.block1 = _xception_block(64, 128, stride=2, dil=1, use_1st_relu=False)
+    x.block2 = _xception_block(128, 256, stride=2, dil=1)
+    x.block3 = _xception_block(256, 728, stride=b3_s, dil=1)
+    for i in range(16):
+        setattr(x, f"block{i + 4}", _xception_block(728, 728, stride=1, dil=mf_d))
+    x.block20 = _xception_block(728, 1024, stride=1, dil=ef_d[0], exit_flow=True)
+    x.conv3, x.bn3 = _sepconv(1024, 1536, 1, ef_d[1]), nn.BatchNorm2d(1536)
+    x.conv4, x.bn4 = _sepconv(1536, 1536, 1, ef_d[1]), nn.BatchNorm2d(1536)
+    x.conv5, x.bn5 = _sepconv(1536, 2048, 1, ef_d[1]), nn.BatchNorm2d(2048)
+    return x
+
+
 def _init_like_reference_head(*mods):
     """utils/helpers.py:12-22 (initialize_weights): kaiming-normal convs (fan_in, relu), BN gamma=1, beta=1e-4."""
     for mod in mods:
@@ -158,6 +210,7 @@ class _EngineModel(BaseModel):
     def __init__(self):
         super().__init__()
         self._specs = {}
+        self._dwspecs = {}
         self.conv_impl = IMPL_AUTO
         self.engine_dropout = True    # set False to run train-mode parity with p = 0
         self.engine_seed = 0
@@ -173,8 +226,42 @@ class _EngineModel(BaseModel):
         return s
 
     def all_conv_specs(self):
-        """ConvSpec of every nn.Conv2d holder (names = module paths, as used by the forward code)."""
-        return [self._spec(n, m) for n, m in self.named_modules() if isinstance(m, nn.Conv2d)]
+        """ConvSpec of every dense nn.Conv2d holder (names = module paths, as used by the forward code)."""
+        return [self._spec(n, m) for n, m in self.named_modules() if isinstance(m, nn.Conv2d) and m.groups == 1]
+
+    def all_dw_specs(self):
+        return [self._dwspec(n, m) for n, m in self.named_modules() if isinstance(m, nn.Conv2d) and m.groups > 1]
+
+    def _dwspec(self, name, module):
+        s = self._dwspecs.get(name)
+        if s is None or s.m is not module:
+            s = DwSpec(name, module)
+            self._dwspecs[name] = s
+        return s
+
+    def _sep_unit(self, tape, x, prefix, sep, bn_after, relu_after, res=None):
+        """relu'd input -> depthwise -> BN -> pointwise -> BN (+res) (+ReLU of the NEXT unit, fused here)."""
+        y, st = tape.dwconv(x, self._dwspec(prefix + ".conv1", sep.conv1), want_stats=True)
+        a = tape.bn_act(y, sep.bn, st, relu=False)
+        y2, st2 = tape.conv(a, self._spec(prefix + ".pointwise", sep.pointwise), want_stats=True)
+        return tape.bn_act(y2, bn_after, st2, relu=relu_after, res=res)
+
+    def _xblock(self, tape, x, prefix, blk, relu_out):
+        """Xception Block (deeplabv3_plus.py:123-132).  `x` must already carry the block's leading in-place ReLU (every
+        block but block1); `relu_out` fuses the NEXT block's leading ReLU — which, being in place, is also what that
+        block's skip branch sees."""
+        mods = list(blk.rep.named_children())
+        units = [(i, m) for i, m in mods if isinstance(m, _Holder)]
+        bns = {int(i): m for i, m in mods if isinstance(m, nn.BatchNorm2d)}
+        skip = x
+        if blk.skip is not None:
+            skip = self._cbr(tape, x, prefix + "skip", blk.skip, blk.skipbn, relu=False)
+        h = x
+        for k, (idx, sep) in enumerate(units):
+            last = k == len(units) - 1
+            h = self._sep_unit(tape, h, f"{prefix}rep.{idx}", sep, bns[int(idx) + 1], relu_after=(relu_out if last else True),
+                               res=skip if last else None)
+        return h
 
     def _new_tape(self, training, record):
         ctr = None
@@ -238,12 +325,26 @@ class DeepLab(_EngineModel):
     def __init__(self, num_classes, in_channels=3, backbone="resnet101", pretrained=False, output_stride=16,
                  freeze_bn=False, freeze_backbone=False, **_):
         super().__init__()
-        if "resnet" not in backbone or backbone not in RESNET_BLOCKS:
-            raise NotImplementedError(f"seg_b200.DeepLab: backbone {backbone!r} not built yet (resnet50/101/152 are)")
+        if backbone != "xception" and backbone not in RESNET_BLOCKS:
+            raise NotImplementedError(f"seg_b200.DeepLab: backbone {backbone!r} not built (xception, resnet50/101/152 are)")
         if pretrained:
             raise RuntimeError("pretrained weights need network access; load a state_dict instead")
         assert output_stride in (8, 16)
         self.num_classes, self.output_stride, self.backbone_name = num_classes, output_stride, backbone
+        if backbone == "xception":
+            self._build_heads(num_classes, output_stride, low_level_channels=128)
+            self.backbone = _xception_trunk(output_stride)
+            # keep the reference's registration order: backbone, ASSP, decoder
+            assp, dec = self.ASSP, self.decoder
+            del self.ASSP, self.decoder
+            self.ASSP, self.decoder = assp, dec
+            _init_like_reference_head(self.backbone, self.ASSP, self.decoder)
+            if freeze_bn:
+                self.freeze_bn()
+            if freeze_backbone:
+                for p in self.backbone.parameters():
+                    p.requires_grad = False
+            return
         # deeplabv3_plus.py:35-53: os16 -> layer3 stride 2, layer4 every conv2 d=2 ; os8 -> layer3 d=2, layer4 d=4
         if output_stride == 16:
             plan = [(1, 1, 1), (2, 1, 1), (2, 1, 1), (1, 2, 2)]
@@ -254,6 +355,16 @@ class DeepLab(_EngineModel):
         bb.layer0 = nn.Sequential(c0, b0, nn.ReLU(inplace=True), nn.MaxPool2d(kernel_size=3, stride=2, padding=1))
         bb.layer1, bb.layer2, bb.layer3, bb.layer4 = _res_layers(RESNET_BLOCKS[backbone], 64, plan)
         self.backbone = bb
+        self._build_heads(num_classes, output_stride, low_level_channels=256)
+        _init_like_torchvision_trunk(bb.layer1, bb.layer2, bb.layer3, bb.layer4)
+        _init_like_reference_head(bb.layer0, self.ASSP, self.decoder)
+        if freeze_bn:
+            self.freeze_bn()
+        if freeze_backbone:
+            for p in self.backbone.parameters():
+                p.requires_grad = False
+
+    def _build_heads(self, num_classes, output_stride, low_level_channels):
         dil = (1, 6, 12, 18) if output_stride == 16 else (1, 12, 24, 36)
         a = _Holder()
         for i, k in zip((1, 2, 3, 4), (1, 3, 3, 3)):
@@ -265,24 +376,29 @@ class DeepLab(_EngineModel):
         a.relu, a.dropout = nn.ReLU(inplace=True), nn.Dropout(0.5)
         self.ASSP = a
         d = _Holder()
-        d.conv1, d.bn1 = _cbn(256, 48, 1)
+        d.conv1, d.bn1 = _cbn(low_level_channels, 48, 1)
         d.relu = nn.ReLU(inplace=True)
         c1, n1 = _cbn(48 + 256, 256, 3)
         c2, n2 = _cbn(256, 256, 3)
         d.output = nn.Sequential(c1, n1, nn.ReLU(inplace=True), c2, n2, nn.ReLU(inplace=True), nn.Dropout(0.1),
                                  nn.Conv2d(256, num_classes, 1, stride=1))
         self.decoder = d
-        _init_like_torchvision_trunk(bb.layer1, bb.layer2, bb.layer3, bb.layer4)
-        _init_like_reference_head(bb.layer0, self.ASSP, self.decoder)
-        if freeze_bn:
-            self.freeze_bn()
-        if freeze_backbone:
-            for p in self.backbone.parameters():
-                p.requires_grad = False
 
     # ---- engine forward: returns the stride-4 fp32 logits Act (NHWC) ----
-    def _features(self, tape, x):
-        N = x.shape[0]
+    def _trunk_xception(self, tape, x):
+        """Xception.forward (deeplabv3_plus.py:201-247); low-level features = block1 output BEFORE the ReLU."""
+        bb = self.backbone
+        a = self._cbr(tape, x, "backbone.conv1", bb.conv1, bb.bn1)
+        a = self._cbr(tape, a, "backbone.conv2", bb.conv2, bb.bn2, relu=False)
+        low = self._xblock(tape, a, "backbone.block1.", bb.block1, relu_out=False)
+        a = tape.relu(low)
+        for i in range(2, 21):
+            a = self._xblock(tape, a, f"backbone.block{i}.", getattr(bb, f"block{i}"), relu_out=True)
+        for n in (3, 4, 5):
+            a = self._sep_unit(tape, a, f"backbone.conv{n}", getattr(bb, f"conv{n}"), getattr(bb, f"bn{n}"), relu_after=True)
+        return a, low
+
+    def _trunk_resnet(self, tape, x):
         bb = self.backbone
         a = self._cbr(tape, x, "backbone.layer0.0", bb.layer0[0], bb.layer0[1])
         a = tape.maxpool(a)
@@ -293,6 +409,11 @@ class DeepLab(_EngineModel):
                 a = self._block(tape, a, f"backbone.layer{li}.{bi}.", blk)
             if li == 1:
                 low = a
+        return a, low
+
+    def _features(self, tape, x):
+        N = x.shape[0]
+        a, low = self._trunk_xception(tape, x) if self.backbone_name == "xception" else self._trunk_resnet(tape, x)
         # ---- ASPP (deeplabv3_plus.py:286-297): five branches written straight into one 1280-channel buffer ----
         Hf, Wf = a.t.shape[1], a.t.shape[2]
         A = self.ASSP
@@ -417,3 +538,103 @@ class PSPNet(_EngineModel):
 
     def get_decoder_params(self):
         return chain(self.master_branch.parameters(), self.auxiliary_branch.parameters())
+
+
+# ----------------------------------------------------------------------------------------------- UperNet
+class UperNet(_EngineModel):
+    """UperNet (object path) — replaces models/upernet.py:119-154: torchvision-ResNet trunk returning four feature maps
+    (:40-87, output stride 16), PSPModule bins {1,2,4,6} (:9-38), FPN_fuse (:92-117), 3x3 head, bilinear(align_corners=
+    False) to the input size.  Quirks kept: ONE smooth conv shared by the three FPN levels (three aliased state_dict
+    entries), non-cumulative top-down path, laterals / smooth / head carry a bias, conv_fusion does not.
+    (The reference constructor itself raises NameError: freeze_backbone, upernet.py:133 — here the argument works.)"""
+
+    def __init__(self, num_classes, in_channels=3, backbone="resnet101", pretrained=False, use_aux=True, fpn_out=256,
+                 freeze_bn=False, freeze_backbone=False, **_):
+        super().__init__()
+        if backbone not in RESNET_BLOCKS:
+            raise NotImplementedError(f"seg_b200.UperNet: backbone {backbone!r} not built (bottleneck ResNets are)")
+        if pretrained:
+            raise RuntimeError("pretrained weights need network access; load a state_dict instead")
+        self.num_classes = num_classes
+        bb = _Holder()
+        c0, b0 = nn.Conv2d(in_channels, 64, 7, stride=2, padding=3, bias=False), nn.BatchNorm2d(64)
+        bb.initial = nn.Sequential(c0, b0, nn.ReLU(inplace=True), nn.MaxPool2d(kernel_size=3, stride=2, padding=1))
+        bb.layer1, bb.layer2, bb.layer3, bb.layer4 = _res_layers(RESNET_BLOCKS[backbone], 64, [(1, 1, 1), (2, 1, 1), (2, 1, 1), (1, 2, 2)])
+        self.backbone = bb
+        feats = [256, 512, 1024, 2048]
+        ppn = _Holder()
+        self.bins = (1, 2, 4, 6)
+        stages = []
+        for b in self.bins:
+            c, n = _cbn(feats[-1], feats[-1] // 4, 1)
+            stages.append(nn.Sequential(nn.AdaptiveAvgPool2d(output_size=b), c, n, nn.ReLU(inplace=True)))
+        ppn.stages = nn.ModuleList(stages)
+        c, n = _cbn(feats[-1] * 2, feats[-1], 3)
+        ppn.bottleneck = nn.Sequential(c, n, nn.ReLU(inplace=True), nn.Dropout2d(0.1))
+        self.PPN = ppn
+        fpn = _Holder()
+        fpn.conv1x1 = nn.ModuleList([nn.Conv2d(f, fpn_out, kernel_size=1) for f in feats[1:]])
+        fpn.smooth_conv = nn.ModuleList([nn.Conv2d(fpn_out, fpn_out, kernel_size=3, padding=1)] * (len(feats) - 1))
+        c, n = _cbn(len(feats) * fpn_out, fpn_out, 3)
+        fpn.conv_fusion = nn.Sequential(c, n, nn.ReLU(inplace=True))
+        self.FPN = fpn
+        self.head = nn.Conv2d(fpn_out, num_classes, kernel_size=3, padding=1)
+        _init_like_torchvision_trunk(bb.layer1, bb.layer2, bb.layer3, bb.layer4)
+        _init_like_reference_head(bb.initial)
+        if freeze_bn:
+            self.freeze_bn()
+        if freeze_backbone:
+            for p in self.backbone.parameters():
+                p.requires_grad = False
+
+    def _forward_heads(self, tape, x):
+        N = x.shape[0]
+        bb = self.backbone
+        a = self._cbr(tape, x, "backbone.initial.0", bb.initial[0], bb.initial[1])
+        a = tape.maxpool(a)
+        feats = []
+        for li in (1, 2, 3, 4):
+            for bi, blk in enumerate(getattr(bb, f"layer{li}")):
+                a = self._block(tape, a, f"backbone.layer{li}.{bi}.", blk)
+            feats.append(a)
+        # ---- PPN on the last feature map (upernet.py:31-38) ----
+        f4 = feats[-1]
+        Hf, Wf = f4.t.shape[1], f4.t.shape[2]
+        cat, sl = tape.concat(N, Hf, Wf, [2048, 512, 512, 512, 512], f4.t.device)
+        br = [tape.copy_into(f4, sl[0])]
+        for i, b in enumerate(self.bins):
+            st = self.PPN.stages[i]
+            p = tape.avgpool(f4, b)
+            p = self._cbr(tape, p, f"PPN.stages.{i}.1", st[1], st[2])
+            br.append(tape.bilinear(p, Hf, Wf, True, out=sl[i + 1]))
+        tape.bind_slices(cat, br)
+        pb = self.PPN.bottleneck
+        feats[-1] = self._cbr(tape, cat, "PPN.bottleneck.0", pb[0], pb[1], drop_p=pb[3].p)
+        # ---- FPN_fuse (upernet.py:103-117) ----
+        F_ = self.FPN
+        lat = [feats[0]]
+        for i in range(3):
+            y, _ = tape.conv(feats[i + 1], self._spec(f"FPN.conv1x1.{i}", F_.conv1x1[i]))
+            lat.append(y)
+        smooth = self._spec("FPN.smooth_conv.0", F_.smooth_conv[0])  # one shared conv, applied three times
+        P = []
+        for i in (3, 2, 1):
+            u = tape.up_add(lat[i], lat[i - 1])
+            y, _ = tape.conv(u, smooth)
+            P.append(y)
+        P = list(reversed(P)) + [lat[-1]]
+        H1, W1 = P[0].t.shape[1], P[0].t.shape[2]
+        cat2, sl2 = tape.concat(N, H1, W1, [256] * 4, x.device)
+        parts = [tape.copy_into(P[0], sl2[0])]
+        for j in (1, 2, 3):
+            parts.append(tape.bilinear(P[j], H1, W1, True, out=sl2[j]))
+        tape.bind_slices(cat2, parts)
+        y = self._cbr(tape, cat2, "FPN.conv_fusion.0", F_.conv_fusion[0], F_.conv_fusion[1])
+        lo, _ = tape.conv(y, self._spec("head", self.head), out_dtype=torch.float32)
+        return [(lo, False)]  # upernet.py:143: F.interpolate default align_corners=False
+
+    def get_backbone_params(self):
+        return self.backbone.parameters()
+
+    def get_decoder_params(self):
+        return chain(self.PPN.parameters(), self.FPN.parameters(), self.head.parameters())

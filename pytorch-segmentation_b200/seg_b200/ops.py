@@ -131,6 +131,56 @@ def conv2d_wgrad(dy, x, R, S, stride=1, pad=0, dil=1, out=None, impl=IMPL_AUTO):
     return out
 
 
+# ---------------------------------------------------------------- depthwise 3x3
+def dw_pack_weight(w_c133):
+    C = w_c133.shape[0]
+    w9 = torch.empty((9, C), dtype=torch.float32, device=w_c133.device)
+    call("seg_dw_pack_weight", ptr(w_c133), ptr(w9), C)
+    return w9
+
+
+def dw_unpack_wgrad(g9, out, beta=0.0):
+    call("seg_dw_unpack_wgrad", ptr(g9), ptr(out), g9.shape[1], float(beta))
+    return out
+
+
+def _dw_desc(x_shape, stride, pad, dil, ldx, ldy):
+    N, H, W, C = x_shape
+    return make_conv_desc(N, H, W, C, C, 3, 3, stride, pad, dil, ldx=ldx, ldy=ldy)
+
+
+def dwconv_fwd(x, w9, stride=1, pad=1, dil=1, out=None, stats=None):
+    N, H, W, C = x.shape
+    d = _dw_desc(x.shape, stride, pad, dil, ld(x), C)
+    if out is None:
+        out = torch.empty((N, d.P, d.Q, C), dtype=torch.bfloat16, device=x.device)
+    d.ldy = ld(out)
+    scratch = torch.empty(16 * 2 * C, dtype=torch.float32, device=x.device) if stats is not None else None
+    call("seg_dwconv3x3_fwd", ctypes.byref(d), ptr(x), ptr(w9), ptr(out), ptr(stats), ptr(scratch))
+    return out
+
+
+def dwconv_bwd_data(dy, w9, x_shape, stride=1, pad=1, dil=1, out=None, beta=0.0):
+    if out is None:
+        out = torch.empty(x_shape, dtype=torch.bfloat16, device=dy.device)
+        beta = 0.0
+    d = _dw_desc(x_shape, stride, pad, dil, ld(out), ld(dy))
+    assert (d.P, d.Q) == (dy.shape[1], dy.shape[2])
+    call("seg_dwconv3x3_bwd_data", ctypes.byref(d), ptr(dy), ptr(w9), ptr(out), float(beta))
+    return out
+
+
+def dwconv_bwd_weight(dy, x, stride=1, pad=1, dil=1, out=None, beta=0.0):
+    C = x.shape[-1]
+    if out is None:
+        out = torch.empty((9, C), dtype=torch.float32, device=x.device)
+        beta = 0.0
+    d = _dw_desc(x.shape, stride, pad, dil, ld(x), ld(dy))
+    scratch = torch.empty(int(lib.load().seg_dwconv_scratch_floats(C)), dtype=torch.float32, device=x.device)
+    call("seg_dwconv3x3_bwd_weight", ctypes.byref(d), ptr(dy), ptr(x), ptr(out), float(beta), ptr(scratch))
+    return out
+
+
 def im2col(x, R, S, stride, pad, dil, kpad, nchw_f32):
     if nchw_f32:
         N, C, H, W = x.shape
@@ -297,6 +347,24 @@ def ce_nchw_bwd(logits, target, ignore_index, accum, gscale=None):
     return dl
 
 
+def dice_nchw_fwd(logits, target, smooth=1.0):
+    N, C, H, W = logits.shape
+    assert logits.is_contiguous() and logits.dtype == torch.float32 and target.dtype == torch.int64 and target.is_contiguous()
+    accum = torch.zeros(2, dtype=torch.float64, device=logits.device)
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    call("seg_dice_nchw_fwd", ptr(logits), ptr(target), N, C, H, W, float(smooth), ptr(accum), ptr(loss))
+    return loss, accum
+
+
+def dice_nchw_bwd(logits, target, accum, smooth=1.0, gscale=None, out=None, beta=0.0):
+    N, C, H, W = logits.shape
+    if out is None:
+        out = torch.empty_like(logits)
+        beta = 0.0
+    call("seg_dice_nchw_bwd", ptr(logits), ptr(target), N, C, H, W, ptr(accum), float(smooth), ptr(gscale), ptr(out), float(beta))
+    return out
+
+
 def upsample_ce_fwd(logits_lo, target, align_corners, ignore_index, want_argmax=False):
     N, Hi, Wi, C = logits_lo.shape
     _, Ho, Wo = target.shape
@@ -326,6 +394,17 @@ def nhwc_to_nchw_f32(x):
     y = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
     call("seg_nhwc_to_nchw_f32", ptr(x), ld(x), DT_BF16 if x.dtype == torch.bfloat16 else DT_F32, ptr(y), N, H, W, C)
     return y
+
+
+def relu_fwd(x):
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    call("seg_relu_fwd", ptr(x), ld(x), ptr(y), ld(y), rows(x), x.shape[-1])
+    return y
+
+
+def relu_bwd(dy, y, dx, beta):
+    call("seg_relu_bwd", ptr(dy), ld(dy), ptr(y), ld(y), ptr(dx), ld(dx), rows(y), y.shape[-1], float(beta))
+    return dx
 
 
 def axpby(x, y, beta):

@@ -54,6 +54,8 @@ class FusedTrainStep:
         let ONE launch pack all weights / unpack all weight gradients (instead of 2 x ~114 small launches)."""
         specs = [s for s in self.model.all_conv_specs()]
         self.specs = specs
+        for ds in self.model.all_dw_specs():
+            ds.always_repack = True  # the in-place SGD kernel does not bump autograd versions
         dt = np.dtype([("oihw", "<u8"), ("packed", "<u8"), ("K", "<i4"), ("C", "<i4"), ("R", "<i4"), ("S", "<i4"),
                        ("Cpad", "<i4"), ("explicit", "<i4"), ("start", "<i8")])
         assert dt.itemsize == lib.load().seg_pack_entry_bytes()

@@ -10,6 +10,13 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 
+try:  # the oracle's ATen-CPU ops crawl with 128 oversubscribed threads on the GPU hosts (measured 10x slower than 16)
+    import torch
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+except Exception:
+    pass
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
 

@@ -86,6 +86,55 @@ def conv2d_wgrad(dy, x, R, S, stride=1, pad=0, dil=1, out=None, impl=0):
     return out
 
 
+def dw_pack_weight(w_c133):
+    C = w_c133.shape[0]
+    return w_c133.detach().reshape(C, 9).t().contiguous().float()
+
+
+def dw_unpack_wgrad(g9, out, beta=0.0):
+    g = g9.t().reshape(out.shape)
+    out.copy_(out * beta + g if beta else g)
+    return out
+
+
+def _dw_w(w9):
+    C = w9.shape[1]
+    return w9.t().reshape(C, 1, 3, 3).float()
+
+
+def dwconv_fwd(x, w9, stride=1, pad=1, dil=1, out=None, stats=None):
+    C = x.shape[-1]
+    y = F.conv2d(_nchw(x), _w_round(_dw_w(w9)), None, stride, pad, dil, groups=C).permute(0, 2, 3, 1)
+    if stats is not None:
+        stats[:C] += y.reshape(-1, C).sum(0)
+        stats[C:] += (y * y).reshape(-1, C).sum(0)
+    if out is None:
+        out = torch.empty(y.shape, dtype=ACT_DTYPE)
+    return _store(out, y)
+
+
+def dwconv_bwd_data(dy, w9, x_shape, stride=1, pad=1, dil=1, out=None, beta=0.0):
+    N, H, W, C = x_shape
+    g = torch.nn.grad.conv2d_input((N, C, H, W), _w_round(_dw_w(w9)), _nchw(dy), stride, pad, dil, groups=C).permute(0, 2, 3, 1)
+    if out is None:
+        out = torch.empty(x_shape, dtype=ACT_DTYPE)
+        beta = 0.0
+    return _store(out, g, beta)
+
+
+def dwconv_bwd_weight(dy, x, stride=1, pad=1, dil=1, out=None, beta=0.0):
+    C = x.shape[-1]
+    g = torch.nn.grad.conv2d_weight(_nchw(x), (C, 1, 3, 3), _nchw(dy), stride, pad, dil, groups=C).reshape(C, 9).t()
+    if out is None:
+        return g.contiguous()
+    out.copy_(out * beta + g if beta else g)
+    return out
+
+
+def _w_round(w):
+    return w  # depthwise taps stay fp32 in the kernels (registers), no bf16 rounding
+
+
 def im2col(x, R, S, stride, pad, dil, kpad, nchw_f32):
     xn = x.float() if nchw_f32 else _nchw(x)
     N, C, H, W = xn.shape
@@ -252,6 +301,14 @@ def ce_nchw_bwd(logits, target, ignore_index, accum, gscale=None):
         l = logits.detach().clone().requires_grad_(True)
         F.cross_entropy(l, target, ignore_index=ignore_index, reduction="mean").backward()
     return l.grad * (gscale.reshape(()) if gscale is not None else 1.0)
+
+
+def relu_fwd(x):
+    return x.float().clamp(min=0).to(ACT_DTYPE)
+
+
+def relu_bwd(dy, y, dx, beta):
+    return _store(dx, dy.float() * (y.float() > 0), beta)
 
 
 def counter_add(ctr, inc=1):

@@ -45,9 +45,15 @@ def cosine(a, b):
 
 
 def build(kind, nc, backbone, seed, **kw):
-    if kind == "deeplab":
+    if kind == "deeplab" and backbone == "xception":
+        sd = weights.deeplab_xception_state_dict(nc, seed=seed, randomize_bn=True, **kw)
+        m = seg_b200.DeepLab(nc, backbone=backbone, pretrained=False, **kw)
+    elif kind == "deeplab":
         sd = weights.deeplab_resnet_state_dict(nc, backbone, seed=seed, randomize_bn=True)
         m = seg_b200.DeepLab(nc, backbone=backbone, pretrained=False, **kw)
+    elif kind == "upernet":
+        sd = weights.upernet_state_dict(nc, backbone, seed=seed, randomize_bn=True)
+        m = seg_b200.UperNet(nc, backbone=backbone, pretrained=False, **kw)
     else:
         sd = weights.pspnet_state_dict(nc, backbone, seed=seed, randomize_bn=True)
         m = seg_b200.PSPNet(nc, backbone=backbone, pretrained=False, **kw)
@@ -59,6 +65,8 @@ def build(kind, nc, backbone, seed, **kw):
 def oracle_forward(kind, osd, x, backbone, kw, train):
     if kind == "deeplab":
         return om.deeplab_forward(osd, x, backbone=backbone, train=train, **kw), None
+    if kind == "upernet":
+        return om.upernet_forward(osd, x, backbone=backbone, train=train), None
     out = om.pspnet_forward(osd, x, backbone=backbone, train=train)
     return out if isinstance(out, tuple) else (out, None)
 
@@ -67,8 +75,10 @@ CASES = [
     ("deeplab", 19, "resnet101", 0, dict(output_stride=16), 9001),
     ("deeplab", 19, "resnet50", 2, dict(output_stride=8), 9001),
     ("pspnet", 21, "resnet50", 1, dict(), 9002),
+    ("upernet", 150, "resnet50", 3, dict(), 9004),
+    ("deeplab", 19, "xception", 4, dict(output_stride=16), 9001),
 ]
-IDS = ["deeplab_r101_os16", "deeplab_r50_os8", "pspnet_r50"]
+IDS = ["deeplab_r101_os16", "deeplab_r50_os8", "pspnet_r50", "upernet_r50", "deeplab_xception_os16"]
 
 
 def argmax_report(gpu_out_dir, tag, out, ref):
@@ -161,7 +171,9 @@ def test_batchstat_train_step(kind, nc, backbone, seed, kw, xseed, gpu_out_dir):
     log(gpu_out_dir, f"{tag} grad cosine vs fp32 oracle (chaotic regime, informational): median {cos_t.median():.4f}, min {cos_t.min():.4f}")
     # early layers are upstream of little chaos: the stem's running statistics must match tightly
     esd = m.state_dict()
-    stem_bn = "backbone.layer0.1" if kind == "deeplab" else "initial.0.1"
+    stem_bn = {"deeplab": "backbone.layer0.1", "pspnet": "initial.0.1", "upernet": "backbone.initial.1"}[kind]
+    if backbone == "xception":
+        stem_bn = "backbone.bn1"
     for k in (stem_bn + ".running_mean", stem_bn + ".running_var"):
         assert relerr(esd[k], osd[k]) < 1e-2, k
     rs = max(relerr(esd[k], osd[k]) for k in esd if k.endswith("running_mean") or k.endswith("running_var"))
@@ -254,5 +266,10 @@ def test_state_dict_keys_match_reference_inventory():
     assert list(m.state_dict().keys()) == list(weights.deeplab_resnet_state_dict(19, "resnet101").keys())
     p = seg_b200.PSPNet(21, backbone="resnet50")
     assert list(p.state_dict().keys()) == list(weights.pspnet_state_dict(21, "resnet50").keys())
+    xm = seg_b200.DeepLab(19, backbone="xception")
+    assert list(xm.state_dict().keys()) == list(weights.deeplab_xception_state_dict(19).keys()) and xm._n_trainable() == 54704803
+    u = seg_b200.UperNet(150, backbone="resnet101")
+    assert list(u.state_dict().keys()) == list(weights.upernet_state_dict(150, "resnet101").keys())
+    assert u._n_trainable() == 126414038
     assert p._n_trainable() == 51446762 and seg_b200.PSPNet(19)._n_trainable() == 51444710
     assert len(list(m.get_backbone_params())) + len(list(m.get_decoder_params())) == len(list(m.parameters()))

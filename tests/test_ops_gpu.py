@@ -324,3 +324,81 @@ def test_fused_upsample_ce(C, ignore, ac, gpu_out_dir):
     dx, dlo = ops.upsample_ce_bwd(lod, target.to(DEV), ac, ignore, accum, ldx)
     check(f"fused_ce_bwd C={C} ac={ac}", dlo.permute(0, 3, 1, 2), lo.grad, 1e-4, gpu_out_dir)
     check(f"fused_ce_bwd_bf16 C={C} ac={ac}", dx[..., :C].permute(0, 3, 1, 2), lo.grad, 1e-2, gpu_out_dir)
+
+
+def test_dice_and_ce_dice_match_oracle_and_golden(gpu_out_dir):
+    """DiceLoss / CE_DiceLoss (utils/losses.py:33-50,67-77) incl. the in-place target fix-up, against the oracle and the
+    values captured from the reference itself (tests/golden/losses_syncbn.npz)."""
+    import numpy as np
+    import seg_b200
+    from oracle import losses as ol
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "losses_syncbn.npz"))
+    logits = torch.from_numpy(g["c7/logits"])
+    target = torch.from_numpy(g["c7/target"])
+    # Dice with ignored pixels present: the reference overwrites them with target.min() in place
+    lg = logits.clone().cuda().requires_grad_(True)
+    tg = target.clone().cuda()
+    loss = seg_b200.DiceLoss(ignore_index=255)(lg, tg)
+    loss.backward()
+    check("dice_loss vs reference golden", loss.detach().cpu(), torch.tensor(float(g["c7/dice/loss"])), 1e-5, gpu_out_dir)
+    check("dice_grad vs reference golden", lg.grad.cpu(), torch.from_numpy(g["c7/dice/grad"]), 1e-4, gpu_out_dir)
+    assert (tg.cpu().numpy() == g["c7/dice/target_after"]).all(), "target mutation (losses.py:40-42) not reproduced"
+    # CE + Dice on a target without ignored pixels (the only combination the reference can run on torch >= 1.5)
+    t_in = torch.from_numpy(g["c7/ce_dice/target_in"])
+    lg = logits.clone().cuda().requires_grad_(True)
+    loss = seg_b200.CE_DiceLoss(ignore_index=255)(lg, t_in.clone().cuda())
+    loss.backward()
+    check("ce_dice_loss vs reference golden", loss.detach().cpu(), torch.tensor(float(g["c7/ce_dice/loss"])), 1e-5, gpu_out_dir)
+    check("ce_dice_grad vs reference golden", lg.grad.cpu(), torch.from_numpy(g["c7/ce_dice/grad"]), 1e-4, gpu_out_dir)
+    # a larger random case against the oracle
+    gen = torch.Generator().manual_seed(12)
+    lo = (torch.randn(2, 21, 37, 41, generator=gen) * 2)
+    tt = torch.randint(0, 21, (2, 37, 41), generator=gen)
+    tt[:, :3] = 255
+    ref_l = lo.clone().requires_grad_(True)
+    rl = ol.dice_loss(ref_l, tt.clone(), 1.0, 255)
+    rl.backward()
+    lg = lo.clone().cuda().requires_grad_(True)
+    l2 = seg_b200.DiceLoss(ignore_index=255)(lg, tt.clone().cuda())
+    l2.backward()
+    check("dice_loss vs oracle", l2.detach().cpu(), rl.detach(), 1e-5, gpu_out_dir)
+    check("dice_grad vs oracle", lg.grad.cpu(), ref_l.grad, 1e-4, gpu_out_dir)
+
+
+@pytest.mark.parametrize("shape", [(2, 33, 35, 64, 1, 1), (2, 33, 33, 728, 1, 2), (1, 34, 30, 128, 2, 1), (2, 17, 17, 1536, 1, 4)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_depthwise_conv(shape, gpu_out_dir):
+    """SeparableConv2d.conv1 (deeplabv3_plus.py:77-78): groups == channels, 3x3, 'same' padding = dilation."""
+    N, H, W, C, stride, dil = shape
+    g = torch.Generator().manual_seed(13)
+    x = bf(torch.randn(N, C, H, W, generator=g)).requires_grad_(True)
+    w = (torch.randn(C, 1, 3, 3, generator=g) * 0.4).requires_grad_(True)
+    y = F.conv2d(x, w, None, stride, dil, dil, groups=C)
+    dy = bf(torch.randn(y.shape, generator=g))
+    y.backward(dy)
+    w9 = ops.dw_pack_weight(w.detach().to(DEV))
+    stats = torch.zeros(2 * C, device=DEV)
+    yd = ops.dwconv_fwd(to_nhwc_dev(x.detach()), w9, stride, dil, dil, stats=stats)
+    torch.cuda.synchronize()
+    check(f"dwconv_fwd {shape}", yd.permute(0, 3, 1, 2), y, 1e-2, gpu_out_dir)
+    yr = y.detach()
+    check(f"dwconv_stats {shape}", stats, torch.cat([yr.sum((0, 2, 3)), (yr * yr).sum((0, 2, 3))]), 2e-3, gpu_out_dir)
+    dx = ops.dwconv_bwd_data(to_nhwc_dev(dy), w9, (N, H, W, C), stride, dil, dil)
+    check(f"dwconv_bwd_data {shape}", dx.permute(0, 3, 1, 2), x.grad, 1e-2, gpu_out_dir)
+    dx2 = ops.dwconv_bwd_data(to_nhwc_dev(dy), w9, (N, H, W, C), stride, dil, dil, out=dx.clone(), beta=1.0)
+    check(f"dwconv_bwd_data_beta1 {shape}", dx2.permute(0, 3, 1, 2), 2 * x.grad, 1.5e-2, gpu_out_dir)
+    g9 = ops.dwconv_bwd_weight(to_nhwc_dev(dy), to_nhwc_dev(x.detach()), stride, dil, dil)
+    gw = torch.empty(C, 1, 3, 3, device=DEV)
+    ops.dw_unpack_wgrad(g9, gw)
+    check(f"dwconv_bwd_weight {shape}", gw, w.grad, 2e-3, gpu_out_dir)
+
+
+def test_relu_standalone(gpu_out_dir):
+    g = torch.Generator().manual_seed(14)
+    x = bf(torch.randn(2, 9, 9, 64, generator=g))
+    y = ops.relu_fwd(x.to(DEV, torch.bfloat16))
+    check("relu_fwd", y, x.clamp(min=0), 0.0, gpu_out_dir)
+    dy = bf(torch.randn(2, 9, 9, 64, generator=g))
+    dx = torch.ones(2, 9, 9, 64, device=DEV, dtype=torch.bfloat16)
+    ops.relu_bwd(dy.to(DEV, torch.bfloat16), y, dx, 1.0)
+    check("relu_bwd_beta1", dx, 1.0 + dy * (x > 0), 1e-2, gpu_out_dir)
