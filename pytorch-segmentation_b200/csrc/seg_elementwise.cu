@@ -50,9 +50,9 @@ __device__ __forceinline__ int find_entry(const PackEntry* __restrict__ tab, int
 }
 
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackEntry* __restrict__ tab, int n, long long total) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const PackEntry e = tab[find_entry(tab, n, i)];
-    const long long j = i - e.start;  // index into the packed tensor
+  const PackEntry e = tab[blockIdx.y];  // one block row per conv: no per-element table search
+  const long long count = (blockIdx.y + 1 < n ? tab[blockIdx.y + 1].start : total) - e.start;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < count; j += (long long)gridDim.x * blockDim.x) {
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.packed);
     float v = 0.f;
     if (e.explicit_rsc) {
@@ -78,9 +78,9 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackEnt
 // OIHW fp32 grad (+)= packed fp32 grad.  Work items index the OIHW tensor.
 __global__ void __launch_bounds__(256) unpack_wgrads_batched_kernel(const PackEntry* __restrict__ tab, int n, long long total,
                                                                     float beta) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const PackEntry e = tab[find_entry(tab, n, i)];
-    const long long j = i - e.start;  // index into the OIHW tensor
+  const PackEntry e = tab[blockIdx.y];
+  const long long count = (blockIdx.y + 1 < n ? tab[blockIdx.y + 1].start : total) - e.start;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < count; j += (long long)gridDim.x * blockDim.x) {
     const int s = (int)(j % e.S);
     long long t = j / e.S;
     const int r = (int)(t % e.R);
@@ -688,11 +688,42 @@ __global__ void __launch_bounds__(256) bilinear_fwd_kernel(const __nv_bfloat16* 
   }
 }
 
+// weights of input index `y` in every output index of [lo, hi]: w[k] for output lo+k (0 when y is not a source of it)
+__device__ __forceinline__ int lerp_weights(int y, float scale, int in_size, int out_size, int ac, float* w, int maxn, int& lo) {
+  int hi;
+  dst_range(y, scale, out_size, ac, lo, hi);
+  // trim the conservative range to the outputs that really reference y
+  int n = 0, first = -1, last = -1;
+  for (int o = lo; o <= hi; ++o) {
+    const Lerp l = src_index(o, scale, in_size, ac);
+    float wy = 0.f;
+    if (l.i0 == y) wy += 1.f - l.l1;
+    if (l.i1 == y) wy += l.l1;
+    if (wy != 0.f) {
+      if (first < 0) first = o;
+      last = o;
+    }
+  }
+  if (first < 0) return 0;
+  n = last - first + 1;
+  if (n > maxn) return -1;
+  for (int k = 0; k < n; ++k) {
+    const Lerp l = src_index(first + k, scale, in_size, ac);
+    float wy = 0.f;
+    if (l.i0 == y) wy += 1.f - l.l1;
+    if (l.i1 == y) wy += l.l1;
+    w[k] = wy;
+  }
+  lo = first;
+  return n;
+}
+
 __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy,
                                                            __nv_bfloat16* __restrict__ dx, int lddx, int N, int Hi, int Wi,
                                                            int Ho, int Wo, int C, int ac, float sh, float sw, float beta) {
   const int G = C >> 3;
   const int64_t total = (int64_t)N * Hi * Wi * G;
+  constexpr int MAXN = 24;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i % G);
     int64_t t = i / G;
@@ -700,29 +731,49 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const __nv_bfloat16* 
     t /= Wi;
     const int y = (int)(t % Hi);
     const int n = (int)(t / Hi);
-    int oy0, oy1, ox0, ox1;
-    dst_range(y, sh, Ho, ac, oy0, oy1);
-    dst_range(x, sw, Wo, ac, ox0, ox1);
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    for (int oy = oy0; oy <= oy1; ++oy) {
-      const Lerp ly = src_index(oy, sh, Hi, ac);
-      float wy = 0.f;
-      if (ly.i0 == y) wy += 1.f - ly.l1;
-      if (ly.i1 == y) wy += ly.l1;
-      if (wy == 0.f) continue;
-      for (int ox = ox0; ox <= ox1; ++ox) {
-        const Lerp lx = src_index(ox, sw, Wi, ac);
-        float wx = 0.f;
-        if (lx.i0 == x) wx += 1.f - lx.l1;
-        if (lx.i1 == x) wx += lx.l1;
-        if (wx == 0.f) continue;
-        float f[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(dy + (((int64_t)n * Ho + oy) * Wo + ox) * lddy + g * 8), f);
-        const float wgt = wy * wx;
+    float wy[MAXN], wx[MAXN];
+    int oy0, ox0;
+    const int ny = lerp_weights(y, sh, Hi, Ho, ac, wy, MAXN, oy0);
+    const int nx = lerp_weights(x, sw, Wi, Wo, ac, wx, MAXN, ox0);
+    if (ny >= 0 && nx >= 0) {
+      for (int a = 0; a < ny; ++a) {
+        if (wy[a] == 0.f) continue;
+        const __nv_bfloat16* rowp = dy + (((int64_t)n * Ho + oy0 + a) * Wo + ox0) * lddy + g * 8;
+        for (int b = 0; b < nx; ++b) {
+          if (wx[b] == 0.f) continue;
+          float f[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(rowp + (int64_t)b * lddy), f);
+          const float wgt = wy[a] * wx[b];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += wgt * f[k];
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, f[k], acc[k]);
+        }
+      }
+    } else {
+      // very large magnification (e.g. the 1x1 global-pool branch): generic loop over the conservative range
+      int oy1, ox1;
+      dst_range(y, sh, Ho, ac, oy0, oy1);
+      dst_range(x, sw, Wo, ac, ox0, ox1);
+      for (int oy = oy0; oy <= oy1; ++oy) {
+        const Lerp ly = src_index(oy, sh, Hi, ac);
+        float wyy = 0.f;
+        if (ly.i0 == y) wyy += 1.f - ly.l1;
+        if (ly.i1 == y) wyy += ly.l1;
+        if (wyy == 0.f) continue;
+        for (int ox = ox0; ox <= ox1; ++ox) {
+          const Lerp lx = src_index(ox, sw, Wi, ac);
+          float wxx = 0.f;
+          if (lx.i0 == x) wxx += 1.f - lx.l1;
+          if (lx.i1 == x) wxx += lx.l1;
+          if (wxx == 0.f) continue;
+          float f[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(dy + (((int64_t)n * Ho + oy) * Wo + ox) * lddy + g * 8), f);
+          const float wgt = wyy * wxx;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, f[k], acc[k]);
+        }
       }
     }
     __nv_bfloat16* o = dx + (((int64_t)n * Hi + y) * Wi + x) * lddx + g * 8;
@@ -920,13 +971,15 @@ int seg_unpack_wgrad(const float* dw, float* g, int K, int C, int R, int S, int 
 }
 int seg_pack_weights_batched(const void* table, int n, int64_t total, void* stream) {
   if (n <= 0) return 0;
-  pack_weights_batched_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const PackEntry*>(table), n, total);
+  SEG_REQUIRE(n <= 65535, "too many convs");
+  pack_weights_batched_kernel<<<dim3(48, (unsigned)n, 1), 256, 0, ST(stream)>>>(reinterpret_cast<const PackEntry*>(table), n, total);
   return check_launch("pack_weights_batched");
 }
 int seg_unpack_wgrads_batched(const void* table, int n, int64_t total, float beta, void* stream) {
   if (n <= 0) return 0;
-  unpack_wgrads_batched_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const PackEntry*>(table), n, total,
-                                                                              beta);
+  SEG_REQUIRE(n <= 65535, "too many convs");
+  unpack_wgrads_batched_kernel<<<dim3(48, (unsigned)n, 1), 256, 0, ST(stream)>>>(reinterpret_cast<const PackEntry*>(table), n,
+                                                                                 total, beta);
   return check_launch("unpack_wgrads_batched");
 }
 int seg_pack_entry_bytes(void) { return (int)sizeof(PackEntry); }
