@@ -60,8 +60,6 @@ class ConvSpec:
         self._packed = None
         self._version = None
         self.always_repack = False  # set while a CUDA graph of the train step is captured / replayed
-        self.external_pack = False  # FusedTrainStep packs every weight with ONE batched launch and owns `_packed`
-        self.dw_buffer = None       # persistent fp32 packed weight-gradient buffer (FusedTrainStep); None -> per-call
 
     @property
     def stride(self):
@@ -79,8 +77,6 @@ class ConvSpec:
         return (1, self.K, self.kpad) if self.explicit else (self.R * self.S, self.K, self.C)
 
     def packed(self):
-        if self.external_pack:
-            return self._packed
         w = self.m.weight
         key = (w._version, w.data_ptr())
         if self._packed is None or self._version != key or self.always_repack:
@@ -129,6 +125,10 @@ class Tape:
         self.seed = seed
         self.sync = sync  # object with .allreduce_(fp32 vector, step_ctr) and .world ; None = local BN
         self.step_ctr = step_ctr  # device int64 step counter mixed into dropout seeds / SyncBN epochs (graph-replay safe)
+        # FusedTrainStep hands in persistent buffers: bf16 packed weights (one batched pack launch per step) and fp32
+        # packed weight-gradient accumulators (one batched unpack launch per step).  Empty for the autograd/plugin path.
+        self.packed_override = {}
+        self.dw_buffers = {}
         self.clamp_eps = clamp_eps
         self._drop_ctr = 0
         self.bn_modules = []
@@ -153,7 +153,9 @@ class Tape:
     # ------------------------------------------------------------------ conv
     def conv(self, x, spec, out=None, out_dtype=None, want_stats=False):
         """x: Act (NHWC bf16) — or, for an explicit-im2col conv, a raw NCHW fp32 tensor (the network input)."""
-        wp = spec.packed()
+        wp = self.packed_override.get(spec)
+        if wp is None:
+            wp = spec.packed()
         bias = spec.m.bias
         stats = None
         if out_dtype is None:
@@ -178,9 +180,9 @@ class Tape:
                 if dy is None:
                     return
                 R, S, stride, pad, dil = geo
-                if spec.m.weight.requires_grad and spec.dw_buffer is not None:
+                if spec.m.weight.requires_grad and spec in self.dw_buffers:
                     # accumulate into the trainer's persistent packed-gradient buffer; unpacked once per step, batched
-                    ops.conv2d_wgrad(dy, xin, R, S, stride, pad, dil, out=spec.dw_buffer, impl=self.impl)
+                    ops.conv2d_wgrad(dy, xin, R, S, stride, pad, dil, out=self.dw_buffers[spec], impl=self.impl)
                 elif spec.m.weight.requires_grad:
                     dwp = ops.conv2d_wgrad(dy, xin, R, S, stride, pad, dil, impl=self.impl)
                     if spec.explicit:

@@ -63,19 +63,21 @@ class FusedTrainStep:
         self.flat_dwp = torch.zeros(n_dw, dtype=torch.float32, device=dev)
         pack = np.zeros(len(specs), dtype=dt)
         unp = []
+        self.packed_bufs, self.dw_bufs = {}, {}
         p_start = u_start = off = 0
         for i, s in enumerate(specs):
             shape = s.packed_shape()
-            s._packed = torch.empty(shape, dtype=torch.bfloat16, device=dev)
-            s.external_pack = True
+            buf = torch.empty(shape, dtype=torch.bfloat16, device=dev)
+            self.packed_bufs[s] = buf
             w = s.m.weight
-            pack[i] = (w.data_ptr(), s._packed.data_ptr(), s.K, s.C, s.R, s.S, shape[2], int(s.explicit), p_start)
+            pack[i] = (w.data_ptr(), buf.data_ptr(), s.K, s.C, s.R, s.S, shape[2], int(s.explicit), p_start)
             p_start += int(np.prod(shape))
             if w.requires_grad:
                 n = int(np.prod(shape))
-                s.dw_buffer = self.flat_dwp[off:off + n].view(shape)
+                dwb = self.flat_dwp[off:off + n].view(shape)
+                self.dw_bufs[s] = dwb
                 off += n
-                unp.append((self.grad_views[w].data_ptr(), s.dw_buffer.data_ptr(), s.K, s.C, s.R, s.S, shape[2], int(s.explicit), u_start))
+                unp.append((self.grad_views[w].data_ptr(), dwb.data_ptr(), s.K, s.C, s.R, s.S, shape[2], int(s.explicit), u_start))
                 u_start += w.numel()
         self.pack_total, self.unpack_total = p_start, u_start
         self.pack_table = torch.from_numpy(pack.view(np.uint8).copy()).to(dev)
@@ -95,7 +97,14 @@ class FusedTrainStep:
         self._static[1].copy_(target, non_blocking=True)
         self._graph.replay()
         self.steps += 1
+        self._invalidate_param_caches()
         return self._static[2]
+
+    def _invalidate_param_caches(self):
+        """The SGD kernel updates parameters in place without bumping autograd version counters: drop the per-parameter
+        packed-weight caches the autograd/plugin path keeps, so a later model(x) call repacks the updated weights."""
+        for s in self.specs:
+            s._version = None
 
     def _capture(self, x, target):
         xs, ys = x.clone(), target.clone()
@@ -119,6 +128,7 @@ class FusedTrainStep:
         lib.call("seg_pack_weights_batched", self.pack_table.data_ptr(), len(self.specs), self.pack_total)
         tape = m._new_tape(True, True)
         tape.grads = dict(self.grad_views)  # pre-bound views: every parameter gradient lands in the flat buffer
+        tape.packed_override, tape.dw_buffers = self.packed_bufs, self.dw_bufs
         heads = m._forward_heads(tape, x.contiguous().float())
         total = None
         for i, (lo, ac) in enumerate(heads):
@@ -137,5 +147,6 @@ class FusedTrainStep:
         lib.call("seg_sgd_step", self.p_ptrs.data_ptr(), self.g_ptrs.data_ptr(), self.m_ptrs.data_ptr(), self.sizes.data_ptr(),
                  self.lrs.data_ptr(), len(self.params), float(self.momentum), float(self.wd), 0, 1.0 / self.world)
         # (momentum buffers start at zero, so "first step: buf = d" of torch.optim.SGD is the general formula)
+        self._invalidate_param_caches()
         self.steps += 1
         return total

@@ -273,3 +273,33 @@ def test_state_dict_keys_match_reference_inventory():
     assert u._n_trainable() == 126414038
     assert p._n_trainable() == 51446762 and seg_b200.PSPNet(19)._n_trainable() == 51444710
     assert len(list(m.get_backbone_params())) + len(list(m.get_decoder_params())) == len(list(m.parameters()))
+
+
+def test_plugin_path_after_fused_steps_sees_updated_weights():
+    """FusedTrainStep updates parameters in place (no autograd version bump) and keeps its own packed buffers; the
+    autograd/plugin path used afterwards must repack the UPDATED weights and return a gradient for every parameter."""
+    sd, m = build("deeplab", 7, "resnet14", 8, output_stride=16)
+    x, y = synth.make_batch(2, 65, 65, 7, 255, seed=9006)
+    xd, yd = x.cuda(), y.cuda()
+    m.train()
+    with torch.no_grad():
+        m.eval()
+        before = m(xd).clone()
+        m.train()
+    st = FusedTrainStep(m, ignore_index=255, lr=0.05)
+    for _ in range(2):
+        st.step(xd, yd)
+    m.eval()
+    with torch.no_grad():
+        after = m(xd)
+    fresh = seg_b200.DeepLab(7, backbone="resnet14", output_stride=16).cuda()
+    fresh.load_state_dict(m.state_dict())
+    fresh.eval()
+    with torch.no_grad():
+        ref = fresh(xd)
+    assert relerr(after, ref) < 1e-6, "plugin path used stale packed weights"
+    assert relerr(after, before) > 1e-3, "the fused steps did not change the weights"
+    m.train()
+    out = m(xd)
+    seg_b200.CrossEntropyLoss2d(ignore_index=255)(out, yd).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
