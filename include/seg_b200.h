@@ -178,6 +178,18 @@ int seg_dice_nchw_fwd(const float* logits, const int64_t* target, int N, int C, 
 /* dlogits = beta*dlogits + gscale * d(dice)/d(logits) */
 int seg_dice_nchw_bwd(const float* logits, const int64_t* target, int N, int C, int H, int W, const double* accum,
                       float smooth, const float* gscale, float* dlogits, float beta, void* stream);
+/* LovaszSoftmax (utils/losses.py:79-89 -> utils/lovasz_losses.py:153-199,19-31; classes='present', per_image=False):
+ * all present classes at once on the device — 64-bit keys [class rank|~error bits|fg|pixel], one LSD radix sort,
+ * tiled scans, Jaccard differences — instead of the reference's per-class sort + host sync.
+ *   seg_lovasz_count: counts (int32 [C+1], zeroed here): valid pixels per class, counts[C] = all valid pixels.
+ *   The caller reads counts back (the one host sync; the reference does C of them), then passes P = counts[C],
+ *   n_present = #{c: counts[c] > 0}, two uint64 key buffers of P*n_present elements and a byte workspace.
+ *   seg_lovasz_softmax_nchw: loss (fp32 scalar) and dlogits = d loss / d logits (NCHW fp32; also scratch). */
+int seg_lovasz_count(const int64_t* target, int64_t npix, int C, int64_t ignore_index, int32_t* counts, void* stream);
+int64_t seg_lovasz_workspace_bytes(int64_t P, int n_present, int C);
+int seg_lovasz_softmax_nchw(const float* logits, const int64_t* target, int N, int C, int H, int W, int64_t ignore_index,
+                            const int32_t* counts, int64_t P, int n_present, void* keys0, void* keys1, void* workspace,
+                            float* loss, float* dlogits, void* stream);
 /* fused: bilinear upsample (low-res NHWC fp32 logits) + log-softmax + NLL, no full-res logits in HBM.
  * Also emits the arg-max label map (int32 [N,Ho,Wo], lowest index wins ties) when argmax != NULL. */
 int seg_upsample_ce_fwd(const float* logits_lo, const int64_t* target, int N, int Hi, int Wi, int Ho, int Wo, int C,

@@ -13,4 +13,4 @@ if REFERENCE_UTILS is not None:
         if not _n.startswith("_"):
             globals()[_n] = getattr(_ref, _n)
 
-from seg_b200.losses import CE_DiceLoss, CrossEntropyLoss2d, DiceLoss  # noqa: E402,F401
+from seg_b200.losses import CE_DiceLoss, CrossEntropyLoss2d, DiceLoss, LovaszSoftmax  # noqa: E402,F401

@@ -13,6 +13,7 @@ _LAZY = {
     "CrossEntropyLoss2d": ("losses", "CrossEntropyLoss2d"),
     "DiceLoss": ("losses", "DiceLoss"),
     "CE_DiceLoss": ("losses", "CE_DiceLoss"),
+    "LovaszSoftmax": ("losses", "LovaszSoftmax"),
     "FusedTrainStep": ("train", "FusedTrainStep"),
 }
 

@@ -3,6 +3,7 @@
     CrossEntropyLoss2d(weight=None, ignore_index=255, reduction='mean')   — utils/losses.py:24-31
     DiceLoss(smooth=1., ignore_index=255)                                 — utils/losses.py:33-50
     CE_DiceLoss(smooth=1, reduction='mean', ignore_index=255, weight=None) — utils/losses.py:67-77
+    LovaszSoftmax(classes='present', per_image=False, ignore_index=255)   — utils/losses.py:79-89
 
 forward(output fp32 [B,C,H,W], target int64 [B,H,W]) -> 0-dim tensor with autograd, computed by the sm_100a kernels
 (`seg_ce_nchw_fwd/bwd`); `.item()` works as the trainer expects (trainer.py:72,81).  CUDA tensors only.
@@ -94,3 +95,31 @@ class CE_DiceLoss(nn.Module):
     def forward(self, output, target):
         ce = _CEFn.apply(output, target, self.ignore_index)  # CE first: it sees the target before Dice mutates it
         return ce + self.dice(output, target)
+
+
+class _LovaszFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        loss, dl = ops.lovasz_softmax_nchw(logits.contiguous().float(), target.contiguous(), ignore_index)
+        ctx.save_for_backward(dl)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        (dl,) = ctx.saved_tensors
+        return dl * gout, None, None
+
+
+class LovaszSoftmax(nn.Module):
+    def __init__(self, classes="present", per_image=False, ignore_index=255):
+        super().__init__()
+        if classes != "present" or per_image:
+            raise NotImplementedError("seg_b200.LovaszSoftmax: classes='present', per_image=False (the configs' setting)")
+        self.smooth = classes  # the reference stores `classes` under this (unused) name, utils/losses.py:82
+        self.per_image = per_image
+        self.ignore_index = ignore_index
+
+    def forward(self, output, target):
+        if not output.is_cuda:
+            raise RuntimeError("seg_b200 losses run on a B200 only; there is no CPU fallback")
+        return _LovaszFn.apply(output, target, self.ignore_index)

@@ -365,6 +365,26 @@ def dice_nchw_bwd(logits, target, accum, smooth=1.0, gscale=None, out=None, beta
     return out
 
 
+def lovasz_softmax_nchw(logits, target, ignore_index):
+    """Returns (loss scalar tensor, dlogits NCHW fp32).  One host sync to size the key buffers."""
+    N, C, H, W = logits.shape
+    assert logits.is_contiguous() and logits.dtype == torch.float32 and target.dtype == torch.int64 and target.is_contiguous()
+    dev = logits.device
+    counts = torch.empty(C + 1, dtype=torch.int32, device=dev)
+    call("seg_lovasz_count", ptr(target), N * H * W, C, int(ignore_index), ptr(counts))
+    ch = counts.cpu()
+    P, n_present = int(ch[C]), int((ch[:C] > 0).sum())
+    nkeys = max(P * n_present, 1)
+    keys0 = torch.empty(nkeys, dtype=torch.int64, device=dev)
+    keys1 = torch.empty(nkeys, dtype=torch.int64, device=dev)
+    ws = torch.empty(int(lib.load().seg_lovasz_workspace_bytes(P, n_present, C)), dtype=torch.uint8, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    dl = torch.empty_like(logits)
+    call("seg_lovasz_softmax_nchw", ptr(logits), ptr(target), N, C, H, W, int(ignore_index), ptr(counts), P, n_present,
+         ptr(keys0), ptr(keys1), ptr(ws), ptr(loss), ptr(dl))
+    return loss, dl
+
+
 def upsample_ce_fwd(logits_lo, target, align_corners, ignore_index, want_argmax=False):
     N, Hi, Wi, C = logits_lo.shape
     _, Ho, Wo = target.shape

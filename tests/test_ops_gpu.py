@@ -402,3 +402,36 @@ def test_relu_standalone(gpu_out_dir):
     dx = torch.ones(2, 9, 9, 64, device=DEV, dtype=torch.bfloat16)
     ops.relu_bwd(dy.to(DEV, torch.bfloat16), y, dx, 1.0)
     check("relu_bwd_beta1", dx, 1.0 + dy * (x > 0), 1e-2, gpu_out_dir)
+
+
+def test_lovasz_softmax_matches_reference_golden_and_oracle(gpu_out_dir):
+    """LovaszSoftmax (utils/losses.py:79-89) — device radix-sort implementation against the values captured from the
+    reference itself (C=7 ignore 255; C=150 ignore -1) and against the oracle on a larger random case."""
+    import numpy as np
+    import seg_b200
+    from oracle import losses as ol
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "losses_syncbn.npz"))
+    for tag, ignore in (("c7", 255), ("c150", -1)):
+        lg = torch.from_numpy(g[f"{tag}/logits"]).cuda().requires_grad_(True)
+        tg = torch.from_numpy(g[f"{tag}/target"]).cuda()
+        loss = seg_b200.LovaszSoftmax(ignore_index=ignore)(lg, tg)
+        loss.backward()
+        check(f"lovasz_loss {tag} vs reference golden", loss.detach().cpu(), torch.tensor(float(g[f"{tag}/lovasz/loss"])), 1e-5, gpu_out_dir)
+        check(f"lovasz_grad {tag} vs reference golden", lg.grad.cpu(), torch.from_numpy(g[f"{tag}/lovasz/grad"]), 1e-4, gpu_out_dir)
+    gen = torch.Generator().manual_seed(15)
+    lo = torch.randn(3, 21, 61, 67, generator=gen) * 2
+    tt = torch.randint(0, 19, (3, 61, 67), generator=gen)  # classes 19, 20 absent
+    tt[:, :5] = 255
+    ref_l = lo.clone().requires_grad_(True)
+    rl = ol.lovasz_softmax(ref_l, tt, 255)
+    rl.backward()
+    lg = lo.clone().cuda().requires_grad_(True)
+    l2 = seg_b200.LovaszSoftmax(ignore_index=255)(lg, tt.cuda()) * 2.0
+    l2.backward()
+    check("lovasz_loss vs oracle", l2.detach().cpu() / 2, rl.detach(), 1e-5, gpu_out_dir)
+    check("lovasz_grad vs oracle (x2 upstream)", lg.grad.cpu() / 2, ref_l.grad, 1e-4, gpu_out_dir)
+    # only void pixels: zero loss, zero gradient (lovasz_losses.py:178-180)
+    lg = lo.clone().cuda().requires_grad_(True)
+    l3 = seg_b200.LovaszSoftmax(ignore_index=255)(lg, torch.full((3, 61, 67), 255, dtype=torch.long, device="cuda"))
+    l3.backward()
+    assert float(l3) == 0.0 and float(lg.grad.abs().max()) == 0.0
