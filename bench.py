@@ -195,7 +195,7 @@ def main():
         return ms
 
     # ------------------------------------------------------------ device-resident fused step  -> `value`
-    use_graph = bool(args.graph) and world == 1  # NCCL inside a captured graph is left for the next round
+    use_graph = bool(args.graph)  # the whole step (NCCL all-reduce and the SyncBN peer exchanges included) is one CUDA graph
     stepper = FusedTrainStep(model, ignore_index=IGNORE, lr=0.01, backbone_lr_scale=0.1, momentum=0.9, weight_decay=1e-4, world=world,
                              cuda_graph=use_graph)
     for _ in range(W):

@@ -220,16 +220,15 @@ int seg_sgd_step(float* const* params, float* const* grads, float* const* moment
  * Each rank owns a symmetric buffer of seg_comm_buffer_bytes(world, n_max) bytes (seg_comm_alloc, zeroed), exports it
  * with seg_comm_ipc_get, opens its peers' with seg_comm_ipc_open, and passes the world's pointers (indexed by rank;
  * its own pointer at [rank]) as a DEVICE array.  seg_syncbn_exchange(vals[n]) leaves the rank-ordered sum over all
- * ranks in vals on every rank (bit-identical everywhere).  The effective epoch is epoch + (*step_ctr << 12) when
- * step_ctr != NULL; it must differ from the previous call's, be non-zero and be the same on all ranks. */
+ * ranks in vals on every rank (bit-identical everywhere).  All ranks must issue the same sequence of exchanges; the
+ * sequence number lives in the symmetric buffer on the device, so the call can be captured in a CUDA graph. */
 size_t seg_comm_buffer_bytes(int world, int n_max);
 int seg_comm_alloc(size_t bytes, void** ptr);
 int seg_comm_free(void* ptr);
 int seg_comm_ipc_get(void* ptr, void* handle64);
 int seg_comm_ipc_open(const void* handle64, void** ptr);
 int seg_comm_ipc_close(void* ptr);
-int seg_syncbn_exchange(void* const* peer_bufs, int rank, int world, float* local_vals, int n, int n_max,
-                        uint32_t epoch, const uint64_t* step_ctr, void* stream);
+int seg_syncbn_exchange(void* const* peer_bufs, int rank, int world, float* local_vals, int n, int n_max, void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,12 +5,15 @@
 // queue round trip per BN layer — by ONE kernel per layer: every rank stores its <=16 KB vector (sum, sum of squares)
 // straight into a slot of every peer's symmetric buffer (P2P stores through NVSwitch), raises a flag with release
 // semantics, waits for the world's flags, and sums the world's vectors locally in rank order (so every rank gets
-// bit-identical totals and no broadcast is needed).  Two slots alternate by epoch parity; a rank can run at most one
-// exchange ahead of the slowest peer, so a slot is never overwritten while still being read.
+// bit-identical totals and no broadcast is needed).  Every rank keeps a DEVICE-side sequence number in its own buffer
+// (all ranks issue the same exchanges in the same order, so the numbers agree): it is the flag value, and its parity
+// picks one of two slots.  A rank can run at most one exchange ahead of the slowest peer, so a slot is never
+// overwritten while still being read — and, the number living on the device, a captured CUDA graph replays correctly.
 //
 // Symmetric buffer layout (per rank, allocated by seg_comm_alloc, exported with CUDA IPC):
 //   float    data [2][world][n_max]
 //   uint32_t flags[2][world]         (at byte offset 2*world*n_max*4, 128-byte aligned)
+//   uint32_t seq                     (next 128-byte line; number of exchanges this rank has completed)
 #include "seg_common.cuh"
 
 namespace seg {
@@ -29,10 +32,16 @@ __host__ __device__ inline size_t flags_offset(int world, int n_max) {
   return (b + 127) & ~(size_t)127;
 }
 
+__host__ __device__ inline size_t seq_offset(int world, int n_max) {
+  size_t b = flags_offset(world, n_max) + (size_t)2 * world * sizeof(uint32_t);
+  return (b + 127) & ~(size_t)127;
+}
+
 __global__ void __launch_bounds__(1024) syncbn_exchange_kernel(void* const* __restrict__ peers, int rank, int world,
-                                                               float* __restrict__ vals, int n, int n_max,
-                                                               uint32_t epoch, const uint64_t* __restrict__ step_ctr) {
-  if (step_ctr) epoch += (uint32_t)(*step_ctr) << 12;  // device-side step counter (CUDA-graph replays): step*4096 + index
+                                                               float* __restrict__ vals, int n, int n_max) {
+  uint32_t* seq = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(peers[rank]) + seq_offset(world, n_max));
+  uint32_t epoch = *seq + 1u;  // written only by thread 0 at the very end of the previous exchange on this stream
+  if (epoch == 0u) epoch = 2u;  // flags start at 0: skip it on wrap-around, keeping the parity alternation
   const int slot = epoch & 1;
   const size_t foff = flags_offset(world, n_max);
   // 1. scatter my vector into slot[rank] of every peer (including myself)
@@ -67,6 +76,7 @@ __global__ void __launch_bounds__(1024) syncbn_exchange_kernel(void* const* __re
     for (int p = 0; p < world; ++p) s += __ldcv(my + (size_t)p * n_max + i);
     vals[i] = s;
   }
+  if (threadIdx.x == 0) *seq = epoch;  // every thread read *seq before the first __syncthreads above
 }
 
 }  // namespace seg
@@ -75,7 +85,7 @@ using namespace seg;
 
 extern "C" {
 
-size_t seg_comm_buffer_bytes(int world, int n_max) { return flags_offset(world, n_max) + (size_t)2 * world * sizeof(uint32_t) + 128; }
+size_t seg_comm_buffer_bytes(int world, int n_max) { return seq_offset(world, n_max) + 128; }
 
 int seg_comm_alloc(size_t bytes, void** ptr) {
   cudaError_t e = cudaMalloc(ptr, bytes);
@@ -108,14 +118,12 @@ int seg_comm_ipc_close(void* ptr) {
   return 0;
 }
 
-int seg_syncbn_exchange(void* const* peer_bufs, int rank, int world, float* local_vals, int n, int n_max, uint32_t epoch,
-                        const uint64_t* step_ctr, void* stream) {
+int seg_syncbn_exchange(void* const* peer_bufs, int rank, int world, float* local_vals, int n, int n_max, void* stream) {
   SEG_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "bad rank/world %d/%d", rank, world);
   SEG_REQUIRE(n > 0 && n <= n_max, "syncbn exchange: n=%d exceeds n_max=%d", n, n_max);
-  SEG_REQUIRE(epoch != 0, "epoch must be non-zero (buffers are zero-initialised)");
   const int threads = n >= 1024 ? 1024 : ((n + 31) / 32 * 32 < 64 ? 64 : (n + 31) / 32 * 32);
   syncbn_exchange_kernel<<<1, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(peer_bufs, rank, world, local_vals, n,
-                                                                                     n_max, epoch, step_ctr);
+                                                                                     n_max);
   return check_launch("syncbn_exchange");
 }
 

@@ -14,14 +14,13 @@ from . import lib
 
 
 class SyncBNGroup:
-    """Symmetric peer buffers + epoch counter for `seg_syncbn_exchange`.  `allreduce_(vec)` sums an fp32 vector
+    """Symmetric peer buffers for `seg_syncbn_exchange`.  `allreduce_(vec)` sums an fp32 vector
     (<= n_max floats) over all ranks in place, bit-identically on every rank."""
 
     def __init__(self, n_max=8192, group=None):
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.n_max = n_max
-        self.epoch = 0
         L = lib.load()
         nbytes = L.seg_comm_buffer_bytes(self.world, n_max)
         mine = ctypes.c_void_p()
@@ -48,17 +47,9 @@ class SyncBNGroup:
         self.peers = torch.tensor(ptrs, dtype=torch.int64, device="cuda")
         dist.barrier(group=group)
 
-    def begin_step(self):
-        """Called at the start of every training forward: exchanges inside a step are numbered 1, 2, ... and the
-        device-side step counter supplies the high bits, so a captured CUDA graph replays with fresh epochs."""
-        self.epoch = 0
-
-    def allreduce_(self, vec, step_ctr=None):
+    def allreduce_(self, vec):
         assert vec.dtype == torch.float32 and vec.is_contiguous() and vec.numel() <= self.n_max
-        self.epoch += 1
-        assert self.epoch < 4096
-        lib.call("seg_syncbn_exchange", self.peers.data_ptr(), self.rank, self.world, vec.data_ptr(), vec.numel(), self.n_max,
-                 self.epoch, lib.ptr(step_ctr))
+        lib.call("seg_syncbn_exchange", self.peers.data_ptr(), self.rank, self.world, vec.data_ptr(), vec.numel(), self.n_max)
         return vec
 
     def close(self):
@@ -74,7 +65,7 @@ class LocalLoopbackGroup:
     """world == 1 stand-in with the same interface (used by single-GPU tests of the exchange kernel)."""
 
     def __init__(self, n_max=8192):
-        self.rank, self.world, self.n_max, self.epoch = 0, 1, n_max, 0
+        self.rank, self.world, self.n_max = 0, 1, n_max
         L = lib.load()
         mine = ctypes.c_void_p()
         if L.seg_comm_alloc(L.seg_comm_buffer_bytes(1, n_max), ctypes.byref(mine)) != 0:
@@ -82,13 +73,8 @@ class LocalLoopbackGroup:
         self._mine = mine
         self.peers = torch.tensor([mine.value], dtype=torch.int64, device="cuda")
 
-    def begin_step(self):
-        self.epoch = 0
-
-    def allreduce_(self, vec, step_ctr=None):
-        self.epoch += 1
-        lib.call("seg_syncbn_exchange", self.peers.data_ptr(), 0, 1, vec.data_ptr(), vec.numel(), self.n_max, self.epoch,
-                 lib.ptr(step_ctr))
+    def allreduce_(self, vec):
+        lib.call("seg_syncbn_exchange", self.peers.data_ptr(), 0, 1, vec.data_ptr(), vec.numel(), self.n_max)
         return vec
 
 

@@ -123,7 +123,7 @@ class Tape:
         self.impl = impl
         self.dropout = dropout
         self.seed = seed
-        self.sync = sync  # object with .allreduce_(fp32 vector, step_ctr) and .world ; None = local BN
+        self.sync = sync  # object with .allreduce_(fp32 vector) and .world ; None = local BN
         self.step_ctr = step_ctr  # device int64 step counter mixed into dropout seeds / SyncBN epochs (graph-replay safe)
         # FusedTrainStep hands in persistent buffers: bf16 packed weights (one batched pack launch per step) and fp32
         # packed weight-gradient accumulators (one batched unpack launch per step).  Empty for the autograd/plugin path.
@@ -262,7 +262,7 @@ class Tape:
                 stats = ops.bn_stats(y.t)
             count = count_local
             if self.sync is not None and self.sync.world > 1:
-                self.sync.allreduce_(stats, self.step_ctr)
+                self.sync.allreduce_(stats)
                 count = count_local * self.sync.world
             ss, save = ops.bn_finalize(stats, count, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum if bn.momentum is not None else BN_MOM,
                                        1 if (self.clamp_eps and self.sync is not None and self.sync.world > 1) else 0,
@@ -293,7 +293,7 @@ class Tape:
                     gsums = torch.zeros_like(sums)  # frozen BN (freeze_bn): dx = gamma * inv_std * dz
                 elif self.sync is not None and self.sync.world > 1:
                     gsums = sums.clone()
-                    self.sync.allreduce_(gsums, self.step_ctr)
+                    self.sync.allreduce_(gsums)
                 dy = torch.empty(y.t.shape, dtype=ACT_DTYPE, device=a.device)
                 dres, beta_res = (None, 0.0)
                 if res is not None and res.needs_grad:

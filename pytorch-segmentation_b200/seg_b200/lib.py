@@ -91,7 +91,7 @@ _SIGS = {
     "seg_comm_ipc_get": (c_int, [c_void_p, c_void_p]),
     "seg_comm_ipc_open": (c_int, [c_void_p, POINTER(c_void_p)]),
     "seg_comm_ipc_close": (c_int, [c_void_p]),
-    "seg_syncbn_exchange": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_uint32, c_void_p, c_void_p]),
+    "seg_syncbn_exchange": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "seg_sgd_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_int, c_float, c_void_p]),
 }
 

@@ -271,8 +271,6 @@ class _EngineModel(BaseModel):
                 self._step_ctr = torch.zeros(1, dtype=torch.int64, device=dev)
             ctr = self._step_ctr
             ops.counter_add(ctr, 1)  # device-side: stays correct when the step is replayed from a CUDA graph
-            if self.bn_sync is not None:
-                self.bn_sync.begin_step()
         return Tape(training, record=record, impl=self.conv_impl, dropout=self.engine_dropout, seed=self.engine_seed,
                     sync=self.bn_sync, clamp_eps=self.syncbn_clamp_eps, step_ctr=ctr)
 

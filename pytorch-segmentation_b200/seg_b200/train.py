@@ -111,13 +111,24 @@ class FusedTrainStep:
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
-        with torch.cuda.stream(side):  # warm-up outside the capture: lazy one-time initialisation, allocator pools
+        # warm-up outside the capture (lazy one-time initialisation, allocator pools): two real steps whose effect on
+        # the training state (parameters, momentum, BN running statistics) is rolled back afterwards
+        state = [p.data for p in self.params] + [self.flat_mom] + [b for b in self.model.buffers()]
+        with torch.cuda.stream(side):
+            saved = [t.clone() for t in state]
             for _ in range(2):
                 self._step_impl(xs, ys)
+            for t, sv in zip(state, saved):
+                t.copy_(sv)
+            del saved
+        self.steps -= 2
         cur.wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        if self.world > 1:  # every rank must have finished its eager warm-up exchanges before anyone starts capturing
+            dist.barrier()
+        # NCCL's all-reduce is captured with the rest (its watchdog thread polls events: relaxed capture mode)
+        with torch.cuda.graph(g, capture_error_mode="thread_local" if self.world > 1 else "global"):
             loss = self._step_impl(xs, ys)
         self._graph, self._static = g, (xs, ys, loss)
 

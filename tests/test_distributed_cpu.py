@@ -19,10 +19,7 @@ class GlooSync:
     def __init__(self):
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
 
-    def begin_step(self):
-        pass
-
-    def allreduce_(self, vec, step_ctr=None):
+    def allreduce_(self, vec):
         dist.all_reduce(vec)
         return vec
 

@@ -303,3 +303,28 @@ def test_plugin_path_after_fused_steps_sees_updated_weights():
     out = m(xd)
     seg_b200.CrossEntropyLoss2d(ignore_index=255)(out, yd).backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+def test_graph_replayed_steps_equal_eager_steps(gpu_out_dir):
+    """CUDA-graph replay of the fused step (train.py: FusedTrainStep(cuda_graph=True)) is the same training as the eager
+    step: the capture's two warm-up steps are rolled back, every replay is a fresh step (device-side counters)."""
+    sd, m_e = build("deeplab", 7, "resnet14", 8, output_stride=16)
+    _, m_g = build("deeplab", 7, "resnet14", 8, output_stride=16)
+    for m in (m_e, m_g):
+        m.engine_dropout = False
+        m.train()
+    x, y = synth.make_batch(2, 65, 65, 7, 255, seed=9010)
+    xd, yd = x.cuda(), y.cuda()
+    se, sg = FusedTrainStep(m_e, lr=0.02), FusedTrainStep(m_g, lr=0.02, cuda_graph=True)
+    for i in range(3):
+        le, lg = se.step(xd, yd), sg.step(xd, yd)
+        assert abs(float(le) - float(lg)) < 2e-2 * abs(float(le)), (i, float(le), float(lg))
+    assert sg.steps == 3
+    ue = torch.cat([(p.detach().cpu() - sd[n]).reshape(-1) for n, p in m_e.named_parameters()])
+    ug = torch.cat([(p.detach().cpu() - sd[n]).reshape(-1) for n, p in m_g.named_parameters()])
+    c = cosine(ue, ug)
+    log(gpu_out_dir, f"graph-vs-eager 3 steps: update cosine {c:.5f}")
+    assert c > 0.98
+    for (n, a), (_, b) in zip(m_e.named_buffers(), m_g.named_buffers()):
+        if n.endswith("num_batches_tracked"):
+            assert int(a) == int(b) == 3, n
