@@ -338,7 +338,9 @@ def main():
                        "dropout": "on (p=0.5 ASPP, p=0.1 decoder)", "cuda_graph": use_graph, "last_loss": last_loss},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }))
+    sys.stdout.flush()
     if world > 1:
+        stepper.release_graph()  # a live graph holding NCCL kernels blocks the communicator's destruction
         dist.barrier()
         dist.destroy_process_group()
 

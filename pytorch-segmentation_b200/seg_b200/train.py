@@ -100,6 +100,14 @@ class FusedTrainStep:
         self._invalidate_param_caches()
         return self._static[2]
 
+    def release_graph(self):
+        """Drop the captured graph.  Required before torch.distributed.destroy_process_group() when world > 1: NCCL
+        keeps a communicator alive (and its destruction blocks) while a graph that captured its kernels exists."""
+        torch.cuda.synchronize()
+        self._graph = None
+        self._static = None
+        torch.cuda.synchronize()
+
     def _invalidate_param_caches(self):
         """The SGD kernel updates parameters in place without bumping autograd version counters: drop the per-parameter
         packed-weight caches the autograd/plugin path keeps, so a later model(x) call repacks the updated weights."""

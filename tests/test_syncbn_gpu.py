@@ -96,6 +96,7 @@ def _worker(rank, world, port, out_path, graph=False, nsteps=1):
         torch.save({"loss2": (lt / world).item(), "loss1": loss1.item(),
                     "cos": torch.nn.functional.cosine_similarity(upd2.double(), upd1.double(), dim=0).item(),
                     "stats_rel": ((rs2 - rs1).abs().max() / rs1.abs().max()).item()}, out_path)
+    st.release_graph()
     dist.barrier()
     dist.destroy_process_group()
 
