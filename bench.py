@@ -297,7 +297,7 @@ def main():
     if args.trace and rank == 0:
         lib.TRACE = []
         for _ in range(2):
-            stepper.step(x_dev, y_dev)
+            stepper._step_impl(x_dev, y_dev)  # eager: every C-ABI call is timed with its own event pair
         torch.cuda.synchronize()
         tr, lib.TRACE = lib.TRACE, None
         agg = {}

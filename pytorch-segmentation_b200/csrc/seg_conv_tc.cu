@@ -69,6 +69,8 @@ struct TcParams {
   int kblocks_total, kblocks_per_split;
   float* dw;
   int dw_K, dw_C;
+  CUtensorMap mapC;  // v2 TMA epilogue: the destination as a 2-D map with [32 rows][64 columns] boxes
+  int dbg;  // tuning experiments only (env SEG_TC_DBG): 1 skip global stores/loads, 2 skip statistics, 4 skip TMEM drain
 };
 
 template <int BN, int STAGES_>
@@ -505,6 +507,15 @@ static int launch_bn(int bn, const TcParams& p, dim3 grid, cudaStream_t stream) 
   }
   set_error("bad BN %d", bn);
   return 1;
+}
+
+static int env_dbg() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SEG_TC_DBG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
 }
 
 }  // namespace tc

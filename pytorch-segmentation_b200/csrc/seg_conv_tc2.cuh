@@ -9,10 +9,11 @@
 //   warp 0      : TMA producer (im2col-mode / 2-D activation tiles + weight tiles)
 //   warp 1      : TMEM alloc (256 cols) + tcgen05.mma issue + tcgen05.commit
 //   warps 2..9  : epilogue; warp (lg = warp%4, h = (warp-2)/4) owns TMEM lanes 32*lg.. and columns 64*h.. of the tile:
-//                 tcgen05.ld -> BN statistics (warp transpose-reduce, then shared-memory accumulators that persist
-//                 across the CTA's tiles and are flushed with one atomic per channel when the column block changes)
-//                 -> bf16 -> XOR-swizzled staging tile -> 128-byte-contiguous global stores.  The TMEM buffer is
-//                 released right after the tcgen05.ld, before the global stores.
+//                 tcgen05.ld -> bf16 -> XOR-swizzled staging tile -> [BN statistics: column sums of the staged rows
+//                 into shared-memory accumulators that persist across the CTA's tiles and are flushed with one atomic
+//                 per channel when the column block changes] -> 128-byte-contiguous global stores.  The TMEM buffer
+//                 is released right after the tcgen05.ld, before the global stores.  BETA variant (dgrad accumulating
+//                 into an existing gradient): the destination is prefetched before the accumulator wait.
 #pragma once
 
 namespace seg {
@@ -23,29 +24,70 @@ constexpr int V2_STAGES = 5;
 constexpr int V2_STAGE_BYTES = A_BYTES + V2_BN * 128;  // 32 KB
 constexpr int V2_THREADS = 320;
 constexpr int V2_STAGING_BYTES = BM * V2_BN * 2;       // 32 KB
-constexpr int V2_SMEM = V2_STAGES * V2_STAGE_BYTES + V2_STAGING_BYTES + 1024 /*stat accumulators*/ + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int V2_STAT_BYTES = 4 * 2 * V2_BN * 4;         // [lane group][sum, sum of squares][column] fp32
+constexpr int V2_SMEM = V2_STAGES * V2_STAGE_BYTES + V2_STAGING_BYTES + V2_STAT_BYTES + 256 /*barriers*/ + 1024 /*align*/;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int KIND>
+constexpr int EPI_MANUAL = 0;       // per-thread 16-byte global stores (strided sub-grid outputs, unaligned outputs)
+constexpr int EPI_MANUAL_BETA = 1;  // the same, accumulating into the destination (prefetched)
+constexpr int EPI_TMA = 2;          // per-warp TMA store / bf16 reduce-add of a [32 rows][64 columns] box
+
+// Column sums / sums of squares of 32 staged bf16 rows x 64 columns by one warp: lane = 2 adjacent columns.
+// `base` = first row of the warp's region (+ 4 * (lane & 3)), `cx` = un-swizzled byte offset of the lane's 16-byte chunk.
+template <int ROW_BYTES, int SWZ_MASK>
+__device__ __forceinline__ void warp_column_stats(const uint8_t* base, uint32_t cx, int rmax, float* slot, int slot_stride) {
+  float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f}, q0[2] = {0.f, 0.f}, q1[2] = {0.f, 0.f};
+  if (rmax >= 32) {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {  // row offsets and swizzle masks are immediates
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(base + r * ROW_BYTES + (cx ^ ((uint32_t)(r & SWZ_MASK) << 4)));
+      const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
+      a0[r & 1] += x0;
+      a1[r & 1] += x1;
+      q0[r & 1] = fmaf(x0, x0, q0[r & 1]);
+      q1[r & 1] = fmaf(x1, x1, q1[r & 1]);
+    }
+  } else {
+    for (int r = 0; r < rmax; ++r) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(base + r * ROW_BYTES + (cx ^ ((uint32_t)(r & SWZ_MASK) << 4)));
+      const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
+      a0[0] += x0;
+      a1[0] += x1;
+      q0[0] = fmaf(x0, x0, q0[0]);
+      q1[0] = fmaf(x1, x1, q1[0]);
+    }
+  }
+  // the calling warp is the only writer of its (lane group, column) slots: plain read-modify-write, no atomics
+  float2 s1 = *reinterpret_cast<float2*>(slot), s2 = *reinterpret_cast<float2*>(slot + slot_stride);
+  s1.x += a0[0] + a0[1];
+  s1.y += a1[0] + a1[1];
+  s2.x += q0[0] + q0[1];
+  s2.y += q1[0] + q1[1];
+  *reinterpret_cast<float2*>(slot) = s1;
+  *reinterpret_cast<float2*>(slot + slot_stride) = s2;
+}
+
+template <int KIND, int EPI>
 __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_constant__ TcParams p) {
   constexpr int BN = V2_BN;
+  constexpr bool BETA = (EPI == EPI_MANUAL_BETA);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t smem0 = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem0 - raw_addr);
   uint8_t* stage = smem_gen + V2_STAGES * V2_STAGE_BYTES;                       // staging tile [128][256 B]
-  float* stat_sm = reinterpret_cast<float*>(stage + V2_STAGING_BYTES);          // [2][128]
-  const uint32_t bar0 = smem0 + V2_STAGES * V2_STAGE_BYTES + V2_STAGING_BYTES + 1024;
+  float* stat_sm = reinterpret_cast<float*>(stage + V2_STAGING_BYTES);          // [4][2][128]
+  const uint32_t bar0 = smem0 + V2_STAGES * V2_STAGE_BYTES + V2_STAGING_BYTES + V2_STAT_BYTES;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (V2_STAGES + s); };
   auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * V2_STAGES + b); };
   auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * V2_STAGES + 2 + b); };
   const uint32_t tmem_ptr_addr = bar0 + 8u * (2 * V2_STAGES + 4);
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(
-      smem_gen + V2_STAGES * V2_STAGE_BYTES + V2_STAGING_BYTES + 1024 + 8 * (2 * V2_STAGES + 4));
+      smem_gen + V2_STAGES * V2_STAGE_BYTES + V2_STAGING_BYTES + V2_STAT_BYTES + 8 * (2 * V2_STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -57,6 +99,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_cons
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.mapA);
     prefetch_tmap(&p.mapB);
+    if (EPI == EPI_TMA) prefetch_tmap(&p.mapC);
     for (int s = 0; s < V2_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -71,7 +114,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_cons
     tmem_alloc(tmem_ptr_addr, 2 * BN);
     tmem_relinquish();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) stat_sm[threadIdx.x - 64] = 0.f;
+  for (int i = threadIdx.x; i < V2_STAT_BYTES / 4; i += V2_THREADS) stat_sm[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -157,9 +200,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_cons
       if (n_tile >= 0) {
         const int c = etid & 127, which = etid >> 7;
         const int col = n_tile * BN + c;
-        const float val = stat_sm[which * BN + c];
+        float val = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          val += stat_sm[(g * 2 + which) * BN + c];
+          stat_sm[(g * 2 + which) * BN + c] = 0.f;
+        }
         if (col < p.Ncols && val != 0.f) atomicAdd(p.stats + (size_t)which * p.Ncols + col, val);
-        stat_sm[which * BN + c] = 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     };
@@ -167,108 +214,131 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_cons
       const int b = i & 1;
       const int n_tile = t % n_tiles;
       const int m0 = (t / n_tiles) * BM, n0 = n_tile * BN;
-      const int row = m0 + trow;
-      const bool row_ok = row < p.M;
-      if (p.stats && n_tile != cur_n) {
+      if (EPI != EPI_MANUAL_BETA && p.stats && n_tile != cur_n) {
         flush_stats(cur_n);
         cur_n = n_tile;
       }
+      if constexpr (EPI == EPI_TMA) {
+        // ---- TMA epilogue: this warp owns rows 32*lg.. and columns 64*h.. of the tile = one [32][64] box whose
+        //      staging region (4 KB, 128-byte rows, SWIZZLE_128B pattern) only this warp touches ----
+        uint8_t* region = stage + h * 16384 + lg * 4096;
+        if (lane == 0) bulk_wait_group_read0();  // my previous box has been read out of shared memory
+        __syncwarp();
+        mbar_wait(tfull_bar(b), ((uint32_t)i >> 1) & 1u);
+        tc_fence_after();
+        float v1[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * BN + h * 64), v);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * BN + h * 64 + 32), v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(b));  // accumulator drained: the MMA warp may reuse it
+        if (!(p.dbg & 4)) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            *reinterpret_cast<bf16x8*>(region + lane * 128 + ((g ^ (lane & 7)) << 4)) = pack8(v + g * 8);
+            *reinterpret_cast<bf16x8*>(region + lane * 128 + (((4 + g) ^ (lane & 7)) << 4)) = pack8(v1 + g * 8);
+          }
+        }
+        __syncwarp();
+        if (p.stats && !(p.dbg & 2))
+          warp_column_stats<128, 7>(region + (lane & 3) * 4, (uint32_t)(lane >> 2) << 4, min(32, p.M - m0 - lg * 32),
+                                    stat_sm + (size_t)(lg * 2) * BN + h * 64 + (lane >> 2) * 8 + (lane & 3) * 2, BN);
+        fence_proxy_async();  // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0 && !(p.dbg & 1) && m0 + lg * 32 < p.M && n0 + h * 64 < p.Ncols) {
+          if (p.beta != 0.f)
+            tma_reduce_add_2d(&p.mapC, smem_u32(region), n0 + h * 64, m0 + lg * 32);  // dst += tile, bf16 add in L2
+          else
+            tma_store_2d(&p.mapC, smem_u32(region), n0 + h * 64, m0 + lg * 32);
+          bulk_commit_group();
+        }
+        continue;
+      }
+      // beta-accumulate (dgrad into a gradient that already holds the skip branch): fetch this lane's eight 16-byte
+      // pieces of the destination NOW — eight loads in flight per thread while the accumulator is still being
+      // produced, instead of one dependent load per store (which left the epilogue bound by DRAM latency)
+      const int ncols_tile = min(BN, p.Ncols - n0);
+      const bool vec_ok = ((p.ldo * 2) & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.out) + (size_t)n0 * 2) & 15) == 0;
+      const int c16 = h * 8 + (lane & 7);
+      const int first_col = c16 * 8;
+      const bool col_ok = first_col < ncols_tile;
+      const bool vec = vec_ok && first_col + 8 <= ncols_tile;
+      long long off[8];
+      bf16x8 resid[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int grow = m0 + lg * 32 + (lane >> 3) + 4 * k;
+        off[k] = -1;
+        if (col_ok && grow < p.M) {
+          long long pixel = grow;
+          if (p.out_strided) {
+            const int n = grow / p.PQ;
+            const int rem = grow - n * p.PQ;
+            const int ii = rem / p.Q, jj = rem - ii * p.Q;
+            pixel = ((long long)n * p.out_H + (ii * p.osy + p.opy)) * p.out_W + (jj * p.osx + p.opx);
+          }
+          off[k] = pixel * p.ldo + n0 + first_col;
+          if (BETA && vec && !(p.dbg & 1)) resid[k] = *reinterpret_cast<const bf16x8*>(reinterpret_cast<const __nv_bfloat16*>(p.out) + off[k]);
+        }
+      }
       mbar_wait(tfull_bar(b), ((uint32_t)i >> 1) & 1u);
       tc_fence_after();
-      float st1[2], st2[2];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
+        if (p.dbg & 4) break;
         const int ch = h * 2 + c;  // 32-column chunk of the tile
         tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * BN + ch * 32), v);
         tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const int c16 = ch * 4 + g;
-          *reinterpret_cast<bf16x8*>(stage + (size_t)trow * (BN * 2) + ((c16 ^ (trow & 15)) << 4)) = pack8(v + g * 8);
-        }
-        st1[c] = st2[c] = 0.f;
-        if (p.stats) {
-          float s1[32], s2[32];
-#pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const float x = row_ok ? v[q] : 0.f;
-            s1[q] = x;
-            s2[q] = x * x;
-          }
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool up = (lane & off) != 0;
-#pragma unroll
-            for (int j = 0; j < off; ++j) {
-              const float send1 = up ? s1[j] : s1[j + off];
-              const float keep1 = up ? s1[j + off] : s1[j];
-              s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
-              const float send2 = up ? s2[j] : s2[j + off];
-              const float keep2 = up ? s2[j + off] : s2[j];
-              s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
-            }
-          }
-          st1[c] = s1[0];
-          st2[c] = s2[0];
+          const int cc = ch * 4 + g;
+          *reinterpret_cast<bf16x8*>(stage + (size_t)trow * (BN * 2) + ((cc ^ (trow & 15)) << 4)) = pack8(v + g * 8);
         }
       }
       // accumulator fully read: hand the TMEM buffer back to the MMA warp before touching global memory
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(b));
-      if (p.stats) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int col = (h * 2 + c) * 32 + lane;
-          atomicAdd(stat_sm + col, st1[c]);
-          atomicAdd(stat_sm + BN + col, st2[c]);
-        }
+      if (!BETA && p.stats && !(p.dbg & 2)) {
+        // BN statistics of the tile as STORED (bf16-rounded, i.e. exactly what bn_apply will normalise): every lane
+        // sums two adjacent columns over this warp's 32 staged rows — conflict-free 4-byte shared loads, no shuffles
+        warp_column_stats<BN * 2, 15>(stage + (size_t)(lg * 32) * (BN * 2) + (lane & 3) * 4, (uint32_t)(h * 8 + (lane >> 2)) << 4,
+                                      min(32, p.M - m0 - lg * 32),
+                                      stat_sm + (size_t)(lg * 2) * BN + h * 64 + (lane >> 2) * 8 + (lane & 3) * 2, BN);
       }
       // stream this warp's 32 rows x 64 columns out: 8 lanes cover one 128-byte row segment, 4 rows per instruction
-      const int ncols_tile = min(BN, p.Ncols - n0);
-      const bool vec_ok = ((p.ldo * 2) & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.out) + (size_t)n0 * 2) & 15) == 0;
-#pragma unroll 2
-      for (int idx = lane; idx < 32 * 8; idx += 32) {
-        const int rr = idx >> 3;
-        const int c16 = h * 8 + (idx & 7);
-        const int first_col = c16 * 8;
-        if (first_col >= ncols_tile) continue;
-        const int tr = lg * 32 + rr;
-        const int grow = m0 + tr;
-        if (grow >= p.M) continue;
-        long long pixel = grow;
-        if (p.out_strided) {
-          const int n = grow / p.PQ;
-          const int rem = grow - n * p.PQ;
-          const int ii = rem / p.Q, jj = rem - ii * p.Q;
-          pixel = ((long long)n * p.out_H + (ii * p.osy + p.opy)) * p.out_W + (jj * p.osx + p.opx);
-        }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (off[k] < 0 || (p.dbg & 1)) continue;
+        const int tr = lg * 32 + (lane >> 3) + 4 * k;
         bf16x8 val = *reinterpret_cast<const bf16x8*>(stage + (size_t)tr * (BN * 2) + ((c16 ^ (tr & 15)) << 4));
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)pixel * p.ldo + n0 + first_col;
-        if (vec_ok && first_col + 8 <= ncols_tile) {
-          if (p.beta != 0.f) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + off[k];
+        if (vec) {
+          if (BETA) {
             float a[8], bb[8];
             unpack8(val, a);
-            unpack8(*reinterpret_cast<const bf16x8*>(dst), bb);
+            unpack8(resid[k], bb);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] += p.beta * bb[k];
+            for (int q = 0; q < 8; ++q) a[q] += p.beta * bb[q];
             val = pack8(a);
           }
           *reinterpret_cast<bf16x8*>(dst) = val;
         } else {
           float a[8];
           unpack8(val, a);
-          for (int k = 0; k < 8; ++k)
-            if (first_col + k < ncols_tile) {
-              float o = a[k];
-              if (p.beta != 0.f) o += p.beta * bf2f(dst[k]);
-              dst[k] = f2bf(o);
+          for (int q = 0; q < 8; ++q)
+            if (first_col + q < ncols_tile) {
+              float o = a[q];
+              if (BETA) o += p.beta * bf2f(dst[q]);
+              dst[q] = f2bf(o);
             }
         }
       }
       __syncwarp();  // the staging region of this warp is reused by its next tile
     }
-    if (p.stats) flush_stats(cur_n);
+    if (EPI != EPI_MANUAL_BETA && p.stats) flush_stats(cur_n);
+    if (EPI == EPI_TMA && lane == 0) bulk_wait_group0();  // all boxes written before the CTA retires
     tc_fence_before();
   }
   __syncthreads();
@@ -278,10 +348,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_cons
   }
 }
 
-template <int KIND>
-static int launch_v2(const TcParams& p, cudaStream_t stream) {
+template <int KIND, int EPI>
+static int launch_v2_impl(const TcParams& p, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kfn = conv_gemm_tc2<KIND>;
+  auto kfn = conv_gemm_tc2<KIND, EPI>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM);
     SEG_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(v2 smem=%d): %s", V2_SMEM, cudaGetErrorString(e));
@@ -296,6 +366,23 @@ static int launch_v2(const TcParams& p, cudaStream_t stream) {
   if ((int64_t)grid > num_tiles) grid = (int)num_tiles;
   kfn<<<grid, V2_THREADS, V2_SMEM, stream>>>(p);
   return check_launch("conv_gemm_tc2");
+}
+
+// `p` by value: the destination map and the experiment flags are filled in here
+template <int KIND>
+static int launch_v2(TcParams p, cudaStream_t stream) {
+  p.dbg = env_dbg();
+  const bool tma_ok = !p.out_strided && p.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+                      (p.beta == 0.f || p.beta == 1.f) && !(p.dbg & 16);
+  if (tma_ok) {
+    if (make_map_2d(&p.mapC, p.out, p.M, p.Ncols, p.ldo, 32)) return 1;
+    return launch_v2_impl<KIND, EPI_TMA>(p, stream);
+  }
+  if (p.beta != 0.f) {
+    SEG_REQUIRE(p.stats == nullptr, "conv_gemm_tc2: beta-accumulate and BN statistics are not combined on this path");
+    return launch_v2_impl<KIND, EPI_MANUAL_BETA>(p, stream);
+  }
+  return launch_v2_impl<KIND, EPI_MANUAL>(p, stream);
 }
 
 }  // namespace tc

@@ -138,6 +138,7 @@ class FusedTrainStep:
         # NCCL's all-reduce is captured with the rest (its watchdog thread polls events: relaxed capture mode)
         with torch.cuda.graph(g, capture_error_mode="thread_local" if self.world > 1 else "global"):
             loss = self._step_impl(xs, ys)
+        self.steps -= 1  # the capture pass itself executed nothing
         self._graph, self._static = g, (xs, ys, loss)
 
     def _step_impl(self, x, target):

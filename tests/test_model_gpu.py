@@ -307,24 +307,27 @@ def test_plugin_path_after_fused_steps_sees_updated_weights():
 
 def test_graph_replayed_steps_equal_eager_steps(gpu_out_dir):
     """CUDA-graph replay of the fused step (train.py: FusedTrainStep(cuda_graph=True)) is the same training as the eager
-    step: the capture's two warm-up steps are rolled back, every replay is a fresh step (device-side counters)."""
-    sd, m_e = build("deeplab", 7, "resnet14", 8, output_stride=16)
-    _, m_g = build("deeplab", 7, "resnet14", 8, output_stride=16)
-    for m in (m_e, m_g):
+    step: the capture's two warm-up steps are rolled back, every replay is a fresh step (device-side counters).
+    A second eager trainer is the control for run-to-run noise (split-K wgrad uses fp32 atomics)."""
+    models = [build("deeplab", 7, "resnet14", 8, output_stride=16) for _ in range(3)]
+    sd = models[0][0]
+    m_e, m_c, m_g = (m for _, m in models)
+    for m in (m_e, m_c, m_g):
         m.engine_dropout = False
         m.train()
     x, y = synth.make_batch(2, 65, 65, 7, 255, seed=9010)
     xd, yd = x.cuda(), y.cuda()
-    se, sg = FusedTrainStep(m_e, lr=0.02), FusedTrainStep(m_g, lr=0.02, cuda_graph=True)
+    se, sc, sg = FusedTrainStep(m_e, lr=0.005), FusedTrainStep(m_c, lr=0.005), FusedTrainStep(m_g, lr=0.005, cuda_graph=True)
     for i in range(3):
-        le, lg = se.step(xd, yd), sg.step(xd, yd)
-        assert abs(float(le) - float(lg)) < 2e-2 * abs(float(le)), (i, float(le), float(lg))
+        le, lc, lg = float(se.step(xd, yd)), float(sc.step(xd, yd)), float(sg.step(xd, yd))
+        noise = abs(le - lc) / abs(le)
+        log(gpu_out_dir, f"graph-vs-eager step {i}: eager {le:.6f} control {lc:.6f} graph {lg:.6f}")
+        assert abs(le - lg) < max(1e-3 if i == 0 else 2e-2, 4 * noise) * abs(le), (i, le, lc, lg)
     assert sg.steps == 3
-    ue = torch.cat([(p.detach().cpu() - sd[n]).reshape(-1) for n, p in m_e.named_parameters()])
-    ug = torch.cat([(p.detach().cpu() - sd[n]).reshape(-1) for n, p in m_g.named_parameters()])
-    c = cosine(ue, ug)
-    log(gpu_out_dir, f"graph-vs-eager 3 steps: update cosine {c:.5f}")
-    assert c > 0.98
+    upd = [torch.cat([(p.detach().cpu() - sd[n]).reshape(-1) for n, p in m.named_parameters()]) for m in (m_e, m_c, m_g)]
+    c_ctrl, c_graph = cosine(upd[0], upd[1]), cosine(upd[0], upd[2])
+    log(gpu_out_dir, f"graph-vs-eager 3 steps: update cosine {c_graph:.5f} (eager-vs-eager control {c_ctrl:.5f})")
+    assert c_graph > min(0.98, c_ctrl - 0.02)
     for (n, a), (_, b) in zip(m_e.named_buffers(), m_g.named_buffers()):
         if n.endswith("num_batches_tracked"):
             assert int(a) == int(b) == 3, n

@@ -16,7 +16,7 @@ import torch  # noqa: E402
 from seg_b200 import lib, ops  # noqa: E402
 
 
-def run(shape, kind, iters, stats, impl):
+def run(shape, kind, iters, stats, impl, beta=0.0):
     N, H, W, C, K, ks, stride, dil = shape
     pad = dil * (ks - 1) // 2
     P = lib.conv_out_size(H, ks, stride, pad, dil)
@@ -26,8 +26,8 @@ def run(shape, kind, iters, stats, impl):
     dys = [torch.randn(N, P, Q, K, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
     w = torch.randn(K, C, ks, ks, device="cuda") / (C * ks * ks) ** 0.5
     wp = ops.pack_weight(w)
-    out_y = torch.empty(N, P, Q, K, device="cuda", dtype=torch.bfloat16)
-    out_dx = torch.empty(N, H, W, C, device="cuda", dtype=torch.bfloat16)
+    out_ys = [torch.empty(N, P, Q, K, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
+    out_dxs = [torch.zeros(N, H, W, C, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]  # rotated: cold in L2
     dwp = torch.zeros(ks * ks, K, C, device="cuda")
     st = torch.zeros(2 * K, device="cuda") if stats else None
     flops = 2.0 * N * P * Q * K * C * ks * ks
@@ -35,9 +35,9 @@ def run(shape, kind, iters, stats, impl):
 
     def one(k, i):
         if k == "fwd":
-            ops.conv2d_fwd(xs[i % nbuf], wp, K, ks, ks, stride, pad, dil, out=out_y, stats=st, impl=impl)
+            ops.conv2d_fwd(xs[i % nbuf], wp, K, ks, ks, stride, pad, dil, out=out_ys[i % nbuf], stats=st, impl=impl)
         elif k == "dgrad":
-            ops.conv2d_dgrad(dys[i % nbuf], wp, (N, H, W, C), ks, ks, stride, pad, dil, out=out_dx, impl=impl)
+            ops.conv2d_dgrad(dys[i % nbuf], wp, (N, H, W, C), ks, ks, stride, pad, dil, out=out_dxs[i % nbuf], impl=impl, beta=beta)
         else:
             ops.conv2d_wgrad(dys[i % nbuf], xs[i % nbuf], ks, ks, stride, pad, dil, out=dwp, impl=impl)
 
@@ -52,7 +52,7 @@ def run(shape, kind, iters, stats, impl):
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / iters
-        print(f"{k:6s} shape={shape} stats={int(bool(stats))}: {us:8.2f} us  {flops / us / 1e6:8.1f} TFLOP/s  {byt[k] / us / 1e3:8.1f} GB/s")
+        print(f"{k:6s} shape={shape} stats={int(bool(stats))} beta={beta} dbg={os.environ.get("SEG_TC_DBG", "0")}: {us:8.2f} us  {flops / us / 1e6:8.1f} TFLOP/s  {byt[k] / us / 1e3:8.1f} GB/s")
 
 
 if __name__ == "__main__":
@@ -62,7 +62,8 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--stats", type=int, default=1)
     ap.add_argument("--impl", type=int, default=0)
+    ap.add_argument("--beta", type=float, default=0.0, help="dgrad: accumulate into the existing gradient")
     a = ap.parse_args()
     lib.require_device()
     for s in a.shape:
-        run(tuple(int(v) for v in s.split(",")), a.kind, a.iters, a.stats, a.impl)
+        run(tuple(int(v) for v in s.split(",")), a.kind, a.iters, a.stats, a.impl, a.beta)
