@@ -315,8 +315,8 @@ def main():
             f.write(f"# per-step totals over 2 traced steps; sum of call times {tot:.2f} ms\n")
             for name, ms in sorted(by_name.items(), key=lambda kv: -kv[1]):
                 f.write(f"{name:28s} {ms:9.3f} ms  {100 * ms / tot:5.1f}%\n")
-            f.write("\n# name (N,H,W,C,K,R,stride,dil) ms/step calls/2steps TFLOP/s\n")
-            for (name, meta), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:70]:
+            f.write("\n# name (N,H,W,C,K,R,stride,dil | rows,C,flag) ms/step calls/2steps TFLOP/s (conv) or TB/s algorithmic (streaming)\n")
+            for (name, meta), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:110]:
                 tf = v[2] / (v[0] * 1e-3) / 1e12 if v[0] > 0 and v[2] > 0 else 0.0
                 f.write(f"{name:22s} {str(meta):48s} {v[0]:8.3f} {v[1]:4d} {tf:8.1f}\n")
 

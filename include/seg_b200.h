@@ -117,16 +117,24 @@ int seg_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const 
  * (nn.ReLU(inplace) + residual add torchvision Bottleneck; nn.Dropout deeplabv3_plus.py:282,318) */
 int seg_bn_apply(const void* x, int ldx, const float* scale_shift, const void* res, int ldr, void* out, int ldo,
                  int64_t M, int C, int relu, float drop_p, uint64_t seed, const uint64_t* step_ctr, void* stream);
+/* seg_bn_finalize + seg_bn_apply in ONE launch (training mode): coefficients are derived from the batch sums inside the
+ * kernel; save[2C] = (mean, 1/std) for the backward pass and the running statistics are written by one block row. */
+int seg_bn_apply_train(const void* x, int ldx, const float* stats, double count, const float* gamma, const float* beta,
+                       float eps, float momentum, int clamp_eps, float* running_mean, float* running_var, float* save,
+                       const void* res, int ldr, void* out, int ldo, int64_t M, int C, int relu, float drop_p,
+                       uint64_t seed, const uint64_t* step_ctr, void* stream);
 /* device-side step counter (*ctr += inc): mixed into dropout seeds and SyncBN epochs so a captured CUDA graph of the
  * train step stays correct on every replay */
 int seg_counter_add(uint64_t* ctr, uint64_t inc, void* stream);
 /* backward, pass 1 (two-stage reduction: slotted partial sums, then a finalising kernel): sums[0:C] = sum(dz), sums[C:2C] = sum(dz*xhat),
  * dz = dout * (out>0) * 1/(1-drop_p) if relu.  scratch: seg_bn_bwd_reduce_scratch_floats(M, C) floats.  If given,
- * dbeta (=|+=) sums[0:C] and dgamma (=|+=) sums[C:2C] — the parameter gradients from the LOCAL sums. */
+ * dbeta (=|+=) sums[0:C] and dgamma (=|+=) sums[C:2C] — the parameter gradients from the LOCAL sums.
+ * scratch_is_zero != 0: the caller guarantees zeroed scratch (e.g. a per-step arena cleared once) and the reduction is
+ * ONE launch — the last block to finish folds the slot rows; otherwise memset + reduce + fold (three stream ops). */
 int64_t seg_bn_bwd_reduce_scratch_floats(int64_t M, int C);
 int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx,
                       const float* save_mean_istd, int64_t M, int C, int relu, float drop_p, float* sums,
-                      float* scratch, float* dgamma, float* dbeta, int accumulate, void* stream);
+                      float* scratch, float* dgamma, float* dbeta, int accumulate, int scratch_is_zero, void* stream);
 /* backward, pass 2: dx = gamma*istd*(dz - sums0/count - xhat*sums1/count); dres = beta_res*dres + dz (optional).
  * `sums` are the (possibly all-reduced) sums, `count` the matching element count. */
 int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx,

@@ -168,6 +168,7 @@ __device__ __forceinline__ void column_reduce(int64_t M, int C, float* out /*[NA
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
   if (g < G && rl < rows_par) {
+#pragma unroll 2
     for (int64_t row = (int64_t)blockIdx.x * rows_par + rl; row < M; row += (int64_t)gridDim.x * rows_par)
       f(row, g, acc);
   }
@@ -269,18 +270,61 @@ __device__ __forceinline__ void ld8(const float* p, float* v) {
   *reinterpret_cast<float4*>(v + 4) = __ldg(reinterpret_cast<const float4*>(p + 4));
 }
 
+// Training-mode coefficients computed in the consumer (no separate finalize launch): every thread derives scale/shift of
+// its 8 channels from the batch sums; the threads of block row 0 also record (mean, 1/std) for the backward pass and
+// update the running statistics (nn.BatchNorm2d semantics: momentum, unbiased variance).
+struct BnTrain {
+  const float* stats;  // [2C] sum, sum of squares over `count` elements (null: use the precomputed scale_shift)
+  double count;
+  const float *gamma, *beta;
+  float eps, momentum;
+  int clamp_eps;
+  float *running_mean, *running_var, *save;
+};
+
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                        const float* __restrict__ ss, const __nv_bfloat16* __restrict__ res,
                                                        int ldr, __nv_bfloat16* __restrict__ out, int ldo, int64_t M, int C,
                                                        int relu, float drop_p, uint64_t seed,
-                                                       const uint64_t* __restrict__ step_ctr) {
+                                                       const uint64_t* __restrict__ step_ctr, const BnTrain tr) {
   const RowMap rm = row_map(C);
   if (!rm.active) return;
   if (step_ctr) seed += (*step_ctr) * 0x9E3779B97F4A7C15ull;  // device-side step counter keeps CUDA-graph replays fresh
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   float sc[8], sh[8];
-  ld8(ss + rm.g * 8, sc);
-  ld8(ss + C + rm.g * 8, sh);
+  if (tr.stats) {
+    float s1[8], s2[8], gm[8], bt[8];
+    ld8(tr.stats + rm.g * 8, s1);
+    ld8(tr.stats + C + rm.g * 8, s2);
+    ld8(tr.gamma + rm.g * 8, gm);
+    ld8(tr.beta + rm.g * 8, bt);
+    const bool writer = blockIdx.x == 0 && rm.rl == 0;
+    const double inv_count = 1.0 / tr.count;  // one division; the per-channel math below is multiply-add + fp32 rsqrt
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const double mean = (double)s1[j] * inv_count;
+      double var = fma((double)s2[j], inv_count, -mean * mean);
+      if (var < 0) var = 0;
+      const float vf = tr.clamp_eps ? fmaxf((float)var, tr.eps) : (float)(var + (double)tr.eps);
+      float istd = rsqrtf(vf);
+      istd = istd * (1.5f - 0.5f * vf * istd * istd);  // one Newton step: fp32-exact 1/sqrt
+      sc[j] = gm[j] * istd;
+      sh[j] = fmaf(-(float)mean, sc[j], bt[j]);
+      if (writer) {
+        const int c = rm.g * 8 + j;
+        tr.save[c] = (float)mean;
+        tr.save[C + c] = istd;
+        if (tr.running_mean) {
+          const double unbiased = tr.count > 1 ? var * tr.count / (tr.count - 1) : var;
+          tr.running_mean[c] = (float)((1.0 - tr.momentum) * tr.running_mean[c] + tr.momentum * mean);
+          tr.running_var[c] = (float)((1.0 - tr.momentum) * tr.running_var[c] + tr.momentum * unbiased);
+        }
+      }
+    }
+  } else {
+    ld8(ss + rm.g * 8, sc);
+    ld8(ss + C + rm.g * 8, sh);
+  }
   const int64_t step = (int64_t)gridDim.x * rm.rows_par;
   const int co = rm.g * 8;
   for (int64_t row = (int64_t)blockIdx.x * rm.rows_par + rm.rl; row < M; row += 2 * step) {
@@ -325,7 +369,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256)
     bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ out, int ldo,
                          const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save, int64_t M, int C,
-                         int relu, float drop_p, float* __restrict__ sums) {
+                         int relu, float drop_p, float* __restrict__ sums, unsigned int* ticket, float* final_sums,
+                         float* dgamma, float* dbeta, int accumulate) {
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const RowMap rm = row_map(C);
   float mean[8], istd[8];
@@ -351,6 +396,30 @@ __global__ void __launch_bounds__(256)
       acc[1][i] += dz[i] * (xv[i] - mean[i]) * istd[i];
     }
   });
+  if (ticket == nullptr) return;
+  // single-launch mode (slot rows pre-zeroed by the caller): the last block to finish folds the slot rows
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x * gridDim.y - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int b = 0; b < REDUCE_SLOTS; ++b) {
+      s0 += __ldcg(sums + ((size_t)b * 2 + 0) * C + c);
+      s1 += __ldcg(sums + ((size_t)b * 2 + 1) * C + c);
+    }
+    final_sums[c] = s0;
+    final_sums[C + c] = s1;
+    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + s0 : s0;
+    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + s1 : s1;
+  }
 }
 
 // dx = A*dz + B*x + Cc with A = gamma*istd, B = -gamma*istd^2*s1/count, Cc = -gamma*istd*s0/count + gamma*istd^2*mean*s1/count
@@ -992,12 +1061,18 @@ int seg_im2col(const seg_conv_desc* d, const void* x, int x_nchw_f32, void* col,
 }
 
 // grid for the channel-group-stationary streaming kernels: full occupancy (8 blocks of 256 threads per SM)
-static dim3 rowmap_grid(int64_t M, int C, int rows_per_iter) {
+// Grid of the channel-group-stationary streaming kernels.  Every thread pays a fixed prologue (per-channel coefficients,
+// and for the reductions a block-level fold + atomics), so small maps get FEWER, fatter blocks: aim at >= 8 rows per
+// thread, but never fewer than two blocks per SM (or one row group per block), and at most eight blocks per SM.
+static dim3 rowmap_grid(int64_t M, int C, int rows_per_thread = 8) {
   const int G = C / 8;
   const int GB = G < 256 ? G : 256;
   const int rows_par = 256 / GB;
   const int gy = ceil_div(G, GB);
-  int64_t gx = ceil_div64(M, (int64_t)rows_par * rows_per_iter);
+  const int64_t groups = ceil_div64(M, rows_par);  // block-iterations needed to cover all rows
+  int64_t gx = ceil_div64(groups, rows_per_thread);
+  const int64_t floor_blocks = ((int64_t)num_sms() * 2 + gy - 1) / gy;
+  if (gx < floor_blocks) gx = floor_blocks < groups ? floor_blocks : groups;
   const int64_t cap = ((int64_t)num_sms() * 8 + gy - 1) / gy;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
@@ -1036,32 +1111,42 @@ int seg_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const 
 int seg_bn_apply(const void* x, int ldx, const float* ss, const void* res, int ldr, void* out, int ldo, int64_t M, int C,
                  int relu, float drop_p, uint64_t seed, const uint64_t* step_ctr, void* stream) {
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldr % 8 == 0), "bn_apply: alignment");
-  bn_apply_kernel<<<rowmap_grid(M, C, 2), 256, 0, ST(stream)>>>(CBF(x), ldx, ss, CBF(res), ldr, BF(out), ldo, M, C, relu,
-                                                                drop_p, seed, step_ctr);
+  BnTrain tr;
+  memset(&tr, 0, sizeof(tr));
+  bn_apply_kernel<<<rowmap_grid(M, C), 256, 0, ST(stream)>>>(CBF(x), ldx, ss, CBF(res), ldr, BF(out), ldo, M, C, relu,
+                                                                drop_p, seed, step_ctr, tr);
   return check_launch("bn_apply");
 }
-static dim3 reduce2_grid(int64_t M, int C) {
-  const int G = C / 8;
-  const int GB = G < 256 ? G : 256;
-  const int rows_par = 256 / GB;
-  const int gy = ceil_div(G, GB);
-  int64_t gx = ceil_div64(M, (int64_t)rows_par * 2);
-  const int64_t cap = ((int64_t)num_sms() * 8 + gy - 1) / gy;
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  return dim3((unsigned)gx, (unsigned)gy, 1);
+int seg_bn_apply_train(const void* x, int ldx, const float* stats, double count, const float* gamma, const float* beta,
+                       float eps, float momentum, int clamp_eps, float* running_mean, float* running_var, float* save,
+                       const void* res, int ldr, void* out, int ldo, int64_t M, int C, int relu, float drop_p,
+                       uint64_t seed, const uint64_t* step_ctr, void* stream) {
+  SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldr % 8 == 0), "bn_apply_train: alignment");
+  SEG_REQUIRE(stats && gamma && beta && save && count > 0, "bn_apply_train: stats, gamma, beta, save required");
+  BnTrain tr = {stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var, save};
+  bn_apply_kernel<<<rowmap_grid(M, C), 256, 0, ST(stream)>>>(CBF(x), ldx, nullptr, CBF(res), ldr, BF(out), ldo, M, C, relu,
+                                                                drop_p, seed, step_ctr, tr);
+  return check_launch("bn_apply_train");
 }
-int64_t seg_bn_bwd_reduce_scratch_floats(int64_t M, int C) { return (int64_t)REDUCE_SLOTS * 2 * C; }
+// reductions end with a block fold + 16 C atomics per block: fewer blocks still (>= 32 rows per thread)
+static dim3 reduce2_grid(int64_t M, int C) { return rowmap_grid(M, C, 32); }
+int64_t seg_bn_bwd_reduce_scratch_floats(int64_t M, int C) { return (int64_t)REDUCE_SLOTS * 2 * C + 4; }
 
 int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,
                       int64_t M, int C, int relu, float drop_p, float* sums, float* scratch, float* dgamma, float* dbeta,
-                      int accumulate, void* stream) {
+                      int accumulate, int scratch_is_zero, void* stream) {
   SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && (!relu || ldo % 8 == 0), "bn_bwd_reduce: alignment");
   SEG_REQUIRE(scratch != nullptr, "bn_bwd_reduce: scratch of seg_bn_bwd_reduce_scratch_floats(M, C) floats required");
   const dim3 grid = reduce2_grid(M, C);
+  if (scratch_is_zero) {  // one launch: the last block folds the slot rows (ticket counter behind them)
+    bn_bwd_reduce_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p,
+                                                       scratch, reinterpret_cast<unsigned int*>(scratch + (size_t)REDUCE_SLOTS * 2 * C),
+                                                       sums, dgamma, dbeta, accumulate);
+    return check_launch("bn_bwd_reduce");
+  }
   cudaMemsetAsync(scratch, 0, (size_t)REDUCE_SLOTS * 2 * C * sizeof(float), ST(stream));
   bn_bwd_reduce_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p,
-                                                     scratch);
+                                                     scratch, nullptr, nullptr, nullptr, nullptr, 0);
   if (check_launch("bn_bwd_reduce")) return 1;
   bn_bwd_reduce_final_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(scratch, REDUCE_SLOTS, C, sums, dgamma, dbeta, accumulate);
   return check_launch("bn_bwd_reduce_final");
@@ -1070,7 +1155,7 @@ int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const
                      const float* gamma, const float* sums, double count, int64_t M, int C, int relu, float drop_p,
                      void* dx, int lddx, void* dres, int lddres, float beta_res, void* stream) {
   SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0, "bn_bwd_apply: alignment");
-  bn_bwd_apply_kernel<<<rowmap_grid(M, C, 1), 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, gamma,
+  bn_bwd_apply_kernel<<<rowmap_grid(M, C), 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, gamma,
                                                                     sums, (float)(1.0 / count), M, C, relu, drop_p, BF(dx),
                                                                     lddx, BF(dres), lddres, beta_res);
   return check_launch("bn_bwd_apply");

@@ -115,7 +115,7 @@ class DwSpec:
 
 class Tape:
     def __init__(self, training, record=None, grads=None, impl=IMPL_AUTO, dropout=True, seed=0, sync=None, clamp_eps=False,
-                 step_ctr=None):
+                 step_ctr=None, arena_floats=0, owner=None):
         self.training = training                                  # module.training semantics (batch stats, dropout)
         self.record = training if record is None else record      # record backward closures
         self.back = []
@@ -132,8 +132,27 @@ class Tape:
         self.clamp_eps = clamp_eps
         self._drop_ctr = 0
         self.bn_modules = []
+        # zero-initialised fp32 arena: BN-statistics accumulators and reduction slots of the whole step come out of ONE
+        # zero fill instead of one fill per layer (arena_floats = what the previous step used; grows in 1M-float chunks)
+        self.owner = owner  # the model: remembers how much arena a step needs
+        self._arena_hint = int(arena_floats)
+        self._arena = None
+        self._arena_off = 0
+        self.arena_used = 0
 
     # ------------------------------------------------------------------ helpers
+    def zalloc(self, n, device):
+        """n zeroed floats (128-byte aligned) from the step's arena."""
+        n_al = (int(n) + 31) // 32 * 32
+        if self._arena is None or self._arena_off + n_al > self._arena.numel() or self._arena.device != device:
+            size = max(self._arena_hint if self._arena is None else 0, n_al, 1 << 20)
+            self._arena = torch.zeros(size, dtype=torch.float32, device=device)
+            self._arena_off = 0
+        v = self._arena[self._arena_off:self._arena_off + int(n)]
+        self._arena_off += n_al
+        self.arena_used += n_al
+        return v
+
     def _param_grad(self, p, value_fn):
         """Write (or accumulate into) the fp32 gradient of parameter p.  value_fn(out, beta) fills it."""
         if not p.requires_grad:
@@ -148,6 +167,8 @@ class Tape:
     def backward(self):
         for fn in reversed(self.back):
             fn()
+        if self.owner is not None and self.arena_used:
+            self.owner._arena_floats = self.arena_used
         self.back = []
 
     # ------------------------------------------------------------------ conv
@@ -161,7 +182,7 @@ class Tape:
         if out_dtype is None:
             out_dtype = ACT_DTYPE
         if want_stats and self.training:
-            stats = torch.zeros(2 * spec.K, dtype=torch.float32, device=wp.device)
+            stats = self.zalloc(2 * spec.K, wp.device)
         if spec.explicit:
             nchw = not isinstance(x, Act)
             src = x if nchw else x.t
@@ -212,7 +233,7 @@ class Tape:
     def dwconv(self, x, spec, want_stats=False):
         """Depthwise 3x3 (SeparableConv2d.conv1).  Returns (raw output Act, BN statistics or None)."""
         w9 = spec.packed()
-        stats = torch.zeros(2 * spec.C, dtype=torch.float32, device=w9.device) if (want_stats and self.training) else None
+        stats = self.zalloc(2 * spec.C, w9.device) if (want_stats and self.training) else None
         y = ops.dwconv_fwd(x.t, w9, spec.stride, spec.pad, spec.dil, stats=stats)
         ya = Act(y)
         if self.record:
@@ -264,16 +285,19 @@ class Tape:
             if self.sync is not None and self.sync.world > 1:
                 self.sync.allreduce_(stats)
                 count = count_local * self.sync.world
-            ss, save = ops.bn_finalize(stats, count, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum if bn.momentum is not None else BN_MOM,
-                                       1 if (self.clamp_eps and self.sync is not None and self.sync.world > 1) else 0,
-                                       bn.running_mean, bn.running_var)
+            # finalize (coefficients, saved mean / 1/std, running statistics) happens inside the apply kernel
+            a, save = ops.bn_apply_train(y.t, stats, count, bn.weight.detach(), bn.bias.detach(), bn.eps,
+                                         bn.momentum if bn.momentum is not None else BN_MOM,
+                                         1 if (self.clamp_eps and self.sync is not None and self.sync.world > 1) else 0,
+                                         bn.running_mean, bn.running_var, res=res.t if res is not None else None, out=out,
+                                         relu=relu, drop_p=drop_p, seed=seed, step_ctr=self.step_ctr if drop_p > 0.0 else None)
             self.bn_modules.append(bn)
         else:
             ss, save = ops.bn_eval_scale_shift(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps,
                                                want_save=True)
             count = count_local
-        a = ops.bn_apply(y.t, ss, res=res.t if res is not None else None, out=out, relu=relu, drop_p=drop_p, seed=seed,
-                         step_ctr=self.step_ctr if drop_p > 0.0 else None)
+            a = ops.bn_apply(y.t, ss, res=res.t if res is not None else None, out=out, relu=relu, drop_p=drop_p, seed=seed,
+                             step_ctr=self.step_ctr if drop_p > 0.0 else None)
         aa = Act(a)
         if self.record:
             def bwd():
@@ -287,7 +311,8 @@ class Tape:
                     self.grads[bn.bias] = torch.empty(C, dtype=torch.float32, device=a.device)
                 sums = ops.bn_bwd_reduce(da, a, y.t, save, relu=relu, drop_p=drop_p,
                                          dgamma=self.grads[bn.weight] if want_pg else None,
-                                         dbeta=self.grads[bn.bias] if want_pg else None, accumulate=acc_pg)
+                                         dbeta=self.grads[bn.bias] if want_pg else None, accumulate=acc_pg,
+                                         zero_scratch=self.zalloc(ops.bn_bwd_reduce_scratch_floats(C), a.device))
                 gsums = sums
                 if not use_batch_stats:
                     gsums = torch.zeros_like(sums)  # frozen BN (freeze_bn): dx = gamma * inv_std * dz

@@ -272,7 +272,8 @@ class _EngineModel(BaseModel):
             ctr = self._step_ctr
             ops.counter_add(ctr, 1)  # device-side: stays correct when the step is replayed from a CUDA graph
         return Tape(training, record=record, impl=self.conv_impl, dropout=self.engine_dropout, seed=self.engine_seed,
-                    sync=self.bn_sync, clamp_eps=self.syncbn_clamp_eps, step_ctr=ctr)
+                    sync=self.bn_sync, clamp_eps=self.syncbn_clamp_eps, step_ctr=ctr,
+                    arena_floats=getattr(self, "_arena_floats", 0) if training else 0, owner=self)
 
     def _cbr(self, tape, x, name, conv, bn, relu=True, res=None, out=None, drop_p=0.0):
         y, st = tape.conv(x, self._spec(name, conv), want_stats=True)

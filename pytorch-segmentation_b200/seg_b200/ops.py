@@ -21,6 +21,13 @@ def _meta(d):
     return (d.N, d.H, d.W, d.C, d.K, d.R, d.stride, d.dil, 2.0 * d.N * d.P * d.Q * d.K * d.C * d.R * d.S)
 
 
+def _meta_rows(M, C, passes, flag=0):
+    """Trace metadata of a streaming kernel: (rows, channels, flag) and its algorithmic bytes (bf16 passes over M x C)."""
+    if lib.TRACE is None:
+        return None
+    return (int(M), int(C), int(flag), 0, 0, 0, 0, 0, 2.0 * M * C * passes)
+
+
 def _prof(kind, d):
     """Context helper: CUDA events on the launching stream around one conv launch (bench.py's roofline leg)."""
     if PROFILE is None:
@@ -233,15 +240,35 @@ def counter_add(ctr, inc=1):
     call("seg_counter_add", ptr(ctr), int(inc))
 
 
-def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False):
-    """Returns sums [2C] = (sum dz, sum dz*xhat); optionally writes the parameter gradients from them."""
+def bn_bwd_reduce_scratch_floats(C):
+    return int(lib.load().seg_bn_bwd_reduce_scratch_floats(0, C))
+
+
+def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, zero_scratch=None):
+    """Returns sums [2C] = (sum dz, sum dz*xhat); optionally writes the parameter gradients from them.
+    zero_scratch: bn_bwd_reduce_scratch_floats(C) ZEROED floats -> one launch (the last block folds the slot rows)."""
     C = x.shape[-1]
     M = rows(x)
     sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
-    scratch = torch.empty(int(lib.load().seg_bn_bwd_reduce_scratch_floats(M, C)), dtype=torch.float32, device=x.device)
+    scratch = zero_scratch if zero_scratch is not None else torch.empty(bn_bwd_reduce_scratch_floats(C), dtype=torch.float32, device=x.device)
     call("seg_bn_bwd_reduce", ptr(dout), ld(dout), ptr(out), ld(out) if out is not None else 0, ptr(x), ld(x), ptr(save),
-         M, C, int(relu), float(drop_p), ptr(sums), ptr(scratch), ptr(dgamma), ptr(dbeta), int(accumulate))
+         M, C, int(relu), float(drop_p), ptr(sums), ptr(scratch), ptr(dgamma), ptr(dbeta), int(accumulate),
+         int(zero_scratch is not None), meta=_meta_rows(M, C, 3 if relu else 2))
     return sums
+
+
+def bn_apply_train(x, stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var, res=None, out=None,
+                   relu=True, drop_p=0.0, seed=0, step_ctr=None):
+    """Training-mode BN (+residual, ReLU, dropout) straight from the batch sums.  Returns (out, save[2C])."""
+    C = x.shape[-1]
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    save = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+    call("seg_bn_apply_train", ptr(x), ld(x), ptr(stats), float(count), ptr(gamma), ptr(beta), float(eps), float(momentum),
+         int(clamp_eps), ptr(running_mean), ptr(running_var), ptr(save), ptr(res), ld(res) if res is not None else 0,
+         ptr(out), ld(out), rows(x), C, int(relu), float(drop_p), int(seed), ptr(step_ctr),
+         meta=_meta_rows(rows(x), C, 3 if res is not None else 2, res is not None))
+    return out, save
 
 
 def bn_bwd_apply(dout, out, x, save, gamma, sums, count, relu=True, drop_p=0.0, dx=None, dres=None, beta_res=0.0):
@@ -250,7 +277,8 @@ def bn_bwd_apply(dout, out, x, save, gamma, sums, count, relu=True, drop_p=0.0, 
         dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     call("seg_bn_bwd_apply", ptr(dout), ld(dout), ptr(out), ld(out) if out is not None else 0, ptr(x), ld(x), ptr(save),
          ptr(gamma), ptr(sums), float(count), rows(x), C, int(relu), float(drop_p), ptr(dx), ld(dx), ptr(dres),
-         ld(dres) if dres is not None else 0, float(beta_res))
+         ld(dres) if dres is not None else 0, float(beta_res),
+         meta=_meta_rows(rows(x), C, (3 if relu else 2) + 1 + (0 if dres is None else (2 if beta_res != 0.0 else 1)), dres is not None))
     return dx
 
 

@@ -189,6 +189,16 @@ def bn_apply(x, ss, res=None, out=None, relu=True, drop_p=0.0, seed=0, step_ctr=
     return _store(out, v)
 
 
+def bn_apply_train(x, stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var, res=None, out=None,
+                   relu=True, drop_p=0.0, seed=0, step_ctr=None):
+    ss, save = bn_finalize(stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var)
+    return bn_apply(x, ss, res=res, out=out, relu=relu, drop_p=drop_p, seed=seed, step_ctr=step_ctr), save
+
+
+def bn_bwd_reduce_scratch_floats(C):
+    return 32 * C + 4
+
+
 def _dz(dout, out, relu, drop_p):
     dz = dout.float()
     if relu:
@@ -196,7 +206,7 @@ def _dz(dout, out, relu, drop_p):
     return dz
 
 
-def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False):
+def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, zero_scratch=None):
     C = x.shape[-1]
     dz = _dz(dout, out, relu, drop_p).reshape(-1, C)
     xhat = ((x.float() - save[:C]) * save[C:]).reshape(-1, C)

