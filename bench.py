@@ -233,20 +233,29 @@ def main():
     value = world * B * K / (ms_total * 1e-3)
 
     # roofline of the dominant kernel family (tcgen05 implicit-GEMM conv: fprop + dgrad + wgrad launches)
-    conv_ms = sum(a.elapsed_time(b) for _, _, a, b in prof)
-    conv_flops = sum(f for _, f, _, _ in prof)
+    conv_ms = sum(a.elapsed_time(b) for _, _, a, b, _ in prof)
+    conv_flops = sum(f for _, f, _, _, _ in prof)
+    conv_bytes = sum(nb for _, _, _, _, nb in prof)
     by_kind = {}
-    for kind, f, a, b in prof:
+    for kind, f, a, b, _ in prof:
         d = by_kind.setdefault(kind, [0.0, 0.0, 0])
         d[0] += f
         d[1] += a.elapsed_time(b)
         d[2] += 1
     peak_tf, peak_hbm, peak_src = measured_peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic_r01.json")
+    if os.path.exists(tpath):  # dram__bytes_read+write per conv launch from the committed ncu launch list of this workload
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/roofline_traffic_r01.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over %d conv launches)" % tj.get("launches", 0)
     roofline = {
         "bound": "tensor", "kernel": "conv_gemm_tc<BN,KIND> (tcgen05 implicit GEMM; fprop+dgrad+wgrad launches)",
         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src,
-        "traffic": None, "launches": len(prof), "conv_share_of_step": (conv_ms / conv_steps) / (ms_total / K) if ms_total else None,
+        "traffic": traffic, "traffic_unit": "bytes/launch (DRAM)", "traffic_source": traffic_src,
+        "algorithmic_bytes_per_launch": conv_bytes / max(len(prof), 1), "algorithmic_flops_per_launch": conv_flops / max(len(prof), 1),
+        "launches": len(prof), "conv_share_of_step": (conv_ms / conv_steps) / (ms_total / K) if ms_total else None,
         "timed_on": "the timed steps" if not use_graph else "2 eager steps after the graph-replayed timed region (identical kernels)",
         "by_kind_tflops": {k: (v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0) for k, v in by_kind.items()},
         "whole_step_frac_of_peak": value / world * TRAIN_GFLOP_PER_IMG / 1e3 / peak_tf,

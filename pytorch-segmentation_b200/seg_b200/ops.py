@@ -34,7 +34,9 @@ def _prof(kind, d):
         return None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     flops = 2.0 * d.N * d.P * d.Q * d.K * d.C * d.R * d.S
-    PROFILE.append((kind, flops, e0, e1))
+    # algorithmic bytes of the launch: both bf16 activation operands once + the weights (bf16 fprop/dgrad, fp32 wgrad output)
+    nbytes = 2.0 * (d.N * d.H * d.W * d.C + d.N * d.P * d.Q * d.K) + (4.0 if kind == "wgrad" else 2.0) * d.K * d.C * d.R * d.S
+    PROFILE.append((kind, flops, e0, e1, nbytes))
     e0.record()
     return e1
 
