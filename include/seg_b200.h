@@ -198,6 +198,11 @@ int64_t seg_lovasz_workspace_bytes(int64_t P, int n_present, int C);
 int seg_lovasz_softmax_nchw(const float* logits, const int64_t* target, int N, int C, int H, int W, int64_t ignore_index,
                             const int32_t* counts, int64_t P, int n_present, void* keys0, void* keys1, void* workspace,
                             float* loss, float* dlogits, void* stream);
+/* eval_metrics (utils/metrics.py:42-67: argmax, batch_pix_accuracy :41-45, batch_intersection_union :47-57) in one
+ * pass over the NCHW fp32 logits.  out: int64 [2 + 3*num_class] (zeroed here) = correct, labeled, area_inter[K],
+ * area_pred[K], area_lab[K]; union = pred + lab - inter.  Integer counters: bit-exact with the reference. */
+int seg_eval_metrics_nchw(const float* logits, const int64_t* target, int N, int C, int H, int W, int num_class,
+                          int64_t* out, void* stream);
 /* fused: bilinear upsample (low-res NHWC fp32 logits) + log-softmax + NLL, no full-res logits in HBM.
  * Also emits the arg-max label map (int32 [N,Ho,Wo], lowest index wins ties) when argmax != NULL. */
 int seg_upsample_ce_fwd(const float* logits_lo, const int64_t* target, int N, int Hi, int Wi, int Ho, int Wo, int C,

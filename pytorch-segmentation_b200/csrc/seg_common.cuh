@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 #include <atomic>
+#include <cstdlib>
+#include <cstring>
 #include "../../include/seg_b200.h"
 
 namespace seg {
@@ -75,6 +77,42 @@ __device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t idx) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   z = z ^ (z >> 31);
   return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// The hot kernels of the train step are launched with the programmatic-stream-serialization attribute: their CTAs may be
+// scheduled, and run their prologue, while the previous kernel in the stream drains.  Every such kernel executes
+// pdl_wait() before its first global-memory access (it returns once the previous grid has COMPLETED and flushed), so the
+// data flow is unchanged; pdl_trigger() at the top lets the next kernel do the same with this one.  Both instructions
+// are no-ops in a kernel launched the ordinary way.  MEASURED (profiles/pdl_ab_r01.txt): inside the CUDA-graph replay of
+// the step the launch gaps are already hidden — PDL gave 24.54 ms vs 24.24 ms without (early trigger: 25.43 ms) — so it
+// is OFF by default; SEG_PDL=1 in the environment turns it on.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SEG_PDL");
+    v = e ? atoi(e) : 0;
+  }
+  return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 inline int num_sms() {

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_tc(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_wait();  // setup above overlapped the previous kernel's tail; global memory is touched only from here on
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_tc(const __grid_constant__
         umma_commit(empty_bar(st));  // frees the smem slot when these MMAs retire
       }
       umma_commit(tmem_full_bar);  // accumulator complete
+      pdl_trigger();               // loads and MMAs of this CTA are issued: dependents may be scheduled
     }
   } else {
     // =============================== epilogue (warps 2..5) ===============================
@@ -492,7 +494,7 @@ static int launch_kernel(const TcParams& p, dim3 grid, cudaStream_t stream) {
     SEG_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(smem=%d): %s", Cfg<BN, STAGES>::SMEM, cudaGetErrorString(e));
     attr_set = true;
   }
-  kfn<<<grid, NTHREADS, Cfg<BN, STAGES>::SMEM, stream>>>(p);
+  launch_pdl(kfn, grid, dim3(NTHREADS), (size_t)Cfg<BN, STAGES>::SMEM, stream, p);
   return check_launch("conv_gemm_tc");
 }
 

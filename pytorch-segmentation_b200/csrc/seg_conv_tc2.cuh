@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_wait();  // setup above overlapped the previous kernel's tail; global memory is touched only from here on
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_cons
         }
         umma_commit(tfull_bar(b));
       }
+      pdl_trigger();  // this CTA's loads and MMAs are all issued: the next kernel's CTAs may take their places now
     }
   } else {
     // =============================== epilogue (warps 2..9) ===============================
@@ -364,7 +366,7 @@ static int launch_v2_impl(const TcParams& p, cudaStream_t stream) {
   // hot and the BN-statistics accumulators are flushed once per CTA instead of once per tile
   if (n_tiles <= grid) grid = (grid / n_tiles) * n_tiles;
   if ((int64_t)grid > num_tiles) grid = (int)num_tiles;
-  kfn<<<grid, V2_THREADS, V2_SMEM, stream>>>(p);
+  launch_pdl(kfn, dim3(grid), dim3(V2_THREADS), (size_t)V2_SMEM, stream, p);
   return check_launch("conv_gemm_tc2");
 }
 

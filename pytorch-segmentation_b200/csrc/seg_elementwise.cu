@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
                                                        int ldr, __nv_bfloat16* __restrict__ out, int ldo, int64_t M, int C,
                                                        int relu, float drop_p, uint64_t seed,
                                                        const uint64_t* __restrict__ step_ctr, const BnTrain tr) {
+  pdl_wait();
   const RowMap rm = row_map(C);
   if (!rm.active) return;
   if (step_ctr) seed += (*step_ctr) * 0x9E3779B97F4A7C15ull;  // device-side step counter keeps CUDA-graph replays fresh
@@ -364,6 +365,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
       *reinterpret_cast<bf16x8*>(out + r * ldo + co) = pack8(f);
     }
   }
+  pdl_trigger();
 }
 
 __global__ void __launch_bounds__(256)
@@ -371,6 +373,7 @@ __global__ void __launch_bounds__(256)
                          const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save, int64_t M, int C,
                          int relu, float drop_p, float* __restrict__ sums, unsigned int* ticket, float* final_sums,
                          float* dgamma, float* dbeta, int accumulate) {
+  pdl_wait();
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const RowMap rm = row_map(C);
   float mean[8], istd[8];
@@ -396,6 +399,7 @@ __global__ void __launch_bounds__(256)
       acc[1][i] += dz[i] * (xv[i] - mean[i]) * istd[i];
     }
   });
+  pdl_trigger();
   if (ticket == nullptr) return;
   // single-launch mode (slot rows pre-zeroed by the caller): the last block to finish folds the slot rows
   __shared__ bool last;
@@ -429,6 +433,7 @@ __global__ void __launch_bounds__(256)
                         const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count, int64_t M, int C,
                         int relu, float drop_p, __nv_bfloat16* __restrict__ dx, int lddx, __nv_bfloat16* dres, int lddres,
                         float beta_res) {
+  pdl_wait();
   const RowMap rm = row_map(C);
   if (!rm.active) return;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -479,6 +484,7 @@ __global__ void __launch_bounds__(256)
     for (int j = 0; j < 8; ++j) o8[j] = fmaf(cA[j], dz[j], fmaf(cB[j], xv[j], cC[j]));
     *reinterpret_cast<bf16x8*>(dx + row * lddx + co) = pack8(o8);
   }
+  pdl_trigger();
 }
 
 // stage 2 of the BN backward reduction: sums[a][c] = sum_b partial[b][a][c]; optionally the parameter gradients
@@ -1113,8 +1119,8 @@ int seg_bn_apply(const void* x, int ldx, const float* ss, const void* res, int l
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldr % 8 == 0), "bn_apply: alignment");
   BnTrain tr;
   memset(&tr, 0, sizeof(tr));
-  bn_apply_kernel<<<rowmap_grid(M, C), 256, 0, ST(stream)>>>(CBF(x), ldx, ss, CBF(res), ldr, BF(out), ldo, M, C, relu,
-                                                                drop_p, seed, step_ctr, tr);
+  launch_pdl(bn_apply_kernel, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(x), ldx, ss, CBF(res), ldr, BF(out), ldo, M, C, relu,
+             drop_p, seed, step_ctr, tr);
   return check_launch("bn_apply");
 }
 int seg_bn_apply_train(const void* x, int ldx, const float* stats, double count, const float* gamma, const float* beta,
@@ -1124,8 +1130,8 @@ int seg_bn_apply_train(const void* x, int ldx, const float* stats, double count,
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldr % 8 == 0), "bn_apply_train: alignment");
   SEG_REQUIRE(stats && gamma && beta && save && count > 0, "bn_apply_train: stats, gamma, beta, save required");
   BnTrain tr = {stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var, save};
-  bn_apply_kernel<<<rowmap_grid(M, C), 256, 0, ST(stream)>>>(CBF(x), ldx, nullptr, CBF(res), ldr, BF(out), ldo, M, C, relu,
-                                                                drop_p, seed, step_ctr, tr);
+  launch_pdl(bn_apply_kernel, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(x), ldx, (const float*)nullptr, CBF(res), ldr, BF(out),
+             ldo, M, C, relu, drop_p, seed, step_ctr, tr);
   return check_launch("bn_apply_train");
 }
 // reductions end with a block fold + 16 C atomics per block: fewer blocks still (>= 32 rows per thread)
@@ -1139,9 +1145,9 @@ int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, cons
   SEG_REQUIRE(scratch != nullptr, "bn_bwd_reduce: scratch of seg_bn_bwd_reduce_scratch_floats(M, C) floats required");
   const dim3 grid = reduce2_grid(M, C);
   if (scratch_is_zero) {  // one launch: the last block folds the slot rows (ticket counter behind them)
-    bn_bwd_reduce_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p,
-                                                       scratch, reinterpret_cast<unsigned int*>(scratch + (size_t)REDUCE_SLOTS * 2 * C),
-                                                       sums, dgamma, dbeta, accumulate);
+    launch_pdl(bn_bwd_reduce_kernel, grid, dim3(256), 0, ST(stream), CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu,
+               drop_p, scratch, reinterpret_cast<unsigned int*>(scratch + (size_t)REDUCE_SLOTS * 2 * C), sums, dgamma, dbeta,
+               accumulate);
     return check_launch("bn_bwd_reduce");
   }
   cudaMemsetAsync(scratch, 0, (size_t)REDUCE_SLOTS * 2 * C * sizeof(float), ST(stream));
@@ -1155,9 +1161,8 @@ int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const
                      const float* gamma, const float* sums, double count, int64_t M, int C, int relu, float drop_p,
                      void* dx, int lddx, void* dres, int lddres, float beta_res, void* stream) {
   SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0, "bn_bwd_apply: alignment");
-  bn_bwd_apply_kernel<<<rowmap_grid(M, C), 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, gamma,
-                                                                    sums, (float)(1.0 / count), M, C, relu, drop_p, BF(dx),
-                                                                    lddx, BF(dres), lddres, beta_res);
+  launch_pdl(bn_bwd_apply_kernel, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save,
+             gamma, sums, (float)(1.0 / count), M, C, relu, drop_p, BF(dx), lddx, BF(dres), lddres, beta_res);
   return check_launch("bn_bwd_apply");
 }
 int seg_bn_param_grad(const float* sums, int C, float* dgamma, float* dbeta, int accumulate, void* stream) {

@@ -374,3 +374,62 @@ int seg_upsample_ce_bwd(const float* logits_lo, const int64_t* target, int N, in
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ eval_metrics (utils/metrics.py:42-67)
+// One pass over the NCHW fp32 logits: per-pixel argmax, pixel accuracy and the per-class histograms the reference gets
+// from three torch.histc calls — integer counters, bit-exact.  out (int64, pre-zeroed by the entry point):
+//   [0] correct  [1] labeled  [2 .. 2+K) area_inter  [2+K .. 2+2K) area_pred  [2+2K .. 2+3K) area_lab      (K = num_class)
+namespace seg {
+__global__ void __launch_bounds__(256)
+    eval_metrics_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target, int N, int C, int64_t HW, int K,
+                        unsigned long long* __restrict__ out) {
+  extern __shared__ unsigned int hist[];  // [3][K] + correct + labeled
+  for (int i = threadIdx.x; i < 3 * K + 2; i += blockDim.x) hist[i] = 0u;
+  __syncthreads();
+  const int64_t total = (int64_t)N * HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = target[i];
+    if (t < 0 || t >= K) continue;  // labeled = (target+1 > 0) & (target+1 <= num_class)
+    const int n = (int)(i / HW);
+    const float* l = logits + (int64_t)n * C * HW + (i - (int64_t)n * HW);
+    float best = l[0];
+    int arg = 0;
+    for (int c = 1; c < C; ++c) {
+      const float v = l[(int64_t)c * HW];
+      if (v > best) {  // first maximum wins, like torch.max
+        best = v;
+        arg = c;
+      }
+    }
+    atomicAdd(&hist[3 * K + 1], 1u);
+    if (arg < K) atomicAdd(&hist[K + arg], 1u);  // area_pred (histc range [1, K] on predict+1)
+    atomicAdd(&hist[2 * K + (int)t], 1u);         // area_lab
+    if (arg == (int)t) {
+      atomicAdd(&hist[3 * K], 1u);
+      atomicAdd(&hist[(int)t], 1u);  // area_inter
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * K + 2; i += blockDim.x) {
+    const unsigned int v = hist[i];
+    if (v == 0u) continue;
+    const int dst = (i == 3 * K) ? 0 : (i == 3 * K + 1) ? 1 : 2 + i;
+    atomicAdd(out + dst, (unsigned long long)v);
+  }
+}
+}  // namespace seg
+
+extern "C" int seg_eval_metrics_nchw(const float* logits, const int64_t* target, int N, int C, int H, int W, int num_class,
+                                     int64_t* out, void* stream) {
+  using namespace seg;
+  SEG_REQUIRE(N > 0 && C > 0 && num_class > 0 && num_class <= 4096, "eval_metrics: bad sizes (C=%d num_class=%d)", C, num_class);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(out, 0, (size_t)(2 + 3 * num_class) * sizeof(int64_t), st);
+  const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  eval_metrics_kernel<<<(unsigned)blocks, 256, (size_t)(3 * num_class + 2) * sizeof(unsigned int), st>>>(
+      logits, target, N, C, HW, num_class, reinterpret_cast<unsigned long long*>(out));
+  return check_launch("eval_metrics");
+}

@@ -14,6 +14,8 @@ _LAZY = {
     "DiceLoss": ("losses", "DiceLoss"),
     "CE_DiceLoss": ("losses", "CE_DiceLoss"),
     "LovaszSoftmax": ("losses", "LovaszSoftmax"),
+    "eval_metrics": ("metrics", "eval_metrics"),
+    "AverageMeter": ("metrics", "AverageMeter"),
     "FusedTrainStep": ("train", "FusedTrainStep"),
 }
 

@@ -415,6 +415,15 @@ def lovasz_softmax_nchw(logits, target, ignore_index):
     return loss, dl
 
 
+def eval_metrics_nchw(logits, target, num_class):
+    """int64 device vector [2 + 3K]: correct, labeled, area_inter[K], area_pred[K], area_lab[K]."""
+    N, C, H, W = logits.shape
+    assert logits.is_contiguous() and logits.dtype == torch.float32 and target.dtype == torch.int64 and target.is_contiguous()
+    out = torch.empty(2 + 3 * num_class, dtype=torch.int64, device=logits.device)
+    call("seg_eval_metrics_nchw", ptr(logits), ptr(target), N, C, H, W, int(num_class), ptr(out))
+    return out
+
+
 def upsample_ce_fwd(logits_lo, target, align_corners, ignore_index, want_argmax=False):
     N, Hi, Wi, C = logits_lo.shape
     _, Ho, Wo = target.shape

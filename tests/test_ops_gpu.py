@@ -447,3 +447,24 @@ def test_lovasz_softmax_matches_reference_golden_and_oracle(gpu_out_dir):
     l3 = seg_b200.LovaszSoftmax(ignore_index=255)(lg, torch.full((3, 61, 67), 255, dtype=torch.long, device="cuda"))
     l3.backward()
     assert float(l3) == 0.0 and float(lg.grad.abs().max()) == 0.0
+
+
+def test_eval_metrics_bit_exact_vs_reference_golden_and_oracle(gpu_out_dir):
+    """seg_b200.eval_metrics (one device pass, utils/metrics.py:59-67) — integer counters, bit-exact."""
+    import numpy as np
+    import seg_b200
+    from oracle import metrics as om
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics.npz"))
+    for tag, K in (("c7", 7), ("c19", 19), ("c150", 150)):
+        out = seg_b200.eval_metrics(torch.from_numpy(g[f"{tag}/logits"]).cuda(), torch.from_numpy(g[f"{tag}/target"]).cuda(), K)
+        assert int(out[0]) == int(g[f"{tag}/correct"]) and int(out[1]) == int(g[f"{tag}/labeled"]), tag
+        assert np.array_equal(out[2], g[f"{tag}/inter"]) and np.array_equal(out[3], g[f"{tag}/union"]), tag
+    gen = torch.Generator().manual_seed(77)
+    lo = torch.randn(4, 21, 129, 131, generator=gen)
+    tt = torch.randint(0, 21, (4, 129, 131), generator=gen)
+    tt[:, :7] = 255
+    lo.scatter_add_(1, tt.clamp(0, 20).unsqueeze(1), (torch.rand(4, 1, 129, 131, generator=gen) < 0.5).float() * 5)
+    ref = om.eval_metrics(lo.numpy(), tt.numpy(), 21)
+    out = seg_b200.eval_metrics(lo.cuda(), tt.cuda(), 21)
+    for a, b in zip(out, ref):
+        assert np.array_equal(np.asarray(a), np.asarray(b))

@@ -135,3 +135,14 @@ def test_state_dict_inventory():
     names = set(om.param_names(sd))
     n = sum(v.numel() for k, v in sd.items() if k in names)
     assert n == 51444710  # tutorial.ipynb:5408, the reference's one published golden scalar
+
+
+def test_eval_metrics_oracle_matches_reference_golden():
+    """oracle/metrics.py (restatement of utils/metrics.py:41-67) against values produced by the reference itself."""
+    from oracle import metrics as om
+    g = np.load(os.path.join(GOLD, "metrics.npz"))
+    for tag, K in (("c7", 7), ("c19", 19), ("c150", 150)):
+        out = om.eval_metrics(g[f"{tag}/logits"], g[f"{tag}/target"], K)
+        assert int(out[0]) == int(g[f"{tag}/correct"]) and int(out[1]) == int(g[f"{tag}/labeled"]), tag
+        assert np.array_equal(out[2], g[f"{tag}/inter"]) and np.array_equal(out[3], g[f"{tag}/union"]), tag
+        assert int(out[0]) > 0 and out[2].sum() == out[0]  # the vectors exercise the counters

@@ -15,7 +15,9 @@ import sys
 from seg_b200 import launch
 launch.setup_paths('/root/reference')
 import models, seg_b200
-from utils import losses, lr_scheduler, helpers
+from utils import losses, lr_scheduler, helpers, metrics
+assert metrics.eval_metrics is seg_b200.eval_metrics and metrics.AverageMeter is seg_b200.AverageMeter
+assert hasattr(metrics, 'batch_pix_accuracy') and losses.LovaszSoftmax is seg_b200.LovaszSoftmax
 assert models.DeepLab is seg_b200.DeepLab and models.PSPNet is seg_b200.PSPNet, (models.DeepLab, models.PSPNet)
 assert models.UNet.__module__.endswith('unet') and 'reference' in models.UNet.__init__.__code__.co_filename
 assert losses.CrossEntropyLoss2d is seg_b200.CrossEntropyLoss2d
