@@ -127,6 +127,37 @@ def cpu_port_step_time(batch, steps, warmup, threads):
     return sum(times) / len(times)
 
 
+def gpu_aten_step_time(batch, steps, warmup, device):
+    """The reference's OWN GPU path on this box: the oracle port (the same ATen modules/functions the reference calls —
+    cuDNN convolutions, ATen batch-norm, bilinear, CE, torch.optim.SGD; fp32, NCHW, cudnn.benchmark as trainer.py:35 sets)
+    on one B200.  Informational denominator for BASELINE.json's "x the reference's cuDNN-backed GPU images/sec"."""
+    from oracle import losses as ol
+    from oracle import models as om
+    from oracle import weights
+    torch.backends.cudnn.benchmark = True
+    sd0 = weights.deeplab_resnet_state_dict(NUM_CLASSES, "resnet101", seed=0)
+    sd = om.clone_sd({k: v.to(device) for k, v in sd0.items()}, requires_grad=True)
+    names = om.param_names(sd)
+    bb = [sd[n] for n in names if n.startswith("backbone.")]
+    dec = [sd[n] for n in names if not n.startswith("backbone.")]
+    opt = torch.optim.SGD([{"params": dec}, {"params": bb, "lr": 0.001}], lr=0.01, momentum=0.9, weight_decay=1e-4)
+    x, y = synthetic_batch(batch, 1234)
+    x, y = x.to(device), y.to(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(warmup + steps):
+        if i == warmup:
+            torch.cuda.synchronize()
+            e0.record()
+        opt.zero_grad()
+        out = om.deeplab_forward(sd, x, backbone="resnet101", train=True, dropout=True)
+        loss = ol.cross_entropy2d(out, y, IGNORE)
+        loss.backward()
+        opt.step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / steps
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -156,6 +187,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gpu-aten", action="store_true", help="skip the informational ATen/cuDNN timing of the oracle port on the GPU")
     ap.add_argument("--backbone", default="resnet101")
     ap.add_argument("--graph", type=int, default=int(os.environ.get("SEG_CUDA_GRAPH", "1")), help="replay the fused step from a CUDA graph")
     ap.add_argument("--trace", default=None, help="after the timed runs, trace 2 steps per C-ABI call and write a table here")
@@ -269,9 +301,28 @@ def main():
                               lr=0.01, momentum=0.9, weight_decay=1e-4)
         ddp_bufs = [p for p in model.parameters()]
 
+        # the reference's DataPrefetcher (base/base_dataloader.py:49-85) copies the NEXT batch on a side stream while the
+        # current step computes; same here: every step's batch still crosses PCIe once, inside the timed region
+        copy_stream = torch.cuda.Stream()
+        slots = [(torch.empty_like(x_dev), torch.empty_like(y_dev), torch.cuda.Event()) for _ in range(2)]
+        state = {"i": 0}
+
+        def prefetch(slot):
+            xd, yd, ev = slots[slot]
+            copy_stream.wait_stream(torch.cuda.current_stream())  # the slot's previous consumer has been enqueued
+            with torch.cuda.stream(copy_stream):
+                xd.copy_(x_pin, non_blocking=True)
+                yd.copy_(y_pin, non_blocking=True)
+                ev.record(copy_stream)
+
+        prefetch(0)
+
         def plugin_step():
-            xd = x_pin.to(dev, non_blocking=True)
-            yd = y_pin.to(dev, non_blocking=True)
+            cur = state["i"] & 1
+            state["i"] += 1
+            xd, yd, ev = slots[cur]
+            torch.cuda.current_stream().wait_event(ev)
+            prefetch(cur ^ 1)  # next step's batch, overlapped with this step's kernels
             opt.zero_grad(set_to_none=True)
             out = model(xd)
             l = crit(out, yd)
@@ -300,7 +351,7 @@ def main():
         ms_e2e = max_over_ranks(t0.elapsed_time(t1))
         e2e = {"value": world * B * Ke / (ms_e2e * 1e-3), "unit": "images/sec",
                "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 8), "d2h_bytes_per_step": 4,
-               "api": "seg_b200.DeepLab.forward -> seg_b200.CrossEntropyLoss2d -> backward -> torch.optim.SGD.step (train.py plugin surface)",
+               "api": "seg_b200.DeepLab.forward -> seg_b200.CrossEntropyLoss2d -> backward -> torch.optim.SGD.step (train.py plugin surface); batch prefetched on a side stream like the reference's DataPrefetcher",
                "ms_per_step": ms_e2e / Ke}
 
     if args.trace and rank == 0:
@@ -335,6 +386,15 @@ def main():
         t = cpu_port_step_time(args.cpu_batch, 2, 1, threads)
         cpu_baseline = {"value": args.cpu_batch / t, "unit": "images/sec", "cores": threads, "kind": "port",
                         "sample": f"2 timed steps (after 1 warm-up) of batch {args.cpu_batch} of the same 513x513 train step, fp32 oracle port, {threads} threads"}
+        if not args.no_gpu_aten:
+            try:  # same leg, same port, on the GPU through ATen/cuDNN: what the reference itself would run on this B200
+                del stepper, model
+                torch.cuda.empty_cache()
+                tg = gpu_aten_step_time(B, 5, 3, dev)
+                cpu_baseline["reference_gpu_path"] = {"value": B / tg, "unit": "images/sec", "ms_per_step": tg * 1e3, "batch": B,
+                                                      "how": "oracle port on cuda:0 = the reference's ATen/cuDNN fp32 NCHW path (cudnn.benchmark), 5 timed steps after 3 warm-up, CUDA events"}
+            except Exception as e:  # informational only
+                cpu_baseline["reference_gpu_path"] = {"unavailable": repr(e)[:200]}
 
     if rank == 0:
         print(json.dumps({

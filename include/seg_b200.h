@@ -130,17 +130,21 @@ int seg_counter_add(uint64_t* ctr, uint64_t inc, void* stream);
  * dz = dout * (out>0) * 1/(1-drop_p) if relu.  scratch: seg_bn_bwd_reduce_scratch_floats(M, C) floats.  If given,
  * dbeta (=|+=) sums[0:C] and dgamma (=|+=) sums[C:2C] — the parameter gradients from the LOCAL sums.
  * scratch_is_zero != 0: the caller guarantees zeroed scratch (e.g. a per-step arena cleared once) and the reduction is
- * ONE launch — the last block to finish folds the slot rows; otherwise memset + reduce + fold (three stream ops). */
+ * ONE launch — the last block to finish folds the slot rows; otherwise memset + reduce + fold (three stream ops).
+ * out == NULL with relu (both backward passes): the ReLU mask is recomputed from x with the forward's own coefficients
+ * (sc = gamma/std, sh = fma(-mean, sc, beta)) instead of being read from the stored activation — valid for
+ * conv -> BN(batch statistics) -> ReLU with no residual and no dropout; needs gamma and beta. */
 int64_t seg_bn_bwd_reduce_scratch_floats(int64_t M, int C);
 int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx,
                       const float* save_mean_istd, int64_t M, int C, int relu, float drop_p, float* sums,
-                      float* scratch, float* dgamma, float* dbeta, int accumulate, int scratch_is_zero, void* stream);
+                      float* scratch, float* dgamma, float* dbeta, int accumulate, int scratch_is_zero,
+                      const float* gamma, const float* beta, void* stream);
 /* backward, pass 2: dx = gamma*istd*(dz - sums0/count - xhat*sums1/count); dres = beta_res*dres + dz (optional).
  * `sums` are the (possibly all-reduced) sums, `count` the matching element count. */
 int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx,
                      const float* save_mean_istd, const float* gamma, const float* sums, double count, int64_t M,
                      int C, int relu, float drop_p, void* dx, int lddx, void* dres, int lddres, float beta_res,
-                     void* stream);
+                     const float* beta, void* stream);
 /* parameter grads from the LOCAL sums: dbeta (=|+=) sums[0:C], dgamma (=|+=) sums[C:2C] */
 int seg_bn_param_grad(const float* sums, int C, float* dgamma, float* dbeta, int accumulate, void* stream);
 

@@ -372,14 +372,29 @@ __global__ void __launch_bounds__(256)
     bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ out, int ldo,
                          const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save, int64_t M, int C,
                          int relu, float drop_p, float* __restrict__ sums, unsigned int* ticket, float* final_sums,
-                         float* dgamma, float* dbeta, int accumulate) {
+                         float* dgamma, float* dbeta, int accumulate, const float* __restrict__ gamma,
+                         const float* __restrict__ beta) {
   pdl_wait();
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const RowMap rm = row_map(C);
-  float mean[8], istd[8];
+  // ReLU mask: from the stored activation, or (out == null: BN -> ReLU with nothing in between, training statistics)
+  // recomputed from x with exactly the forward's coefficients  sc = gamma*istd, sh = fma(-mean, sc, beta)  — one operand
+  // stream less to read
+  const bool remask = relu && out == nullptr;
+  float mean[8], istd[8], sc[8], sh[8];
   if (rm.active) {
     ld8(save + rm.g * 8, mean);
     ld8(save + C + rm.g * 8, istd);
+    if (remask) {
+      float gm[8], bt[8];
+      ld8(gamma + rm.g * 8, gm);
+      ld8(beta + rm.g * 8, bt);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sc[i] = gm[i] * istd[i];
+        sh[i] = fmaf(-mean[i], sc[i], bt[i]);
+      }
+    }
   }
   column_reduce<2, true>(M, C, sums, [&](int64_t row, int g, float(*acc)[8]) {
     float dz[8], xv[8];
@@ -387,7 +402,10 @@ __global__ void __launch_bounds__(256)
     const bf16x8 xx = *reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8);
     unpack8(dv, dz);
     unpack8(xx, xv);
-    if (relu) {
+    if (remask) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dz[i] = (fmaf(xv[i], sc[i], sh[i]) > 0.f) ? dz[i] : 0.f;
+    } else if (relu) {
       float o[8];
       unpack8(*reinterpret_cast<const bf16x8*>(out + row * ldo + g * 8), o);
 #pragma unroll
@@ -432,13 +450,14 @@ __global__ void __launch_bounds__(256)
                         const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save,
                         const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count, int64_t M, int C,
                         int relu, float drop_p, __nv_bfloat16* __restrict__ dx, int lddx, __nv_bfloat16* dres, int lddres,
-                        float beta_res) {
+                        float beta_res, const float* __restrict__ beta) {
   pdl_wait();
   const RowMap rm = row_map(C);
   if (!rm.active) return;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const int co = rm.g * 8;
-  float cA[8], cB[8], cC[8];
+  const bool remask = relu && out == nullptr;  // see bn_bwd_reduce_kernel
+  float cA[8], cB[8], cC[8], sc[8], sh[8];
   {
     float mean[8], istd[8], gm[8], s0[8], s1[8];
     ld8(save + co, mean);
@@ -453,6 +472,15 @@ __global__ void __launch_bounds__(256)
       cB[j] = -a * istd[j] * s1[j] * inv_count;
       cC[j] = -a * s0[j] * inv_count - cB[j] * mean[j];
     }
+    if (remask) {
+      float bt[8];
+      ld8(beta + co, bt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sc[j] = cA[j];
+        sh[j] = fmaf(-mean[j], sc[j], bt[j]);
+      }
+    }
   }
   const int64_t step = (int64_t)gridDim.x * rm.rows_par;
   for (int64_t row = (int64_t)blockIdx.x * rm.rows_par + rm.rl; row < M; row += step) {
@@ -461,7 +489,10 @@ __global__ void __launch_bounds__(256)
     const bf16x8 xx = *reinterpret_cast<const bf16x8*>(x + row * ldx + co);
     unpack8(dv, dz);
     unpack8(xx, xv);
-    if (relu) {
+    if (remask) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dz[j] = (fmaf(xv[j], sc[j], sh[j]) > 0.f) ? dz[j] : 0.f;
+    } else if (relu) {
       float o[8];
       unpack8(*reinterpret_cast<const bf16x8*>(out + row * ldo + co), o);
 #pragma unroll
@@ -1140,29 +1171,31 @@ int64_t seg_bn_bwd_reduce_scratch_floats(int64_t M, int C) { return (int64_t)RED
 
 int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,
                       int64_t M, int C, int relu, float drop_p, float* sums, float* scratch, float* dgamma, float* dbeta,
-                      int accumulate, int scratch_is_zero, void* stream) {
-  SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && (!relu || ldo % 8 == 0), "bn_bwd_reduce: alignment");
+                      int accumulate, int scratch_is_zero, const float* gamma, const float* beta, void* stream) {
+  SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && (!relu || !out || ldo % 8 == 0), "bn_bwd_reduce: alignment");
+  SEG_REQUIRE(!(relu && !out) || (gamma && beta && drop_p == 0.f), "bn_bwd_reduce: out == NULL (mask recomputed from x) needs gamma, beta and no dropout");
   SEG_REQUIRE(scratch != nullptr, "bn_bwd_reduce: scratch of seg_bn_bwd_reduce_scratch_floats(M, C) floats required");
   const dim3 grid = reduce2_grid(M, C);
   if (scratch_is_zero) {  // one launch: the last block folds the slot rows (ticket counter behind them)
     launch_pdl(bn_bwd_reduce_kernel, grid, dim3(256), 0, ST(stream), CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu,
                drop_p, scratch, reinterpret_cast<unsigned int*>(scratch + (size_t)REDUCE_SLOTS * 2 * C), sums, dgamma, dbeta,
-               accumulate);
+               accumulate, gamma, beta);
     return check_launch("bn_bwd_reduce");
   }
   cudaMemsetAsync(scratch, 0, (size_t)REDUCE_SLOTS * 2 * C * sizeof(float), ST(stream));
   bn_bwd_reduce_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p,
-                                                     scratch, nullptr, nullptr, nullptr, nullptr, 0);
+                                                     scratch, nullptr, nullptr, nullptr, nullptr, 0, gamma, beta);
   if (check_launch("bn_bwd_reduce")) return 1;
   bn_bwd_reduce_final_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(scratch, REDUCE_SLOTS, C, sums, dgamma, dbeta, accumulate);
   return check_launch("bn_bwd_reduce_final");
 }
 int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,
                      const float* gamma, const float* sums, double count, int64_t M, int C, int relu, float drop_p,
-                     void* dx, int lddx, void* dres, int lddres, float beta_res, void* stream) {
+                     void* dx, int lddx, void* dres, int lddres, float beta_res, const float* beta, void* stream) {
   SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0, "bn_bwd_apply: alignment");
+  SEG_REQUIRE(!(relu && !out) || (beta && drop_p == 0.f), "bn_bwd_apply: out == NULL (mask recomputed from x) needs beta and no dropout");
   launch_pdl(bn_bwd_apply_kernel, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save,
-             gamma, sums, (float)(1.0 / count), M, C, relu, drop_p, BF(dx), lddx, BF(dres), lddres, beta_res);
+             gamma, sums, (float)(1.0 / count), M, C, relu, drop_p, BF(dx), lddx, BF(dres), lddres, beta_res, beta);
   return check_launch("bn_bwd_apply");
 }
 int seg_bn_param_grad(const float* sums, int C, float* dgamma, float* dbeta, int accumulate, void* stream) {

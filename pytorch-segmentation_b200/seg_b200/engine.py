@@ -299,6 +299,9 @@ class Tape:
             a = ops.bn_apply(y.t, ss, res=res.t if res is not None else None, out=out, relu=relu, drop_p=drop_p, seed=seed,
                              step_ctr=self.step_ctr if drop_p > 0.0 else None)
         aa = Act(a)
+        # conv -> BN(batch statistics) -> ReLU with nothing in between: the backward passes recompute the ReLU mask from
+        # the conv output with the forward's own coefficients instead of re-reading the activation (one stream less)
+        remask = bool(use_batch_stats and relu and res is None and drop_p == 0.0)
         if self.record:
             def bwd():
                 da = aa.grad
@@ -309,7 +312,8 @@ class Tape:
                 if want_pg and not acc_pg:
                     self.grads[bn.weight] = torch.empty(C, dtype=torch.float32, device=a.device)
                     self.grads[bn.bias] = torch.empty(C, dtype=torch.float32, device=a.device)
-                sums = ops.bn_bwd_reduce(da, a, y.t, save, relu=relu, drop_p=drop_p,
+                a_mask = None if remask else a
+                sums = ops.bn_bwd_reduce(da, a_mask, y.t, save, relu=relu, drop_p=drop_p, gamma=bn.weight.detach(), beta=bn.bias.detach(),
                                          dgamma=self.grads[bn.weight] if want_pg else None,
                                          dbeta=self.grads[bn.bias] if want_pg else None, accumulate=acc_pg,
                                          zero_scratch=self.zalloc(ops.bn_bwd_reduce_scratch_floats(C), a.device))
@@ -323,8 +327,8 @@ class Tape:
                 dres, beta_res = (None, 0.0)
                 if res is not None and res.needs_grad:
                     dres, beta_res = res.grad_target()
-                ops.bn_bwd_apply(da, a, y.t, save, bn.weight.detach(), gsums, count, relu=relu, drop_p=drop_p, dx=dy, dres=dres,
-                                 beta_res=beta_res)
+                ops.bn_bwd_apply(da, a_mask, y.t, save, bn.weight.detach(), gsums, count, relu=relu, drop_p=drop_p, dx=dy, dres=dres,
+                                 beta_res=beta_res, beta=bn.bias.detach())
                 y.grad = dy
                 aa.grad = None
             self.back.append(bwd)

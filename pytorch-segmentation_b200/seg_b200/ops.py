@@ -246,16 +246,18 @@ def bn_bwd_reduce_scratch_floats(C):
     return int(lib.load().seg_bn_bwd_reduce_scratch_floats(0, C))
 
 
-def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, zero_scratch=None):
+def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, zero_scratch=None,
+                  gamma=None, beta=None):
     """Returns sums [2C] = (sum dz, sum dz*xhat); optionally writes the parameter gradients from them.
-    zero_scratch: bn_bwd_reduce_scratch_floats(C) ZEROED floats -> one launch (the last block folds the slot rows)."""
+    zero_scratch: bn_bwd_reduce_scratch_floats(C) ZEROED floats -> one launch (the last block folds the slot rows).
+    out=None (with relu, gamma, beta): the ReLU mask is recomputed from x instead of read from the stored activation."""
     C = x.shape[-1]
     M = rows(x)
     sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
     scratch = zero_scratch if zero_scratch is not None else torch.empty(bn_bwd_reduce_scratch_floats(C), dtype=torch.float32, device=x.device)
     call("seg_bn_bwd_reduce", ptr(dout), ld(dout), ptr(out), ld(out) if out is not None else 0, ptr(x), ld(x), ptr(save),
          M, C, int(relu), float(drop_p), ptr(sums), ptr(scratch), ptr(dgamma), ptr(dbeta), int(accumulate),
-         int(zero_scratch is not None), meta=_meta_rows(M, C, 3 if relu else 2))
+         int(zero_scratch is not None), ptr(gamma), ptr(beta), meta=_meta_rows(M, C, 3 if (relu and out is not None) else 2))
     return sums
 
 
@@ -273,14 +275,14 @@ def bn_apply_train(x, stats, count, gamma, beta, eps, momentum, clamp_eps, runni
     return out, save
 
 
-def bn_bwd_apply(dout, out, x, save, gamma, sums, count, relu=True, drop_p=0.0, dx=None, dres=None, beta_res=0.0):
+def bn_bwd_apply(dout, out, x, save, gamma, sums, count, relu=True, drop_p=0.0, dx=None, dres=None, beta_res=0.0, beta=None):
     C = x.shape[-1]
     if dx is None:
         dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     call("seg_bn_bwd_apply", ptr(dout), ld(dout), ptr(out), ld(out) if out is not None else 0, ptr(x), ld(x), ptr(save),
          ptr(gamma), ptr(sums), float(count), rows(x), C, int(relu), float(drop_p), ptr(dx), ld(dx), ptr(dres),
-         ld(dres) if dres is not None else 0, float(beta_res),
-         meta=_meta_rows(rows(x), C, (3 if relu else 2) + 1 + (0 if dres is None else (2 if beta_res != 0.0 else 1)), dres is not None))
+         ld(dres) if dres is not None else 0, float(beta_res), ptr(beta),
+         meta=_meta_rows(rows(x), C, (3 if (relu and out is not None) else 2) + 1 + (0 if dres is None else (2 if beta_res != 0.0 else 1)), dres is not None))
     return dx
 
 

@@ -199,16 +199,21 @@ def bn_bwd_reduce_scratch_floats(C):
     return 32 * C + 4
 
 
-def _dz(dout, out, relu, drop_p):
+def _dz(dout, out, relu, drop_p, x=None, save=None, gamma=None, beta=None):
     dz = dout.float()
-    if relu:
+    if relu and out is None:  # mask recomputed from x with the forward's coefficients
+        C = x.shape[-1]
+        sc = gamma * save[C:]
+        dz = dz * ((x.float() * sc + (beta - save[:C] * sc)) > 0)
+    elif relu:
         dz = dz * (out.float() > 0)
     return dz
 
 
-def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, zero_scratch=None):
+def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, zero_scratch=None,
+                  gamma=None, beta=None):
     C = x.shape[-1]
-    dz = _dz(dout, out, relu, drop_p).reshape(-1, C)
+    dz = _dz(dout, out, relu, drop_p, x, save, gamma, beta).reshape(-1, C)
     xhat = ((x.float() - save[:C]) * save[C:]).reshape(-1, C)
     sums = torch.cat([dz.sum(0), (dz * xhat).sum(0)])
     if dgamma is not None:
@@ -216,9 +221,9 @@ def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=
     return sums
 
 
-def bn_bwd_apply(dout, out, x, save, gamma, sums, count, relu=True, drop_p=0.0, dx=None, dres=None, beta_res=0.0):
+def bn_bwd_apply(dout, out, x, save, gamma, sums, count, relu=True, drop_p=0.0, dx=None, dres=None, beta_res=0.0, beta=None):
     C = x.shape[-1]
-    dz = _dz(dout, out, relu, drop_p)
+    dz = _dz(dout, out, relu, drop_p, x, save, gamma, beta)
     xhat = (x.float() - save[:C]) * save[C:]
     g = gamma * save[C:] * (dz - sums[:C] / count - xhat * sums[C:] / count)
     if dres is not None:

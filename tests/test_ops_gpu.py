@@ -216,6 +216,14 @@ def test_bn_train_fwd_bwd(C, M_shape, gpu_out_dir):
     check(f"bn_bwd_reduce single-launch C={C}", sums2, sums, 1e-5, gpu_out_dir)
     check(f"bn_dgamma accumulate C={C}", dg2 - 1.0, dgamma, 1e-4, gpu_out_dir)
     check(f"bn_dbeta accumulate C={C}", db2 - 1.0, dbeta, 1e-4, gpu_out_dir)
+    # no residual: the ReLU mask recomputed from x (out=None) gives the same sums / dx as the mask read from the activation
+    out3, save3 = ops.bn_apply_train(xd, stats, count, gd, bd, 1e-5, 0.1, 0, None, None, relu=True)
+    s_read = ops.bn_bwd_reduce(dyd, out3, xd, save3, relu=True)
+    s_re = ops.bn_bwd_reduce(dyd, None, xd, save3, relu=True, gamma=gd, beta=bd)
+    check(f"bn_bwd_reduce remask C={C}", s_re, s_read, 1e-5, gpu_out_dir)
+    dx_read = ops.bn_bwd_apply(dyd, out3, xd, save3, gd, s_read, count, relu=True)
+    dx_re = ops.bn_bwd_apply(dyd, None, xd, save3, gd, s_read, count, relu=True, beta=bd)
+    assert torch.equal(dx_re, dx_read)
 
 
 def test_bn_clamp_eps_and_eval(gpu_out_dir):
