@@ -282,7 +282,7 @@ struct BnTrain {
   float *running_mean, *running_var, *save;
 };
 
-__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+__global__ void __launch_bounds__(256, 4) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                        const float* __restrict__ ss, const __nv_bfloat16* __restrict__ res,
                                                        int ldr, __nv_bfloat16* __restrict__ out, int ldo, int64_t M, int C,
                                                        int relu, float drop_p, uint64_t seed,
@@ -368,6 +368,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
   pdl_trigger();
 }
 
+template <bool REMASK>
 __global__ void __launch_bounds__(256)
     bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ out, int ldo,
                          const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save, int64_t M, int C,
@@ -380,18 +381,19 @@ __global__ void __launch_bounds__(256)
   // ReLU mask: from the stored activation, or (out == null: BN -> ReLU with nothing in between, training statistics)
   // recomputed from x with exactly the forward's coefficients  sc = gamma*istd, sh = fma(-mean, sc, beta)  — one operand
   // stream less to read
-  const bool remask = relu && out == nullptr;
-  float mean[8], istd[8], sc[8], sh[8];
+  // 1/std is folded into the weights of the second sum's accumulation only where needed: the loop keeps (mean, and for
+  // REMASK sc, sh) in registers — 1/std scales the centred product, so it is applied through `wi` = istd per channel
+  float mean[8], wi[8], sc[REMASK ? 8 : 1], sh[REMASK ? 8 : 1];
   if (rm.active) {
     ld8(save + rm.g * 8, mean);
-    ld8(save + C + rm.g * 8, istd);
-    if (remask) {
+    ld8(save + C + rm.g * 8, wi);
+    if constexpr (REMASK) {
       float gm[8], bt[8];
       ld8(gamma + rm.g * 8, gm);
       ld8(beta + rm.g * 8, bt);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        sc[i] = gm[i] * istd[i];
+        sc[i] = gm[i] * wi[i];
         sh[i] = fmaf(-mean[i], sc[i], bt[i]);
       }
     }
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(256)
     const bf16x8 xx = *reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8);
     unpack8(dv, dz);
     unpack8(xx, xv);
-    if (remask) {
+    if constexpr (REMASK) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) dz[i] = (fmaf(xv[i], sc[i], sh[i]) > 0.f) ? dz[i] : 0.f;
     } else if (relu) {
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       acc[0][i] += dz[i];
-      acc[1][i] += dz[i] * (xv[i] - mean[i]) * istd[i];
+      acc[1][i] += dz[i] * (xv[i] - mean[i]) * wi[i];
     }
   });
   pdl_trigger();
@@ -445,6 +447,7 @@ __global__ void __launch_bounds__(256)
 }
 
 // dx = A*dz + B*x + Cc with A = gamma*istd, B = -gamma*istd^2*s1/count, Cc = -gamma*istd*s0/count + gamma*istd^2*mean*s1/count
+template <bool REMASK>
 __global__ void __launch_bounds__(256)
     bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ out, int ldo,
                         const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save,
@@ -456,8 +459,8 @@ __global__ void __launch_bounds__(256)
   if (!rm.active) return;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const int co = rm.g * 8;
-  const bool remask = relu && out == nullptr;  // see bn_bwd_reduce_kernel
-  float cA[8], cB[8], cC[8], sc[8], sh[8];
+  constexpr bool remask = REMASK;  // see bn_bwd_reduce_kernel
+  float cA[8], cB[8], cC[8], sh[REMASK ? 8 : 1];
   {
     float mean[8], istd[8], gm[8], s0[8], s1[8];
     ld8(save + co, mean);
@@ -472,14 +475,11 @@ __global__ void __launch_bounds__(256)
       cB[j] = -a * istd[j] * s1[j] * inv_count;
       cC[j] = -a * s0[j] * inv_count - cB[j] * mean[j];
     }
-    if (remask) {
+    if constexpr (REMASK) {
       float bt[8];
       ld8(beta + co, bt);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        sc[j] = cA[j];
-        sh[j] = fmaf(-mean[j], sc[j], bt[j]);
-      }
+      for (int j = 0; j < 8; ++j) sh[j] = fmaf(-mean[j], cA[j], bt[j]);  // forward: sc = gamma*istd (= cA), sh = fma(-mean, sc, beta)
     }
   }
   const int64_t step = (int64_t)gridDim.x * rm.rows_par;
@@ -489,9 +489,9 @@ __global__ void __launch_bounds__(256)
     const bf16x8 xx = *reinterpret_cast<const bf16x8*>(x + row * ldx + co);
     unpack8(dv, dz);
     unpack8(xx, xv);
-    if (remask) {
+    if constexpr (REMASK) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dz[j] = (fmaf(xv[j], sc[j], sh[j]) > 0.f) ? dz[j] : 0.f;
+      for (int j = 0; j < 8; ++j) dz[j] = (fmaf(xv[j], cA[j], sh[j]) > 0.f) ? dz[j] : 0.f;
     } else if (relu) {
       float o[8];
       unpack8(*reinterpret_cast<const bf16x8*>(out + row * ldo + co), o);
@@ -1177,14 +1177,18 @@ int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, cons
   SEG_REQUIRE(scratch != nullptr, "bn_bwd_reduce: scratch of seg_bn_bwd_reduce_scratch_floats(M, C) floats required");
   const dim3 grid = reduce2_grid(M, C);
   if (scratch_is_zero) {  // one launch: the last block folds the slot rows (ticket counter behind them)
-    launch_pdl(bn_bwd_reduce_kernel, grid, dim3(256), 0, ST(stream), CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu,
-               drop_p, scratch, reinterpret_cast<unsigned int*>(scratch + (size_t)REDUCE_SLOTS * 2 * C), sums, dgamma, dbeta,
-               accumulate, gamma, beta);
+    launch_pdl((relu && !out) ? bn_bwd_reduce_kernel<true> : bn_bwd_reduce_kernel<false>, grid, dim3(256), 0, ST(stream), CBF(dout),
+               lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p, scratch,
+               reinterpret_cast<unsigned int*>(scratch + (size_t)REDUCE_SLOTS * 2 * C), sums, dgamma, dbeta, accumulate, gamma, beta);
     return check_launch("bn_bwd_reduce");
   }
   cudaMemsetAsync(scratch, 0, (size_t)REDUCE_SLOTS * 2 * C * sizeof(float), ST(stream));
-  bn_bwd_reduce_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p,
-                                                     scratch, nullptr, nullptr, nullptr, nullptr, 0, gamma, beta);
+  if (relu && !out)
+    bn_bwd_reduce_kernel<true><<<grid, 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p,
+                                                             scratch, nullptr, nullptr, nullptr, nullptr, 0, gamma, beta);
+  else
+    bn_bwd_reduce_kernel<false><<<grid, 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p,
+                                                              scratch, nullptr, nullptr, nullptr, nullptr, 0, gamma, beta);
   if (check_launch("bn_bwd_reduce")) return 1;
   bn_bwd_reduce_final_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(scratch, REDUCE_SLOTS, C, sums, dgamma, dbeta, accumulate);
   return check_launch("bn_bwd_reduce_final");
@@ -1194,7 +1198,8 @@ int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const
                      void* dx, int lddx, void* dres, int lddres, float beta_res, const float* beta, void* stream) {
   SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0, "bn_bwd_apply: alignment");
   SEG_REQUIRE(!(relu && !out) || (beta && drop_p == 0.f), "bn_bwd_apply: out == NULL (mask recomputed from x) needs beta and no dropout");
-  launch_pdl(bn_bwd_apply_kernel, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save,
+  launch_pdl((relu && !out) ? bn_bwd_apply_kernel<true> : bn_bwd_apply_kernel<false>, rowmap_grid(M, C), dim3(256), 0, ST(stream),
+             CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save,
              gamma, sums, (float)(1.0 / count), M, C, relu, drop_p, BF(dx), lddx, BF(dres), lddres, beta_res, beta);
   return check_launch("bn_bwd_apply");
 }

@@ -299,8 +299,10 @@ class Tape:
             a = ops.bn_apply(y.t, ss, res=res.t if res is not None else None, out=out, relu=relu, drop_p=drop_p, seed=seed,
                              step_ctr=self.step_ctr if drop_p > 0.0 else None)
         aa = Act(a)
-        # conv -> BN(batch statistics) -> ReLU with nothing in between: the backward passes recompute the ReLU mask from
-        # the conv output with the forward's own coefficients instead of re-reading the activation (one stream less)
+        # conv -> BN(batch statistics) -> ReLU with nothing in between: the backward APPLY pass recomputes the ReLU mask
+        # from the conv output with the forward's own coefficients instead of re-reading the activation (one stream less).
+        # The reduce pass keeps reading the activation: its mask-recomputing variant needs 74 registers (3 blocks/SM
+        # instead of 4) and measured slower.
         remask = bool(use_batch_stats and relu and res is None and drop_p == 0.0)
         if self.record:
             def bwd():
@@ -313,7 +315,7 @@ class Tape:
                     self.grads[bn.weight] = torch.empty(C, dtype=torch.float32, device=a.device)
                     self.grads[bn.bias] = torch.empty(C, dtype=torch.float32, device=a.device)
                 a_mask = None if remask else a
-                sums = ops.bn_bwd_reduce(da, a_mask, y.t, save, relu=relu, drop_p=drop_p, gamma=bn.weight.detach(), beta=bn.bias.detach(),
+                sums = ops.bn_bwd_reduce(da, a, y.t, save, relu=relu, drop_p=drop_p,
                                          dgamma=self.grads[bn.weight] if want_pg else None,
                                          dbeta=self.grads[bn.bias] if want_pg else None, accumulate=acc_pg,
                                          zero_scratch=self.zalloc(ops.bn_bwd_reduce_scratch_floats(C), a.device))
