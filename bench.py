@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--no-gpu-aten", action="store_true", help="skip the informational ATen/cuDNN timing of the oracle port on the GPU")
     ap.add_argument("--backbone", default="resnet101")
     ap.add_argument("--graph", type=int, default=int(os.environ.get("SEG_CUDA_GRAPH", "1")), help="replay the fused step from a CUDA graph")
+    ap.add_argument("--plugin-graph", type=int, default=int(os.environ.get("SEG_PLUGIN_GRAPH", "1")),
+                    help="e2e leg: replay model(x)/backward from CUDA graphs (seg_b200 model.cuda_graphs())")
     ap.add_argument("--trace", default=None, help="after the timed runs, trace 2 steps per C-ABI call and write a table here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -338,8 +340,23 @@ def main():
             opt.step()
             return l.item()  # device -> host read of the step's result (trainer.py:72)
 
-        for _ in range(min(W, 2)):
-            plugin_step()
+        # graph replay of the plugin path: model(x) and loss.backward() replay captured forward / backward tapes (two
+        # eager calls warm up, the third captures).  If the capture fails the leg is measured eagerly and says so.
+        plugin_graph, plugin_graph_err = bool(args.plugin_graph), None
+        if plugin_graph:
+            model.cuda_graphs(True, warmup=2)
+            try:
+                for _ in range(4):
+                    plugin_step()
+            except Exception as e:  # noqa: BLE001 — reported in the JSON line, the eager leg below still measures e2e
+                plugin_graph, plugin_graph_err = False, repr(e)[:300]
+                model.cuda_graphs(False)
+                torch.cuda.synchronize()
+                state["i"] = 0
+                prefetch(0)
+        if not plugin_graph:
+            for _ in range(min(W, 2)):
+                plugin_step()
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         Ke = K
@@ -352,7 +369,9 @@ def main():
         e2e = {"value": world * B * Ke / (ms_e2e * 1e-3), "unit": "images/sec",
                "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 8), "d2h_bytes_per_step": 4,
                "api": "seg_b200.DeepLab.forward -> seg_b200.CrossEntropyLoss2d -> backward -> torch.optim.SGD.step (train.py plugin surface); batch prefetched on a side stream like the reference's DataPrefetcher",
-               "ms_per_step": ms_e2e / Ke}
+               "ms_per_step": ms_e2e / Ke, "cuda_graph": plugin_graph, "cuda_graph_error": plugin_graph_err}
+        if world > 1:
+            model.release_graphs()
 
     if args.trace and rank == 0:
         lib.TRACE = []

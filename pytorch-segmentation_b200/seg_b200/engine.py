@@ -120,6 +120,7 @@ class Tape:
         self.record = training if record is None else record      # record backward closures
         self.back = []
         self.grads = grads if grads is not None else {}  # Parameter -> fp32 grad tensor (param layout)
+        self.touched = set()  # parameters whose gradient this tape's backward wrote (pre-bound `grads` hide that)
         self.impl = impl
         self.dropout = dropout
         self.seed = seed
@@ -157,6 +158,7 @@ class Tape:
         """Write (or accumulate into) the fp32 gradient of parameter p.  value_fn(out, beta) fills it."""
         if not p.requires_grad:
             return
+        self.touched.add(p)
         if p in self.grads:
             value_fn(self.grads[p], 1.0)
         else:
@@ -204,6 +206,7 @@ class Tape:
                 if spec.m.weight.requires_grad and spec in self.dw_buffers:
                     # accumulate into the trainer's persistent packed-gradient buffer; unpacked once per step, batched
                     ops.conv2d_wgrad(dy, xin, R, S, stride, pad, dil, out=self.dw_buffers[spec], impl=self.impl)
+                    self.touched.add(spec.m.weight)
                 elif spec.m.weight.requires_grad:
                     dwp = ops.conv2d_wgrad(dy, xin, R, S, stride, pad, dil, impl=self.impl)
                     if spec.explicit:
@@ -311,6 +314,8 @@ class Tape:
                     return
                 want_pg = bn.weight.requires_grad
                 acc_pg = want_pg and (bn.weight in self.grads)
+                if want_pg:
+                    self.touched.update((bn.weight, bn.bias))
                 if want_pg and not acc_pg:
                     self.grads[bn.weight] = torch.empty(C, dtype=torch.float32, device=a.device)
                     self.grads[bn.bias] = torch.empty(C, dtype=torch.float32, device=a.device)

@@ -204,6 +204,57 @@ class _EngineFn(torch.autograd.Function):
         return (None, None, None) + tuple(grads.get(p) for p in ctx.params)
 
 
+class _GraphEntry:
+    """Captured CUDA graphs of the plugin path for one (input shape, mode): `fwd` = weight packing + the forward tape up
+    to the full-resolution fp32 NCHW logits, `bwd` = logits gradient -> every parameter gradient (one flat fp32 buffer).
+    Both graphs allocate from one private memory pool, so the activations the forward graph writes are exactly what the
+    backward graph reads; the ~1 000 kernel launches of a step become two `cudaGraphLaunch` calls."""
+
+    def __init__(self, record, ptrs):
+        self.record = record      # gradient recording (training step) or forward only (validation / inference)
+        self.ptrs = ptrs          # data pointers of every parameter and buffer baked into the graphs
+        self.pool = None
+        self.fwd = self.bwd = None
+        self.x = None
+        self.outs = self.douts = None
+        self.flat_grad = None
+        self.param_slices = None  # per model.parameters() entry: (offset, numel, shape) into flat_grad, or None
+        self.wt = None
+        self.pending = False      # forward replayed, backward not yet: another forward would clobber the saved activations
+
+
+class _GraphFn(torch.autograd.Function):
+    """Autograd node of the graph-replayed plugin path (same contract as `_EngineFn`).  The returned logits alias the
+    entry's static output buffer: like torch.cuda.make_graphed_callables, they are valid until the next forward."""
+
+    @staticmethod
+    def forward(ctx, entry, x, *params):
+        entry.x.copy_(x, non_blocking=True)
+        entry.fwd.replay()
+        entry.pending = entry.record
+        ctx.entry = entry
+        outs = tuple(o.detach() for o in entry.outs)
+        return outs if len(outs) > 1 else outs[0]
+
+    @staticmethod
+    def backward(ctx, *douts):
+        e = ctx.entry
+        if e.bwd is None:
+            raise RuntimeError("backward through a forward that ran without gradient recording")
+        for s, d in zip(e.douts, douts):
+            if d is None:
+                s.zero_()
+            else:
+                s.copy_(d, non_blocking=True)
+        e.bwd.replay()
+        e.pending = False
+        # hand autograd a private copy (ONE device copy of 4 bytes per parameter): AccumulateGrad may keep what it is
+        # given, and the static buffer is rewritten by the next replay
+        flat = e.flat_grad.clone()
+        grads = tuple(None if sl is None else flat[sl[0]:sl[0] + sl[1]].view(sl[2]) for sl in e.param_slices)
+        return (None, None) + grads
+
+
 class _EngineModel(BaseModel):
     """Shared plumbing: spec cache, engine options, forward entry."""
 
@@ -217,6 +268,104 @@ class _EngineModel(BaseModel):
         self.bn_sync = None           # seg_b200.comm.SyncBNGroup for multi-GPU SyncBN
         self.syncbn_clamp_eps = True  # reproduce sync_batchnorm/batchnorm.py:145 when stats are synchronised
         self._step_ctr = None
+        self._graphs_enabled = False
+        self._graph_warmup = 2
+        self._graph_entries = {}
+        self._graph_seen = {}
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the plugin path
+    def cuda_graphs(self, enabled=True, warmup=2):
+        """Opt in to graph replay of `model(x)` / `loss.backward()`: the first `warmup` calls with a given input shape
+        and mode run eagerly (they are real steps and double as allocator / tensor-map warm-up), the next one captures
+        the forward and backward tapes once, later calls replay them.  Contract (that of
+        torch.cuda.make_graphed_callables): the returned logits live in a static buffer that the next forward of the
+        same shape overwrites; one backward per forward (a forward issued while a backward is outstanding runs eagerly)."""
+        self._graphs_enabled = bool(enabled)
+        self._graph_warmup = int(warmup)
+        if not enabled:
+            self.release_graphs()
+        return self
+
+    def release_graphs(self):
+        if self._graph_entries:
+            torch.cuda.synchronize()
+            self._graph_entries = {}
+            torch.cuda.synchronize()
+        self._graph_seen = {}
+
+    def _graph_lookup(self, x, record):
+        bn_train = sum(1 for m in self.modules() if isinstance(m, nn.BatchNorm2d) and m.training)
+        key = (tuple(x.shape), x.device.index, self.training, bool(record), bn_train, bool(self.engine_dropout), self.bn_sync is not None)
+        ptrs = tuple(t.data_ptr() for t in chain(self.parameters(), self.buffers()))
+        e = self._graph_entries.get(key)
+        if e is not None and e.ptrs != ptrs:  # a parameter / buffer was re-allocated (model.to(...), .half(), ...)
+            torch.cuda.synchronize()
+            del self._graph_entries[key]
+            e = None
+            self._graph_seen[key] = 0
+        if e is None:
+            n = self._graph_seen.get(key, 0)
+            self._graph_seen[key] = n + 1
+            if n < self._graph_warmup:
+                return None
+            e = _GraphEntry(bool(record), ptrs)
+            try:
+                self._capture(e, x)
+            except Exception:
+                self._graphs_enabled = False  # do not retry every step; the caller sees the error
+                raise
+            self._graph_entries[key] = e
+        return None if e.pending else e
+
+    @torch.no_grad()
+    def _capture(self, e, x):
+        """Capture the forward tape and (when recording) the backward tape of one step into two graphs sharing a pool."""
+        from .train import WeightTables
+        dev = x.device
+        params = list(self.parameters())
+        e.x = x.detach().contiguous().float().clone()
+        views = None
+        if e.record:
+            total = sum(p.numel() for p in params if p.requires_grad)
+            e.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+            views, slices, off = {}, [], 0
+            for p in params:
+                if not p.requires_grad:
+                    slices.append(None)
+                    continue
+                views[p] = e.flat_grad[off:off + p.numel()].view(p.shape)
+                slices.append((off, p.numel(), tuple(p.shape)))
+                off += p.numel()
+        e.wt = WeightTables(self, views, dev)
+        e.pool = torch.cuda.graph_pool_handle()
+        torch.cuda.synchronize()
+        multi = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+        mode = "thread_local" if multi else "global"  # NCCL's watchdog thread polls events while we capture
+        if multi and self.bn_sync is not None:
+            torch.distributed.barrier()  # every rank has finished its eager SyncBN exchanges before anyone captures
+        fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(fwd, pool=e.pool, capture_error_mode=mode):
+            e.wt.pack()
+            outs, tape, heads = self._run(e.x, training=self.training, record=e.record, tables=e.wt, grads=views)
+        e.outs = outs
+        if e.record:
+            e.douts = [torch.zeros_like(o) for o in outs]
+            torch.cuda.synchronize()
+            bwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(bwd, pool=e.pool, capture_error_mode=mode):
+                e.flat_grad.zero_()
+                e.wt.zero_wgrads()
+                for (lo_act, Hl, Wl, ac), d in zip(heads, e.douts):
+                    C = d.shape[1]
+                    g = ops.bilinear_logits_bwd(d, Hl, Wl, ac, (C + 7) // 8 * 8)
+                    lo_act.grad = g[..., :C]
+                tape.backward()
+                e.wt.unpack()
+            e.bwd = bwd
+            # parameters the tape never wrote a gradient for get None, as on the eager path
+            e.param_slices = [sl if (sl is not None and p in tape.touched) else None for p, sl in zip(params, slices)]
+        e.fwd = fwd
+        torch.cuda.synchronize()
 
     def _spec(self, name, module):
         s = self._specs.get(name)
@@ -300,12 +449,20 @@ class _EngineModel(BaseModel):
         self._check_input(x)
         params = [p for p in self.parameters()]
         record = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if self._graphs_enabled:
+            e = self._graph_lookup(x, record)
+            if e is not None:
+                return _GraphFn.apply(e, x, *params)
         return _EngineFn.apply(self, record, x, *params)
 
-    def _run(self, x, training, record):
+    def _run(self, x, training, record, tables=None, grads=None):
         x = x.contiguous().float()
         H, W = x.shape[2], x.shape[3]
         tape = self._new_tape(training, record)
+        if tables is not None:  # graph capture: persistent packed weights / packed weight-gradient accumulators
+            tape.packed_override, tape.dw_buffers = tables.packed_bufs, tables.dw_bufs
+        if grads is not None:
+            tape.grads = dict(grads)  # pre-bound views: every parameter gradient lands in one flat buffer
         heads = self._forward_heads(tape, x)
         outs = tuple(ops.bilinear_logits_fwd(lo.t, H, W, ac) for lo, ac in heads)
         self._finish(tape)

@@ -11,6 +11,65 @@ from . import lib, ops
 from .engine import Tape
 
 
+class WeightTables:
+    """Persistent packed-weight (bf16) and packed-weight-gradient (fp32) buffers for every dense conv of a model, plus the
+    device tables that let ONE launch pack all weights / unpack all weight gradients (instead of 2 x ~114 small
+    launches).  Shared by `FusedTrainStep` and the graph-replayed plugin path (`nets._GraphEntry`).
+
+    grad_views: Parameter -> fp32 gradient tensor in the parameter's OIHW layout (where `unpack()` writes); None =
+    forward only."""
+
+    def __init__(self, model, grad_views, dev):
+        specs = [s for s in model.all_conv_specs()]
+        self.specs = specs
+        for ds in model.all_dw_specs():
+            ds.always_repack = True  # in-place optimiser kernels / graph replays do not go through the version check
+        dt = np.dtype([("oihw", "<u8"), ("packed", "<u8"), ("K", "<i4"), ("C", "<i4"), ("R", "<i4"), ("S", "<i4"),
+                       ("Cpad", "<i4"), ("explicit", "<i4"), ("start", "<i8")])
+        assert dt.itemsize == lib.load().seg_pack_entry_bytes()
+        want_g = grad_views is not None  # forward-only users (validation graphs) need no gradient accumulators
+        n_dw = sum(int(np.prod(s.packed_shape())) for s in specs if s.m.weight.requires_grad) if want_g else 0
+        self.flat_dwp = torch.zeros(n_dw, dtype=torch.float32, device=dev)
+        pack = np.zeros(len(specs), dtype=dt)
+        unp = []
+        self.packed_bufs, self.dw_bufs = {}, {}
+        p_start = u_start = off = 0
+        for i, s in enumerate(specs):
+            shape = s.packed_shape()
+            buf = torch.empty(shape, dtype=torch.bfloat16, device=dev)
+            self.packed_bufs[s] = buf
+            w = s.m.weight
+            pack[i] = (w.data_ptr(), buf.data_ptr(), s.K, s.C, s.R, s.S, shape[2], int(s.explicit), p_start)
+            p_start += int(np.prod(shape))
+            if want_g and w.requires_grad:
+                n = int(np.prod(shape))
+                dwb = self.flat_dwp[off:off + n].view(shape)
+                self.dw_bufs[s] = dwb
+                off += n
+                unp.append((grad_views[w].data_ptr(), dwb.data_ptr(), s.K, s.C, s.R, s.S, shape[2], int(s.explicit), u_start))
+                u_start += w.numel()
+        self.pack_total, self.unpack_total = p_start, u_start
+        self.pack_table = torch.from_numpy(pack.view(np.uint8).copy()).to(dev)
+        self.unpack_n = len(unp)
+        self.unpack_table = torch.from_numpy(np.array(unp, dtype=dt).view(np.uint8).copy()).to(dev) if unp else None
+        self.param_ptrs = [s.m.weight.data_ptr() for s in specs]
+
+    def stale(self):
+        """True when a parameter was re-allocated (e.g. model.to(...), load_state_dict on a fresh module): the tables
+        hold raw pointers."""
+        return any(s.m.weight.data_ptr() != q for s, q in zip(self.specs, self.param_ptrs))
+
+    def pack(self):
+        lib.call("seg_pack_weights_batched", self.pack_table.data_ptr(), len(self.specs), self.pack_total)
+
+    def zero_wgrads(self):
+        self.flat_dwp.zero_()
+
+    def unpack(self):
+        if self.unpack_n:
+            lib.call("seg_unpack_wgrads_batched", self.unpack_table.data_ptr(), self.unpack_n, self.unpack_total, 0.0)
+
+
 class FusedTrainStep:
     def __init__(self, model, ignore_index=255, lr=0.01, backbone_lr_scale=0.1, momentum=0.9, weight_decay=1e-4,
                  aux_weight=0.4, world=1, cuda_graph=False):
@@ -41,48 +100,14 @@ class FusedTrainStep:
         self.m_ptrs = torch.tensor([m.data_ptr() for m in self.mom_views], **i64)
         self.sizes = torch.tensor([p.numel() for p in self.params], **i64)
         self.steps = 0
-        self._build_weight_tables(dev)
+        self.wt = WeightTables(model, self.grad_views, dev)
+        self.specs = self.wt.specs
         # CUDA graph of the whole step (forward, loss, backward, all-reduce, SGD): ~1 200 kernel launches per step are
         # replayed by the driver instead of being re-issued from Python.  Dropout seeds and SyncBN epochs come from a
         # device-side step counter, so every replay is a fresh step.
         self.cuda_graph = cuda_graph
         self._graph = None
         self._static = None
-
-    def _build_weight_tables(self, dev):
-        """Persistent packed-weight (bf16) and packed-gradient (fp32) buffers for every conv + the device tables that
-        let ONE launch pack all weights / unpack all weight gradients (instead of 2 x ~114 small launches)."""
-        specs = [s for s in self.model.all_conv_specs()]
-        self.specs = specs
-        for ds in self.model.all_dw_specs():
-            ds.always_repack = True  # the in-place SGD kernel does not bump autograd versions
-        dt = np.dtype([("oihw", "<u8"), ("packed", "<u8"), ("K", "<i4"), ("C", "<i4"), ("R", "<i4"), ("S", "<i4"),
-                       ("Cpad", "<i4"), ("explicit", "<i4"), ("start", "<i8")])
-        assert dt.itemsize == lib.load().seg_pack_entry_bytes()
-        n_dw = sum(int(np.prod(s.packed_shape())) for s in specs if s.m.weight.requires_grad)
-        self.flat_dwp = torch.zeros(n_dw, dtype=torch.float32, device=dev)
-        pack = np.zeros(len(specs), dtype=dt)
-        unp = []
-        self.packed_bufs, self.dw_bufs = {}, {}
-        p_start = u_start = off = 0
-        for i, s in enumerate(specs):
-            shape = s.packed_shape()
-            buf = torch.empty(shape, dtype=torch.bfloat16, device=dev)
-            self.packed_bufs[s] = buf
-            w = s.m.weight
-            pack[i] = (w.data_ptr(), buf.data_ptr(), s.K, s.C, s.R, s.S, shape[2], int(s.explicit), p_start)
-            p_start += int(np.prod(shape))
-            if w.requires_grad:
-                n = int(np.prod(shape))
-                dwb = self.flat_dwp[off:off + n].view(shape)
-                self.dw_bufs[s] = dwb
-                off += n
-                unp.append((self.grad_views[w].data_ptr(), dwb.data_ptr(), s.K, s.C, s.R, s.S, shape[2], int(s.explicit), u_start))
-                u_start += w.numel()
-        self.pack_total, self.unpack_total = p_start, u_start
-        self.pack_table = torch.from_numpy(pack.view(np.uint8).copy()).to(dev)
-        self.unpack_n = len(unp)
-        self.unpack_table = torch.from_numpy(np.array(unp, dtype=dt).view(np.uint8).copy()).to(dev)
 
     def set_lr_scale(self, scale):
         """Poly / OneCycle schedules multiply the base rates (utils/lr_scheduler.py); host scalar, one tiny op."""
@@ -144,11 +169,11 @@ class FusedTrainStep:
     def _step_impl(self, x, target):
         m = self.model
         self.flat_grad.zero_()
-        self.flat_dwp.zero_()
-        lib.call("seg_pack_weights_batched", self.pack_table.data_ptr(), len(self.specs), self.pack_total)
+        self.wt.zero_wgrads()
+        self.wt.pack()
         tape = m._new_tape(True, True)
         tape.grads = dict(self.grad_views)  # pre-bound views: every parameter gradient lands in the flat buffer
-        tape.packed_override, tape.dw_buffers = self.packed_bufs, self.dw_bufs
+        tape.packed_override, tape.dw_buffers = self.wt.packed_bufs, self.wt.dw_bufs
         heads = m._forward_heads(tape, x.contiguous().float())
         total = None
         for i, (lo, ac) in enumerate(heads):
@@ -161,7 +186,7 @@ class FusedTrainStep:
             total = loss if total is None else total + w * loss
         m._finish(tape)
         tape.backward()
-        lib.call("seg_unpack_wgrads_batched", self.unpack_table.data_ptr(), self.unpack_n, self.unpack_total, 0.0)
+        self.wt.unpack()
         if self.world > 1:
             dist.all_reduce(self.flat_grad)
         lib.call("seg_sgd_step", self.p_ptrs.data_ptr(), self.g_ptrs.data_ptr(), self.m_ptrs.data_ptr(), self.sizes.data_ptr(),
