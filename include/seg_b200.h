@@ -232,6 +232,40 @@ int seg_axpby_bf16(const void* x, int ldx, void* y, int ldy, int64_t M, int C, f
 int seg_sgd_step(float* const* params, float* const* grads, float* const* momentum_bufs, const int64_t* sizes,
                  const float* lrs, int n, float momentum, float weight_decay, int first_step, float grad_scale,
                  void* stream);
+/* same step with (momentum, weight_decay) read from DEVICE memory hyper[0..1]: a momentum schedule
+ * (OneCycle, utils/lr_scheduler.py:24-59) stays effective when the step is replayed from a CUDA graph */
+int seg_sgd_step_dev(float* const* params, float* const* grads, float* const* momentum_bufs, const int64_t* sizes,
+                     const float* lrs, int n, const float* hyper, int first_step, float grad_scale, void* stream);
+/* ---- input pipeline tail: pad + crop + horizontal flip + ToTensor + Normalize on the device ----
+ * Replaces, for a batch that crossed PCIe as uint8, base/base_dataset.py:93-123 (copyMakeBorder value 0, crop at
+ * (start_h, start_w), np.fliplr) and :129-136 (ToTensor, Normalize, label -> int64).  `arena` holds the B images
+ * (HWC uint8, h x w x 3, any sizes) and labels (h x w, uint8 or int32) back to back; `table[b]` says where.  The
+ * random draws (crop origin, flip) stay on the host so a seeded run makes the reference's draws; mean3/std3 are HOST
+ * pointers.  out_nchw fp32 [B,3,crop_h,crop_w], out_labels int64 [B,crop_h,crop_w] (NULL: images only).
+ * Bit-exact: fp32 (u8/255 - mean)/std with IEEE divisions, the operations torchvision performs. */
+typedef struct seg_aug_entry {
+  int64_t img_off;   /* byte offset of the image in the arena */
+  int64_t lbl_off;   /* byte offset of the label map, or -1 */
+  int32_t h, w;      /* image size before padding */
+  int32_t y0, x0;    /* crop origin in the (bottom/right zero-padded) image */
+  int32_t flip;      /* 1: flip the crop horizontally */
+  int32_t lbl_bytes; /* 1 (uint8) or 4 (int32) */
+} seg_aug_entry;
+int seg_aug_entry_bytes(void);
+int seg_augment_batch_u8(const uint8_t* arena, const seg_aug_entry* table, int B, int crop_h, int crop_w, const float* mean3,
+                         const float* std3, float* out_nchw, int64_t* out_labels, void* stream);
+/* ---- inference-side resampling (inference.py:26-79), fp32 NCHW score maps, `planes` = N*C ----
+ * resize: dst = beta*dst + alpha*flip_x?(bilinear resize of src to Hd x Wd).  align_corners=1 is both ndimage.zoom(order=1)
+ * (inference.py:65) and nn.Upsample(align_corners=True) (:60); same size + flip_x = tensor.flip(-1) (:48,:70). */
+int seg_resize_nchw_f32(const float* src, int64_t planes, int Hs, int Ws, float* dst, int Hd, int Wd, int align_corners,
+                        int flip_x, float alpha, float beta, void* stream);
+/* dst[:, y0:y0+h, x0:x0+w] += alpha * flip_x?(src)[:, :h, :w]  — sliding-window accumulation (inference.py:49-53) */
+int seg_window_add_nchw_f32(const float* src, int64_t planes, int Hs, int Ws, float* dst, int Hd, int Wd, int y0, int x0, int h,
+                            int w, int flip_x, float alpha, void* stream);
+/* x[p] /= count  (count fp32 [H,W]; inference.py:55) */
+int seg_div_by_count_nchw_f32(float* x, int64_t planes, int H, int W, const float* count_hw, void* stream);
+/* labels int64 [N,H,W] = argmax over the C planes, first maximum wins (inference.py:156 without the softmax pass) */
+int seg_argmax_nchw_f32(const float* scores, int N, int C, int H, int W, int64_t* labels, void* stream);
 /* ---- SyncBN one-shot exchange over NVLink peer memory (replaces ReduceAddCoalesced + Broadcast,
  *      sync_batchnorm/batchnorm.py:117,120 and the thread pipes of sync_batchnorm/comm.py) ----
  * Each rank owns a symmetric buffer of seg_comm_buffer_bytes(world, n_max) bytes (seg_comm_alloc, zeroed), exports it

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Golden vectors for the sample-pipeline tail, produced by the REFERENCE's own BaseDataSet.__getitem__
+(/root/reference/base/base_dataset.py, read-only) on synthetic uint8 samples with scale / rotate / blur off, so the only
+operations are the ones seg_augment_batch_u8 replaces: pad, crop, flip, ToTensor, Normalize.  The crop / flip draws are
+recovered by replaying Python's `random` from the same seed.  Writes tests/golden/data_tail.npz.
+Run:  python oracle/make_golden_data.py"""
+import os
+import random
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("SEG_REFERENCE_ROOT", "/root/reference")
+MEAN, STD = [0.45734706, 0.43338275, 0.40058118], [0.23965294, 0.23532275, 0.2398498]  # dataloaders/voc.py
+CROP = 48
+
+
+def main():
+    sys.path.insert(0, REF)
+    for name in ("skimage", "skimage.filters"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.gaussian = lambda *a, **k: None
+            sys.modules[name] = m
+    from base.base_dataset import BaseDataSet
+
+    rs = np.random.RandomState(9500)
+    sizes = [(33, 70), (48, 48), (90, 41), (64, 80), (20, 30), (75, 49)]
+    samples = [(rs.randint(0, 256, (h, w, 3)).astype(np.uint8), rs.randint(0, 21, (h, w)).astype(np.int32)) for h, w in sizes]
+
+    class Synth(BaseDataSet):
+        def _set_files(self):
+            self.files = list(range(len(samples)))
+
+        def _load_data(self, index):
+            im, lb = samples[index]
+            return im.astype(np.float32), lb, str(index)  # loaders hand float32 images to _augmentation (dataloaders/voc.py:44)
+
+    ds = Synth(root=None, split="train", mean=MEAN, std=STD, base_size=None, augment=True, val=False, crop_size=CROP,
+               scale=False, flip=True, rotate=False, blur=False)
+    rec = {"mean": np.asarray(MEAN), "std": np.asarray(STD), "crop": np.asarray(CROP), "n": np.asarray(len(samples))}
+    for i, (im, lb) in enumerate(samples):
+        random.seed(100 + i)
+        x, y = ds[i]
+        random.seed(100 + i)  # replay the draws of base_dataset.py:107-121
+        h, w = im.shape[:2]
+        ph, pw = max(h, CROP), max(w, CROP)
+        y0 = random.randint(0, ph - CROP)
+        x0 = random.randint(0, pw - CROP)
+        flip = random.random() > 0.5
+        rec[f"{i}/image"], rec[f"{i}/label"] = im, lb
+        rec[f"{i}/draw"] = np.asarray([y0, x0, int(flip)])
+        rec[f"{i}/x"], rec[f"{i}/y"] = x.numpy(), y.numpy()
+        print(i, im.shape, (y0, x0, flip), x.shape, y.shape, float(x.mean()))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "data_tail.npz"), **rec)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,213 @@
+// seg_data.cu — the two callers either side of the train step that SURVEY.md §8(f) ranks next:
+//   * the tail of the input pipeline (base/base_dataset.py:88-136: pad -> crop -> horizontal flip -> ToTensor ->
+//     Normalize) on uint8 images that crossed PCIe as bytes (4x fewer than the reference's fp32 batches), and
+//   * the resampling / accumulation arithmetic of inference.py:26-79 (multi-scale + flip, sliding window) on fp32 NCHW
+//     score maps that never leave the device.
+// All kernels are HBM streaming kernels: one thread per output element along x (coalesced fp32 stores), grid-stride.
+#include "seg_common.cuh"
+
+namespace seg {
+
+static inline int grid_for(int64_t work_items, int threads, int max_blocks_per_sm = 8) {
+  int64_t b = ceil_div64(work_items, threads);
+  int64_t cap = (int64_t)num_sms() * max_blocks_per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------ pad + crop + flip + ToTensor + Normalize
+// out[b][c][y][x] = ((float)u8 / 255 - mean[c]) / std[c], u8 = pixel (y + y0, xs + x0) of image b (xs = x, or
+// crop_w-1-x when the image is flipped AFTER cropping as base_dataset.py:119-123 does); positions outside the h x w image
+// are the zero padding of cv2.copyMakeBorder(value=0) (base_dataset.py:93-105) — for the label too.
+// Division (not reciprocal multiplication) in fp32, the order torchvision's to_tensor / normalize use: bit-exact.
+struct AugParams {
+  float mean[3];
+  float stdv[3];
+};
+__global__ void __launch_bounds__(256) augment_u8_kernel(const uint8_t* __restrict__ arena, const seg_aug_entry* __restrict__ table,
+                                                         int crop_h, int crop_w, AugParams prm, float* __restrict__ out,
+                                                         int64_t* __restrict__ labels) {
+  const int b = blockIdx.y;
+  const seg_aug_entry e = table[b];
+  const uint8_t* img = arena + e.img_off;
+  const uint8_t* lbl = e.lbl_off >= 0 ? arena + e.lbl_off : nullptr;
+  const int64_t plane = (int64_t)crop_h * crop_w;
+  float* o = out + (int64_t)b * 3 * plane;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < plane; i += (int64_t)gridDim.x * blockDim.x) {
+    const int y = (int)(i / crop_w), x = (int)(i - (int64_t)y * crop_w);
+    const int xs = e.flip ? crop_w - 1 - x : x;
+    const int sy = y + e.y0, sx = xs + e.x0;
+    const bool inside = sy < e.h && sx < e.w;
+    unsigned r = 0, g = 0, bl = 0;
+    if (inside) {
+      const uint8_t* p = img + ((int64_t)sy * e.w + sx) * 3;
+      r = p[0];
+      g = p[1];
+      bl = p[2];
+    }
+    o[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)r, 255.f), prm.mean[0]), prm.stdv[0]);
+    o[plane + i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)g, 255.f), prm.mean[1]), prm.stdv[1]);
+    o[2 * plane + i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)bl, 255.f), prm.mean[2]), prm.stdv[2]);
+    if (labels != nullptr) {
+      int64_t v = 0;
+      if (inside && lbl != nullptr) {
+        const int64_t k = (int64_t)sy * e.w + sx;
+        v = e.lbl_bytes == 1 ? (int64_t)lbl[k] : (int64_t)reinterpret_cast<const int32_t*>(lbl)[k];
+      }
+      labels[(int64_t)b * plane + i] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ bilinear resize of fp32 NCHW planes
+// Source index exactly as ATen's area_pixel_compute_source_index (float arithmetic) — same helper as seg_elementwise.cu.
+struct Lerp {
+  int i0, i1;
+  float l1;
+};
+__device__ __forceinline__ Lerp src_index(int dst, float scale, int in_size, int align_corners) {
+  float s;
+  if (align_corners) {
+    s = scale * (float)dst;
+  } else {
+    s = scale * ((float)dst + 0.5f) - 0.5f;
+    if (s < 0.f) s = 0.f;
+  }
+  Lerp r;
+  r.i0 = (int)s;
+  if (r.i0 > in_size - 1) r.i0 = in_size - 1;
+  r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
+  r.l1 = s - (float)r.i0;
+  return r;
+}
+static inline float resize_scale(int in_size, int out_size, int align_corners) {
+  if (align_corners) return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+  return (float)in_size / (float)out_size;
+}
+
+// dst[p][oy][ox] = beta * dst + alpha * R[p][oy][flip_x ? Wd-1-ox : ox],  R = bilinear resize of src plane p to Hd x Wd
+__global__ void __launch_bounds__(256) resize_nchw_kernel(const float* __restrict__ src, int64_t planes, int Hs, int Ws,
+                                                          float* __restrict__ dst, int Hd, int Wd, int ac, float sh, float sw,
+                                                          int flip_x, float alpha, float beta) {
+  const int64_t total = planes * Hd * Wd;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Wd);
+    const int64_t t = i / Wd;
+    const int oy = (int)(t % Hd);
+    const int64_t p = t / Hd;
+    const Lerp ly = src_index(oy, sh, Hs, ac), lx = src_index(flip_x ? Wd - 1 - ox : ox, sw, Ws, ac);
+    const float* base = src + p * Hs * Ws;
+    const float a = base[(int64_t)ly.i0 * Ws + lx.i0], b = base[(int64_t)ly.i0 * Ws + lx.i1];
+    const float c = base[(int64_t)ly.i1 * Ws + lx.i0], d = base[(int64_t)ly.i1 * Ws + lx.i1];
+    const float h1 = ly.l1, h0 = 1.f - h1, w1 = lx.l1, w0 = 1.f - w1;
+    const float v = alpha * (h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d));
+    dst[i] = beta != 0.f ? beta * dst[i] + v : v;
+  }
+}
+
+// dst[p][y0 + y][x0 + x] += alpha * src[p][y][flip_x ? Ws-1-x : x]   for y < h, x < w   (sliding-window accumulation)
+__global__ void __launch_bounds__(256) window_add_kernel(const float* __restrict__ src, int64_t planes, int Hs, int Ws,
+                                                         float* __restrict__ dst, int Hd, int Wd, int y0, int x0, int h, int w,
+                                                         int flip_x, float alpha) {
+  const int64_t total = planes * h * w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const int64_t t = i / w;
+    const int y = (int)(t % h);
+    const int64_t p = t / h;
+    const float v = src[(p * Hs + y) * Ws + (flip_x ? Ws - 1 - x : x)];
+    float* o = dst + (p * Hd + y0 + y) * Wd + x0 + x;
+    *o += alpha * v;
+  }
+}
+
+// x[p][y][x] /= count[y][x]  (sliding-window average, inference.py:55)
+__global__ void __launch_bounds__(256) div_by_count_kernel(float* __restrict__ x, int64_t planes, int64_t hw,
+                                                           const float* __restrict__ count) {
+  const int64_t total = planes * hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = __fdiv_rn(x[i], count[i % hw]);
+}
+
+// labels[n][y][x] = first index of the maximum over the C planes (torch.argmax's tie rule); softmax is monotone, so this
+// is `F.softmax(prediction, dim=0).argmax(0)` of inference.py:156 without the softmax pass
+__global__ void __launch_bounds__(256) argmax_nchw_kernel(const float* __restrict__ s, int N, int C, int64_t hw,
+                                                          int64_t* __restrict__ labels) {
+  const int64_t total = (int64_t)N * hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / hw, q = i - n * hw;
+    const float* p = s + n * C * hw + q;
+    float best = p[0];
+    int arg = 0;
+    for (int c = 1; c < C; ++c) {
+      const float v = p[(int64_t)c * hw];
+      if (v > best) {
+        best = v;
+        arg = c;
+      }
+    }
+    labels[i] = arg;
+  }
+}
+
+}  // namespace seg
+
+using namespace seg;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int seg_aug_entry_bytes(void) { return (int)sizeof(seg_aug_entry); }
+
+int seg_augment_batch_u8(const uint8_t* arena, const seg_aug_entry* table, int B, int crop_h, int crop_w, const float* mean3,
+                         const float* std3, float* out_nchw, int64_t* out_labels, void* stream) {
+  SEG_REQUIRE(arena != nullptr && table != nullptr && out_nchw != nullptr && mean3 != nullptr && std3 != nullptr, "augment: null pointer");
+  SEG_REQUIRE(B > 0 && B <= 65535 && crop_h > 0 && crop_w > 0, "augment: bad batch / crop size");
+  AugParams prm;
+  for (int c = 0; c < 3; ++c) {
+    prm.mean[c] = mean3[c];  // host pointers: six floats by value into the kernel arguments
+    prm.stdv[c] = std3[c];
+    SEG_REQUIRE(std3[c] != 0.f, "augment: std must be non-zero");
+  }
+  // blockIdx.y = image; the B images share ~8 blocks per SM between them
+  int64_t per_image = ((int64_t)num_sms() * 8 + B - 1) / B;
+  const int64_t need = ceil_div64((int64_t)crop_h * crop_w, 256);
+  if (per_image > need) per_image = need;
+  if (per_image < 1) per_image = 1;
+  dim3 grid((unsigned)per_image, (unsigned)B, 1);
+  augment_u8_kernel<<<grid, 256, 0, ST(stream)>>>(arena, table, crop_h, crop_w, prm, out_nchw, out_labels);
+  return check_launch("augment_batch_u8");
+}
+
+int seg_resize_nchw_f32(const float* src, int64_t planes, int Hs, int Ws, float* dst, int Hd, int Wd, int align_corners,
+                        int flip_x, float alpha, float beta, void* stream) {
+  SEG_REQUIRE(planes > 0 && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0, "resize: bad size");
+  SEG_REQUIRE(src != dst, "resize: in-place is not supported");
+  resize_nchw_kernel<<<grid_for(planes * Hd * Wd, 256), 256, 0, ST(stream)>>>(
+      src, planes, Hs, Ws, dst, Hd, Wd, align_corners, resize_scale(Hs, Hd, align_corners), resize_scale(Ws, Wd, align_corners),
+      flip_x, alpha, beta);
+  return check_launch("resize_nchw_f32");
+}
+
+int seg_window_add_nchw_f32(const float* src, int64_t planes, int Hs, int Ws, float* dst, int Hd, int Wd, int y0, int x0, int h,
+                            int w, int flip_x, float alpha, void* stream) {
+  SEG_REQUIRE(planes > 0 && h > 0 && w > 0 && h <= Hs && w <= Ws && y0 >= 0 && x0 >= 0 && y0 + h <= Hd && x0 + w <= Wd,
+              "window_add: window (%d,%d)+(%dx%d) does not fit src %dx%d / dst %dx%d", y0, x0, h, w, Hs, Ws, Hd, Wd);
+  window_add_kernel<<<grid_for(planes * h * w, 256), 256, 0, ST(stream)>>>(src, planes, Hs, Ws, dst, Hd, Wd, y0, x0, h, w, flip_x, alpha);
+  return check_launch("window_add_nchw_f32");
+}
+
+int seg_div_by_count_nchw_f32(float* x, int64_t planes, int H, int W, const float* count_hw, void* stream) {
+  SEG_REQUIRE(planes > 0 && H > 0 && W > 0, "div_by_count: bad size");
+  div_by_count_kernel<<<grid_for(planes * H * W, 256), 256, 0, ST(stream)>>>(x, planes, (int64_t)H * W, count_hw);
+  return check_launch("div_by_count_nchw_f32");
+}
+
+int seg_argmax_nchw_f32(const float* scores, int N, int C, int H, int W, int64_t* labels, void* stream) {
+  SEG_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, "argmax: bad size");
+  argmax_nchw_kernel<<<grid_for((int64_t)N * H * W, 256), 256, 0, ST(stream)>>>(scores, N, C, (int64_t)H * W, labels);
+  return check_launch("argmax_nchw_f32");
+}
+
+}  // extern "C"

@@ -1037,7 +1037,14 @@ struct SgdChunkArgs {
   const float* lrs;
 };
 // one block-row (blockIdx.y) per tensor, grid-stride inside
-__global__ void sgd_kernel(SgdChunkArgs a, float momentum, float wd, int first_step, float grad_scale) {
+// hyper != nullptr: (momentum, weight decay) are read from device memory, so a schedule that changes the momentum every
+// iteration (OneCycle, utils/lr_scheduler.py:24-59) also works when the step is replayed from a CUDA graph
+__global__ void sgd_kernel(SgdChunkArgs a, float momentum, float wd, int first_step, float grad_scale,
+                           const float* __restrict__ hyper) {
+  if (hyper != nullptr) {
+    momentum = hyper[0];
+    wd = hyper[1];
+  }
   const int t = blockIdx.y;
   float* p = a.params[t];
   const float* g = a.grads[t];
@@ -1292,8 +1299,17 @@ int seg_sgd_step(float* const* params, float* const* grads, float* const* bufs, 
   if (n <= 0) return 0;
   SgdChunkArgs a{params, grads, bufs, sizes, lrs};
   dim3 grid(64, (unsigned)n, 1);
-  sgd_kernel<<<grid, 256, 0, ST(stream)>>>(a, momentum, weight_decay, first_step, grad_scale);
+  sgd_kernel<<<grid, 256, 0, ST(stream)>>>(a, momentum, weight_decay, first_step, grad_scale, nullptr);
   return check_launch("sgd_step");
+}
+int seg_sgd_step_dev(float* const* params, float* const* grads, float* const* bufs, const int64_t* sizes, const float* lrs,
+                     int n, const float* hyper, int first_step, float grad_scale, void* stream) {
+  if (n <= 0) return 0;
+  SEG_REQUIRE(hyper != nullptr, "sgd_step_dev: hyper (device [momentum, weight_decay]) is required");
+  SgdChunkArgs a{params, grads, bufs, sizes, lrs};
+  dim3 grid(64, (unsigned)n, 1);
+  sgd_kernel<<<grid, 256, 0, ST(stream)>>>(a, 0.f, 0.f, first_step, grad_scale, hyper);
+  return check_launch("sgd_step_dev");
 }
 
 }  // extern "C"

@@ -19,7 +19,7 @@ _LAZY = {
     "FusedTrainStep": ("train", "FusedTrainStep"),
 }
 
-__all__ = list(_LAZY) + ["lib", "ops", "nets", "losses", "engine", "comm", "train", "launch"]
+__all__ = list(_LAZY) + ["lib", "ops", "nets", "losses", "engine", "comm", "train", "launch", "lr_scheduler", "data", "inference"]
 
 
 def __getattr__(name):
@@ -27,6 +27,6 @@ def __getattr__(name):
     if name in _LAZY:
         mod, attr = _LAZY[name]
         return getattr(importlib.import_module(f"{__name__}.{mod}"), attr)
-    if name in ("lib", "ops", "nets", "losses", "engine", "comm", "train", "launch"):
+    if name in ("lib", "ops", "nets", "losses", "engine", "comm", "train", "launch", "lr_scheduler", "data", "inference"):
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -1,0 +1,140 @@
+"""Input pipeline tail on the device.
+
+The reference finishes every sample on a CPU worker — zero-pad to the crop size, random crop, random horizontal flip,
+`ToTensor`, `Normalize`, label -> int64 (base/base_dataset.py:93-123,129-136) — and ships fp32 images + int64 labels over
+PCIe (20 bytes per pixel) through `DataPrefetcher` (base/base_dataloader.py:49-85).  Here the scaled/rotated uint8 sample
+crosses PCIe as it is (4 bytes per pixel with a uint8 label) and ONE kernel (`seg_augment_batch_u8`) performs the tail
+for the whole batch, bit-exactly (same fp32 operations).  The random draws stay on the host, in the reference's order
+(crop row, crop column, flip), so a seeded run is reproducible against the reference.
+
+    DeviceBatcher(mean, std, crop_size, device)      — stage(samples) -> (images fp32 [B,3,crop,crop], labels int64 [B,crop,crop])
+    DevicePrefetcher(loader, device, stop_after=None, batcher=None) — drop-in for the reference's DataPrefetcher;
+        a loader that yields ready (float image batch, long label batch) pairs is passed through exactly as the reference
+        does, a loader that yields lists of raw samples goes through the batcher.
+"""
+import random
+
+import numpy as np
+import torch
+
+from . import lib, ops
+
+_ENTRY = np.dtype([("img_off", "<i8"), ("lbl_off", "<i8"), ("h", "<i4"), ("w", "<i4"), ("y0", "<i4"), ("x0", "<i4"),
+                   ("flip", "<i4"), ("lbl_bytes", "<i4")])
+
+
+def draw_crop_flip(h, w, crop_size, flip=True, rng=random):
+    """The draws of base_dataset.py:107-121 in the reference's order: crop origin in the padded image, then the flip."""
+    ph, pw = max(h, crop_size), max(w, crop_size)
+    y0 = rng.randint(0, ph - crop_size)
+    x0 = rng.randint(0, pw - crop_size)
+    f = bool(flip and rng.random() > 0.5)
+    return y0, x0, f
+
+
+class DeviceBatcher:
+    def __init__(self, mean, std, crop_size, device, max_bytes=64 << 20):
+        assert _ENTRY.itemsize == lib.load().seg_aug_entry_bytes()
+        self.mean, self.std = [float(v) for v in mean], [float(v) for v in std]
+        self.crop = int(crop_size)
+        self.device = torch.device(device)
+        self.capacity = int(max_bytes)
+        self._host = [torch.empty(self.capacity, dtype=torch.uint8).pin_memory() for _ in range(2)]  # double-buffered staging
+        self._slot = 0
+        self._events = [None, None]
+
+    def stage(self, samples):
+        """samples: sequence of (image uint8 [h,w,3], label uint8|int32 [h,w] or None, y0, x0, flip).  Packs them into
+        pinned memory, copies once, launches the kernel on the current stream.  Returns (images, labels)."""
+        B = len(samples)
+        slot = self._slot
+        self._slot ^= 1
+        if self._events[slot] is not None:
+            self._events[slot].synchronize()  # the previous H2D copy out of this staging buffer has finished
+        host = self._host[slot].numpy()
+        table = np.zeros(B, dtype=_ENTRY)
+        off = B * _ENTRY.itemsize
+        want_labels = samples[0][1] is not None
+        for b, (img, lbl, y0, x0, flip) in enumerate(samples):
+            img = np.ascontiguousarray(img, dtype=np.uint8)
+            h, w = img.shape[:2]
+            assert img.shape == (h, w, 3), "images are HWC uint8 with 3 channels"
+            n = img.size
+            lb, lbl_off = 1, -1
+            if lbl is not None:
+                lbl = np.ascontiguousarray(lbl)
+                assert lbl.shape == (h, w) and lbl.dtype in (np.uint8, np.int32), "labels are uint8 or int32 [h,w]"
+                lb = lbl.dtype.itemsize
+            need = off + n + 8 + (h * w * lb if lbl is not None else 0)
+            if need > self.capacity:
+                raise RuntimeError(f"DeviceBatcher: batch needs more than max_bytes={self.capacity} of staging memory")
+            host[off:off + n] = img.reshape(-1)
+            img_off = off
+            off += (n + 3) // 4 * 4  # keep int32 label maps 4-byte aligned
+            if lbl is not None:
+                nb = h * w * lb
+                host[off:off + nb] = lbl.reshape(-1).view(np.uint8)
+                lbl_off = off
+                off += (nb + 3) // 4 * 4
+            table[b] = (img_off, lbl_off, h, w, int(y0), int(x0), int(bool(flip)), lb)
+        host[:B * _ENTRY.itemsize] = table.view(np.uint8)
+        dev = self._host[slot][:off].to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._events[slot] = ev
+        tab = dev[:B * _ENTRY.itemsize]
+        return ops.augment_batch_u8(dev, tab, B, self.crop, self.crop, self.mean, self.std, want_labels=want_labels)
+
+    def stage_random(self, raw, flip=True, rng=random):
+        """raw: sequence of (image, label).  Draws crop origin / flip per sample like the reference's worker would."""
+        return self.stage([(im, lb) + draw_crop_flip(im.shape[0], im.shape[1], self.crop, flip, rng) for im, lb in raw])
+
+
+class DevicePrefetcher:
+    """base/base_dataloader.py:49-85 with the same protocol (`len`, iteration yields (input, target) on the device, the
+    next batch is staged on a side stream while the current one is consumed, `stop_after`)."""
+
+    def __init__(self, loader, device, stop_after=None, batcher=None):
+        self.loader = loader
+        self.dataset = getattr(loader, "dataset", None)
+        self.stream = torch.cuda.Stream()
+        self.stop_after = stop_after
+        self.next_input = None
+        self.next_target = None
+        self.device = device
+        self.batcher = batcher
+
+    def __len__(self):
+        return len(self.loader)
+
+    def preload(self):
+        try:
+            item = next(self.loaditer)
+        except StopIteration:
+            self.next_input = None
+            self.next_target = None
+            return
+        with torch.cuda.stream(self.stream):
+            if isinstance(item, (tuple, list)) and len(item) == 2 and isinstance(item[0], torch.Tensor) and item[0].is_floating_point():
+                self.next_input = item[0].cuda(device=self.device, non_blocking=True)   # the reference's path, unchanged
+                self.next_target = item[1].cuda(device=self.device, non_blocking=True)
+            else:
+                if self.batcher is None:
+                    raise RuntimeError("DevicePrefetcher: the loader yields raw uint8 samples but no DeviceBatcher was given")
+                self.next_input, self.next_target = self.batcher.stage(item)
+
+    def __iter__(self):
+        count = 0
+        self.loaditer = iter(self.loader)
+        self.preload()
+        while self.next_input is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            input, target = self.next_input, self.next_target
+            input.record_stream(torch.cuda.current_stream())
+            if target is not None:
+                target.record_stream(torch.cuda.current_stream())
+            self.preload()
+            count += 1
+            yield input, target
+            if type(self.stop_after) is int and (count > self.stop_after):
+                break

@@ -471,3 +471,51 @@ def relu_bwd(dy, y, dx, beta):
 def axpby(x, y, beta):
     call("seg_axpby_bf16", ptr(x), ld(x), ptr(y), ld(y), rows(x), x.shape[-1], float(beta))
     return y
+
+
+# ---------------------------------------------------------------- input pipeline tail / inference resampling (seg_data.cu)
+def resize_nchw(src, Hd, Wd, align_corners=True, flip_x=False, alpha=1.0, out=None, beta=0.0):
+    """out = beta*out + alpha * [flip](bilinear resize of fp32 NCHW `src` to Hd x Wd)."""
+    N, C, Hs, Ws = src.shape
+    assert src.is_contiguous() and src.dtype == torch.float32
+    if out is None:
+        out = torch.empty((N, C, Hd, Wd), dtype=torch.float32, device=src.device)
+        beta = 0.0
+    assert out.is_contiguous() and out.shape == (N, C, Hd, Wd) and out.dtype == torch.float32
+    call("seg_resize_nchw_f32", ptr(src), N * C, Hs, Ws, ptr(out), Hd, Wd, int(align_corners), int(flip_x), float(alpha), float(beta))
+    return out
+
+
+def window_add_nchw(src, dst, y0, x0, h, w, flip_x=False, alpha=1.0):
+    """dst[:, :, y0:y0+h, x0:x0+w] += alpha * [flip](src)[:, :, :h, :w]"""
+    N, C, Hs, Ws = src.shape
+    assert src.is_contiguous() and dst.is_contiguous() and src.dtype == dst.dtype == torch.float32 and dst.shape[:2] == (N, C)
+    call("seg_window_add_nchw_f32", ptr(src), N * C, Hs, Ws, ptr(dst), dst.shape[2], dst.shape[3], int(y0), int(x0), int(h), int(w),
+         int(flip_x), float(alpha))
+    return dst
+
+
+def div_by_count_nchw(x, count_hw):
+    N, C, H, W = x.shape
+    assert x.is_contiguous() and count_hw.is_contiguous() and count_hw.shape == (H, W) and count_hw.dtype == torch.float32
+    call("seg_div_by_count_nchw_f32", ptr(x), N * C, H, W, ptr(count_hw))
+    return x
+
+
+def argmax_nchw(scores):
+    N, C, H, W = scores.shape
+    assert scores.is_contiguous() and scores.dtype == torch.float32
+    labels = torch.empty((N, H, W), dtype=torch.int64, device=scores.device)
+    call("seg_argmax_nchw_f32", ptr(scores), N, C, H, W, ptr(labels))
+    return labels
+
+
+def augment_batch_u8(arena, table, B, crop_h, crop_w, mean, std, want_labels=True):
+    """arena: uint8 device tensor (images + labels back to back), table: uint8 device tensor of B seg_aug_entry records."""
+    assert arena.dtype == torch.uint8 and table.dtype == torch.uint8 and table.numel() == B * lib.load().seg_aug_entry_bytes()
+    out = torch.empty((B, 3, crop_h, crop_w), dtype=torch.float32, device=arena.device)
+    labels = torch.empty((B, crop_h, crop_w), dtype=torch.int64, device=arena.device) if want_labels else None
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    call("seg_augment_batch_u8", ptr(arena), ptr(table), int(B), int(crop_h), int(crop_w), m3, s3, ptr(out), ptr(labels))
+    return out, labels

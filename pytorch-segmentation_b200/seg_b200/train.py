@@ -75,7 +75,7 @@ class FusedTrainStep:
                  aux_weight=0.4, world=1, cuda_graph=False):
         self.model = model
         self.ignore_index = ignore_index
-        self.momentum, self.wd = momentum, weight_decay
+        self._momentum, self.wd = float(momentum), float(weight_decay)
         self.aux_weight = aux_weight
         self.world = world
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -99,6 +99,7 @@ class FusedTrainStep:
         self.g_ptrs = torch.tensor([self.grad_views[p].data_ptr() for p in self.params], **i64)
         self.m_ptrs = torch.tensor([m.data_ptr() for m in self.mom_views], **i64)
         self.sizes = torch.tensor([p.numel() for p in self.params], **i64)
+        self.hyper = torch.tensor([self._momentum, self.wd], dtype=torch.float32, device=dev)  # read by the SGD kernel
         self.steps = 0
         self.wt = WeightTables(model, self.grad_views, dev)
         self.specs = self.wt.specs
@@ -108,6 +109,17 @@ class FusedTrainStep:
         self.cuda_graph = cuda_graph
         self._graph = None
         self._static = None
+
+    @property
+    def momentum(self):
+        return self._momentum
+
+    @momentum.setter
+    def momentum(self, value):
+        """OneCycle moves the momentum every iteration: kept in device memory so graph replays see the new value."""
+        if float(value) != self._momentum:
+            self._momentum = float(value)
+            self.hyper[0:1].fill_(self._momentum)
 
     def set_lr_scale(self, scale):
         """Poly / OneCycle schedules multiply the base rates (utils/lr_scheduler.py); host scalar, one tiny op."""
@@ -189,8 +201,8 @@ class FusedTrainStep:
         self.wt.unpack()
         if self.world > 1:
             dist.all_reduce(self.flat_grad)
-        lib.call("seg_sgd_step", self.p_ptrs.data_ptr(), self.g_ptrs.data_ptr(), self.m_ptrs.data_ptr(), self.sizes.data_ptr(),
-                 self.lrs.data_ptr(), len(self.params), float(self.momentum), float(self.wd), 0, 1.0 / self.world)
+        lib.call("seg_sgd_step_dev", self.p_ptrs.data_ptr(), self.g_ptrs.data_ptr(), self.m_ptrs.data_ptr(), self.sizes.data_ptr(),
+                 self.lrs.data_ptr(), len(self.params), self.hyper.data_ptr(), 0, 1.0 / self.world)
         # (momentum buffers start at zero, so "first step: buf = d" of torch.optim.SGD is the general formula)
         self._invalidate_param_caches()
         self.steps += 1

@@ -1,0 +1,72 @@
+"""seg_augment_batch_u8 (pad + crop + flip + ToTensor + Normalize on the device) against the golden vectors of the
+reference's BaseDataSet.__getitem__ — bit-exact — and the DevicePrefetcher protocol."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import data as od
+
+if torch.cuda.is_available():
+    from seg_b200.data import DeviceBatcher, DevicePrefetcher
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data_tail.npz")
+
+
+def golden_samples(label_dtype=np.int32):
+    g = np.load(GOLD)
+    n, crop = int(g["n"]), int(g["crop"])
+    samples = [(g[f"{i}/image"], g[f"{i}/label"].astype(label_dtype)) + tuple(int(v) for v in g[f"{i}/draw"]) for i in range(n)]
+    xs = torch.from_numpy(np.stack([g[f"{i}/x"] for i in range(n)]))
+    ys = torch.from_numpy(np.stack([g[f"{i}/y"] for i in range(n)]))
+    return g, crop, samples, xs, ys
+
+
+@pytest.mark.parametrize("label_dtype", [np.int32, np.uint8])
+def test_device_tail_is_bit_exact_against_reference(label_dtype):
+    g, crop, samples, xs, ys = golden_samples(label_dtype)
+    b = DeviceBatcher(g["mean"].tolist(), g["std"].tolist(), crop, "cuda:0", max_bytes=1 << 20)
+    for _ in range(3):  # both staging slots get reused
+        x, y = b.stage(samples)
+        torch.cuda.synchronize()
+        assert x.dtype == torch.float32 and y.dtype == torch.int64 and x.shape == xs.shape and y.shape == ys.shape
+        assert torch.equal(x.cpu(), xs), "normalised images differ from the reference's ToTensor/Normalize output"
+        assert torch.equal(y.cpu(), ys)
+
+
+def test_larger_batch_against_oracle_and_images_only():
+    rs = np.random.RandomState(7)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    crop = 129
+    samples = []
+    for i in range(9):
+        h, w = int(rs.randint(60, 300)), int(rs.randint(60, 300))
+        im = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        lb = rs.randint(0, 256, (h, w)).astype(np.uint8)
+        ph, pw = max(h, crop), max(w, crop)
+        samples.append((im, lb, int(rs.randint(0, ph - crop + 1)), int(rs.randint(0, pw - crop + 1)), bool(rs.rand() > 0.5)))
+    b = DeviceBatcher(mean, std, crop, "cuda:0")
+    x, y = b.stage(samples)
+    for i, (im, lb, y0, x0, f) in enumerate(samples):
+        rx, ry = od.sample_tail(im, lb, crop, y0, x0, f, mean, std)
+        assert torch.equal(x[i].cpu(), rx) and torch.equal(y[i].cpu(), ry), i
+    x2, y2 = b.stage([(im, None, y0, x0, f) for im, _, y0, x0, f in samples])
+    assert y2 is None and torch.equal(x2, x)
+
+
+def test_prefetcher_protocol():
+    g, crop, samples, xs, ys = golden_samples()
+    b = DeviceBatcher(g["mean"].tolist(), g["std"].tolist(), crop, "cuda:0", max_bytes=1 << 20)
+    raw_loader = [samples[:3], samples[3:]]                      # raw uint8 samples -> device tail
+    ready_loader = [(xs[:3], ys[:3]), (xs[3:], ys[3:])]          # the reference's kind of batch -> passed through
+    for loader in (raw_loader, ready_loader):
+        pf = DevicePrefetcher(loader, torch.device("cuda:0"), batcher=b)
+        assert len(pf) == 2
+        got = [(x.cpu(), y.cpu()) for x, y in pf]
+        assert len(got) == 2
+        assert torch.equal(torch.cat([x for x, _ in got]), xs) and torch.equal(torch.cat([y for _, y in got]), ys)
+    pf = DevicePrefetcher(ready_loader * 3, torch.device("cuda:0"), stop_after=1)
+    assert len(list(pf)) == 2  # the reference's `count > stop_after` rule (base_dataloader.py:84)
