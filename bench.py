@@ -192,6 +192,8 @@ def main():
     ap.add_argument("--graph", type=int, default=int(os.environ.get("SEG_CUDA_GRAPH", "1")), help="replay the fused step from a CUDA graph")
     ap.add_argument("--plugin-graph", type=int, default=int(os.environ.get("SEG_PLUGIN_GRAPH", "1")),
                     help="e2e leg: replay model(x)/backward from CUDA graphs (seg_b200 model.cuda_graphs())")
+    ap.add_argument("--plugin-optim", default=os.environ.get("SEG_PLUGIN_OPTIM", "fused"), choices=["fused", "torch"],
+                    help="e2e leg optimiser: seg_b200.optim.SGD (torch.optim.SGD subclass, one kernel per group) or stock torch.optim.SGD")
     ap.add_argument("--trace", default=None, help="after the timed runs, trace 2 steps per C-ABI call and write a table here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -299,8 +301,12 @@ def main():
     e2e = None
     if not args.no_e2e:
         crit = seg_b200.CrossEntropyLoss2d(ignore_index=IGNORE)
-        opt = torch.optim.SGD([{"params": list(model.get_decoder_params())}, {"params": list(model.get_backbone_params()), "lr": 0.001}],
-                              lr=0.01, momentum=0.9, weight_decay=1e-4)
+        # seg_b200.optim.SGD IS a torch.optim.SGD (param_groups / state_dict / schedulers unchanged) whose step() is one
+        # multi-tensor kernel per group; the launcher installs it as torch.optim.SGD for the unmodified train.py
+        from seg_b200.optim import SGD as FusedSGD
+        opt_cls = FusedSGD if args.plugin_optim == "fused" else torch.optim.SGD
+        opt = opt_cls([{"params": list(model.get_decoder_params())}, {"params": list(model.get_backbone_params()), "lr": 0.001}],
+                      lr=0.01, momentum=0.9, weight_decay=1e-4)
         ddp_bufs = [p for p in model.parameters()]
 
         # the reference's DataPrefetcher (base/base_dataloader.py:49-85) copies the NEXT batch on a side stream while the
@@ -368,7 +374,8 @@ def main():
         ms_e2e = max_over_ranks(t0.elapsed_time(t1))
         e2e = {"value": world * B * Ke / (ms_e2e * 1e-3), "unit": "images/sec",
                "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 8), "d2h_bytes_per_step": 4,
-               "api": "seg_b200.DeepLab.forward -> seg_b200.CrossEntropyLoss2d -> backward -> torch.optim.SGD.step (train.py plugin surface); batch prefetched on a side stream like the reference's DataPrefetcher",
+               "api": "seg_b200.DeepLab.forward -> seg_b200.CrossEntropyLoss2d -> backward -> " + ("seg_b200.optim.SGD" if args.plugin_optim == "fused" else "torch.optim.SGD") + ".step (train.py plugin surface); batch prefetched on a side stream like the reference's DataPrefetcher",
+               "optimizer": args.plugin_optim,
                "ms_per_step": ms_e2e / Ke, "cuda_graph": plugin_graph, "cuda_graph_error": plugin_graph_err}
         if world > 1:
             model.release_graphs()

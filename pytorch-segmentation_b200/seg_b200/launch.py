@@ -46,6 +46,12 @@ def main():
     setup_paths(os.path.dirname(script))
     if "LOCAL_RANK" in os.environ and "CUDA_VISIBLE_DEVICES" not in os.environ:
         os.environ["CUDA_VISIBLE_DEVICES"] = os.environ["LOCAL_RANK"]
+    if os.environ.get("SEG_FUSED_OPTIM", "1") != "0":
+        # base/base_trainer.py:57 builds getattr(torch.optim, config['optimizer']['type']): "SGD" over CUDA fp32
+        # parameters resolves to the torch.optim.SGD subclass whose step() is the multi-tensor kernel (same param_groups /
+        # state_dict / schedulers); any other use gets the stock class
+        from seg_b200 import optim
+        optim.install()
     sys.argv = [script] + sys.argv[2:]
     runpy.run_path(script, run_name="__main__")
 
