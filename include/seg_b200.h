@@ -255,10 +255,12 @@ int seg_aug_entry_bytes(void);
 int seg_augment_batch_u8(const uint8_t* arena, const seg_aug_entry* table, int B, int crop_h, int crop_w, const float* mean3,
                          const float* std3, float* out_nchw, int64_t* out_labels, void* stream);
 /* ---- inference-side resampling (inference.py:26-79), fp32 NCHW score maps, `planes` = N*C ----
- * resize: dst = beta*dst + alpha*flip_x?(bilinear resize of src to Hd x Wd).  align_corners=1 is both ndimage.zoom(order=1)
- * (inference.py:65) and nn.Upsample(align_corners=True) (:60); same size + flip_x = tensor.flip(-1) (:48,:70). */
-int seg_resize_nchw_f32(const float* src, int64_t planes, int Hs, int Ws, float* dst, int Hd, int Wd, int align_corners,
-                        int flip_x, float alpha, float beta, void* stream);
+ * resize: dst = beta*dst + alpha*flip_x?(bilinear resize of src to Hd x Wd).  mode 0 / 1 = ATen bilinear with
+ * align_corners False / True (1 = nn.Upsample(align_corners=True), inference.py:60; same size + flip_x = tensor.flip(-1),
+ * :48,:70); mode 2 = scipy.ndimage.zoom(order=1, prefilter=False) (inference.py:65): float64 coordinates and the
+ * library's mode='constant' rule that zeroes an output whose coordinate rounds past the last input sample. */
+int seg_resize_nchw_f32(const float* src, int64_t planes, int Hs, int Ws, float* dst, int Hd, int Wd, int mode, int flip_x,
+                        float alpha, float beta, void* stream);
 /* dst[:, y0:y0+h, x0:x0+w] += alpha * flip_x?(src)[:, :h, :w]  — sliding-window accumulation (inference.py:49-53) */
 int seg_window_add_nchw_f32(const float* src, int64_t planes, int Hs, int Ws, float* dst, int Hd, int Wd, int y0, int x0, int h,
                             int w, int flip_x, float alpha, void* stream);

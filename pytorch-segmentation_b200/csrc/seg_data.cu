@@ -86,22 +86,43 @@ static inline float resize_scale(int in_size, int out_size, int align_corners) {
   return (float)in_size / (float)out_size;
 }
 
-// dst[p][oy][ox] = beta * dst + alpha * R[p][oy][flip_x ? Wd-1-ox : ox],  R = bilinear resize of src plane p to Hd x Wd
+// dst[p][oy][ox] = beta * dst + alpha * R[p][oy][flip_x ? Wd-1-ox : ox],  R = bilinear resize of src plane p to Hd x Wd.
+// mode 0 / 1 = ATen's bilinear with align_corners False / True (float source index, as F.interpolate / nn.Upsample);
+// mode 2 = scipy.ndimage.zoom(order=1, prefilter=False) as inference.py:65 calls it: float64 coordinate o * (in-1)/(out-1),
+// and — the library's mode='constant' rule — an output whose coordinate rounds to MORE than in-1 is the fill value 0
+// (for some size pairs the last row / column of the zoomed image is black in the reference; reproduced, not fixed).
 __global__ void __launch_bounds__(256) resize_nchw_kernel(const float* __restrict__ src, int64_t planes, int Hs, int Ws,
-                                                          float* __restrict__ dst, int Hd, int Wd, int ac, float sh, float sw,
-                                                          int flip_x, float alpha, float beta) {
+                                                          float* __restrict__ dst, int Hd, int Wd, int mode, float sh, float sw,
+                                                          double zh, double zw, int flip_x, float alpha, float beta) {
   const int64_t total = planes * Hd * Wd;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int ox = (int)(i % Wd);
     const int64_t t = i / Wd;
     const int oy = (int)(t % Hd);
     const int64_t p = t / Hd;
-    const Lerp ly = src_index(oy, sh, Hs, ac), lx = src_index(flip_x ? Wd - 1 - ox : ox, sw, Ws, ac);
+    const int sx = flip_x ? Wd - 1 - ox : ox;
     const float* base = src + p * Hs * Ws;
-    const float a = base[(int64_t)ly.i0 * Ws + lx.i0], b = base[(int64_t)ly.i0 * Ws + lx.i1];
-    const float c = base[(int64_t)ly.i1 * Ws + lx.i0], d = base[(int64_t)ly.i1 * Ws + lx.i1];
-    const float h1 = ly.l1, h0 = 1.f - h1, w1 = lx.l1, w0 = 1.f - w1;
-    const float v = alpha * (h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d));
+    float r;
+    if (mode == 2) {
+      const double cy = (double)oy * zh, cx = (double)sx * zw;
+      if (cy > (double)(Hs - 1) || cx > (double)(Ws - 1)) {
+        r = 0.f;
+      } else {
+        const int y0 = (int)cy, x0 = (int)cx;  // cy, cx >= 0
+        const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+        const double ty = cy - (double)y0, tx = cx - (double)x0;
+        const double a = base[(int64_t)y0 * Ws + x0], b = base[(int64_t)y0 * Ws + x1];
+        const double c = base[(int64_t)y1 * Ws + x0], d = base[(int64_t)y1 * Ws + x1];
+        r = (float)((1.0 - ty) * ((1.0 - tx) * a + tx * b) + ty * ((1.0 - tx) * c + tx * d));
+      }
+    } else {
+      const Lerp ly = src_index(oy, sh, Hs, mode), lx = src_index(sx, sw, Ws, mode);
+      const float a = base[(int64_t)ly.i0 * Ws + lx.i0], b = base[(int64_t)ly.i0 * Ws + lx.i1];
+      const float c = base[(int64_t)ly.i1 * Ws + lx.i0], d = base[(int64_t)ly.i1 * Ws + lx.i1];
+      const float h1 = ly.l1, h0 = 1.f - h1, w1 = lx.l1, w0 = 1.f - w1;
+      r = h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d);
+    }
+    const float v = alpha * r;
     dst[i] = beta != 0.f ? beta * dst[i] + v : v;
   }
 }
@@ -180,13 +201,16 @@ int seg_augment_batch_u8(const uint8_t* arena, const seg_aug_entry* table, int B
   return check_launch("augment_batch_u8");
 }
 
-int seg_resize_nchw_f32(const float* src, int64_t planes, int Hs, int Ws, float* dst, int Hd, int Wd, int align_corners,
-                        int flip_x, float alpha, float beta, void* stream) {
+int seg_resize_nchw_f32(const float* src, int64_t planes, int Hs, int Ws, float* dst, int Hd, int Wd, int mode, int flip_x,
+                        float alpha, float beta, void* stream) {
   SEG_REQUIRE(planes > 0 && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0, "resize: bad size");
   SEG_REQUIRE(src != dst, "resize: in-place is not supported");
+  SEG_REQUIRE(mode >= 0 && mode <= 2, "resize: mode must be 0 (align_corners=False), 1 (True) or 2 (ndimage.zoom)");
+  const int ac = mode == 0 ? 0 : 1;
+  // ndimage.zoom: zoom = (in - 1) / (out - 1) per axis in float64, 1 where out == 1 (scipy/ndimage/_interpolation.py)
+  const double zh = Hd > 1 ? (double)(Hs - 1) / (double)(Hd - 1) : 1.0, zw = Wd > 1 ? (double)(Ws - 1) / (double)(Wd - 1) : 1.0;
   resize_nchw_kernel<<<grid_for(planes * Hd * Wd, 256), 256, 0, ST(stream)>>>(
-      src, planes, Hs, Ws, dst, Hd, Wd, align_corners, resize_scale(Hs, Hd, align_corners), resize_scale(Ws, Wd, align_corners),
-      flip_x, alpha, beta);
+      src, planes, Hs, Ws, dst, Hd, Wd, mode, resize_scale(Hs, Hd, ac), resize_scale(Ws, Wd, ac), zh, zw, flip_x, alpha, beta);
   return check_launch("resize_nchw_f32");
 }
 

@@ -78,6 +78,7 @@ class DeviceBatcher:
                 off += (nb + 3) // 4 * 4
             table[b] = (img_off, lbl_off, h, w, int(y0), int(x0), int(bool(flip)), lb)
         host[:B * _ENTRY.itemsize] = table.view(np.uint8)
+        self.last_staged_bytes = off
         dev = self._host[slot][:off].to(self.device, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()

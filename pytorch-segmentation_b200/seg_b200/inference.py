@@ -8,8 +8,10 @@ Same signatures and arithmetic; what changes is where it runs.  The reference ro
 (`ndimage.zoom` on a numpy copy, `model(...).cpu()`, `nn.Upsample` on the CPU, float64 numpy accumulation); here the
 image pyramid, the flips, the up-sampling back to the input size and the accumulation are the fp32 kernels of
 `seg_data.cu` and nothing leaves the GPU until the caller asks for the label map.  `ndimage.zoom(order=1)` with the
-default `grid_mode=False` maps output pixel o to input o*(in-1)/(out-1), i.e. bilinear with align_corners=True, and
-rounds the output size with Python's round() — both reproduced.  Returns a device tensor [num_classes, H, W] (the
+default `grid_mode=False` maps output pixel o to input o*(in-1)/(out-1) in float64 (bilinear with align_corners=True),
+rounds the output size with Python's round(), and — mode='constant' — writes 0 where that coordinate rounds past the last
+input sample (for some size pairs the last row / column of a zoomed image is black in the reference): all reproduced
+(`seg_resize_nchw_f32` mode 2).  Returns a device tensor [num_classes, H, W] (the
 reference returns the same values as a float64 numpy array).
 """
 from math import ceil
@@ -35,7 +37,7 @@ def multi_scale_predict(model, image, scales, num_classes, device=None, flip=Fal
     with torch.no_grad():
         for scale in scales:
             Hs, Ws = int(round(H * float(scale))), int(round(W * float(scale)))
-            scaled = image if (Hs, Ws) == (H, W) else ops.resize_nchw(image, Hs, Ws, align_corners=True)
+            scaled = image if (Hs, Ws) == (H, W) else ops.resize_nchw(image, Hs, Ws, zoom=True)
             pred = model(scaled).contiguous().float()
             if flip:
                 flipped = ops.resize_nchw(scaled, Hs, Ws, align_corners=True, flip_x=True)  # same size: an exact flip

@@ -474,15 +474,16 @@ def axpby(x, y, beta):
 
 
 # ---------------------------------------------------------------- input pipeline tail / inference resampling (seg_data.cu)
-def resize_nchw(src, Hd, Wd, align_corners=True, flip_x=False, alpha=1.0, out=None, beta=0.0):
-    """out = beta*out + alpha * [flip](bilinear resize of fp32 NCHW `src` to Hd x Wd)."""
+def resize_nchw(src, Hd, Wd, align_corners=True, flip_x=False, alpha=1.0, out=None, beta=0.0, zoom=False):
+    """out = beta*out + alpha * [flip](bilinear resize of fp32 NCHW `src` to Hd x Wd).  zoom=True: scipy.ndimage.zoom(order=1)
+    semantics (float64 coordinates, outputs past the last input sample are 0) instead of ATen's."""
     N, C, Hs, Ws = src.shape
     assert src.is_contiguous() and src.dtype == torch.float32
     if out is None:
         out = torch.empty((N, C, Hd, Wd), dtype=torch.float32, device=src.device)
         beta = 0.0
     assert out.is_contiguous() and out.shape == (N, C, Hd, Wd) and out.dtype == torch.float32
-    call("seg_resize_nchw_f32", ptr(src), N * C, Hs, Ws, ptr(out), Hd, Wd, int(align_corners), int(flip_x), float(alpha), float(beta))
+    call("seg_resize_nchw_f32", ptr(src), N * C, Hs, Ws, ptr(out), Hd, Wd, 2 if zoom else int(bool(align_corners)), int(flip_x), float(alpha), float(beta))
     return out
 
 

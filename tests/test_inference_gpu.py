@@ -23,7 +23,7 @@ if torch.cuda.is_available():  # the fp32 stand-in network must not run its conv
     torch.backends.cuda.matmul.allow_tf32 = False
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inference.npz")
-TOL = 2e-4  # fp32 source-index arithmetic (ATen's float formula) vs scipy's float64 coordinates + float64 accumulation
+TOL = 2e-5  # fp32 accumulation over scales / windows against the reference's float64 numpy accumulation
 
 
 def rel(a, b):
@@ -81,6 +81,24 @@ def test_resize_flip_window_kernels_vs_aten():
     s = torch.randn(2, 7, 19, 23, generator=gen).cuda()
     s[:, 3] = s[:, 1]  # ties: the first maximum wins
     assert torch.equal(ops.argmax_nchw(s), s.argmax(1))
+
+
+def test_zoom_mode_matches_scipy_including_its_black_edge():
+    """seg_resize_nchw_f32 mode 2 against scipy.ndimage.zoom(order=1, prefilter=False) itself — including the size pairs
+    (e.g. 48 -> 84) where scipy's float64 coordinate of the last column rounds past the last sample and the column is
+    filled with 0 (mode='constant')."""
+    from scipy import ndimage
+    gen = torch.Generator().manual_seed(11)
+    saw_black = False
+    for (H, W) in ((64, 48), (37, 53), (97, 129)):
+        x = torch.randn(1, 3, H, W, generator=gen) + 4.0
+        for s in (0.75, 1.25, 1.5, 1.75, 2.0, 2.25):
+            ref = ndimage.zoom(x.numpy(), (1.0, 1.0, float(s), float(s)), order=1, prefilter=False)
+            got = ops.resize_nchw(x.cuda(), ref.shape[2], ref.shape[3], zoom=True).cpu().numpy()
+            assert got.shape == ref.shape == (1, 3, int(round(H * s)), int(round(W * s)))
+            assert np.abs(got - ref).max() < 2e-6, (H, W, s, np.abs(got - ref).max())
+            saw_black |= bool((ref[..., :, -1] == 0).all() or (ref[..., -1, :] == 0).all())
+    assert saw_black, "the parameter list is meant to include a pair that triggers scipy's constant-fill edge"
 
 
 def test_engine_model_multi_scale_shapes_and_agreement(gpu_out_dir):

@@ -57,9 +57,7 @@ def flat(grads, names):
     return torch.cat([grads[n].reshape(-1) for n in names])
 
 
-@pytest.mark.parametrize("kind", ["deeplab", "pspnet"])
-def test_graphed_plugin_step_equals_eager_step(kind, gpu_out_dir):
-    nc = 7
+def build(kind, nc=7):
     if kind == "deeplab":
         sd = weights.deeplab_resnet_state_dict(nc, "resnet14", seed=21, randomize_bn=True)
         m = seg_b200.DeepLab(nc, backbone="resnet14", output_stride=16)
@@ -70,7 +68,23 @@ def test_graphed_plugin_step_equals_eager_step(kind, gpu_out_dir):
         size = 49
     m.load_state_dict(sd, strict=True)
     m.engine_dropout = False
-    m = m.cuda().train()
+    return m.cuda().train(), size
+
+
+def log(gpu_out_dir, msg):
+    print(msg)
+    with open(f"{gpu_out_dir}/model_parity.txt", "a") as f:
+        f.write(msg + "\n")
+
+
+@pytest.mark.parametrize("kind", ["deeplab", "pspnet"])
+def test_graphed_plugin_step_equals_eager_step_frozen_bn(kind, gpu_out_dir):
+    """The sharp check.  With BatchNorm frozen (`freeze_bn()`, the reference's `arch.args.freeze_bn`) the forward has no
+    atomics and the network is well conditioned, so the replayed tapes must reproduce the eager tape's logits exactly and
+    its gradients up to the fp32-atomic order of split-K wgrad.  PSPNet also exercises the (out, aux) pair."""
+    nc = 7
+    m, size = build(kind, nc)
+    m.freeze_bn()
     crit = seg_b200.CrossEntropyLoss2d(ignore_index=255)
     opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
     m.cuda_graphs(True, warmup=1)
@@ -81,37 +95,66 @@ def test_graphed_plugin_step_equals_eager_step(kind, gpu_out_dir):
         xd, yd = x.cuda(), y.cuda()
         snap = snapshot(m)
         out_a, loss_a, g_a, _ = one_step(m, crit, xd, yd)
-        stats_a = snapshot(m)
         restore(m, snap)
         out_b, loss_b, g_b, _ = one_step(m, crit, xd, yd)          # control: eager again from the same state
         restore(m, snap)
         m._graphs_enabled = True
         out_g, loss_g, g_g, (n_fwd, n_bwd) = one_step(m, crit, xd, yd)  # i = 0: eager warm-up, 1: capture + replay, 2..: replay
         m._graphs_enabled = False
-        stats_g = snapshot(m)
         names = sorted(g_a)
         assert sorted(g_g) == names == sorted(g_b), "graph path returned gradients for a different parameter set"
-        noise_o, noise_l = relerr(out_b, out_a), abs(loss_b - loss_a) / abs(loss_a)
+        noise_o = relerr(out_b, out_a)
         c_ctrl, c_graph = cosine(flat(g_b, names), flat(g_a, names)), cosine(flat(g_g, names), flat(g_a, names))
-        msg = (f"[plugin-graph {kind}] step {i}: logits relerr {relerr(out_g, out_a):.2e} (control {noise_o:.2e}) "
-               f"loss {loss_g:.6f} vs {loss_a:.6f} grad cosine {c_graph:.6f} (control {c_ctrl:.6f}) launches fwd/bwd {n_fwd}/{n_bwd}")
-        print(msg)
-        with open(f"{gpu_out_dir}/model_parity.txt", "a") as f:
-            f.write(msg + "\n")
-        assert relerr(out_g, out_a) <= max(2e-3, 4 * noise_o)
-        assert abs(loss_g - loss_a) <= max(1e-4, 4 * noise_l) * abs(loss_a)
-        assert c_graph >= min(0.999, c_ctrl - 0.02)
-        for k in stats_a:
-            if k.endswith("running_mean") or k.endswith("running_var"):
-                assert relerr(stats_g[k], stats_a[k]) < 1e-3, k
-            if k.endswith("num_batches_tracked"):
-                assert int(stats_g[k]) == int(stats_a[k]), k
+        log(gpu_out_dir, f"[plugin-graph frozen-BN {kind}] step {i}: logits relerr {relerr(out_g, out_a):.2e} (control {noise_o:.2e}) "
+            f"loss {loss_g:.6f} vs {loss_a:.6f} grad cosine {c_graph:.6f} (control {c_ctrl:.6f}) launches fwd/bwd {n_fwd}/{n_bwd}")
+        assert relerr(out_g, out_a) <= max(1e-6, 2 * noise_o)
+        assert abs(loss_g - loss_a) <= 1e-5 * abs(loss_a)
+        assert c_graph >= min(0.9999, c_ctrl - 1e-3)
         if i >= 2:  # pure replay: the model's kernels are launched by cudaGraphLaunch, not through the C ABI
             assert n_fwd == 0 and n_bwd <= 8, (n_fwd, n_bwd)  # backward: only the CE kernels of the eager loss
             replayed += 1
-        # take the step (from the graph run's gradients) so the next iteration starts from new weights
-        opt.step()
+        opt.step()  # from the graph run's gradients: the next iteration starts from new weights
     assert replayed == 2 and len(m._graph_entries) == 1
+
+
+def test_graphed_plugin_step_batch_statistics(gpu_out_dir):
+    """Batch-statistics BatchNorm through the replayed tapes: running statistics, num_batches_tracked and the loss follow
+    the eager tape.  A random-init network with batch-stat BN on 5x5 maps amplifies the fp32-atomic order of the
+    statistics sums (eager vs eager from the same state differs by up to several percent in the logits — the control), so
+    the bounds scale with the control."""
+    nc = 7
+    m, size = build("deeplab", nc)
+    crit = seg_b200.CrossEntropyLoss2d(ignore_index=255)
+    m.cuda_graphs(True, warmup=1)
+    m._graphs_enabled = False
+    for i in range(4):
+        x, y = synth.make_batch(2, size, size, nc, 255, seed=9150 + i)
+        xd, yd = x.cuda(), y.cuda()
+        snap = snapshot(m)
+        out_a, loss_a, g_a, _ = one_step(m, crit, xd, yd)
+        stats_a = snapshot(m)
+        restore(m, snap)
+        out_b, loss_b, g_b, _ = one_step(m, crit, xd, yd)
+        stats_b = snapshot(m)
+        restore(m, snap)
+        m._graphs_enabled = True
+        out_g, loss_g, g_g, _ = one_step(m, crit, xd, yd)
+        m._graphs_enabled = False
+        stats_g = snapshot(m)
+        noise_o, noise_l = relerr(out_b, out_a), abs(loss_b - loss_a) / abs(loss_a)
+        worst_ctrl = worst = 0.0
+        for k in stats_a:
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                worst_ctrl = max(worst_ctrl, relerr(stats_b[k], stats_a[k]))
+                worst = max(worst, relerr(stats_g[k], stats_a[k]))
+            if k.endswith("num_batches_tracked"):
+                assert int(stats_g[k]) == int(stats_a[k]) == int(snap[k]) + 1, k
+        log(gpu_out_dir, f"[plugin-graph batch-stat deeplab] step {i}: logits relerr {relerr(out_g, out_a):.2e} (control {noise_o:.2e}) "
+            f"loss {loss_g:.6f} vs {loss_a:.6f} (control {loss_b:.6f}) running stats {worst:.2e} (control {worst_ctrl:.2e})")
+        assert all(torch.isfinite(v).all() for v in g_g.values()) and sorted(g_g) == sorted(g_a)
+        assert relerr(out_g, out_a) <= max(5e-3, 6 * noise_o)
+        assert abs(loss_g - loss_a) <= max(2e-3, 6 * noise_l) * abs(loss_a)
+        assert worst <= max(5e-3, 6 * worst_ctrl)
 
 
 def test_graphed_eval_forward_and_release():
