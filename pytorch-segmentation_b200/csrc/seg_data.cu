@@ -34,28 +34,41 @@ __global__ void __launch_bounds__(256) augment_u8_kernel(const uint8_t* __restri
   const uint8_t* lbl = e.lbl_off >= 0 ? arena + e.lbl_off : nullptr;
   const int64_t plane = (int64_t)crop_h * crop_w;
   float* o = out + (int64_t)b * 3 * plane;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < plane; i += (int64_t)gridDim.x * blockDim.x) {
-    const int y = (int)(i / crop_w), x = (int)(i - (int64_t)y * crop_w);
-    const int xs = e.flip ? crop_w - 1 - x : x;
-    const int sy = y + e.y0, sx = xs + e.x0;
-    const bool inside = sy < e.h && sx < e.w;
-    unsigned r = 0, g = 0, bl = 0;
-    if (inside) {
-      const uint8_t* p = img + ((int64_t)sy * e.w + sx) * 3;
-      r = p[0];
-      g = p[1];
-      bl = p[2];
-    }
-    o[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)r, 255.f), prm.mean[0]), prm.stdv[0]);
-    o[plane + i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)g, 255.f), prm.mean[1]), prm.stdv[1]);
-    o[2 * plane + i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)bl, 255.f), prm.mean[2]), prm.stdv[2]);
-    if (labels != nullptr) {
-      int64_t v = 0;
-      if (inside && lbl != nullptr) {
-        const int64_t k = (int64_t)sy * e.w + sx;
-        v = e.lbl_bytes == 1 ? (int64_t)lbl[k] : (int64_t)reinterpret_cast<const int32_t*>(lbl)[k];
+  // four pixels per thread and iteration, all loads issued before the (division-heavy) arithmetic: 4x the bytes in flight
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < plane; i0 += stride * U) {
+    unsigned r[U], g[U], bl[U];
+    int64_t lab[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      r[u] = g[u] = bl[u] = 0;
+      lab[u] = 0;
+      if (i < plane) {
+        const int y = (int)(i / crop_w), x = (int)(i - (int64_t)y * crop_w);
+        const int xs = e.flip ? crop_w - 1 - x : x;
+        const int sy = y + e.y0, sx = xs + e.x0;
+        if (sy < e.h && sx < e.w) {
+          const int64_t k = (int64_t)sy * e.w + sx;
+          const uint8_t* p = img + k * 3;
+          r[u] = p[0];
+          g[u] = p[1];
+          bl[u] = p[2];
+          if (labels != nullptr && lbl != nullptr)
+            lab[u] = e.lbl_bytes == 1 ? (int64_t)lbl[k] : (int64_t)reinterpret_cast<const int32_t*>(lbl)[k];
+        }
       }
-      labels[(int64_t)b * plane + i] = v;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < plane) {
+        o[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)r[u], 255.f), prm.mean[0]), prm.stdv[0]);
+        o[plane + i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)g[u], 255.f), prm.mean[1]), prm.stdv[1]);
+        o[2 * plane + i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)bl[u], 255.f), prm.mean[2]), prm.stdv[2]);
+        if (labels != nullptr) labels[(int64_t)b * plane + i] = lab[u];
+      }
     }
   }
 }

