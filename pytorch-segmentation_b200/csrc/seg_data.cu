@@ -28,25 +28,35 @@ struct AugParams {
 __global__ void __launch_bounds__(256) augment_u8_kernel(const uint8_t* __restrict__ arena, const seg_aug_entry* __restrict__ table,
                                                          int crop_h, int crop_w, AugParams prm, float* __restrict__ out,
                                                          int64_t* __restrict__ labels) {
+  // A uint8 channel has 256 possible values: the block evaluates the exact fp32 formula once per (channel, value) into
+  // shared memory and every pixel becomes three table look-ups.  (First version: six IEEE divisions per pixel — ncu showed
+  // the kernel instruction-bound, 220 instructions per pixel, 0.37 of the HBM roofline.)
+  __shared__ float lut[3][256];
+  for (int t = threadIdx.x; t < 768; t += blockDim.x) {
+    const int c = t >> 8, v = t & 255;
+    lut[c][v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), prm.mean[c]), prm.stdv[c]);
+  }
+  __syncthreads();
   const int b = blockIdx.y;
   const seg_aug_entry e = table[b];
   const uint8_t* img = arena + e.img_off;
-  const uint8_t* lbl = e.lbl_off >= 0 ? arena + e.lbl_off : nullptr;
-  const int64_t plane = (int64_t)crop_h * crop_w;
+  const uint8_t* lbl = (e.lbl_off >= 0 && labels != nullptr) ? arena + e.lbl_off : nullptr;
+  const int plane = crop_h * crop_w;  // < 2^31 (checked on the host)
   float* o = out + (int64_t)b * 3 * plane;
-  // four pixels per thread and iteration, all loads issued before the (division-heavy) arithmetic: 4x the bytes in flight
+  int64_t* lo = labels != nullptr ? labels + (int64_t)b * plane : nullptr;
+  // four pixels per thread and iteration, all loads issued before the stores: 4x the bytes in flight
   constexpr int U = 4;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < plane; i0 += stride * U) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < plane; i0 += stride * U) {
     unsigned r[U], g[U], bl[U];
-    int64_t lab[U];
+    int lab[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t i = i0 + u * stride;
+      const int i = i0 + u * stride;
       r[u] = g[u] = bl[u] = 0;
       lab[u] = 0;
       if (i < plane) {
-        const int y = (int)(i / crop_w), x = (int)(i - (int64_t)y * crop_w);
+        const int y = i / crop_w, x = i - y * crop_w;
         const int xs = e.flip ? crop_w - 1 - x : x;
         const int sy = y + e.y0, sx = xs + e.x0;
         if (sy < e.h && sx < e.w) {
@@ -55,19 +65,18 @@ __global__ void __launch_bounds__(256) augment_u8_kernel(const uint8_t* __restri
           r[u] = p[0];
           g[u] = p[1];
           bl[u] = p[2];
-          if (labels != nullptr && lbl != nullptr)
-            lab[u] = e.lbl_bytes == 1 ? (int64_t)lbl[k] : (int64_t)reinterpret_cast<const int32_t*>(lbl)[k];
+          if (lbl != nullptr) lab[u] = e.lbl_bytes == 1 ? (int)lbl[k] : reinterpret_cast<const int32_t*>(lbl)[k];
         }
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t i = i0 + u * stride;
+      const int i = i0 + u * stride;
       if (i < plane) {
-        o[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)r[u], 255.f), prm.mean[0]), prm.stdv[0]);
-        o[plane + i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)g[u], 255.f), prm.mean[1]), prm.stdv[1]);
-        o[2 * plane + i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)bl[u], 255.f), prm.mean[2]), prm.stdv[2]);
-        if (labels != nullptr) labels[(int64_t)b * plane + i] = lab[u];
+        o[i] = lut[0][r[u]];
+        o[plane + i] = lut[1][g[u]];
+        o[2 * (int64_t)plane + i] = lut[2][bl[u]];
+        if (lo != nullptr) lo[i] = (int64_t)lab[u];
       }
     }
   }
@@ -197,7 +206,7 @@ int seg_aug_entry_bytes(void) { return (int)sizeof(seg_aug_entry); }
 int seg_augment_batch_u8(const uint8_t* arena, const seg_aug_entry* table, int B, int crop_h, int crop_w, const float* mean3,
                          const float* std3, float* out_nchw, int64_t* out_labels, void* stream) {
   SEG_REQUIRE(arena != nullptr && table != nullptr && out_nchw != nullptr && mean3 != nullptr && std3 != nullptr, "augment: null pointer");
-  SEG_REQUIRE(B > 0 && B <= 65535 && crop_h > 0 && crop_w > 0, "augment: bad batch / crop size");
+  SEG_REQUIRE(B > 0 && B <= 65535 && crop_h > 0 && crop_w > 0 && (int64_t)crop_h * crop_w < (1ll << 30), "augment: bad batch / crop size");
   AugParams prm;
   for (int c = 0; c < 3; ++c) {
     prm.mean[c] = mean3[c];  // host pointers: six floats by value into the kernel arguments

@@ -305,29 +305,40 @@ def test_plugin_path_after_fused_steps_sees_updated_weights():
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
 
 
-def test_graph_replayed_steps_equal_eager_steps(gpu_out_dir):
+@pytest.mark.parametrize("frozen_bn", [True, False], ids=["frozen-bn", "batch-stat"])
+def test_graph_replayed_steps_equal_eager_steps(frozen_bn, gpu_out_dir):
     """CUDA-graph replay of the fused step (train.py: FusedTrainStep(cuda_graph=True)) is the same training as the eager
     step: the capture's two warm-up steps are rolled back, every replay is a fresh step (device-side counters).
-    A second eager trainer is the control for run-to-run noise (split-K wgrad uses fp32 atomics)."""
+    A second eager trainer is the control for run-to-run noise.  frozen-bn: the forward has no atomics, so the loss
+    trajectories must agree tightly (the sharp check; a tiny rate keeps the badly conditioned frozen network finite).
+    batch-stat: the fp32-atomic order of the BN statistics sums is amplified by the batch-2 image-pooling branch (two
+    samples per channel) into ~1e-3 loss differences between two EAGER runs from the same state, so the bounds are loose."""
     models = [build("deeplab", 7, "resnet14", 8, output_stride=16) for _ in range(3)]
     sd = models[0][0]
     m_e, m_c, m_g = (m for _, m in models)
     for m in (m_e, m_c, m_g):
         m.engine_dropout = False
         m.train()
+        if frozen_bn:
+            m.freeze_bn()
     x, y = synth.make_batch(2, 65, 65, 7, 255, seed=9010)
     xd, yd = x.cuda(), y.cuda()
-    se, sc, sg = FusedTrainStep(m_e, lr=0.005), FusedTrainStep(m_c, lr=0.005), FusedTrainStep(m_g, lr=0.005, cuda_graph=True)
+    lr = 1e-7 if frozen_bn else 0.005
+    se, sc, sg = FusedTrainStep(m_e, lr=lr), FusedTrainStep(m_c, lr=lr), FusedTrainStep(m_g, lr=lr, cuda_graph=True)
     for i in range(3):
         le, lc, lg = float(se.step(xd, yd)), float(sc.step(xd, yd)), float(sg.step(xd, yd))
         noise = abs(le - lc) / abs(le)
-        log(gpu_out_dir, f"graph-vs-eager step {i}: eager {le:.6f} control {lc:.6f} graph {lg:.6f}")
-        assert abs(le - lg) < max(1e-3 if i == 0 else 2e-2, 4 * noise) * abs(le), (i, le, lc, lg)
+        log(gpu_out_dir, f"graph-vs-eager [{'frozen-bn' if frozen_bn else 'batch-stat'}] step {i}: eager {le:.6f} control {lc:.6f} graph {lg:.6f}")
+        floor = 1e-5 if frozen_bn else (1e-2 if i == 0 else 3e-2)
+        assert le == le and abs(le - lg) < max(floor, 4 * noise) * abs(le), (i, le, lc, lg)
     assert sg.steps == 3
     upd = [torch.cat([(p.detach().cpu() - sd[n]).reshape(-1) for n, p in m.named_parameters()]) for m in (m_e, m_c, m_g)]
     c_ctrl, c_graph = cosine(upd[0], upd[1]), cosine(upd[0], upd[2])
-    log(gpu_out_dir, f"graph-vs-eager 3 steps: update cosine {c_graph:.5f} (eager-vs-eager control {c_ctrl:.5f})")
-    assert c_graph > min(0.9, c_ctrl - 0.08)  # bf16 + fp32-atomic run-to-run noise: the loss trajectory above is the sharp check
-    for (n, a), (_, b) in zip(m_e.named_buffers(), m_g.named_buffers()):
-        if n.endswith("num_batches_tracked"):
-            assert int(a) == int(b) == 3, n
+    log(gpu_out_dir, f"graph-vs-eager [{'frozen-bn' if frozen_bn else 'batch-stat'}] 3 steps: update cosine {c_graph:.5f} (eager-vs-eager control {c_ctrl:.5f})")
+    if frozen_bn:
+        assert c_graph > 0.999
+    else:
+        assert c_graph > min(0.9, c_ctrl - 0.08)  # chaotic regime: the loss trajectory above is the check
+        for (n, a), (_, b) in zip(m_e.named_buffers(), m_g.named_buffers()):
+            if n.endswith("num_batches_tracked"):
+                assert int(a) == int(b) == 3, n
