@@ -190,8 +190,9 @@ def main():
     ap.add_argument("--no-gpu-aten", action="store_true", help="skip the informational ATen/cuDNN timing of the oracle port on the GPU")
     ap.add_argument("--backbone", default="resnet101")
     ap.add_argument("--graph", type=int, default=int(os.environ.get("SEG_CUDA_GRAPH", "1")), help="replay the fused step from a CUDA graph")
-    ap.add_argument("--plugin-graph", type=int, default=int(os.environ.get("SEG_PLUGIN_GRAPH", "1")),
-                    help="e2e leg: replay model(x)/backward from CUDA graphs (seg_b200 model.cuda_graphs())")
+    ap.add_argument("--plugin-graph", type=int, default=int(os.environ.get("SEG_PLUGIN_GRAPH", "-1")),
+                    help="e2e leg: replay model(x)/backward from CUDA graphs (seg_b200 model.cuda_graphs()); -1 = on at N=1, "
+                         "off at N>1 (the N>1 capture with SyncBN exchanges inside is built but was not measured this round)")
     ap.add_argument("--plugin-optim", default=os.environ.get("SEG_PLUGIN_OPTIM", "fused"), choices=["fused", "torch"],
                     help="e2e leg optimiser: seg_b200.optim.SGD (torch.optim.SGD subclass, one kernel per group) or stock torch.optim.SGD")
     ap.add_argument("--trace", default=None, help="after the timed runs, trace 2 steps per C-ABI call and write a table here")
@@ -348,7 +349,7 @@ def main():
 
         # graph replay of the plugin path: model(x) and loss.backward() replay captured forward / backward tapes (two
         # eager calls warm up, the third captures).  If the capture fails the leg is measured eagerly and says so.
-        plugin_graph, plugin_graph_err = bool(args.plugin_graph), None
+        plugin_graph, plugin_graph_err = (world == 1) if args.plugin_graph < 0 else bool(args.plugin_graph), None
         if plugin_graph:
             model.cuda_graphs(True, warmup=2)
             try:
