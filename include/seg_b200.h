@@ -254,6 +254,24 @@ typedef struct seg_aug_entry {
 int seg_aug_entry_bytes(void);
 int seg_augment_batch_u8(const uint8_t* arena, const seg_aug_entry* table, int B, int crop_h, int crop_w, const float* mean3,
                          const float* std3, float* out_nchw, int64_t* out_labels, void* stream);
+/* The same tail with the random-scale resize of base/base_dataset.py:66-75 fused in front: `arena` holds the RAW samples
+ * (src_h x src_w), each output pixel interpolates from the raw image (cv2.resize INTER_LINEAR arithmetic of OpenCV's own
+ * float path, truncated to uint8 as `np.uint8(image)` does at base_dataset.py:133; INTER_NEAREST for the label) at the
+ * position the crop / flip selects in the resized h x w image.  scale_x = 1.0 / ((double)w / src_w), scale_y likewise —
+ * computed by the HOST in float64 exactly as cv::resize does. */
+typedef struct seg_aug_scale_entry {
+  int64_t img_off;        /* byte offset of the raw image (HWC uint8) in the arena */
+  int64_t lbl_off;        /* byte offset of the raw label map, or -1 */
+  double scale_x, scale_y;
+  int32_t src_h, src_w;   /* raw sample size */
+  int32_t h, w;           /* size after the resize (before padding) */
+  int32_t y0, x0;         /* crop origin in the (bottom/right zero-padded) resized image */
+  int32_t flip;
+  int32_t lbl_bytes;      /* 1 (uint8) or 4 (int32) */
+} seg_aug_scale_entry;
+int seg_aug_scale_entry_bytes(void);
+int seg_augment_scale_batch_u8(const uint8_t* arena, const seg_aug_scale_entry* table, int B, int crop_h, int crop_w,
+                               const float* mean3, const float* std3, float* out_nchw, int64_t* out_labels, void* stream);
 /* ---- inference-side resampling (inference.py:26-79), fp32 NCHW score maps, `planes` = N*C ----
  * resize: dst = beta*dst + alpha*flip_x?(bilinear resize of src to Hd x Wd).  mode 0 / 1 = ATen bilinear with
  * align_corners False / True (1 = nn.Upsample(align_corners=True), inference.py:60; same size + flip_x = tensor.flip(-1),

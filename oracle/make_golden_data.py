@@ -54,6 +54,25 @@ def main():
         rec[f"{i}/draw"] = np.asarray([y0, x0, int(flip)])
         rec[f"{i}/x"], rec[f"{i}/y"] = x.numpy(), y.numpy()
         print(i, im.shape, (y0, x0, flip), x.shape, y.shape, float(x.mean()))
+    # ---- with the random-scale resize in front (base_dataset.py:66-75): base_size set, scale=True
+    BASE = 60
+    ds2 = Synth(root=None, split="train", mean=MEAN, std=STD, base_size=BASE, augment=True, val=False, crop_size=CROP,
+                scale=True, flip=True, rotate=False, blur=False)
+    rec["base_size"] = np.asarray(BASE)
+    for i, (im, lb) in enumerate(samples):
+        random.seed(200 + i)
+        x, y = ds2[i]
+        random.seed(200 + i)  # replay: long side, crop row, crop column, flip
+        h0, w0 = im.shape[:2]
+        longside = random.randint(int(BASE * 0.5), int(BASE * 2.0))
+        h, w = (longside, int(1.0 * longside * w0 / h0 + 0.5)) if h0 > w0 else (int(1.0 * longside * h0 / w0 + 0.5), longside)
+        ph, pw = max(h, CROP), max(w, CROP)
+        y0 = random.randint(0, ph - CROP)
+        x0 = random.randint(0, pw - CROP)
+        flip = random.random() > 0.5
+        rec[f"s{i}/draw"] = np.asarray([h, w, y0, x0, int(flip)])
+        rec[f"s{i}/x"], rec[f"s{i}/y"] = x.numpy(), y.numpy()
+        print("scaled", i, im.shape, (h, w), (y0, x0, flip), float(x.mean()))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "data_tail.npz"), **rec)
 
 

@@ -82,6 +82,95 @@ __global__ void __launch_bounds__(256) augment_u8_kernel(const uint8_t* __restri
   }
 }
 
+// ------------------------------------------------------------------ random-scale resize fused in front of the tail
+// base_dataset.py:66-75 resizes the sample (cv2.resize: INTER_LINEAR on the float32 image, INTER_NEAREST on the label)
+// before the pad / crop / flip / np.uint8 / ToTensor / Normalize tail.  Here the RAW uint8 sample crosses PCIe and each
+// output pixel of the crop interpolates its value straight from the raw image: no resized intermediate exists.
+// Arithmetic = OpenCV's own float path (modules/imgproc/src/resize.cpp, resizeGeneric_ / HResizeLinear / VResizeLinear):
+//   f = (float)((d + 0.5) * scale - 0.5) with scale = 1 / (dst / src) in float64;  s = floor(f);  f -= s;
+//   x: s < 0 -> (0, f = 0);  s >= src-1 -> (src-1, f = 0);      y: coefficient kept, ROW indices clipped to [0, src-1]
+//   H = S[s]*(1-fx) + S[s+1]*fx   (fp32, no fma);   V = H0*(1-fy) + H1*fy   (fp32, no fma);   u8 = (uint8)V  (np.uint8 truncates)
+//   label: src index = min(floor(d * scale), src-1)
+// (opencv-python wheels route float32 resize through Intel IPP, whose closed-source arithmetic differs from the above by
+// <= 3e-3 before the uint8 truncation: against the reference AS RUN the images agree except ~0.1 % of the pixels by one
+// level; against OpenCV's own code path — cv2.ipp.setUseIPP(False) — and the oracle restatement they are bit-exact.)
+__device__ __forceinline__ void cv_linear_coord(int d, double scale, int src, bool clamp, int& s, float& f) {
+  const float fv = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);
+  const float fl = floorf(fv);
+  s = (int)fl;
+  f = __fsub_rn(fv, fl);
+  if (clamp) {
+    if (s < 0) {
+      s = 0;
+      f = 0.f;
+    }
+    if (s >= src - 1) {
+      s = src - 1;
+      f = 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) augment_scale_u8_kernel(const uint8_t* __restrict__ arena,
+                                                               const seg_aug_scale_entry* __restrict__ table, int crop_h, int crop_w,
+                                                               AugParams prm, float* __restrict__ out, int64_t* __restrict__ labels) {
+  __shared__ float lut[3][256];
+  for (int t = threadIdx.x; t < 768; t += blockDim.x) {
+    const int c = t >> 8, v = t & 255;
+    lut[c][v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), prm.mean[c]), prm.stdv[c]);
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const seg_aug_scale_entry e = table[b];
+  const uint8_t* img = arena + e.img_off;
+  const uint8_t* lbl = (e.lbl_off >= 0 && labels != nullptr) ? arena + e.lbl_off : nullptr;
+  const int plane = crop_h * crop_w;
+  float* o = out + (int64_t)b * 3 * plane;
+  int64_t* lo = labels != nullptr ? labels + (int64_t)b * plane : nullptr;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += stride) {
+    const int y = i / crop_w, x = i - y * crop_w;
+    const int xs = e.flip ? crop_w - 1 - x : x;
+    const int dy = y + e.y0, dx = xs + e.x0;  // position in the RESIZED (h x w) image; outside = zero padding
+    unsigned r = 0, g = 0, bl = 0;
+    int lab = 0;
+    if (dy < e.h && dx < e.w) {
+      int sx, sy;
+      float fx, fy;
+      cv_linear_coord(dx, e.scale_x, e.src_w, true, sx, fx);
+      cv_linear_coord(dy, e.scale_y, e.src_h, false, sy, fy);
+      const int sx1 = sx + 1 < e.src_w ? sx + 1 : e.src_w - 1;
+      const int y0c = min(max(sy, 0), e.src_h - 1), y1c = min(max(sy + 1, 0), e.src_h - 1);
+      const float ax0 = __fsub_rn(1.f, fx), ay0 = __fsub_rn(1.f, fy);
+      const uint8_t* r0 = img + (int64_t)y0c * e.src_w * 3;
+      const uint8_t* r1 = img + (int64_t)y1c * e.src_w * 3;
+      unsigned res[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float h0 = __fadd_rn(__fmul_rn((float)r0[sx * 3 + c], ax0), __fmul_rn((float)r0[sx1 * 3 + c], fx));
+        const float h1 = __fadd_rn(__fmul_rn((float)r1[sx * 3 + c], ax0), __fmul_rn((float)r1[sx1 * 3 + c], fx));
+        const float v = __fadd_rn(__fmul_rn(h0, ay0), __fmul_rn(h1, fy));
+        res[c] = (unsigned)v;  // np.uint8(float): truncation; v is a convex combination of [0, 255] values
+        if (res[c] > 255u) res[c] = 255u;
+      }
+      r = res[0];
+      g = res[1];
+      bl = res[2];
+      if (lbl != nullptr) {
+        int lx = (int)floor(__dmul_rn((double)dx, e.scale_x)), ly = (int)floor(__dmul_rn((double)dy, e.scale_y));
+        lx = lx < e.src_w - 1 ? lx : e.src_w - 1;
+        ly = ly < e.src_h - 1 ? ly : e.src_h - 1;
+        const int64_t k = (int64_t)ly * e.src_w + lx;
+        lab = e.lbl_bytes == 1 ? (int)lbl[k] : reinterpret_cast<const int32_t*>(lbl)[k];
+      }
+    }
+    o[i] = lut[0][r];
+    o[plane + i] = lut[1][g];
+    o[2 * (int64_t)plane + i] = lut[2][bl];
+    if (lo != nullptr) lo[i] = (int64_t)lab;
+  }
+}
+
 // ------------------------------------------------------------------ bilinear resize of fp32 NCHW planes
 // Source index exactly as ATen's area_pixel_compute_source_index (float arithmetic) — same helper as seg_elementwise.cu.
 struct Lerp {
@@ -221,6 +310,27 @@ int seg_augment_batch_u8(const uint8_t* arena, const seg_aug_entry* table, int B
   dim3 grid((unsigned)per_image, (unsigned)B, 1);
   augment_u8_kernel<<<grid, 256, 0, ST(stream)>>>(arena, table, crop_h, crop_w, prm, out_nchw, out_labels);
   return check_launch("augment_batch_u8");
+}
+
+int seg_aug_scale_entry_bytes(void) { return (int)sizeof(seg_aug_scale_entry); }
+
+int seg_augment_scale_batch_u8(const uint8_t* arena, const seg_aug_scale_entry* table, int B, int crop_h, int crop_w,
+                               const float* mean3, const float* std3, float* out_nchw, int64_t* out_labels, void* stream) {
+  SEG_REQUIRE(arena != nullptr && table != nullptr && out_nchw != nullptr && mean3 != nullptr && std3 != nullptr, "augment_scale: null pointer");
+  SEG_REQUIRE(B > 0 && B <= 65535 && crop_h > 0 && crop_w > 0 && (int64_t)crop_h * crop_w < (1ll << 30), "augment_scale: bad batch / crop size");
+  AugParams prm;
+  for (int c = 0; c < 3; ++c) {
+    prm.mean[c] = mean3[c];
+    prm.stdv[c] = std3[c];
+    SEG_REQUIRE(std3[c] != 0.f, "augment_scale: std must be non-zero");
+  }
+  int64_t per_image = ((int64_t)num_sms() * 8 + B - 1) / B;
+  const int64_t need = ceil_div64((int64_t)crop_h * crop_w, 256);
+  if (per_image > need) per_image = need;
+  if (per_image < 1) per_image = 1;
+  dim3 grid((unsigned)per_image, (unsigned)B, 1);
+  augment_scale_u8_kernel<<<grid, 256, 0, ST(stream)>>>(arena, table, crop_h, crop_w, prm, out_nchw, out_labels);
+  return check_launch("augment_scale_batch_u8");
 }
 
 int seg_resize_nchw_f32(const float* src, int64_t planes, int Hs, int Ws, float* dst, int Hd, int Wd, int mode, int flip_x,

@@ -23,6 +23,18 @@ _ENTRY = np.dtype([("img_off", "<i8"), ("lbl_off", "<i8"), ("h", "<i4"), ("w", "
                    ("flip", "<i4"), ("lbl_bytes", "<i4")])
 
 
+_SCALE_ENTRY = np.dtype([("img_off", "<i8"), ("lbl_off", "<i8"), ("scale_x", "<f8"), ("scale_y", "<f8"), ("src_h", "<i4"),
+                         ("src_w", "<i4"), ("h", "<i4"), ("w", "<i4"), ("y0", "<i4"), ("x0", "<i4"), ("flip", "<i4"), ("lbl_bytes", "<i4")])
+
+
+def draw_scale(h, w, base_size, scale=True, rng=random):
+    """Size after the random-scale resize of base_dataset.py:66-72 (the long side becomes a draw in [0.5, 2] x base_size)."""
+    if not base_size:
+        return h, w
+    longside = rng.randint(int(base_size * 0.5), int(base_size * 2.0)) if scale else base_size
+    return (longside, int(1.0 * longside * w / h + 0.5)) if h > w else (int(1.0 * longside * h / w + 0.5), longside)
+
+
 def draw_crop_flip(h, w, crop_size, flip=True, rng=random):
     """The draws of base_dataset.py:107-121 in the reference's order: crop origin in the padded image, then the flip."""
     ph, pw = max(h, crop_size), max(w, crop_size)
@@ -85,6 +97,51 @@ class DeviceBatcher:
         self._events[slot] = ev
         tab = dev[:B * _ENTRY.itemsize]
         return ops.augment_batch_u8(dev, tab, B, self.crop, self.crop, self.mean, self.std, want_labels=want_labels)
+
+    def stage_scaled(self, samples):
+        """samples: sequence of (RAW image uint8 [H,W,3], RAW label uint8|int32 [H,W] or None, h, w, y0, x0, flip): the sample
+        is resized to h x w (cv2.resize arithmetic, base_dataset.py:66-75) and then padded / cropped / flipped / normalised
+        — in one kernel, without a resized intermediate (`seg_augment_scale_batch_u8`)."""
+        assert _SCALE_ENTRY.itemsize == lib.load().seg_aug_scale_entry_bytes()
+        B = len(samples)
+        slot = self._slot
+        self._slot ^= 1
+        if self._events[slot] is not None:
+            self._events[slot].synchronize()
+        host = self._host[slot].numpy()
+        table = np.zeros(B, dtype=_SCALE_ENTRY)
+        off = B * _SCALE_ENTRY.itemsize
+        want_labels = samples[0][1] is not None
+        for b, (img, lbl, h, w, y0, x0, flip) in enumerate(samples):
+            img = np.ascontiguousarray(img, dtype=np.uint8)
+            H, W = img.shape[:2]
+            assert img.shape == (H, W, 3), "images are HWC uint8 with 3 channels"
+            n = img.size
+            lb, lbl_off = 1, -1
+            if lbl is not None:
+                lbl = np.ascontiguousarray(lbl)
+                assert lbl.shape == (H, W) and lbl.dtype in (np.uint8, np.int32), "labels are uint8 or int32 [H,W]"
+                lb = lbl.dtype.itemsize
+            if off + n + 8 + (H * W * lb if lbl is not None else 0) > self.capacity:
+                raise RuntimeError(f"DeviceBatcher: batch needs more than max_bytes={self.capacity} of staging memory")
+            host[off:off + n] = img.reshape(-1)
+            img_off = off
+            off += (n + 3) // 4 * 4
+            if lbl is not None:
+                nb = H * W * lb
+                host[off:off + nb] = lbl.reshape(-1).view(np.uint8)
+                lbl_off = off
+                off += (nb + 3) // 4 * 4
+            # cv::resize: inv_scale = dsize / ssize, scale = 1. / inv_scale — float64, computed here so the kernel sees the same bits
+            table[b] = (img_off, lbl_off, 1.0 / (int(w) / W), 1.0 / (int(h) / H), H, W, int(h), int(w), int(y0), int(x0), int(bool(flip)), lb)
+        host[:B * _SCALE_ENTRY.itemsize] = table.view(np.uint8)
+        self.last_staged_bytes = off
+        dev = self._host[slot][:off].to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._events[slot] = ev
+        return ops.augment_scale_batch_u8(dev, dev[:B * _SCALE_ENTRY.itemsize], B, self.crop, self.crop, self.mean, self.std,
+                                          want_labels=want_labels)
 
     def stage_random(self, raw, flip=True, rng=random):
         """raw: sequence of (image, label).  Draws crop origin / flip per sample like the reference's worker would."""
