@@ -64,9 +64,65 @@ def cv_resize_nearest(lbl, w, h):
     return lbl[ys][:, xs]
 
 
-def sample_scale_tail(image, label, h, w, crop_size, y0, x0, flip, mean, std):
-    """base_dataset.py:66-75 (random-scale resize to h x w) followed by the tail above; the float image is truncated to
-    uint8 where the reference does it (np.uint8(image), base_dataset.py:133) — truncation commutes with pad/crop/flip."""
-    img = np.uint8(cv_resize_linear_f32(image, w, h))
+def cv_rotation_matrix(center, angle_deg, scale=1.0):
+    """cv2.getRotationMatrix2D (modules/imgproc/src/imgwarp.cpp): float64 throughout."""
+    import math
+    a = angle_deg * (math.pi / 180.0)  # angle *= CV_PI/180
+    alpha, beta = math.cos(a) * scale, math.sin(a) * scale
+    cx, cy = float(np.float32(center[0])), float(np.float32(center[1]))  # Point2f
+    return np.array([[alpha, beta, (1 - alpha) * cx - beta * cy], [-beta, alpha, beta * cx + (1 - alpha) * cy]], dtype=np.float64)
+
+
+def cv_warp_affine(img, M, w, h, linear):
+    """cv2.warpAffine(img, M, (w, h), flags=INTER_LINEAR | INTER_NEAREST) with the default constant-0 border, as
+    base_dataset.py:77-83 calls it (float32 image / int32 label).  OpenCV inverts M in float64, walks the destination with
+    FIXED-POINT source coordinates (10 fractional bits: per-column terms round(M00*x*1024), per-row terms
+    round((M01*y + M02)*1024) + rounding offset), and for INTER_LINEAR keeps 5 fractional bits (a 1/32-pixel grid) whose
+    bilinear weights are float32 products (1-fy)(1-fx), (1-fy)fx, fy(1-fx), fy*fx; taps outside the image contribute 0.
+    Bit-exact against cv2 with IPP on or off (tests/test_data_tail_oracle_cpu.py)."""
+    AB_BITS, INTER_BITS = 10, 5
+    AB_SCALE, TAB = 1 << AB_BITS, 1 << INTER_BITS
+    M = np.asarray(M, dtype=np.float64)
+    D = M[0, 0] * M[1, 1] - M[0, 1] * M[1, 0]
+    D = 1.0 / D if D != 0 else 0.0
+    A11, A22, A12, A21 = M[1, 1] * D, M[0, 0] * D, -M[0, 1] * D, -M[1, 0] * D
+    b1, b2 = -A11 * M[0, 2] - A12 * M[1, 2], -A21 * M[0, 2] - A22 * M[1, 2]
+    sh, sw = img.shape[:2]
+    xs, ys = np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64)
+    rnd = lambda v: np.rint(v).astype(np.int64)  # noqa: E731  saturate_cast<int>(double): round half to even
+    delta = AB_SCALE // TAB // 2 if linear else AB_SCALE // 2
+    X = (rnd((A12 * ys + b1) * AB_SCALE) + delta)[:, None] + rnd(A11 * xs * AB_SCALE)[None, :]
+    Y = (rnd((A22 * ys + b2) * AB_SCALE) + delta)[:, None] + rnd(A21 * xs * AB_SCALE)[None, :]
+
+    def tap(yy, xx):
+        ok = (xx >= 0) & (xx < sw) & (yy >= 0) & (yy < sh)
+        v = img[np.clip(yy, 0, sh - 1), np.clip(xx, 0, sw - 1)]
+        return np.where(ok[..., None] if img.ndim == 3 else ok, v, 0)
+
+    if not linear:
+        return tap(Y >> AB_BITS, X >> AB_BITS).astype(img.dtype)
+    Xf, Yf = X >> (AB_BITS - INTER_BITS), Y >> (AB_BITS - INTER_BITS)
+    xi, yi = Xf >> INTER_BITS, Yf >> INTER_BITS
+    fx = (Xf & (TAB - 1)).astype(np.float32) / np.float32(TAB)
+    fy = (Yf & (TAB - 1)).astype(np.float32) / np.float32(TAB)
+    ex = (lambda a: a[..., None]) if img.ndim == 3 else (lambda a: a)
+    one = np.float32(1)
+    w00, w01, w10, w11 = ex((one - fy) * (one - fx)), ex((one - fy) * fx), ex(fy * (one - fx)), ex(fy * fx)
+    f = img.astype(np.float32)
+    sav, img = img, f
+    out = tap(yi, xi) * w00 + tap(yi, xi + 1) * w01 + tap(yi + 1, xi) * w10 + tap(yi + 1, xi + 1) * w11
+    img = sav
+    return out.astype(np.float32)
+
+
+def sample_scale_tail(image, label, h, w, crop_size, y0, x0, flip, mean, std, angle=None):
+    """base_dataset.py:66-75 (random-scale resize to h x w), optionally :77-83 (rotation by `angle` degrees about the centre
+    of the resized image), then the tail above; the float image is truncated to uint8 where the reference does it
+    (np.uint8(image), base_dataset.py:133) — truncation commutes with pad/crop/flip."""
+    img = cv_resize_linear_f32(image, w, h)
     lab = cv_resize_nearest(np.asarray(label), w, h)
-    return sample_tail(img, lab, crop_size, y0, x0, flip, mean, std)
+    if angle is not None:
+        M = cv_rotation_matrix((w / 2, h / 2), angle, 1.0)
+        img = cv_warp_affine(img, M, w, h, linear=True)
+        lab = cv_warp_affine(lab, M, w, h, linear=False)
+    return sample_tail(np.uint8(img), lab, crop_size, y0, x0, flip, mean, std)

@@ -73,6 +73,24 @@ def main():
         rec[f"s{i}/draw"] = np.asarray([h, w, y0, x0, int(flip)])
         rec[f"s{i}/x"], rec[f"s{i}/y"] = x.numpy(), y.numpy()
         print("scaled", i, im.shape, (h, w), (y0, x0, flip), float(x.mean()))
+    # ---- scale + rotate (base_dataset.py:77-83), the shipped config.json's setting
+    ds3 = Synth(root=None, split="train", mean=MEAN, std=STD, base_size=BASE, augment=True, val=False, crop_size=CROP,
+                scale=True, flip=True, rotate=True, blur=False)
+    for i, (im, lb) in enumerate(samples):
+        random.seed(300 + i)
+        x, y = ds3[i]
+        random.seed(300 + i)  # replay: long side, angle, crop row, crop column, flip
+        h0, w0 = im.shape[:2]
+        longside = random.randint(int(BASE * 0.5), int(BASE * 2.0))
+        h, w = (longside, int(1.0 * longside * w0 / h0 + 0.5)) if h0 > w0 else (int(1.0 * longside * h0 / w0 + 0.5), longside)
+        angle = random.randint(-10, 10)
+        ph, pw = max(h, CROP), max(w, CROP)
+        y0 = random.randint(0, ph - CROP)
+        x0 = random.randint(0, pw - CROP)
+        flip = random.random() > 0.5
+        rec[f"r{i}/draw"] = np.asarray([h, w, angle, y0, x0, int(flip)])
+        rec[f"r{i}/x"], rec[f"r{i}/y"] = x.numpy(), y.numpy()
+        print("rotated", i, im.shape, (h, w), angle, (y0, x0, flip), float(x.mean()))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "data_tail.npz"), **rec)
 
 

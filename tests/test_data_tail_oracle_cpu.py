@@ -76,3 +76,36 @@ def test_draw_scale_matches_reference():
         h, w = draw_scale(h0, w0, base, scale=True)
         y0, x0, flip = draw_crop_flip(h, w, crop, flip=True)
         assert [h, w, y0, x0, int(flip)] == [int(v) for v in g[f"s{i}/draw"]], i
+
+
+def test_oracle_rotation_is_opencvs_arithmetic():
+    """oracle.data.cv_rotation_matrix / cv_warp_affine against cv2.getRotationMatrix2D / cv2.warpAffine: bit-exact, with
+    IPP on or off (warpAffine's fixed-point coordinate walk is OpenCV's own code either way)."""
+    cv2 = __import__("pytest").importorskip("cv2")
+    rs = np.random.RandomState(8)
+    for _ in range(40):
+        h, w = int(rs.randint(20, 140)), int(rs.randint(20, 140))
+        img = (rs.rand(h, w, 3) * 255).astype(np.float32)
+        lbl = rs.randint(0, 21, (h, w)).astype(np.int32)
+        angle = int(rs.randint(-10, 11))
+        M = od.cv_rotation_matrix((w / 2, h / 2), angle)
+        assert np.array_equal(M, cv2.getRotationMatrix2D((w / 2, h / 2), angle, 1.0))
+        assert np.array_equal(cv2.warpAffine(img, M, (w, h), flags=cv2.INTER_LINEAR), od.cv_warp_affine(img, M, w, h, True))
+        assert np.array_equal(cv2.warpAffine(lbl, M, (w, h), flags=cv2.INTER_NEAREST), od.cv_warp_affine(lbl, M, w, h, False))
+
+
+def test_oracle_scale_rotate_tail_against_reference():
+    """The whole default augmentation chain of config.json minus blur — scale, rotate, pad, crop, flip, ToTensor, Normalize —
+    against the reference's BaseDataSet.__getitem__ as run: labels exact, images within one uint8 level on < 1 % of the
+    pixels (the IPP float resize, see above; the rotation itself is restated exactly)."""
+    g = np.load(GOLD)
+    crop = int(g["crop"])
+    mean, std = g["mean"].tolist(), g["std"].tolist()
+    one_level = 1.0 / 255.0 / min(std) * 1.001
+    for i in range(int(g["n"])):
+        h, w, angle, y0, x0, flip = (int(v) for v in g[f"r{i}/draw"])
+        x, y = od.sample_scale_tail(g[f"{i}/image"], g[f"{i}/label"], h, w, crop, y0, x0, bool(flip), mean, std, angle=angle)
+        assert torch.equal(y, torch.from_numpy(g[f"r{i}/y"])), i
+        d = (x - torch.from_numpy(g[f"r{i}/x"])).abs()
+        assert d.max().item() <= one_level, (i, d.max().item())
+        assert (d > 0).float().mean().item() < 0.01, (i, (d > 0).float().mean().item())
