@@ -272,6 +272,23 @@ typedef struct seg_aug_scale_entry {
 int seg_aug_scale_entry_bytes(void);
 int seg_augment_scale_batch_u8(const uint8_t* arena, const seg_aug_scale_entry* table, int B, int crop_h, int crop_w,
                                const float* mean3, const float* std3, float* out_nchw, int64_t* out_labels, void* stream);
+/* EXPERIMENTAL (compiled and exported, not yet run on a GPU): the same with the rotation of base/base_dataset.py:77-83
+ * between the resize and the tail.  (a11 a12 b1; a21 a22 b2) = the INVERSE of cv2.getRotationMatrix2D((w/2, h/2), angle, 1)
+ * computed by the host in float64 exactly as cv::warpAffine does (oracle/data.py::cv_warp_affine); identity = no rotation. */
+typedef struct seg_aug_full_entry {
+  int64_t img_off;
+  int64_t lbl_off;
+  double scale_x, scale_y;
+  double a11, a12, b1, a21, a22, b2;
+  int32_t src_h, src_w;
+  int32_t h, w;
+  int32_t y0, x0;
+  int32_t flip;
+  int32_t lbl_bytes;
+} seg_aug_full_entry;
+int seg_aug_full_entry_bytes(void);
+int seg_augment_full_batch_u8(const uint8_t* arena, const seg_aug_full_entry* table, int B, int crop_h, int crop_w,
+                              const float* mean3, const float* std3, float* out_nchw, int64_t* out_labels, void* stream);
 /* ---- inference-side resampling (inference.py:26-79), fp32 NCHW score maps, `planes` = N*C ----
  * resize: dst = beta*dst + alpha*flip_x?(bilinear resize of src to Hd x Wd).  mode 0 / 1 = ATen bilinear with
  * align_corners False / True (1 = nn.Upsample(align_corners=True), inference.py:60; same size + flip_x = tensor.flip(-1),

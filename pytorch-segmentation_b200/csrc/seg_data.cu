@@ -171,6 +171,115 @@ __global__ void __launch_bounds__(256) augment_scale_u8_kernel(const uint8_t* __
   }
 }
 
+// ------------------------------------------------------------------ scale + ROTATE + tail (experimental: never run on a GPU)
+// base_dataset.py:77-83 rotates the resized float image (cv2.warpAffine INTER_LINEAR) and label (INTER_NEAREST) about the
+// centre by a drawn angle, constant-0 border.  OpenCV's walk, restated bit-exactly in oracle/data.py::cv_warp_affine: the
+// inverse matrix (float64, from the host) gives fixed-point source coordinates with 10 fractional bits,
+//   X = rint((A12*y + b1) * 1024) + delta + rint(A11*x * 1024),  Y likewise,   delta = 16 (linear) / 512 (nearest);
+// INTER_LINEAR keeps 5 fractional bits (a 1/32-pixel grid) and blends the four taps with float32 weight products; taps
+// outside the resized image are 0.  Each tap of the RESIZED image is itself the cv2.resize interpolation of the raw image
+// (augment_scale_u8_kernel's arithmetic, NOT truncated: the rotation consumes the float image), so an output pixel costs up
+// to 16 raw taps and no intermediate image exists.  Written after the round's GPU budget was spent: compiled, exported,
+// reachable only through DeviceBatcher.stage_full / tests gated by SEG_EXPERIMENTAL=1.
+__device__ __forceinline__ void resized_pixel_f32(const uint8_t* __restrict__ img, const seg_aug_full_entry& e, int ry, int rx, float* out3) {
+  if (ry < 0 || ry >= e.h || rx < 0 || rx >= e.w) {
+    out3[0] = out3[1] = out3[2] = 0.f;
+    return;
+  }
+  int sx, sy;
+  float fx, fy;
+  cv_linear_coord(rx, e.scale_x, e.src_w, true, sx, fx);
+  cv_linear_coord(ry, e.scale_y, e.src_h, false, sy, fy);
+  const int sx1 = sx + 1 < e.src_w ? sx + 1 : e.src_w - 1;
+  const int y0c = min(max(sy, 0), e.src_h - 1), y1c = min(max(sy + 1, 0), e.src_h - 1);
+  const float ax0 = __fsub_rn(1.f, fx), ay0 = __fsub_rn(1.f, fy);
+  const uint8_t* r0 = img + (int64_t)y0c * e.src_w * 3;
+  const uint8_t* r1 = img + (int64_t)y1c * e.src_w * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float h0 = __fadd_rn(__fmul_rn((float)r0[sx * 3 + c], ax0), __fmul_rn((float)r0[sx1 * 3 + c], fx));
+    const float h1 = __fadd_rn(__fmul_rn((float)r1[sx * 3 + c], ax0), __fmul_rn((float)r1[sx1 * 3 + c], fx));
+    out3[c] = __fadd_rn(__fmul_rn(h0, ay0), __fmul_rn(h1, fy));
+  }
+}
+
+__device__ __forceinline__ int resized_label(const uint8_t* __restrict__ lbl, const seg_aug_full_entry& e, int ry, int rx) {
+  if (ry < 0 || ry >= e.h || rx < 0 || rx >= e.w) return 0;
+  int lx = (int)floor(__dmul_rn((double)rx, e.scale_x)), ly = (int)floor(__dmul_rn((double)ry, e.scale_y));
+  lx = lx < e.src_w - 1 ? lx : e.src_w - 1;
+  ly = ly < e.src_h - 1 ? ly : e.src_h - 1;
+  const int64_t k = (int64_t)ly * e.src_w + lx;
+  return e.lbl_bytes == 1 ? (int)lbl[k] : reinterpret_cast<const int32_t*>(lbl)[k];
+}
+
+// INTER_NEAREST uses delta = AB_SCALE / 2 on the same rounded row / column terms
+__device__ __forceinline__ long long rowX_nearest_fix(long long row_term, long long col_term) { return row_term + 512 + col_term; }
+
+__global__ void __launch_bounds__(256) augment_full_u8_kernel(const uint8_t* __restrict__ arena, const seg_aug_full_entry* __restrict__ table,
+                                                              int crop_h, int crop_w, AugParams prm, float* __restrict__ out,
+                                                              int64_t* __restrict__ labels) {
+  __shared__ float lut[3][256];
+  for (int t = threadIdx.x; t < 768; t += blockDim.x) {
+    const int c = t >> 8, v = t & 255;
+    lut[c][v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), prm.mean[c]), prm.stdv[c]);
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const seg_aug_full_entry e = table[b];
+  const uint8_t* img = arena + e.img_off;
+  const uint8_t* lbl = (e.lbl_off >= 0 && labels != nullptr) ? arena + e.lbl_off : nullptr;
+  const int plane = crop_h * crop_w;
+  float* o = out + (int64_t)b * 3 * plane;
+  int64_t* lo = labels != nullptr ? labels + (int64_t)b * plane : nullptr;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += stride) {
+    const int y = i / crop_w, x = i - y * crop_w;
+    const int xs = e.flip ? crop_w - 1 - x : x;
+    const int dy = y + e.y0, dx = xs + e.x0;  // position in the rotated h x w image; outside = zero padding
+    unsigned r = 0, g = 0, bl = 0;
+    int lab = 0;
+    if (dy < e.h && dx < e.w) {
+      // fixed-point source coordinates in the resized image (the two rounded terms are added as integers, as OpenCV does)
+      const long long colX = __double2ll_rn(__dmul_rn(__dmul_rn(e.a11, (double)dx), 1024.0));
+      const long long colY = __double2ll_rn(__dmul_rn(__dmul_rn(e.a21, (double)dx), 1024.0));
+      const long long rowX = __double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(e.a12, (double)dy), e.b1), 1024.0));
+      const long long rowY = __double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(e.a22, (double)dy), e.b2), 1024.0));
+      {
+        const long long X = rowX + 16 + colX, Y = rowY + 16 + colY;  // delta = AB_SCALE / INTER_TAB_SIZE / 2
+        const long long Xf = X >> 5, Yf = Y >> 5;                    // 5 fractional bits left
+        const int xi = (int)(Xf >> 5), yi = (int)(Yf >> 5);
+        const float fx = __fdiv_rn((float)(int)(Xf & 31), 32.f), fy = __fdiv_rn((float)(int)(Yf & 31), 32.f);
+        const float one_fx = __fsub_rn(1.f, fx), one_fy = __fsub_rn(1.f, fy);
+        const float w00 = __fmul_rn(one_fy, one_fx), w01 = __fmul_rn(one_fy, fx), w10 = __fmul_rn(fy, one_fx), w11 = __fmul_rn(fy, fx);
+        float p00[3], p01[3], p10[3], p11[3];
+        resized_pixel_f32(img, e, yi, xi, p00);
+        resized_pixel_f32(img, e, yi, xi + 1, p01);
+        resized_pixel_f32(img, e, yi + 1, xi, p10);
+        resized_pixel_f32(img, e, yi + 1, xi + 1, p11);
+        unsigned res[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p00[c], w00), __fmul_rn(p01[c], w01)), __fmul_rn(p10[c], w10)),
+                                    __fmul_rn(p11[c], w11));
+          res[c] = v > 0.f ? (unsigned)v : 0u;  // np.uint8(float) truncates
+          if (res[c] > 255u) res[c] = 255u;
+        }
+        r = res[0];
+        g = res[1];
+        bl = res[2];
+      }
+      if (lbl != nullptr) {
+        const long long X = rowX_nearest_fix(rowX, colX), Y = rowX_nearest_fix(rowY, colY);
+        lab = resized_label(lbl, e, (int)(Y >> 10), (int)(X >> 10));
+      }
+    }
+    o[i] = lut[0][r];
+    o[plane + i] = lut[1][g];
+    o[2 * (int64_t)plane + i] = lut[2][bl];
+    if (lo != nullptr) lo[i] = (int64_t)lab;
+  }
+}
+
 // ------------------------------------------------------------------ bilinear resize of fp32 NCHW planes
 // Source index exactly as ATen's area_pixel_compute_source_index (float arithmetic) — same helper as seg_elementwise.cu.
 struct Lerp {
@@ -331,6 +440,27 @@ int seg_augment_scale_batch_u8(const uint8_t* arena, const seg_aug_scale_entry* 
   dim3 grid((unsigned)per_image, (unsigned)B, 1);
   augment_scale_u8_kernel<<<grid, 256, 0, ST(stream)>>>(arena, table, crop_h, crop_w, prm, out_nchw, out_labels);
   return check_launch("augment_scale_batch_u8");
+}
+
+int seg_aug_full_entry_bytes(void) { return (int)sizeof(seg_aug_full_entry); }
+
+int seg_augment_full_batch_u8(const uint8_t* arena, const seg_aug_full_entry* table, int B, int crop_h, int crop_w,
+                              const float* mean3, const float* std3, float* out_nchw, int64_t* out_labels, void* stream) {
+  SEG_REQUIRE(arena != nullptr && table != nullptr && out_nchw != nullptr && mean3 != nullptr && std3 != nullptr, "augment_full: null pointer");
+  SEG_REQUIRE(B > 0 && B <= 65535 && crop_h > 0 && crop_w > 0 && (int64_t)crop_h * crop_w < (1ll << 30), "augment_full: bad batch / crop size");
+  AugParams prm;
+  for (int c = 0; c < 3; ++c) {
+    prm.mean[c] = mean3[c];
+    prm.stdv[c] = std3[c];
+    SEG_REQUIRE(std3[c] != 0.f, "augment_full: std must be non-zero");
+  }
+  int64_t per_image = ((int64_t)num_sms() * 8 + B - 1) / B;
+  const int64_t need = ceil_div64((int64_t)crop_h * crop_w, 256);
+  if (per_image > need) per_image = need;
+  if (per_image < 1) per_image = 1;
+  dim3 grid((unsigned)per_image, (unsigned)B, 1);
+  augment_full_u8_kernel<<<grid, 256, 0, ST(stream)>>>(arena, table, crop_h, crop_w, prm, out_nchw, out_labels);
+  return check_launch("augment_full_batch_u8");
 }
 
 int seg_resize_nchw_f32(const float* src, int64_t planes, int Hs, int Ws, float* dst, int Hd, int Wd, int mode, int flip_x,

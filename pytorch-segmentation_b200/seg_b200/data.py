@@ -12,6 +12,7 @@ for the whole batch, bit-exactly (same fp32 operations).  The random draws stay 
         a loader that yields ready (float image batch, long label batch) pairs is passed through exactly as the reference
         does, a loader that yields lists of raw samples goes through the batcher.
 """
+import math
 import random
 
 import numpy as np
@@ -25,6 +26,32 @@ _ENTRY = np.dtype([("img_off", "<i8"), ("lbl_off", "<i8"), ("h", "<i4"), ("w", "
 
 _SCALE_ENTRY = np.dtype([("img_off", "<i8"), ("lbl_off", "<i8"), ("scale_x", "<f8"), ("scale_y", "<f8"), ("src_h", "<i4"),
                          ("src_w", "<i4"), ("h", "<i4"), ("w", "<i4"), ("y0", "<i4"), ("x0", "<i4"), ("flip", "<i4"), ("lbl_bytes", "<i4")])
+
+
+_FULL_ENTRY = np.dtype([("img_off", "<i8"), ("lbl_off", "<i8"), ("scale_x", "<f8"), ("scale_y", "<f8"), ("a11", "<f8"), ("a12", "<f8"),
+                        ("b1", "<f8"), ("a21", "<f8"), ("a22", "<f8"), ("b2", "<f8"), ("src_h", "<i4"), ("src_w", "<i4"), ("h", "<i4"),
+                        ("w", "<i4"), ("y0", "<i4"), ("x0", "<i4"), ("flip", "<i4"), ("lbl_bytes", "<i4")])
+
+
+def draw_rotate(rotate=True, rng=random):
+    """The angle draw of base_dataset.py:78 (between the scale draw and the crop draws); None when rotation is off."""
+    return rng.randint(-10, 10) if rotate else None
+
+
+def inverse_rotation(w, h, angle):
+    """(a11, a12, b1, a21, a22, b2): the inverse of cv2.getRotationMatrix2D((w/2, h/2), angle, 1.0) in float64, the operations
+    cv::getRotationMatrix2D and cv::warpAffine perform (imgwarp.cpp) in their order; identity for angle None."""
+    if angle is None:
+        return 1.0, 0.0, 0.0, 0.0, 1.0, 0.0
+    a = angle * (math.pi / 180.0)
+    alpha, beta = math.cos(a) * 1.0, math.sin(a) * 1.0
+    cx, cy = float(np.float32(w / 2)), float(np.float32(h / 2))  # Point2f
+    m00, m01, m02 = alpha, beta, (1 - alpha) * cx - beta * cy
+    m10, m11, m12 = -beta, alpha, beta * cx + (1 - alpha) * cy
+    d = m00 * m11 - m01 * m10
+    d = 1.0 / d if d != 0 else 0.0
+    a11, a22, a12, a21 = m11 * d, m00 * d, -m01 * d, -m10 * d
+    return a11, a12, -a11 * m02 - a12 * m12, a21, a22, -a21 * m02 - a22 * m12
 
 
 def draw_scale(h, w, base_size, scale=True, rng=random):
@@ -142,6 +169,51 @@ class DeviceBatcher:
         self._events[slot] = ev
         return ops.augment_scale_batch_u8(dev, dev[:B * _SCALE_ENTRY.itemsize], B, self.crop, self.crop, self.mean, self.std,
                                           want_labels=want_labels)
+
+    def stage_full(self, samples):
+        """EXPERIMENTAL (compiled, not yet run on a GPU; tests gated by SEG_EXPERIMENTAL=1).  samples: sequence of
+        (RAW image, RAW label or None, h, w, angle or None, y0, x0, flip): resize to h x w, rotate by `angle` degrees about the
+        centre (base_dataset.py:77-83), pad / crop / flip / normalise — one kernel (`seg_augment_full_batch_u8`)."""
+        assert _FULL_ENTRY.itemsize == lib.load().seg_aug_full_entry_bytes()
+        B = len(samples)
+        slot = self._slot
+        self._slot ^= 1
+        if self._events[slot] is not None:
+            self._events[slot].synchronize()
+        host = self._host[slot].numpy()
+        table = np.zeros(B, dtype=_FULL_ENTRY)
+        off = B * _FULL_ENTRY.itemsize
+        want_labels = samples[0][1] is not None
+        for b, (img, lbl, h, w, angle, y0, x0, flip) in enumerate(samples):
+            img = np.ascontiguousarray(img, dtype=np.uint8)
+            H, W = img.shape[:2]
+            assert img.shape == (H, W, 3), "images are HWC uint8 with 3 channels"
+            n = img.size
+            lb, lbl_off = 1, -1
+            if lbl is not None:
+                lbl = np.ascontiguousarray(lbl)
+                assert lbl.shape == (H, W) and lbl.dtype in (np.uint8, np.int32), "labels are uint8 or int32 [H,W]"
+                lb = lbl.dtype.itemsize
+            if off + n + 8 + (H * W * lb if lbl is not None else 0) > self.capacity:
+                raise RuntimeError(f"DeviceBatcher: batch needs more than max_bytes={self.capacity} of staging memory")
+            host[off:off + n] = img.reshape(-1)
+            img_off = off
+            off += (n + 3) // 4 * 4
+            if lbl is not None:
+                nb = H * W * lb
+                host[off:off + nb] = lbl.reshape(-1).view(np.uint8)
+                lbl_off = off
+                off += (nb + 3) // 4 * 4
+            table[b] = (img_off, lbl_off, 1.0 / (int(w) / W), 1.0 / (int(h) / H)) + inverse_rotation(int(w), int(h), angle) + \
+                       (H, W, int(h), int(w), int(y0), int(x0), int(bool(flip)), lb)
+        host[:B * _FULL_ENTRY.itemsize] = table.view(np.uint8)
+        self.last_staged_bytes = off
+        dev = self._host[slot][:off].to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._events[slot] = ev
+        return ops.augment_full_batch_u8(dev, dev[:B * _FULL_ENTRY.itemsize], B, self.crop, self.crop, self.mean, self.std,
+                                         want_labels=want_labels)
 
     def stage_random(self, raw, flip=True, rng=random):
         """raw: sequence of (image, label).  Draws crop origin / flip per sample like the reference's worker would."""

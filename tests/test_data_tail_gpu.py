@@ -106,3 +106,30 @@ def test_device_scaled_tail_is_bit_exact_against_oracle_and_within_one_level_of_
         rx, ry = od.sample_scale_tail(im, lb, h, w, crop2, y0, x0, f, mean, std)
         assert torch.equal(y2[i].cpu(), ry), i
         assert torch.equal(x2[i].cpu(), rx), (i, (x2[i].cpu() - rx).abs().max().item())
+
+
+@pytest.mark.skipif(os.environ.get("SEG_EXPERIMENTAL") != "1",
+                    reason="seg_augment_full_batch_u8 was written after round 1's GPU budget was spent: compiled, CPU-transcription-checked, not yet run")
+def test_device_scale_rotate_tail_experimental():
+    """scale -> rotate -> pad -> crop -> flip -> normalise in one kernel: bit-exact against the staged oracle (which equals
+    cv2's resize / warpAffine arithmetic), labels exact and images within one level of the reference's as-run goldens."""
+    g = np.load(GOLD)
+    n, crop = int(g["n"]), int(g["crop"])
+    mean, std = g["mean"].tolist(), g["std"].tolist()
+    samples = []
+    for i in range(n):
+        h, w, angle, y0, x0, flip = (int(v) for v in g[f"r{i}/draw"])
+        samples.append((g[f"{i}/image"], g[f"{i}/label"].astype(np.int32), h, w, angle, y0, x0, flip))
+    b = DeviceBatcher(mean, std, crop, "cuda:0", max_bytes=1 << 20)
+    x, y = b.stage_full(samples)
+    torch.cuda.synchronize()
+    one_level = 1.0 / 255.0 / min(std) * 1.001
+    for i, (im, lb, h, w, angle, y0, x0, f) in enumerate(samples):
+        rx, ry = od.sample_scale_tail(im, lb, h, w, crop, y0, x0, bool(f), mean, std, angle=angle)
+        assert torch.equal(y[i].cpu(), ry) and torch.equal(x[i].cpu(), rx), (i, (x[i].cpu() - rx).abs().max().item())
+        assert torch.equal(y[i].cpu(), torch.from_numpy(g[f"r{i}/y"])), i
+        d = (x[i].cpu() - torch.from_numpy(g[f"r{i}/x"])).abs()
+        assert d.max().item() <= one_level and (d > 0).float().mean().item() < 0.01, i
+    x0_, y0_ = b.stage_full([s[:4] + (None,) + s[5:] for s in samples])   # no rotation == the scale kernel
+    xs, ys = b.stage_scaled([s[:4] + s[5:] for s in samples])
+    assert torch.equal(x0_, xs) and torch.equal(y0_, ys)

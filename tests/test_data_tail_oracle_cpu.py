@@ -109,3 +109,80 @@ def test_oracle_scale_rotate_tail_against_reference():
         d = (x - torch.from_numpy(g[f"r{i}/x"])).abs()
         assert d.max().item() <= one_level, (i, d.max().item())
         assert (d > 0).float().mean().item() < 0.01, (i, (d > 0).float().mean().item())
+
+
+def _fused_emulation(image, label, h, w, angle, crop, y0, x0, flip, mean, std):
+    """numpy transcription of augment_full_u8_kernel (seg_data.cu): per OUTPUT pixel, fixed-point rotated coordinates ->
+    four taps of the resized image, each interpolated on the fly from the raw image -> truncate -> normalise.  No resized or
+    rotated intermediate, exactly the kernel's operation order."""
+    from seg_b200.data import inverse_rotation
+    H, W = image.shape[:2]
+    sx_scale, sy_scale = 1.0 / (w / W), 1.0 / (h / H)
+    a11, a12, b1, a21, a22, b2 = inverse_rotation(w, h, angle)
+    raw = image.astype(np.float32)
+    f32 = np.float32
+
+    def coord(d, scale, src, clamp):
+        fv = ((d.astype(np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+        fl = np.floor(fv)
+        s = fl.astype(np.int64)
+        f = (fv - fl).astype(np.float32)
+        if clamp:
+            lo, hi = s < 0, s >= src - 1
+            f = np.where(lo | hi, f32(0), f)
+            s = np.where(lo, 0, np.where(hi, src - 1, s))
+        return s, f
+
+    def resized(ry, rx):  # float value of the resized image at integer (ry, rx); 0 outside
+        ok = (ry >= 0) & (ry < h) & (rx >= 0) & (rx < w)
+        ryc, rxc = np.clip(ry, 0, h - 1), np.clip(rx, 0, w - 1)
+        sx, fx = coord(rxc, sx_scale, W, True)
+        sy, fy = coord(ryc, sy_scale, H, False)
+        sx1 = np.minimum(sx + 1, W - 1)
+        y0c, y1c = np.clip(sy, 0, H - 1), np.clip(sy + 1, 0, H - 1)
+        ax0, ay0 = (f32(1) - fx)[..., None], (f32(1) - fy)[..., None]
+        fx_, fy_ = fx[..., None], fy[..., None]
+        h0 = raw[y0c, sx] * ax0 + raw[y0c, sx1] * fx_
+        h1 = raw[y1c, sx] * ax0 + raw[y1c, sx1] * fx_
+        return np.where(ok[..., None], h0 * ay0 + h1 * fy_, f32(0)).astype(np.float32)
+
+    ys, xs = np.meshgrid(np.arange(crop), np.arange(crop), indexing="ij")
+    xs = crop - 1 - xs if flip else xs
+    dy, dx = ys + y0, xs + x0
+    inside = (dy < h) & (dx < w)
+    rnd = lambda v: np.rint(v).astype(np.int64)  # noqa: E731
+    colX, colY = rnd(a11 * dx.astype(np.float64) * 1024.0), rnd(a21 * dx.astype(np.float64) * 1024.0)
+    rowX, rowY = rnd((a12 * dy.astype(np.float64) + b1) * 1024.0), rnd((a22 * dy.astype(np.float64) + b2) * 1024.0)
+    X, Y = rowX + 16 + colX, rowY + 16 + colY
+    Xf, Yf = X >> 5, Y >> 5
+    xi, yi = Xf >> 5, Yf >> 5
+    fx, fy = (Xf & 31).astype(np.float32) / f32(32), (Yf & 31).astype(np.float32) / f32(32)
+    w00, w01 = ((f32(1) - fy) * (f32(1) - fx))[..., None], ((f32(1) - fy) * fx)[..., None]
+    w10, w11 = (fy * (f32(1) - fx))[..., None], (fy * fx)[..., None]
+    v = resized(yi, xi) * w00 + resized(yi, xi + 1) * w01 + resized(yi + 1, xi) * w10 + resized(yi + 1, xi + 1) * w11
+    u8 = np.where(inside[..., None], np.clip(np.where(v > 0, v, 0).astype(np.int64), 0, 255), 0).astype(np.uint8)
+    Xn, Yn = (rowX + 512 + colX) >> 10, (rowY + 512 + colY) >> 10
+    okl = inside & (Yn >= 0) & (Yn < h) & (Xn >= 0) & (Xn < w)
+    lx = np.minimum(np.floor(np.clip(Xn, 0, w - 1).astype(np.float64) * sx_scale).astype(np.int64), W - 1)
+    ly = np.minimum(np.floor(np.clip(Yn, 0, h - 1).astype(np.float64) * sy_scale).astype(np.int64), H - 1)
+    lab = np.where(okl, np.asarray(label)[ly, lx], 0).astype(np.int64)
+    t = torch.from_numpy(u8).permute(2, 0, 1).contiguous().to(torch.float32).div(255)
+    m = torch.as_tensor(mean, dtype=torch.float32).view(-1, 1, 1)
+    s = torch.as_tensor(std, dtype=torch.float32).view(-1, 1, 1)
+    return t.sub_(m).div_(s), torch.from_numpy(lab)
+
+
+def test_fused_scale_rotate_formulation_equals_staged_oracle():
+    """The experimental kernel computes every output pixel from the raw sample in one go (no resized / rotated image).  Its
+    numpy transcription must equal the staged oracle (resize, then warpAffine, then the tail) bit for bit — with and without
+    a rotation — which pins the fusion logic the CUDA code follows line by line."""
+    g = np.load(GOLD)
+    crop = int(g["crop"])
+    mean, std = g["mean"].tolist(), g["std"].tolist()
+    for i in range(int(g["n"])):
+        h, w, angle, y0, x0, flip = (int(v) for v in g[f"r{i}/draw"])
+        for ang in (angle, None, -10, 0):
+            x, y = _fused_emulation(g[f"{i}/image"], g[f"{i}/label"], h, w, ang, crop, y0, x0, bool(flip), mean, std)
+            rx, ry = od.sample_scale_tail(g[f"{i}/image"], g[f"{i}/label"], h, w, crop, y0, x0, bool(flip), mean, std, angle=ang)
+            assert torch.equal(y, ry), (i, ang)
+            assert torch.equal(x, rx), (i, ang, (x - rx).abs().max().item())
