@@ -186,3 +186,16 @@ def test_fused_scale_rotate_formulation_equals_staged_oracle():
             rx, ry = od.sample_scale_tail(g[f"{i}/image"], g[f"{i}/label"], h, w, crop, y0, x0, bool(flip), mean, std, angle=ang)
             assert torch.equal(y, ry), (i, ang)
             assert torch.equal(x, rx), (i, ang, (x - rx).abs().max().item())
+
+
+def test_draw_order_with_rotation_matches_reference():
+    from seg_b200.data import draw_crop_flip, draw_rotate, draw_scale
+    g = np.load(GOLD)
+    crop, base = int(g["crop"]), int(g["base_size"])
+    for i in range(int(g["n"])):
+        h0, w0 = g[f"{i}/image"].shape[:2]
+        random.seed(300 + i)  # the seed the golden generator gave the reference's __getitem__ (scale + rotate on)
+        h, w = draw_scale(h0, w0, base, scale=True)
+        angle = draw_rotate(True)
+        y0, x0, flip = draw_crop_flip(h, w, crop, flip=True)
+        assert [h, w, angle, y0, x0, int(flip)] == [int(v) for v in g[f"r{i}/draw"]], i
