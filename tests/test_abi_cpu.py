@@ -54,3 +54,21 @@ def test_conv_desc_layout_matches_header():
     assert (d.P, d.Q) == (33, 33)
     d = lib.make_conv_desc(1, 513, 513, 3, 64, 7, 7, 2, 3, 1)
     assert (d.P, d.Q) == (257, 257)
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under pytorch-segmentation_b200/ (host package, overlay, kernels) may import,
+    include or execute it — the product path has no CPU restatement to fall back to."""
+    pkg = os.path.join(ROOT, "pytorch-segmentation_b200")
+    offenders = []
+    for d, _, files in os.walk(pkg):
+        if os.path.basename(d) in ("build", "__pycache__"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                src = open(os.path.join(d, f), errors="ignore").read()
+                imports = re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M)          # Python import
+                executes = re.search(r"(#include|open\(|exec\(|runpy)[^\n]*oracle/", src)          # include / read / run
+                if imports or executes:
+                    offenders.append(os.path.relpath(os.path.join(d, f), ROOT))
+    assert not offenders, offenders
