@@ -272,6 +272,7 @@ class _EngineModel(BaseModel):
         self._graph_warmup = 2
         self._graph_entries = {}
         self._graph_seen = {}
+        self._graph_max = 8           # captured (shape, mode) entries kept at most; further shapes run the eager tape
         self._flat_cache = None
 
     # ------------------------------------------------------------------ cached views of the module tree
@@ -311,7 +312,9 @@ class _EngineModel(BaseModel):
         and mode run eagerly (they are real steps and double as allocator / tensor-map warm-up), the next one captures
         the forward and backward tapes once, later calls replay them.  Contract (that of
         torch.cuda.make_graphed_callables): the returned logits live in a static buffer that the next forward of the
-        same shape overwrites; one backward per forward (a forward issued while a backward is outstanding runs eagerly)."""
+        same shape overwrites; one backward per forward (a forward issued while a backward is outstanding runs eagerly).
+        At most `_graph_max` (8) distinct (shape, mode) combinations are captured — each owns a memory pool the size of
+        the step's activations; others keep running the eager tape."""
         self._graphs_enabled = bool(enabled)
         self._graph_warmup = int(warmup)
         if not enabled:
@@ -339,8 +342,8 @@ class _EngineModel(BaseModel):
         if e is None:
             n = self._graph_seen.get(key, 0)
             self._graph_seen[key] = n + 1
-            if n < self._graph_warmup:
-                return None
+            if n < self._graph_warmup or len(self._graph_entries) >= self._graph_max:
+                return None  # every entry owns a private memory pool (the step's activations): bound their number
             e = _GraphEntry(bool(record), ptrs)
             try:
                 self._capture(e, x)
