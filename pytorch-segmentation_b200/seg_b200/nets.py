@@ -1,8 +1,11 @@
 """B200-native drop-in models for the reference's plugin surface (models/__init__.py registry):
 
-    DeepLab(num_classes, in_channels=3, backbone='resnet101', pretrained=False, output_stride=16, freeze_bn=False, **_)
-    PSPNet (num_classes, in_channels=3, backbone='resnet50',  pretrained=False, use_aux=True,   freeze_bn=False, **_)
-    UperNet(num_classes, in_channels=3, backbone='resnet101', pretrained=False, use_aux=True, fpn_out=256, freeze_bn=False, **_)
+    DeepLab(num_classes, in_channels=3, backbone='xception',  pretrained=None, output_stride=16, freeze_bn=False, **_)
+    PSPNet (num_classes, in_channels=3, backbone='resnet152', pretrained=None, use_aux=True,   freeze_bn=False, **_)
+    UperNet(num_classes, in_channels=3, backbone='resnet101', pretrained=None, use_aux=True, fpn_out=256, freeze_bn=False, **_)
+
+(default backbones are the reference's; `pretrained`: the reference defaults to True and downloads ImageNet weights — there is
+no network here, so an explicit True raises and the default (None) initialises randomly with a logged warning)
 
 Same constructor contract, same `state_dict()` keys and OIHW fp32 parameter layout, same `get_backbone_params /
 get_decoder_params / freeze_bn` methods and the same forward contract (fp32 NCHW logits at input resolution; PSPNet
@@ -174,6 +177,18 @@ def _init_like_resnet_s(*mods):
             elif isinstance(m, nn.BatchNorm2d):
                 m.weight.data.fill_(1)
                 m.bias.data.zero_()
+
+
+def _check_pretrained(model, pretrained):
+    """The reference's constructors default to pretrained=True and download ImageNet weights (resnet.py:21-27,
+    deeplabv3_plus.py:172).  No network here: an explicit True raises; the default (None) — what a config that omits the key
+    gets — initialises randomly like pretrained=False and says so once, instead of silently differing from the reference."""
+    if pretrained:
+        raise RuntimeError("pretrained weights need network access; load a state_dict instead")
+    if pretrained is None:
+        model.logger.warning("%s: the reference would download ImageNet weights here (pretrained defaults to True); this "
+                             "build has no network and initialises randomly — load a state_dict, or pass pretrained=False "
+                             "to silence this message", type(model).__name__)
 
 
 # ----------------------------------------------------------------------------------------------- autograd bridge
@@ -514,13 +529,12 @@ class _EngineModel(BaseModel):
 class DeepLab(_EngineModel):
     """DeepLabV3+ with a (dilated) torchvision-style ResNet trunk — replaces models/deeplabv3_plus.py:336-377."""
 
-    def __init__(self, num_classes, in_channels=3, backbone="resnet101", pretrained=False, output_stride=16,
+    def __init__(self, num_classes, in_channels=3, backbone="xception", pretrained=None, output_stride=16,
                  freeze_bn=False, freeze_backbone=False, **_):
         super().__init__()
         if backbone != "xception" and backbone not in RESNET_BLOCKS:
             raise NotImplementedError(f"seg_b200.DeepLab: backbone {backbone!r} not built (xception, resnet50/101/152 are)")
-        if pretrained:
-            raise RuntimeError("pretrained weights need network access; load a state_dict instead")
+        _check_pretrained(self, pretrained)
         assert output_stride in (8, 16)
         self.num_classes, self.output_stride, self.backbone_name = num_classes, output_stride, backbone
         if backbone == "xception":
@@ -646,13 +660,12 @@ class DeepLab(_EngineModel):
 class PSPNet(_EngineModel):
     """PSPNet over the deep-stem dilated ResNet — replaces models/pspnet.py:41-105 + models/resnet.py:124-212."""
 
-    def __init__(self, num_classes, in_channels=3, backbone="resnet50", pretrained=False, use_aux=True, freeze_bn=False,
+    def __init__(self, num_classes, in_channels=3, backbone="resnet152", pretrained=None, use_aux=True, freeze_bn=False,
                  freeze_backbone=False, **_):
         super().__init__()
         if backbone not in RESNET_BLOCKS:
             raise NotImplementedError(f"seg_b200.PSPNet: backbone {backbone!r} not built")
-        if pretrained:
-            raise RuntimeError("pretrained weights need network access; load a state_dict instead")
+        _check_pretrained(self, pretrained)
         if in_channels != 3:
             raise NotImplementedError("in_channels != 3 swaps the deep stem for a 7x7 conv (pspnet.py:50-51); not built")
         self.num_classes, self.use_aux = num_classes, use_aux
@@ -740,13 +753,12 @@ class UperNet(_EngineModel):
     entries), non-cumulative top-down path, laterals / smooth / head carry a bias, conv_fusion does not.
     (The reference constructor itself raises NameError: freeze_backbone, upernet.py:133 — here the argument works.)"""
 
-    def __init__(self, num_classes, in_channels=3, backbone="resnet101", pretrained=False, use_aux=True, fpn_out=256,
+    def __init__(self, num_classes, in_channels=3, backbone="resnet101", pretrained=None, use_aux=True, fpn_out=256,
                  freeze_bn=False, freeze_backbone=False, **_):
         super().__init__()
         if backbone not in RESNET_BLOCKS:
             raise NotImplementedError(f"seg_b200.UperNet: backbone {backbone!r} not built (bottleneck ResNets are)")
-        if pretrained:
-            raise RuntimeError("pretrained weights need network access; load a state_dict instead")
+        _check_pretrained(self, pretrained)
         self.num_classes = num_classes
         bb = _Holder()
         c0, b0 = nn.Conv2d(in_channels, 64, 7, stride=2, padding=3, bias=False), nn.BatchNorm2d(64)

@@ -271,7 +271,7 @@ def test_state_dict_keys_match_reference_inventory():
     u = seg_b200.UperNet(150, backbone="resnet101")
     assert list(u.state_dict().keys()) == list(weights.upernet_state_dict(150, "resnet101").keys())
     assert u._n_trainable() == 126414038
-    assert p._n_trainable() == 51446762 and seg_b200.PSPNet(19)._n_trainable() == 51444710
+    assert p._n_trainable() == 51446762 and seg_b200.PSPNet(19, backbone="resnet50")._n_trainable() == 51444710
     assert len(list(m.get_backbone_params())) + len(list(m.get_decoder_params())) == len(list(m.parameters()))
 
 

@@ -48,3 +48,30 @@ def test_overlay_resolves_registries():
     r = subprocess.run([sys.executable, "-W", "ignore", "-c", CODE], env=env, cwd=REF, capture_output=True, text=True, timeout=600)
     assert "OVERLAY_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
     assert "Nbr of trainable parameters: 51446762" in r.stdout
+
+
+def test_constructor_defaults_match_the_reference():
+    """A config that omits `backbone` must build the architecture the reference would (models/deeplabv3_plus.py:337,
+    models/pspnet.py:42, models/upernet.py:121); `pretrained` cannot be honoured offline: the default only warns."""
+    import inspect
+    import logging
+    import seg_b200
+    want = {"DeepLab": "xception", "PSPNet": "resnet152", "UperNet": "resnet101"}
+    for name, backbone in want.items():
+        sig = inspect.signature(getattr(seg_b200, name).__init__)
+        assert sig.parameters["backbone"].default == backbone, name
+        assert sig.parameters["pretrained"].default is None, name
+        assert list(sig.parameters)[1:3] == ["num_classes", "in_channels"], name
+    records = []
+    h = logging.Handler()
+    h.emit = records.append
+    logging.getLogger("DeepLab").addHandler(h)
+    try:
+        seg_b200.DeepLab(5, backbone="resnet50")                    # default pretrained -> warning, random init
+        n = len(records)
+        seg_b200.DeepLab(5, backbone="resnet50", pretrained=False)  # explicit False -> silent
+    finally:
+        logging.getLogger("DeepLab").removeHandler(h)
+    assert n >= 1 and len(records) == n and "ImageNet" in records[0].getMessage()
+    with pytest.raises(RuntimeError, match="network"):
+        seg_b200.DeepLab(5, backbone="resnet50", pretrained=True)
