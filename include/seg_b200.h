@@ -56,10 +56,15 @@ void seg_launch_count_reset(void);
 /* ---- convolution: replaces nn.Conv2d (models/deeplabv3_plus.py:21,256,268,306,312-319; torchvision
  *      Bottleneck conv1/2/3 + downsample.0 mutated at deeplabv3_plus.py:35-53; models/resnet.py:43-48,80-86) ---- */
 /* y[N,P,Q,K] = conv(x, w) (+bias[K]);  y = beta*y + result.  y_dtype in {bf16, fp32}.
- * stats (optional, fp32 [2*K], must be zeroed by caller): per-channel sum and sum of squares of the fp32 result
- * accumulated atomically (feeds seg_bn_finalize; replaces the reduction half of nn.BatchNorm2d). */
+ * stats (optional, fp32 [2*K], written): per-channel sum and sum of squares of the result as stored — the reduction half
+ * of nn.BatchNorm2d, produced by the conv epilogue.  The cross-CTA sum is a fixed-order ticket tree (no atomics on the
+ * data): the statistics are bit-reproducible from run to run.  It needs two workspaces sized by
+ * seg_conv_stats_workspace: `stats_rows` (floats, uninitialised; may be shared by consecutive calls on one stream) and
+ * `stats_tickets` (uint32, must be ZERO at launch; not shareable). */
+int seg_conv_stats_workspace(const seg_conv_desc* d, int64_t* rows_floats, int64_t* tickets);
 int seg_conv2d_fwd(const seg_conv_desc* d, const void* x, const void* w_packed, void* y, int y_dtype,
-                   const float* bias, float beta, float* stats, int impl, void* stream);
+                   const float* bias, float beta, float* stats, float* stats_rows, void* stats_tickets, int impl,
+                   void* stream);
 /* dx[N,H,W,C] = beta*dx + conv_transpose(dy, w)   (autograd of the above w.r.t. x) */
 int seg_conv2d_dgrad(const seg_conv_desc* d, const void* dy, const void* w_packed, void* dx, float beta,
                      int impl, void* stream);
@@ -70,7 +75,8 @@ int seg_conv2d_wgrad(const seg_conv_desc* d, const void* dy, const void* x, floa
 /* ---- depthwise 3x3 (atrous) convolution: SeparableConv2d.conv1 of the Aligned-Xception backbone
  *      (models/deeplabv3_plus.py:77-78, groups = C).  desc: K == C, R = S = 3.  Packed weights: fp32 [9][C]. ---- */
 int64_t seg_dwconv_scratch_floats(int C);
-/* y = dw(x); stats (optional, fp32 [2C], accumulated) = per-channel sum / sum of squares of y; scratch: 16*2*C floats */
+/* y = dw(x); stats (optional, fp32 [2C], written) = per-channel sum / sum of squares of y (fixed-order cross-block sum);
+ * scratch: seg_dwconv_scratch_floats(C) floats */
 int seg_dwconv3x3_fwd(const seg_conv_desc* d, const void* x, const float* w9, void* y, float* stats, float* scratch,
                       void* stream);
 /* dx = beta*dx + dw^T(dy) */
@@ -100,8 +106,12 @@ int seg_im2col(const seg_conv_desc* d, const void* x, int x_nchw_f32, void* col,
 
 /* ---- batch norm (nn.BatchNorm2d everywhere on the path; sync_batchnorm/batchnorm.py:128-145 for the multi-GPU
  *      variant): statistics, finalize, apply(+residual+ReLU+dropout), backward ---- */
-/* stats[0:C] += sum_x, stats[C:2C] += sum_x^2 over M rows of x[M][ldx] (bf16) */
-int seg_bn_stats(const void* x, int64_t M, int C, int ldx, float* stats, void* stream);
+/* workspace of a deterministic column reduction (seg_bn_stats: nacc = 2, seg_bn_bwd_reduce: nacc = 2) over M rows x C
+ * channels: `rows_floats` floats of uninitialised scratch (shareable between consecutive calls on one stream) and
+ * `tickets` uint32 that must be ZERO at launch */
+int seg_reduce_workspace(int64_t M, int C, int nacc, int64_t* rows_floats, int64_t* tickets);
+/* stats[0:C] = sum_x, stats[C:2C] = sum_x^2 over M rows of x[M][ldx] (bf16); fixed-order cross-block sum */
+int seg_bn_stats(const void* x, int64_t M, int C, int ldx, float* stats, float* fold_rows, void* fold_tickets, void* stream);
 /* mean/var from (possibly all-reduced) sums over `count` elements; writes scale_shift[0:C]=gamma*inv_std,
  * [C:2C]=beta-mean*scale, save_mean_istd[0:C]=mean,[C:2C]=inv_std; updates running stats with momentum and the
  * unbiased variance.  clamp_eps=0: inv_std=(var+eps)^-1/2 (F.batch_norm); 1: clamp(var,eps)^-1/2
@@ -114,30 +124,31 @@ int seg_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const 
                             const float* running_var, float eps, float* scale_shift, float* save_mean_istd,
                             void* stream);
 /* out = dropout(relu?(x*scale+shift (+res)))  — x,res,out bf16 [M][ld*]; drop_p = 0 disables dropout
- * (nn.ReLU(inplace) + residual add torchvision Bottleneck; nn.Dropout deeplabv3_plus.py:282,318) */
+ * (nn.ReLU(inplace) + residual add torchvision Bottleneck; nn.Dropout deeplabv3_plus.py:282,318).
+ * drop_hw = 0: nn.Dropout (one draw per element); drop_hw = H*W: nn.Dropout2d (one draw per image and channel —
+ * models/pspnet.py:22,68, upernet.py:22), rows being the pixels of consecutive images. */
 int seg_bn_apply(const void* x, int ldx, const float* scale_shift, const void* res, int ldr, void* out, int ldo,
-                 int64_t M, int C, int relu, float drop_p, uint64_t seed, const uint64_t* step_ctr, void* stream);
+                 int64_t M, int C, int relu, float drop_p, uint64_t seed, const uint64_t* step_ctr, int drop_hw,
+                 void* stream);
 /* seg_bn_finalize + seg_bn_apply in ONE launch (training mode): coefficients are derived from the batch sums inside the
  * kernel; save[2C] = (mean, 1/std) for the backward pass and the running statistics are written by one block row. */
 int seg_bn_apply_train(const void* x, int ldx, const float* stats, double count, const float* gamma, const float* beta,
                        float eps, float momentum, int clamp_eps, float* running_mean, float* running_var, float* save,
                        const void* res, int ldr, void* out, int ldo, int64_t M, int C, int relu, float drop_p,
-                       uint64_t seed, const uint64_t* step_ctr, void* stream);
+                       uint64_t seed, const uint64_t* step_ctr, int drop_hw, void* stream);
 /* device-side step counter (*ctr += inc): mixed into dropout seeds and SyncBN epochs so a captured CUDA graph of the
  * train step stays correct on every replay */
 int seg_counter_add(uint64_t* ctr, uint64_t inc, void* stream);
-/* backward, pass 1 (two-stage reduction: slotted partial sums, then a finalising kernel): sums[0:C] = sum(dz), sums[C:2C] = sum(dz*xhat),
- * dz = dout * (out>0) * 1/(1-drop_p) if relu.  scratch: seg_bn_bwd_reduce_scratch_floats(M, C) floats.  If given,
- * dbeta (=|+=) sums[0:C] and dgamma (=|+=) sums[C:2C] — the parameter gradients from the LOCAL sums.
- * scratch_is_zero != 0: the caller guarantees zeroed scratch (e.g. a per-step arena cleared once) and the reduction is
- * ONE launch — the last block to finish folds the slot rows; otherwise memset + reduce + fold (three stream ops).
+/* backward, pass 1: sums[0:C] = sum(dz), sums[C:2C] = sum(dz*xhat), dz = dout * (out>0) * 1/(1-drop_p) if relu.  ONE
+ * launch: every block writes its partial sums to its own workspace row, the last block of each ticket group adds the rows
+ * in fixed order (bit-reproducible; workspace from seg_reduce_workspace(M, C, 2): fold_rows uninitialised, fold_tickets
+ * zero).  If given, dbeta (=|+=) sums[0:C] and dgamma (=|+=) sums[C:2C] — the parameter gradients from the LOCAL sums.
  * out == NULL with relu (both backward passes): the ReLU mask is recomputed from x with the forward's own coefficients
  * (sc = gamma/std, sh = fma(-mean, sc, beta)) instead of being read from the stored activation — valid for
  * conv -> BN(batch statistics) -> ReLU with no residual and no dropout; needs gamma and beta. */
-int64_t seg_bn_bwd_reduce_scratch_floats(int64_t M, int C);
 int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx,
                       const float* save_mean_istd, int64_t M, int C, int relu, float drop_p, float* sums,
-                      float* scratch, float* dgamma, float* dbeta, int accumulate, int scratch_is_zero,
+                      float* fold_rows, void* fold_tickets, float* dgamma, float* dbeta, int accumulate,
                       const float* gamma, const float* beta, void* stream);
 /* backward, pass 2: dx = gamma*istd*(dz - sums0/count - xhat*sums1/count); dres = beta_res*dres + dz (optional).
  * `sums` are the (possibly all-reduced) sums, `count` the matching element count. */

@@ -5,6 +5,8 @@
 #include "seg_common.cuh"
 
 namespace seg {
+int bn_stats_launch(const void* x, int64_t M, int C, int ldx, float* stats, float* fold_rows, unsigned* fold_tickets,
+                    cudaStream_t stream);  // seg_elementwise.cu
 namespace simt {
 
 constexpr int TM = 64, TN = 64, TK = 16;
@@ -152,10 +154,6 @@ __global__ void __launch_bounds__(256) igemm_simt(const P p) {
       } else {
         if (p.bias) v += p.bias[n];
         const int64_t ld = (MODE == FWD) ? p.d.ldy : p.d.ldx;
-        if (p.stats) {
-          atomicAdd(p.stats + n, v);
-          atomicAdd(p.stats + p.Ncols + n, v * v);
-        }
         if (p.out_dtype == SEG_DT_BF16) {
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * ld + n;
           if (p.beta != 0.f) v += p.beta * bf2f(*o);
@@ -171,7 +169,9 @@ __global__ void __launch_bounds__(256) igemm_simt(const P p) {
 }
 
 int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int y_dtype, const float* bias, float beta,
-             float* stats, cudaStream_t stream) {
+             float* stats, float* stat_rows, unsigned* stat_tickets, cudaStream_t stream) {
+  SEG_REQUIRE(!stats || (y_dtype == SEG_DT_BF16 && d->K % 8 == 0 && d->ldy % 8 == 0),
+              "CUDA-core conv: BatchNorm statistics need a bf16 output with K, ldy multiples of 8");
   P p;
   p.d = *d;
   p.a = (const __nv_bfloat16*)x;
@@ -180,14 +180,17 @@ int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int 
   p.out_dtype = y_dtype;
   p.beta = beta;
   p.bias = bias;
-  p.stats = stats;
+  p.stats = nullptr;
   p.M = (int64_t)d->N * d->P * d->Q;
   p.Ncols = d->K;
   p.Kdim = (int64_t)d->R * d->S * d->C;
   p.splits = 1;
   dim3 grid((unsigned)ceil_div64(p.M, TM), (unsigned)ceil_div(p.Ncols, TN), 1);
   igemm_simt<FWD><<<grid, 256, 0, stream>>>(p);
-  return check_launch("igemm_simt<FWD>");
+  if (check_launch("igemm_simt<FWD>")) return 1;
+  // statistics of the output AS STORED, by the deterministic column reduction (same workspace contract as the tcgen05 path)
+  if (stats) return bn_stats_launch(y, p.M, d->K, d->ldy, stats, stat_rows, stat_tickets, stream);
+  return 0;
 }
 
 int conv_dgrad(const seg_conv_desc* d, const void* dy, const void* w, void* dx, float beta, cudaStream_t stream) {

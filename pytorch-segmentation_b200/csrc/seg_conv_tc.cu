@@ -29,6 +29,7 @@
 #include <stdlib.h>
 #include "seg_common.cuh"
 #include "seg_ptx.cuh"
+#include "seg_fold.cuh"
 
 namespace seg {
 namespace tc {
@@ -62,7 +63,9 @@ struct TcParams {
   int out_dtype;
   float beta;
   const float* bias;
-  float* stats;      // [2*Ncols] or null
+  float* stats;      // [2*Ncols] or null: per-channel sum / sum of squares of the output (BatchNorm batch statistics)
+  float* stat_rows;        // seg_fold.cuh workspace of the deterministic cross-CTA reduction (rows; uninitialised)
+  unsigned* stat_tickets;  //   "      (tickets; zero at launch)
   // strided sub-grid output (stride>1 dgrad): row (n,i,j) -> pixel (n, i*osy+opy, j*osx+opx) of an out_H x out_W map
   int out_strided, out_H, out_W, osy, osx, opy, opx;
   // MM only
@@ -305,7 +308,9 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_tc(const __grid_constant__
           float s1[32], s2[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float x = row_ok ? v[i] : 0.f;
+            // statistics of the value AS STORED (bf16-rounded) — exactly what bn_apply normalises, and what the
+            // persistent kernel sums from its staged tile
+            const float x = row_ok ? (out_bf16 ? bf2f(f2bf(v[i])) : v[i]) : 0.f;
             s1[i] = x;
             s2[i] = x * x;
           }
@@ -384,20 +389,32 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_tc(const __grid_constant__
           }
         }
       }
-      // -------- phase 3: per-CTA reduction of the BN statistics, one atomic per channel --------
+      // -------- phase 3: BN statistics: this CTA's column sums -> its own row of the column block's fold lane; the last
+      //          CTA of the column block adds the rows in fixed order (seg_fold.cuh) and writes stats[] — no atomics on
+      //          the data, so the statistics are bit-reproducible --------
       if (p.stats) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int e = (warp - 2) * 32 + lane;
-        for (int c = e; c < ncols_tile; c += 128) {
+        const FoldLane L = fold_lane(p.stat_rows, p.stat_tickets, blockIdx.y, gridDim.x, 2 * BN);
+        float* myrow = L.rows1 + (size_t)blockIdx.x * (2 * BN);
+        for (int c = e; c < BN; c += 128) {
           float a = 0.f, b = 0.f;
+          if (c < ncols_tile) {
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            a += stat_sm[(w * 2 + 0) * BN + c];
-            b += stat_sm[(w * 2 + 1) * BN + c];
+            for (int w = 0; w < 4; ++w) {
+              a += stat_sm[(w * 2 + 0) * BN + c];
+              b += stat_sm[(w * 2 + 1) * BN + c];
+            }
           }
-          atomicAdd(p.stats + n0 + c, a);
-          atomicAdd(p.stats + p.Ncols + n0 + c, b);
+          myrow[c] = a;
+          myrow[BN + c] = b;
         }
+        volatile int* flag = reinterpret_cast<volatile int*>(smem_gen + C::STAGES * C::STAGE_BYTES + 128);
+        fold_arrive(L, blockIdx.x, e, 128, [] { asm volatile("bar.sync 1, 128;" ::: "memory"); }, flag,
+                    [&](int c, float v) {
+                      const int which = c / BN, col = c - which * BN;
+                      if (col < ncols_tile) p.stats[(size_t)which * p.Ncols + n0 + col] = v;
+                    });
       }
     }
     tc_fence_before();
@@ -563,8 +580,20 @@ bool supported(const seg_conv_desc* d) {
 
 static bool is_pointwise(const seg_conv_desc* d) { return d->R == 1 && d->S == 1 && d->stride == 1 && d->pad == 0; }
 
+// Upper bound of the statistics-reduction workspace of conv_fwd for this shape (either schedule, any tile width): one
+// fold lane per column block, one row per contributing CTA (seg_fold.cuh).
+void stats_workspace(const seg_conv_desc* d, int64_t* rows_floats, int64_t* tickets) {
+  const int64_t M = (int64_t)d->N * d->P * d->Q;
+  const int64_t m_tiles = ceil_div64(M, BM);
+  const int rows = (int)(m_tiles > num_sms() ? m_tiles : num_sms());
+  // lanes x width: ceil(K/64) lanes of 128 floats, or ceil(K/128) of 256, or ceil(K/256) of 512 — all <= 2 * roundup(K, 256)
+  const int64_t lane_floats_total = 2 * (int64_t)ceil_div(d->K, 256) * 256;
+  *rows_floats = (int64_t)(rows + fold_groups(rows)) * lane_floats_total;
+  *tickets = (int64_t)ceil_div(d->K, 64) * fold_lane_tickets(rows);
+}
+
 int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int y_dtype, const float* bias, float beta,
-             float* stats, cudaStream_t stream) {
+             float* stats, float* stat_rows, unsigned* stat_tickets, cudaStream_t stream) {
   SEG_REQUIRE(supported(d), "tcgen05 conv fwd: unsupported shape (C=%d ldx=%d R=%d pad=%d dil=%d)", d->C, d->ldx, d->R,
               d->pad, d->dil);
   TcParams p;
@@ -591,6 +620,9 @@ int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int 
   p.beta = beta;
   p.bias = bias;
   p.stats = stats;
+  p.stat_rows = stat_rows;
+  p.stat_tickets = stat_tickets;
+  SEG_REQUIRE(!stats || (stat_rows && stat_tickets), "conv fwd: statistics need the reduction workspace");
   const int64_t m_tiles = ceil_div64(M, BM);
   // persistent double-buffered kernel for bf16 outputs wider than 64 channels; the one-tile-per-CTA kernel otherwise
   // (measured: with <= 2 tiles per SM and a long k-loop, two co-resident one-tile CTAs interleave better than one

@@ -193,33 +193,35 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_cons
     const int h = e >> 2;     // column half of the tile
     const int trow = lg * 32 + lane;
     const int etid = e * 32 + lane;  // 0..255
-    int cur_n = -1;
     int i = 0;
     float v[32];
-    auto flush_stats = [&](int n_tile) {
+    // BN statistics: the host sizes the grid as a multiple of the number of column blocks, so this CTA stays on column
+    // block blockIdx.x % n_tiles for all of its tiles and its shared-memory accumulators are written out ONCE, at the end,
+    // as row blockIdx.x / n_tiles of that column block's fold lane (seg_fold.cuh: fixed-order cross-CTA sum, no atomics
+    // on the data -> bit-reproducible statistics)
+    auto finish_stats = [&]() {
       // called by all 256 epilogue threads
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (n_tile >= 0) {
+      const int my_n = blockIdx.x % n_tiles;
+      const FoldLane L = fold_lane(p.stat_rows, p.stat_tickets, my_n, gridDim.x / n_tiles, 2 * BN);
+      const int myrow = blockIdx.x / n_tiles;
+      {
         const int c = etid & 127, which = etid >> 7;
-        const int col = n_tile * BN + c;
         float val = 0.f;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          val += stat_sm[(g * 2 + which) * BN + c];
-          stat_sm[(g * 2 + which) * BN + c] = 0.f;
-        }
-        if (col < p.Ncols && val != 0.f) atomicAdd(p.stats + (size_t)which * p.Ncols + col, val);
+        for (int g = 0; g < 4; ++g) val += stat_sm[(g * 2 + which) * BN + c];
+        L.rows1[(size_t)myrow * (2 * BN) + which * BN + c] = val;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      volatile int* flag = reinterpret_cast<volatile int*>(smem_gen + V2_STAGES * V2_STAGE_BYTES + V2_STAGING_BYTES + V2_STAT_BYTES + 128);
+      fold_arrive(L, myrow, etid, 256, [] { asm volatile("bar.sync 1, 256;" ::: "memory"); }, flag, [&](int c, float v) {
+        const int which = c / BN, col = my_n * BN + (c - which * BN);
+        if (col < p.Ncols) p.stats[(size_t)which * p.Ncols + col] = v;
+      });
     };
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
       const int b = i & 1;
       const int n_tile = t % n_tiles;
       const int m0 = (t / n_tiles) * BM, n0 = n_tile * BN;
-      if (EPI != EPI_MANUAL_BETA && p.stats && n_tile != cur_n) {
-        flush_stats(cur_n);
-        cur_n = n_tile;
-      }
       if constexpr (EPI == EPI_TMA) {
         // ---- TMA epilogue: this warp owns rows 32*lg.. and columns 64*h.. of the tile = one [32][64] box whose
         //      staging region (4 KB, 128-byte rows, SWIZZLE_128B pattern) only this warp touches ----
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_cons
       }
       __syncwarp();  // the staging region of this warp is reused by its next tile
     }
-    if (EPI != EPI_MANUAL_BETA && p.stats) flush_stats(cur_n);
+    if (EPI != EPI_MANUAL_BETA && p.stats) finish_stats();
     if (EPI == EPI_TMA && lane == 0) bulk_wait_group0();  // all boxes written before the CTA retires
     tc_fence_before();
   }
@@ -366,6 +368,7 @@ static int launch_v2_impl(const TcParams& p, cudaStream_t stream) {
   // hot and the BN-statistics accumulators are flushed once per CTA instead of once per tile
   if (n_tiles <= grid) grid = (grid / n_tiles) * n_tiles;
   if ((int64_t)grid > num_tiles) grid = (int)num_tiles;
+  SEG_REQUIRE(p.stats == nullptr || grid % n_tiles == 0, "conv_gemm_tc2: statistics need a grid that pins every CTA to one column block");
   launch_pdl(kfn, dim3(grid), dim3(V2_THREADS), (size_t)V2_SMEM, stream, p);
   return check_launch("conv_gemm_tc2");
 }

@@ -8,10 +8,10 @@
 //   bwd_weight: dw[9][C] += sum_pixels dy * x_shifted   (72 register accumulators per thread, slotted atomics)
 // Packed depthwise weights: fp32 [9][C] (tap-major).
 #include "seg_common.cuh"
+#include "seg_fold.cuh"
 
 namespace seg {
 
-constexpr int DW_SLOTS = 16;
 
 struct DwMap {
   int g, rl, rows_par;
@@ -36,35 +36,50 @@ __device__ __forceinline__ void load_taps(const float* __restrict__ w9, int C, i
   }
 }
 
-// block-level reduction of NACC x 8 per-thread sums over the row lanes, then slotted atomics into out[slot][NACC][C]
+// block-level reduction of NACC x 8 per-thread sums over the row lanes; the block's sums become its row of the channel
+// slab's fold lane (seg_fold.cuh: fixed-order cross-block sum, bit-reproducible); the block that completes the tree writes
+// out[a][c] = beta*out[a][c] + total
 template <int NACC>
-__device__ __forceinline__ void dw_block_reduce(const DwMap& m, int C, float (*acc)[8], float* __restrict__ out) {
+__device__ __forceinline__ void dw_block_reduce(const DwMap& m, int C, float (*acc)[8], float* fold_rows, unsigned* fold_tickets,
+                                                float* __restrict__ out, float beta) {
   __shared__ float red[256 * 8];
+  __shared__ int fold_flag;
   const int GB = min(C >> 3, 256);
   const int gl = threadIdx.x % GB;
+  const int W = GB * 8;
+  const FoldLane L = fold_lane(fold_rows, fold_tickets, blockIdx.y, gridDim.x, NACC * W);
+  float* myrow = L.rows1 + (size_t)blockIdx.x * (NACC * W);
   for (int a = 0; a < NACC; ++a) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = m.active ? acc[a][i] : 0.f;
     __syncthreads();
-    if (m.rl == 0 && m.g < (C >> 3)) {
+    if (m.rl == 0) {
       float s[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) s[i] = 0.f;
-      for (int r = 0; r < m.rows_par; ++r)
+      if (m.g < (C >> 3)) {
+        for (int r = 0; r < m.rows_par; ++r)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s[i] += red[(r * GB + gl) * 8 + i];
-      float* o = out + ((size_t)(blockIdx.x % DW_SLOTS) * NACC + a) * C + m.g * 8;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(o + i, s[i]);
+          for (int i = 0; i < 8; ++i) s[i] += red[(r * GB + gl) * 8 + i];
+      }
+      *reinterpret_cast<float4*>(myrow + a * W + gl * 8) = make_float4(s[0], s[1], s[2], s[3]);
+      *reinterpret_cast<float4*>(myrow + a * W + gl * 8 + 4) = make_float4(s[4], s[5], s[6], s[7]);
     }
   }
+  fold_arrive(L, blockIdx.x, threadIdx.x, 256, [] { __syncthreads(); }, &fold_flag, [&](int c, float v) {
+    const int a = c / W, ch = blockIdx.y * W + (c - a * W);
+    if (ch < C) {
+      float* o = out + (size_t)a * C + ch;
+      *o = (beta != 0.f) ? beta * *o + v : v;
+    }
+  });
 }
 
 __global__ void __launch_bounds__(256)
     dwconv_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ w9, __nv_bfloat16* __restrict__ y,
                       int ldy, int N, int H, int W, int C, int P, int Q, int stride, int pad, int dil,
-                      float* __restrict__ stat_slots) {
+                      float* __restrict__ stats, float* fold_rows, unsigned* fold_tickets) {
   const DwMap m = dw_map(C);
   float w[9][8];
   float acc[2][8];
@@ -97,7 +112,7 @@ __global__ void __launch_bounds__(256)
         }
       }
       *reinterpret_cast<bf16x8*>(y + row * ldy + co) = pack8(o);
-      if (stat_slots) {
+      if (stats) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           acc[0][i] += o[i];
@@ -106,7 +121,7 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
-  if (stat_slots) dw_block_reduce<2>(m, C, acc, stat_slots);
+  if (stats) dw_block_reduce<2>(m, C, acc, fold_rows, fold_tickets, stats, 0.f);
 }
 
 __global__ void __launch_bounds__(256)
@@ -159,7 +174,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     dwconv_bwd_weight_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ x, int ldx,
                              int N, int H, int W, int C, int P, int Q, int stride, int pad, int dil,
-                             float* __restrict__ slots /*[DW_SLOTS][9][C]*/) {
+                             float* fold_rows, unsigned* fold_tickets, float* __restrict__ dw9, float beta) {
   const DwMap m = dw_map(C);
   float acc[9][8];
 #pragma unroll
@@ -192,17 +207,7 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
-  dw_block_reduce<9>(m, C, acc, slots);
-}
-
-// sums the slot rows: out[a][c] (=|+=) sum_s slots[s][a][c]   (a < nacc)
-__global__ void dw_slot_reduce_kernel(const float* __restrict__ slots, int nacc, int C, float* __restrict__ out, float beta) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nacc * C) return;
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < DW_SLOTS; ++k) s += slots[(size_t)k * nacc * C + i];
-  out[i] = (beta != 0.f) ? beta * out[i] + s : s;
+  dw_block_reduce<9>(m, C, acc, fold_rows, fold_tickets, dw9, beta);
 }
 
 // depthwise master weight [C][1][3][3] fp32 <-> packed [9][C] fp32
@@ -220,17 +225,25 @@ __global__ void dw_unpack_kernel(const float* __restrict__ g9, float* __restrict
   g[i] = (beta != 0.f) ? beta * g[i] + v : v;
 }
 
-static dim3 dw_grid(int64_t M, int C) {
+static dim3 dw_grid(int64_t M, int C, int blocks_per_sm = 6) {
   const int G = C / 8;
   const int GB = G < 256 ? G : 256;
   const int rows_par = 256 / GB;
   const int gy = ceil_div(G, GB);
   int64_t gx = ceil_div64(M, (int64_t)rows_par * 2);
-  const int64_t cap = ((int64_t)num_sms() * 6 + gy - 1) / gy;
+  const int64_t cap = ((int64_t)num_sms() * blocks_per_sm + gy - 1) / gy;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   return dim3((unsigned)gx, (unsigned)gy, 1);
 }
+// reduction workspace of a dwconv launch: fold rows (floats), then the tickets, in ONE scratch buffer
+static int64_t dw_ws_rows(dim3 grid, int C, int nacc) {
+  const int G = C / 8;
+  const int GB = G < 256 ? G : 256;
+  return (int64_t)grid.y * fold_lane_floats((int)grid.x, nacc * GB * 8);
+}
+static int64_t dw_ws_tickets(dim3 grid) { return (int64_t)grid.y * fold_lane_tickets((int)grid.x); }
+constexpr int DW_WGRAD_BLOCKS_PER_SM = 2;  // every block writes a [9][C] row of partial sums: keep the rows few
 
 }  // namespace seg
 
@@ -241,7 +254,13 @@ using namespace seg;
 
 extern "C" {
 
-int64_t seg_dwconv_scratch_floats(int C) { return (int64_t)DW_SLOTS * 9 * C; }
+// upper bound (any M) of the scratch a dwconv call needs: fold rows + tickets (seg_fold.cuh)
+int64_t seg_dwconv_scratch_floats(int C) {
+  const int64_t big = (int64_t)1 << 40;
+  const dim3 gf = dw_grid(big, C), gw = dw_grid(big, C, DW_WGRAD_BLOCKS_PER_SM);
+  const int64_t f = dw_ws_rows(gf, C, 2) + dw_ws_tickets(gf), w = dw_ws_rows(gw, C, 9) + dw_ws_tickets(gw);
+  return (f > w ? f : w) + 64;
+}
 
 static int dw_check(const seg_conv_desc* d) {
   SEG_REQUIRE(d && d->R == 3 && d->S == 3 && d->K == d->C, "dwconv: 3x3 depthwise (K == C) only");
@@ -254,17 +273,19 @@ static int dw_check(const seg_conv_desc* d) {
 int seg_dwconv3x3_fwd(const seg_conv_desc* d, const void* x, const float* w9, void* y, float* stats, float* scratch,
                       void* stream) {
   if (dw_check(d)) return 1;
-  SEG_REQUIRE(!stats || scratch, "dwconv fwd: stats need a scratch of 16*2*C floats");
+  SEG_REQUIRE(!stats || scratch, "dwconv fwd: stats need a scratch of seg_dwconv_scratch_floats(C) floats");
   const int64_t M = (int64_t)d->N * d->P * d->Q;
-  if (stats) cudaMemsetAsync(scratch, 0, (size_t)DW_SLOTS * 2 * d->C * sizeof(float), ST(stream));
-  dwconv_fwd_kernel<<<dw_grid(M, d->C), 256, 0, ST(stream)>>>(CBF(x), d->ldx, w9, BF(y), d->ldy, d->N, d->H, d->W, d->C, d->P, d->Q,
-                                                              d->stride, d->pad, d->dil, stats ? scratch : nullptr);
-  if (check_launch("dwconv_fwd")) return 1;
+  const dim3 grid = dw_grid(M, d->C);
+  float* rows = scratch;
+  unsigned* tickets = nullptr;
   if (stats) {
-    dw_slot_reduce_kernel<<<ceil_div(2 * d->C, 128), 128, 0, ST(stream)>>>(scratch, 2, d->C, stats, 1.0f);
-    return check_launch("dw_slot_reduce");
+    const int64_t nr = (dw_ws_rows(grid, d->C, 2) + 31) / 32 * 32;
+    tickets = reinterpret_cast<unsigned*>(scratch + nr);
+    cudaMemsetAsync(tickets, 0, (size_t)dw_ws_tickets(grid) * sizeof(unsigned), ST(stream));
   }
-  return 0;
+  dwconv_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(x), d->ldx, w9, BF(y), d->ldy, d->N, d->H, d->W, d->C, d->P, d->Q,
+                                                  d->stride, d->pad, d->dil, stats, rows, tickets);
+  return check_launch("dwconv_fwd");
 }
 
 int seg_dwconv3x3_bwd_data(const seg_conv_desc* d, const void* dy, const float* w9, void* dx, float beta, void* stream) {
@@ -280,12 +301,13 @@ int seg_dwconv3x3_bwd_weight(const seg_conv_desc* d, const void* dy, const void*
   if (dw_check(d)) return 1;
   SEG_REQUIRE(scratch != nullptr, "dwconv bwd_weight: scratch of seg_dwconv_scratch_floats(C) floats required");
   const int64_t M = (int64_t)d->N * d->P * d->Q;
-  cudaMemsetAsync(scratch, 0, (size_t)DW_SLOTS * 9 * d->C * sizeof(float), ST(stream));
-  dwconv_bwd_weight_kernel<<<dw_grid(M, d->C), 256, 0, ST(stream)>>>(CBF(dy), d->ldy, CBF(x), d->ldx, d->N, d->H, d->W, d->C,
-                                                                     d->P, d->Q, d->stride, d->pad, d->dil, scratch);
-  if (check_launch("dwconv_bwd_weight")) return 1;
-  dw_slot_reduce_kernel<<<ceil_div(9 * d->C, 128), 128, 0, ST(stream)>>>(scratch, 9, d->C, dw9, beta);
-  return check_launch("dw_slot_reduce");
+  const dim3 grid = dw_grid(M, d->C, DW_WGRAD_BLOCKS_PER_SM);
+  const int64_t nr = (dw_ws_rows(grid, d->C, 9) + 31) / 32 * 32;
+  unsigned* tickets = reinterpret_cast<unsigned*>(scratch + nr);
+  cudaMemsetAsync(tickets, 0, (size_t)dw_ws_tickets(grid) * sizeof(unsigned), ST(stream));
+  dwconv_bwd_weight_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(dy), d->ldy, CBF(x), d->ldx, d->N, d->H, d->W, d->C, d->P, d->Q,
+                                                         d->stride, d->pad, d->dil, scratch, tickets, dw9, beta);
+  return check_launch("dwconv_bwd_weight");
 }
 
 int seg_dw_pack_weight(const float* w_c133, float* w9, int C, void* stream) {

@@ -4,6 +4,7 @@
 // 16-byte (8-channel) vectors per thread; reductions use warp shuffles + one atomic per block-column.
 // Reference call sites are cited next to each entry point in include/seg_b200.h.
 #include "seg_common.cuh"
+#include "seg_fold.cuh"
 
 namespace seg {
 
@@ -152,10 +153,11 @@ __global__ void __launch_bounds__(256) im2col_kernel(seg_conv_desc d, const void
 
 // ------------------------------------------------------------------ BatchNorm
 // Column-reduction skeleton shared by bn_stats and bn_bwd_reduce: a 256-thread block owns GB = min(G,256) channel
-// groups (8 channels each) and 256/GB row lanes; rows are grid-strided.
-constexpr int REDUCE_SLOTS = 16;
-template <int NACC, bool PARTIAL = false, class F>
-__device__ __forceinline__ void column_reduce(int64_t M, int C, float* out /*[NACC][C]  (PARTIAL: [gridDim.x][NACC][C])*/, F f) {
+// groups (8 channels each) and 256/GB row lanes; rows are grid-strided.  The block's sums become ITS row of the channel
+// slab's fold lane (seg_fold.cuh): the cross-block sum is a fixed-order ticket tree, not atomics — bit-reproducible.
+// emit(a, channel, total) is called once per (accumulator, channel) by the block that completes the tree.
+template <int NACC, class F, class E>
+__device__ __forceinline__ void column_reduce(int64_t M, int C, float* fold_rows, unsigned* fold_tickets, F f, E emit) {
   const int G = C >> 3;
   const int GB = min(G, 256);
   const int rows_par = 256 / GB;
@@ -173,43 +175,49 @@ __device__ __forceinline__ void column_reduce(int64_t M, int C, float* out /*[NA
       f(row, g, acc);
   }
   __shared__ float red[256 * 8];
+  __shared__ int fold_flag;
+  const int W = GB * 8;  // channels of this slab
+  const FoldLane L = fold_lane(fold_rows, fold_tickets, blockIdx.y, gridDim.x, NACC * W);
+  float* myrow = L.rows1 + (size_t)blockIdx.x * (NACC * W);
   for (int a = 0; a < NACC; ++a) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[a][i];
     __syncthreads();
-    if (rl == 0 && g < G) {
+    if (rl == 0) {
       float s[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) s[i] = 0.f;
-      for (int r = 0; r < rows_par; ++r)
+      if (g < G) {
+        for (int r = 0; r < rows_par; ++r)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s[i] += red[(r * GB + gl) * 8 + i];
-      if (PARTIAL) {  // two-stage: blocks spread their partial sums over REDUCE_SLOTS slot rows (low atomic contention,
-                      // ~gridDim.x/REDUCE_SLOTS adds per address); a tiny second kernel sums the slots
-        float* o = out + ((size_t)(blockIdx.x % REDUCE_SLOTS) * NACC + a) * C + g * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(o + i, s[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(out + (size_t)a * C + g * 8 + i, s[i]);
+          for (int i = 0; i < 8; ++i) s[i] += red[(r * GB + gl) * 8 + i];
       }
+      *reinterpret_cast<float4*>(myrow + a * W + gl * 8) = make_float4(s[0], s[1], s[2], s[3]);
+      *reinterpret_cast<float4*>(myrow + a * W + gl * 8 + 4) = make_float4(s[4], s[5], s[6], s[7]);
     }
   }
+  fold_arrive(L, blockIdx.x, threadIdx.x, 256, [] { __syncthreads(); }, &fold_flag, [&](int c, float v) {
+    const int a = c / W, ch = blockIdx.y * W + (c - a * W);
+    if (ch < C) emit(a, ch, v);
+  });
 }
 
 __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t M, int C, int ldx,
-                                                       float* __restrict__ stats) {
-  column_reduce<2>(M, C, stats, [&](int64_t row, int g, float(*acc)[8]) {
-    const bf16x8 v = *reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8);
-    float f[8];
-    unpack8(v, f);
+                                                       float* __restrict__ stats, float* fold_rows, unsigned* fold_tickets) {
+  column_reduce<2>(
+      M, C, fold_rows, fold_tickets,
+      [&](int64_t row, int g, float(*acc)[8]) {
+        const bf16x8 v = *reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8);
+        float f[8];
+        unpack8(v, f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      acc[0][i] += f[i];
-      acc[1][i] += f[i] * f[i];
-    }
-  });
+        for (int i = 0; i < 8; ++i) {
+          acc[0][i] += f[i];
+          acc[1][i] += f[i] * f[i];
+        }
+      },
+      [&](int a, int ch, float v) { stats[(size_t)a * C + ch] = v; });
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, double count, int C, const float* __restrict__ gamma,
@@ -286,7 +294,7 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const __nv_bfloat16* _
                                                        const float* __restrict__ ss, const __nv_bfloat16* __restrict__ res,
                                                        int ldr, __nv_bfloat16* __restrict__ out, int ldo, int64_t M, int C,
                                                        int relu, float drop_p, uint64_t seed,
-                                                       const uint64_t* __restrict__ step_ctr, const BnTrain tr) {
+                                                       const uint64_t* __restrict__ step_ctr, int drop_hw, const BnTrain tr) {
   pdl_wait();
   const RowMap rm = row_map(C);
   if (!rm.active) return;
@@ -358,7 +366,8 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const __nv_bfloat16* _
       if (drop_p > 0.f) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float uu = hash_uniform(seed, (uint64_t)(r * C + co + j));
+          // nn.Dropout: one draw per element; nn.Dropout2d (drop_hw = H*W > 0): one draw per (image, channel)
+          const float uu = hash_uniform(seed, (uint64_t)((drop_hw > 0 ? r / drop_hw : r) * C + co + j));
           f[j] = (uu >= drop_p) ? f[j] * keep_scale : 0.f;
         }
       }
@@ -372,7 +381,7 @@ template <bool REMASK>
 __global__ void __launch_bounds__(256)
     bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ out, int ldo,
                          const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save, int64_t M, int C,
-                         int relu, float drop_p, float* __restrict__ sums, unsigned int* ticket, float* final_sums,
+                         int relu, float drop_p, float* fold_rows, unsigned* fold_tickets, float* final_sums,
                          float* dgamma, float* dbeta, int accumulate, const float* __restrict__ gamma,
                          const float* __restrict__ beta) {
   pdl_wait();
@@ -381,8 +390,6 @@ __global__ void __launch_bounds__(256)
   // ReLU mask: from the stored activation, or (out == null: BN -> ReLU with nothing in between, training statistics)
   // recomputed from x with exactly the forward's coefficients  sc = gamma*istd, sh = fma(-mean, sc, beta)  — one operand
   // stream less to read
-  // 1/std is folded into the weights of the second sum's accumulation only where needed: the loop keeps (mean, and for
-  // REMASK sc, sh) in registers — 1/std scales the centred product, so it is applied through `wi` = istd per channel
   float mean[8], wi[8], sc[REMASK ? 8 : 1], sh[REMASK ? 8 : 1];
   if (rm.active) {
     ld8(save + rm.g * 8, mean);
@@ -398,52 +405,37 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
-  column_reduce<2, true>(M, C, sums, [&](int64_t row, int g, float(*acc)[8]) {
-    float dz[8], xv[8];
-    const bf16x8 dv = *reinterpret_cast<const bf16x8*>(dout + row * lddo + g * 8);
-    const bf16x8 xx = *reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8);
-    unpack8(dv, dz);
-    unpack8(xx, xv);
-    if constexpr (REMASK) {
+  // cross-block sum: fixed-order ticket tree (seg_fold.cuh); the block that completes it writes the sums and, if asked,
+  // the parameter gradients (dbeta = sum dz, dgamma = sum dz*xhat)
+  column_reduce<2>(
+      M, C, fold_rows, fold_tickets,
+      [&](int64_t row, int g, float(*acc)[8]) {
+        float dz[8], xv[8];
+        const bf16x8 dv = *reinterpret_cast<const bf16x8*>(dout + row * lddo + g * 8);
+        const bf16x8 xx = *reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8);
+        unpack8(dv, dz);
+        unpack8(xx, xv);
+        if constexpr (REMASK) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dz[i] = (fmaf(xv[i], sc[i], sh[i]) > 0.f) ? dz[i] : 0.f;
-    } else if (relu) {
-      float o[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(out + row * ldo + g * 8), o);
+          for (int i = 0; i < 8; ++i) dz[i] = (fmaf(xv[i], sc[i], sh[i]) > 0.f) ? dz[i] : 0.f;
+        } else if (relu) {
+          float o[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(out + row * ldo + g * 8), o);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dz[i] = (o[i] > 0.f) ? dz[i] * keep_scale : 0.f;
-    }
+          for (int i = 0; i < 8; ++i) dz[i] = (o[i] > 0.f) ? dz[i] * keep_scale : 0.f;
+        }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      acc[0][i] += dz[i];
-      acc[1][i] += dz[i] * (xv[i] - mean[i]) * wi[i];
-    }
-  });
+        for (int i = 0; i < 8; ++i) {
+          acc[0][i] += dz[i];
+          acc[1][i] += dz[i] * (xv[i] - mean[i]) * wi[i];
+        }
+      },
+      [&](int a, int ch, float v) {
+        final_sums[(size_t)a * C + ch] = v;
+        float* pg = a == 0 ? dbeta : dgamma;
+        if (pg) pg[ch] = accumulate ? pg[ch] + v : v;
+      });
   pdl_trigger();
-  if (ticket == nullptr) return;
-  // single-launch mode (slot rows pre-zeroed by the caller): the last block to finish folds the slot rows
-  __shared__ bool last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int t = atomicAdd(ticket, 1u);
-    last = (t == gridDim.x * gridDim.y - 1);
-  }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int b = 0; b < REDUCE_SLOTS; ++b) {
-      s0 += __ldcg(sums + ((size_t)b * 2 + 0) * C + c);
-      s1 += __ldcg(sums + ((size_t)b * 2 + 1) * C + c);
-    }
-    final_sums[c] = s0;
-    final_sums[C + c] = s1;
-    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + s0 : s0;
-    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + s1 : s1;
-  }
 }
 
 // dx = A*dz + B*x + Cc with A = gamma*istd, B = -gamma*istd^2*s1/count, Cc = -gamma*istd*s0/count + gamma*istd^2*mean*s1/count
@@ -516,31 +508,6 @@ __global__ void __launch_bounds__(256)
     *reinterpret_cast<bf16x8*>(dx + row * lddx + co) = pack8(o8);
   }
   pdl_trigger();
-}
-
-// stage 2 of the BN backward reduction: sums[a][c] = sum_b partial[b][a][c]; optionally the parameter gradients
-// (dbeta = sum dz, dgamma = sum dz*xhat) from these LOCAL sums.
-__global__ void bn_bwd_reduce_final_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ sums,
-                                           float* dgamma, float* dbeta, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-  int b = 0;
-  for (; b + 1 < nblocks; b += 2) {
-    a0 += partial[((size_t)b * 2 + 0) * C + c];
-    b0 += partial[((size_t)b * 2 + 1) * C + c];
-    a1 += partial[((size_t)(b + 1) * 2 + 0) * C + c];
-    b1 += partial[((size_t)(b + 1) * 2 + 1) * C + c];
-  }
-  if (b < nblocks) {
-    a0 += partial[((size_t)b * 2 + 0) * C + c];
-    b0 += partial[((size_t)b * 2 + 1) * C + c];
-  }
-  const float s0 = a0 + a1, s1 = b0 + b1;
-  sums[c] = s0;
-  sums[C + c] = s1;
-  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + s0 : s0;
-  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + s1 : s1;
 }
 
 __global__ void bn_param_grad_kernel(const float* __restrict__ sums, int C, float* dgamma, float* dbeta, int accumulate) {
@@ -1135,10 +1102,37 @@ static dim3 colreduce_grid(int64_t M, int C) {
   return dim3((unsigned)gx, (unsigned)gy, 1);
 }
 
-int seg_bn_stats(const void* x, int64_t M, int C, int ldx, float* stats, void* stream) {
+// workspace of column_reduce for a given launch grid: per channel slab (grid.y) one fold lane of grid.x rows
+static void reduce_ws(dim3 grid, int C, int nacc, int64_t* rows_floats, int64_t* tickets) {
+  const int G = C / 8;
+  const int GB = G < 256 ? G : 256;
+  *rows_floats = (int64_t)grid.y * fold_lane_floats((int)grid.x, nacc * GB * 8);
+  *tickets = (int64_t)grid.y * fold_lane_tickets((int)grid.x);
+}
+static dim3 reduce2_grid(int64_t M, int C);
+}  // extern "C"
+namespace seg {
+// also used by the CUDA-core conv path (seg_conv_simt.cu) for its BatchNorm statistics
+int bn_stats_launch(const void* x, int64_t M, int C, int ldx, float* stats, float* fold_rows, unsigned* fold_tickets,
+                    cudaStream_t stream) {
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0, "bn_stats: C/ldx must be multiples of 8 (C=%d ldx=%d)", C, ldx);
-  bn_stats_kernel<<<colreduce_grid(M, C), 256, 0, ST(stream)>>>(CBF(x), M, C, ldx, stats);
+  SEG_REQUIRE(fold_rows && fold_tickets, "bn_stats: reduction workspace (seg_reduce_workspace) required");
+  bn_stats_kernel<<<colreduce_grid(M, C), 256, 0, stream>>>(CBF(x), M, C, ldx, stats, fold_rows, fold_tickets);
   return check_launch("bn_stats");
+}
+}  // namespace seg
+extern "C" {
+int seg_reduce_workspace(int64_t M, int C, int nacc, int64_t* rows_floats, int64_t* tickets) {
+  SEG_REQUIRE(C % 8 == 0 && nacc >= 1 && rows_floats && tickets, "seg_reduce_workspace: bad arguments");
+  int64_t r1, t1, r2, t2;
+  reduce_ws(colreduce_grid(M, C), C, nacc, &r1, &t1);
+  reduce_ws(reduce2_grid(M, C), C, nacc, &r2, &t2);
+  *rows_floats = r1 > r2 ? r1 : r2;
+  *tickets = t1 > t2 ? t1 : t2;
+  return 0;
+}
+int seg_bn_stats(const void* x, int64_t M, int C, int ldx, float* stats, float* fold_rows, void* fold_tickets, void* stream) {
+  return bn_stats_launch(x, M, C, ldx, stats, fold_rows, reinterpret_cast<unsigned*>(fold_tickets), ST(stream));
 }
 int seg_bn_finalize(const float* stats, double count, int C, const float* gamma, const float* beta, float eps,
                     float momentum, int clamp_eps, float* running_mean, float* running_var, float* scale_shift,
@@ -1153,52 +1147,39 @@ int seg_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const 
   return check_launch("bn_eval");
 }
 int seg_bn_apply(const void* x, int ldx, const float* ss, const void* res, int ldr, void* out, int ldo, int64_t M, int C,
-                 int relu, float drop_p, uint64_t seed, const uint64_t* step_ctr, void* stream) {
+                 int relu, float drop_p, uint64_t seed, const uint64_t* step_ctr, int drop_hw, void* stream) {
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldr % 8 == 0), "bn_apply: alignment");
   BnTrain tr;
   memset(&tr, 0, sizeof(tr));
   launch_pdl(bn_apply_kernel, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(x), ldx, ss, CBF(res), ldr, BF(out), ldo, M, C, relu,
-             drop_p, seed, step_ctr, tr);
+             drop_p, seed, step_ctr, drop_hw, tr);
   return check_launch("bn_apply");
 }
 int seg_bn_apply_train(const void* x, int ldx, const float* stats, double count, const float* gamma, const float* beta,
                        float eps, float momentum, int clamp_eps, float* running_mean, float* running_var, float* save,
                        const void* res, int ldr, void* out, int ldo, int64_t M, int C, int relu, float drop_p,
-                       uint64_t seed, const uint64_t* step_ctr, void* stream) {
+                       uint64_t seed, const uint64_t* step_ctr, int drop_hw, void* stream) {
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldr % 8 == 0), "bn_apply_train: alignment");
   SEG_REQUIRE(stats && gamma && beta && save && count > 0, "bn_apply_train: stats, gamma, beta, save required");
   BnTrain tr = {stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var, save};
   launch_pdl(bn_apply_kernel, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(x), ldx, (const float*)nullptr, CBF(res), ldr, BF(out),
-             ldo, M, C, relu, drop_p, seed, step_ctr, tr);
+             ldo, M, C, relu, drop_p, seed, step_ctr, drop_hw, tr);
   return check_launch("bn_apply_train");
 }
-// reductions end with a block fold + 16 C atomics per block: fewer blocks still (>= 32 rows per thread)
+// reductions end with a block fold + a ticket: fewer, fatter blocks (>= 32 rows per thread)
 static dim3 reduce2_grid(int64_t M, int C) { return rowmap_grid(M, C, 32); }
-int64_t seg_bn_bwd_reduce_scratch_floats(int64_t M, int C) { return (int64_t)REDUCE_SLOTS * 2 * C + 4; }
 
 int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,
-                      int64_t M, int C, int relu, float drop_p, float* sums, float* scratch, float* dgamma, float* dbeta,
-                      int accumulate, int scratch_is_zero, const float* gamma, const float* beta, void* stream) {
+                      int64_t M, int C, int relu, float drop_p, float* sums, float* fold_rows, void* fold_tickets,
+                      float* dgamma, float* dbeta, int accumulate, const float* gamma, const float* beta, void* stream) {
   SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && (!relu || !out || ldo % 8 == 0), "bn_bwd_reduce: alignment");
   SEG_REQUIRE(!(relu && !out) || (gamma && beta && drop_p == 0.f), "bn_bwd_reduce: out == NULL (mask recomputed from x) needs gamma, beta and no dropout");
-  SEG_REQUIRE(scratch != nullptr, "bn_bwd_reduce: scratch of seg_bn_bwd_reduce_scratch_floats(M, C) floats required");
+  SEG_REQUIRE(fold_rows && fold_tickets, "bn_bwd_reduce: reduction workspace (seg_reduce_workspace(M, C, 2)) required");
   const dim3 grid = reduce2_grid(M, C);
-  if (scratch_is_zero) {  // one launch: the last block folds the slot rows (ticket counter behind them)
-    launch_pdl((relu && !out) ? bn_bwd_reduce_kernel<true> : bn_bwd_reduce_kernel<false>, grid, dim3(256), 0, ST(stream), CBF(dout),
-               lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p, scratch,
-               reinterpret_cast<unsigned int*>(scratch + (size_t)REDUCE_SLOTS * 2 * C), sums, dgamma, dbeta, accumulate, gamma, beta);
-    return check_launch("bn_bwd_reduce");
-  }
-  cudaMemsetAsync(scratch, 0, (size_t)REDUCE_SLOTS * 2 * C * sizeof(float), ST(stream));
-  if (relu && !out)
-    bn_bwd_reduce_kernel<true><<<grid, 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p,
-                                                             scratch, nullptr, nullptr, nullptr, nullptr, 0, gamma, beta);
-  else
-    bn_bwd_reduce_kernel<false><<<grid, 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p,
-                                                              scratch, nullptr, nullptr, nullptr, nullptr, 0, gamma, beta);
-  if (check_launch("bn_bwd_reduce")) return 1;
-  bn_bwd_reduce_final_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(scratch, REDUCE_SLOTS, C, sums, dgamma, dbeta, accumulate);
-  return check_launch("bn_bwd_reduce_final");
+  launch_pdl((relu && !out) ? bn_bwd_reduce_kernel<true> : bn_bwd_reduce_kernel<false>, grid, dim3(256), 0, ST(stream), CBF(dout),
+             lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p, fold_rows, reinterpret_cast<unsigned*>(fold_tickets), sums,
+             dgamma, dbeta, accumulate, gamma, beta);
+  return check_launch("bn_bwd_reduce");
 }
 int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,
                      const float* gamma, const float* sums, double count, int64_t M, int C, int relu, float drop_p,

@@ -183,18 +183,22 @@ class Tape:
         stats = None
         if out_dtype is None:
             out_dtype = ACT_DTYPE
-        if want_stats and self.training:
+        want = want_stats and self.training
+        if want:
             stats = self.zalloc(2 * spec.K, wp.device)
         if spec.explicit:
             nchw = not isinstance(x, Act)
             src = x if nchw else x.t
             col = ops.im2col(src, spec.R, spec.S, spec.stride, spec.pad, spec.dil, spec.kpad, nchw_f32=nchw)
+            tk = self.zalloc(ops.conv_stats_workspace(*col.shape, spec.K, 1, 1)[1], wp.device) if want else None
             y = ops.conv2d_fwd(col, wp, spec.K, 1, 1, out=out, out_dtype=out_dtype,
-                               bias=bias.detach() if bias is not None else None, stats=stats, impl=self.impl)
+                               bias=bias.detach() if bias is not None else None, stats=stats, impl=self.impl, tickets=tk)
             xin, geo = col, (1, 1, 1, 0, 1)
         else:
+            tk = self.zalloc(ops.conv_stats_workspace(*x.t.shape, spec.K, spec.R, spec.S, spec.stride, spec.pad, spec.dil)[1],
+                             wp.device) if want else None
             y = ops.conv2d_fwd(x.t, wp, spec.K, spec.R, spec.S, spec.stride, spec.pad, spec.dil, out=out, out_dtype=out_dtype,
-                               bias=bias.detach() if bias is not None else None, stats=stats, impl=self.impl)
+                               bias=bias.detach() if bias is not None else None, stats=stats, impl=self.impl, tickets=tk)
             xin, geo = x.t, (spec.R, spec.S, spec.stride, spec.pad, spec.dil)
         ya = Act(y)
         if self.record:
@@ -268,8 +272,10 @@ class Tape:
         return ya
 
     # ------------------------------------------------------------------ batch norm (+ residual, ReLU, dropout)
-    def bn_act(self, y, bn, stats=None, relu=True, res=None, out=None, drop_p=0.0):
-        """y: Act holding the raw conv output.  Returns the activated Act."""
+    def bn_act(self, y, bn, stats=None, relu=True, res=None, out=None, drop_p=0.0, drop_channelwise=False):
+        """y: Act holding the raw conv output.  Returns the activated Act.  drop_channelwise: nn.Dropout2d semantics (one
+        draw per image and channel, models/pspnet.py:22,68) instead of nn.Dropout's per-element draws."""
+        drop_hw = y.t.shape[1] * y.t.shape[2] if drop_channelwise else 0
         C = y.t.shape[-1]
         count_local = ops.rows(y.t)
         use_batch_stats = self.training and bn.training
@@ -293,14 +299,15 @@ class Tape:
                                          bn.momentum if bn.momentum is not None else BN_MOM,
                                          1 if (self.clamp_eps and self.sync is not None and self.sync.world > 1) else 0,
                                          bn.running_mean, bn.running_var, res=res.t if res is not None else None, out=out,
-                                         relu=relu, drop_p=drop_p, seed=seed, step_ctr=self.step_ctr if drop_p > 0.0 else None)
+                                         relu=relu, drop_p=drop_p, seed=seed, step_ctr=self.step_ctr if drop_p > 0.0 else None,
+                                         drop_hw=drop_hw)
             self.bn_modules.append(bn)
         else:
             ss, save = ops.bn_eval_scale_shift(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps,
                                                want_save=True)
             count = count_local
             a = ops.bn_apply(y.t, ss, res=res.t if res is not None else None, out=out, relu=relu, drop_p=drop_p, seed=seed,
-                             step_ctr=self.step_ctr if drop_p > 0.0 else None)
+                             step_ctr=self.step_ctr if drop_p > 0.0 else None, drop_hw=drop_hw)
         aa = Act(a)
         # conv -> BN(batch statistics) -> ReLU with nothing in between: the backward APPLY pass recomputes the ReLU mask
         # from the conv output with the forward's own coefficients instead of re-reading the activation (one stream less).
@@ -323,7 +330,7 @@ class Tape:
                 sums = ops.bn_bwd_reduce(da, a, y.t, save, relu=relu, drop_p=drop_p,
                                          dgamma=self.grads[bn.weight] if want_pg else None,
                                          dbeta=self.grads[bn.bias] if want_pg else None, accumulate=acc_pg,
-                                         zero_scratch=self.zalloc(ops.bn_bwd_reduce_scratch_floats(C), a.device))
+                                         tickets=self.zalloc(ops.reduce_workspace(count_local, C, 2)[1], a.device))
                 gsums = sums
                 if not use_batch_stats:
                     gsums = torch.zeros_like(sums)  # frozen BN (freeze_bn): dx = gamma * inv_std * dz

@@ -248,7 +248,13 @@ class _GraphFn(torch.autograd.Function):
         entry.fwd.replay()
         entry.pending = entry.record
         ctx.entry = entry
-        outs = tuple(o.detach() for o in entry.outs)
+        if entry.record:
+            outs = tuple(o.detach() for o in entry.outs)
+        else:
+            # forward-only entries (validation, inference.py's multi-scale / flip / sliding-window loops) hand out COPIES:
+            # those callers keep one prediction alive across the next same-shape forward, which would overwrite a view
+            # of the static buffer
+            outs = tuple(o.detach().clone() for o in entry.outs)
         return outs if len(outs) > 1 else outs[0]
 
     @staticmethod
@@ -279,7 +285,7 @@ class _EngineModel(BaseModel):
         self._dwspecs = {}
         self.conv_impl = IMPL_AUTO
         self.engine_dropout = True    # set False to run train-mode parity with p = 0
-        self.engine_seed = 0
+        self.engine_seed = None       # None: derived from torch.initial_seed() and the data-parallel rank at first use
         self.bn_sync = None           # seg_b200.comm.SyncBNGroup for multi-GPU SyncBN
         self.syncbn_clamp_eps = True  # reproduce sync_batchnorm/batchnorm.py:145 when stats are synchronised
         self._step_ctr = None
@@ -366,7 +372,15 @@ class _EngineModel(BaseModel):
                 self._graphs_enabled = False  # do not retry every step; the caller sees the error
                 raise
             self._graph_entries[key] = e
-        return None if e.pending else e
+        if e.pending:
+            # a recorded forward whose backward never ran (skipped step, exception, probe call): run THIS call on the eager
+            # tape (the outstanding backward, if it still comes, needs the saved activations) and re-arm the entry
+            e.pending = False
+            if not getattr(self, "_graph_pending_warned", False):
+                self._graph_pending_warned = True
+                self.logger.warning("seg_b200: forward issued while a graph-replayed backward was outstanding; this call runs eagerly")
+            return None
+        return e
 
     @torch.no_grad()
     def _capture(self, e, x):
@@ -468,16 +482,28 @@ class _EngineModel(BaseModel):
         if training:
             dev = next(self.parameters()).device
             if self._step_ctr is None or self._step_ctr.device != dev:
-                self._step_ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+                # starts from the first BatchNorm's num_batches_tracked (a checkpointed buffer): a resumed run continues
+                # the dropout-mask sequence instead of repeating it from step 0
+                bns = self._flat()[2]
+                start = bns[0].num_batches_tracked.detach().reshape(1).to(dev, torch.int64) if bns else None
+                self._step_ctr = start.clone() if start is not None else torch.zeros(1, dtype=torch.int64, device=dev)
             ctr = self._step_ctr
             ops.counter_add(ctr, 1)  # device-side: stays correct when the step is replayed from a CUDA graph
-        return Tape(training, record=record, impl=self.conv_impl, dropout=self.engine_dropout, seed=self.engine_seed,
+        return Tape(training, record=record, impl=self.conv_impl, dropout=self.engine_dropout, seed=self._seed(),
                     sync=self.bn_sync, clamp_eps=self.syncbn_clamp_eps, step_ctr=ctr,
                     arena_floats=getattr(self, "_arena_floats", 0) if training else 0, owner=self)
 
-    def _cbr(self, tape, x, name, conv, bn, relu=True, res=None, out=None, drop_p=0.0):
+    def _seed(self):
+        """Dropout seed: follows torch.manual_seed and differs per data-parallel rank (nn.Dropout under DataParallel draws
+        independent masks per replica); the per-step variation comes from the device-side step counter."""
+        if self.engine_seed is None:
+            rank = torch.distributed.get_rank() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
+            self.engine_seed = (int(torch.initial_seed()) * 2654435761 + rank * 0x9E3779B1) & 0x7FFFFFFF
+        return self.engine_seed
+
+    def _cbr(self, tape, x, name, conv, bn, relu=True, res=None, out=None, drop_p=0.0, drop_channelwise=False):
         y, st = tape.conv(x, self._spec(name, conv), want_stats=True)
-        return tape.bn_act(y, bn, st, relu=relu, res=res, out=out, drop_p=drop_p)
+        return tape.bn_act(y, bn, st, relu=relu, res=res, out=out, drop_p=drop_p, drop_channelwise=drop_channelwise)
 
     def _block(self, tape, x, prefix, blk):
         a = self._cbr(tape, x, prefix + "conv1", blk.conv1, blk.bn1)
@@ -617,11 +643,9 @@ class DeepLab(_EngineModel):
                 low = a
         return a, low
 
-    def _features(self, tape, x):
-        N = x.shape[0]
-        a, low = self._trunk_xception(tape, x) if self.backbone_name == "xception" else self._trunk_resnet(tape, x)
-        # ---- ASPP (deeplabv3_plus.py:286-297): five branches written straight into one 1280-channel buffer ----
-        Hf, Wf = a.t.shape[1], a.t.shape[2]
+    def _aspp(self, tape, a):
+        """ASSP.forward (deeplabv3_plus.py:286-297): five branches written straight into one 1280-channel buffer."""
+        N, Hf, Wf = a.t.shape[0], a.t.shape[1], a.t.shape[2]
         A = self.ASSP
         cat, sl = tape.concat(N, Hf, Wf, [256] * 5, a.t.device)
         br = []
@@ -632,11 +656,14 @@ class DeepLab(_EngineModel):
         g = self._cbr(tape, g, "ASSP.avg_pool.1", A.avg_pool[1], A.avg_pool[2])
         br.append(tape.bilinear(g, Hf, Wf, True, out=sl[4]))
         tape.bind_slices(cat, br)
-        f = self._cbr(tape, cat, "ASSP.conv1", A.conv1, A.bn1, drop_p=A.dropout.p)
-        # ---- decoder (deeplabv3_plus.py:323-330): concat order (low-level 48, upsampled 256) ----
+        return self._cbr(tape, cat, "ASSP.conv1", A.conv1, A.bn1, drop_p=A.dropout.p)
+
+    def _decoder(self, tape, f, low):
+        """Decoder.forward (deeplabv3_plus.py:323-330): concat order (low-level 48, upsampled 256); returns the fp32
+        stride-4 logits Act."""
         D = self.decoder
-        Hl, Wl = low.t.shape[1], low.t.shape[2]
-        cat2, sl2 = tape.concat(N, Hl, Wl, [48, 256], a.t.device)
+        N, Hl, Wl = low.t.shape[0], low.t.shape[1], low.t.shape[2]
+        cat2, sl2 = tape.concat(N, Hl, Wl, [48, 256], low.t.device)
         l48 = self._cbr(tape, low, "decoder.conv1", D.conv1, D.bn1, out=sl2[0])
         up = tape.bilinear(f, Hl, Wl, True, out=sl2[1])
         tape.bind_slices(cat2, [l48, up])
@@ -644,6 +671,10 @@ class DeepLab(_EngineModel):
         y = self._cbr(tape, y, "decoder.output.3", D.output[3], D.output[4], drop_p=D.output[6].p)
         lo, _ = tape.conv(y, self._spec("decoder.output.7", D.output[7]), out_dtype=torch.float32)
         return lo
+
+    def _features(self, tape, x):
+        a, low = self._trunk_xception(tape, x) if self.backbone_name == "xception" else self._trunk_resnet(tape, x)
+        return self._decoder(tape, self._aspp(tape, a), low)
 
     def _forward_heads(self, tape, x):
         """[(stride-4 fp32 logits Act, align_corners of the final upsample)]  (deeplabv3_plus.py:361: True)"""
@@ -713,7 +744,18 @@ class PSPNet(_EngineModel):
                 a = self._block(tape, a, f"layer{li}.{bi}.", blk)
             if li == 3:
                 x_aux = a
-        Hf, Wf = a.t.shape[1], a.t.shape[2]
+        lo = self._psp_head(tape, a)
+        heads = [(lo, False)]  # pspnet.py:86,91: F.interpolate default align_corners=False; the crop is a no-op
+        if self.training and self.use_aux:
+            ab = self.auxiliary_branch
+            ya = self._cbr(tape, x_aux, "auxiliary_branch.0", ab[0], ab[1], drop_p=ab[3].p, drop_channelwise=True)
+            la, _ = tape.conv(ya, self._spec("auxiliary_branch.4", ab[4]), out_dtype=torch.float32)
+            heads.append((la, False))
+        return heads
+
+    def _psp_head(self, tape, a):
+        """_PSPModule.forward + the classifier (pspnet.py:31-38, :66-70): returns the fp32 stride-8 logits Act."""
+        N, Hf, Wf = a.t.shape[0], a.t.shape[1], a.t.shape[2]
         psp = self.master_branch[0]
         # pspnet.py:31-38: cat([features, stage1..4]) -> 3x3 bottleneck.  The trunk output is copied into slice 0
         # (it is also the residual-stream tensor, so it cannot simply be produced in place there).
@@ -726,16 +768,10 @@ class PSPNet(_EngineModel):
             p = self._cbr(tape, p, f"master_branch.0.stages.{i}.1", st[1], st[2])
             br.append(tape.bilinear(p, Hf, Wf, True, out=sl[i + 1]))
         tape.bind_slices(cat, br)
-        # Dropout2d (channel-wise) is approximated per element only when dropout is enabled; parity runs use p = 0
-        y = self._cbr(tape, cat, "master_branch.0.bottleneck.0", psp.bottleneck[0], psp.bottleneck[1], drop_p=psp.bottleneck[3].p)
+        y = self._cbr(tape, cat, "master_branch.0.bottleneck.0", psp.bottleneck[0], psp.bottleneck[1], drop_p=psp.bottleneck[3].p,
+                      drop_channelwise=True)
         lo, _ = tape.conv(y, self._spec("master_branch.1", self.master_branch[1]), out_dtype=torch.float32)
-        heads = [(lo, False)]  # pspnet.py:86,91: F.interpolate default align_corners=False; the crop is a no-op
-        if self.training and self.use_aux:
-            ab = self.auxiliary_branch
-            ya = self._cbr(tape, x_aux, "auxiliary_branch.0", ab[0], ab[1], drop_p=ab[3].p)
-            la, _ = tape.conv(ya, self._spec("auxiliary_branch.4", ab[4]), out_dtype=torch.float32)
-            heads.append((la, False))
-        return heads
+        return lo
 
     def get_backbone_params(self):
         return chain(self.initial.parameters(), self.layer1.parameters(), self.layer2.parameters(), self.layer3.parameters(),
@@ -813,7 +849,7 @@ class UperNet(_EngineModel):
             br.append(tape.bilinear(p, Hf, Wf, True, out=sl[i + 1]))
         tape.bind_slices(cat, br)
         pb = self.PPN.bottleneck
-        feats[-1] = self._cbr(tape, cat, "PPN.bottleneck.0", pb[0], pb[1], drop_p=pb[3].p)
+        feats[-1] = self._cbr(tape, cat, "PPN.bottleneck.0", pb[0], pb[1], drop_p=pb[3].p, drop_channelwise=True)
         # ---- FPN_fuse (upernet.py:103-117) ----
         F_ = self.FPN
         lat = [feats[0]]

@@ -95,16 +95,60 @@ def conv_desc_for(x, K, R, S, stride, pad, dil, ldy=None):
     return make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil, ldx=ld(x), ldy=ldy)
 
 
+_WS_CACHE = {}
+
+
+def conv_stats_workspace(N, H, W, C, K, R, S, stride=1, pad=0, dil=1):
+    """(rows_floats, tickets) of the deterministic statistics reduction of conv2d_fwd for this shape (cached)."""
+    key = ("conv", N, H, W, C, K, R, S, stride, pad, dil)
+    v = _WS_CACHE.get(key)
+    if v is None:
+        d = make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil)
+        r, t = ctypes.c_int64(), ctypes.c_int64()
+        if lib.load().seg_conv_stats_workspace(ctypes.byref(d), ctypes.byref(r), ctypes.byref(t)) != 0:
+            raise RuntimeError(lib.last_error())
+        v = _WS_CACHE[key] = (int(r.value), int(t.value))
+    return v
+
+
+def reduce_workspace(M, C, nacc=2):
+    """(rows_floats, tickets) of a deterministic column reduction over M rows x C channels (cached)."""
+    key = ("red", int(M), int(C), int(nacc))
+    v = _WS_CACHE.get(key)
+    if v is None:
+        r, t = ctypes.c_int64(), ctypes.c_int64()
+        if lib.load().seg_reduce_workspace(int(M), int(C), int(nacc), ctypes.byref(r), ctypes.byref(t)) != 0:
+            raise RuntimeError(lib.last_error())
+        v = _WS_CACHE[key] = (int(r.value), int(t.value))
+    return v
+
+
+def _fold_ws(rows_floats, n_tickets, tickets, device):
+    """Workspace pair of a fixed-order cross-block reduction: uninitialised rows + ZERO tickets (from the caller's zeroed
+    arena when given)."""
+    rows = torch.empty(max(rows_floats, 1), dtype=torch.float32, device=device)
+    if tickets is None:
+        tickets = torch.zeros(max(n_tickets, 1), dtype=torch.float32, device=device)
+    assert tickets.numel() >= n_tickets
+    return rows, tickets
+
+
 def conv2d_fwd(x, w_packed, K, R, S, stride=1, pad=0, dil=1, out=None, out_dtype=torch.bfloat16, bias=None, beta=0.0,
-               stats=None, impl=IMPL_AUTO):
+               stats=None, impl=IMPL_AUTO, tickets=None):
+    """stats: fp32 [2K] written with the per-channel sum / sum of squares of the output (bit-reproducible).  tickets: zeroed
+    fp32/int32 words (conv_stats_workspace(...)[1] of them) from the caller's per-step arena; allocated here if None."""
     N, H, W, C = x.shape
     d = make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil, ldx=ld(x))
     if out is None:
         out = torch.empty((N, d.P, d.Q, K), dtype=out_dtype, device=x.device)
     d.ldy = ld(out)
+    rows = None
+    if stats is not None:
+        nr, nt = conv_stats_workspace(N, H, W, C, K, R, S, stride, pad, dil)
+        rows, tickets = _fold_ws(nr, nt, tickets, x.device)
     ev = _prof("fprop", d)
     call("seg_conv2d_fwd", ctypes.byref(d), ptr(x), ptr(w_packed), ptr(out), DT_BF16 if out.dtype == torch.bfloat16 else DT_F32,
-         ptr(bias), float(beta), ptr(stats), _impl(impl), meta=_meta(d))
+         ptr(bias), float(beta), ptr(stats), ptr(rows), ptr(tickets) if stats is not None else None, _impl(impl), meta=_meta(d))
     if ev is not None:
         ev.record()
     return out
@@ -164,7 +208,7 @@ def dwconv_fwd(x, w9, stride=1, pad=1, dil=1, out=None, stats=None):
     if out is None:
         out = torch.empty((N, d.P, d.Q, C), dtype=torch.bfloat16, device=x.device)
     d.ldy = ld(out)
-    scratch = torch.empty(16 * 2 * C, dtype=torch.float32, device=x.device) if stats is not None else None
+    scratch = torch.empty(int(lib.load().seg_dwconv_scratch_floats(C)), dtype=torch.float32, device=x.device) if stats is not None else None
     call("seg_dwconv3x3_fwd", ctypes.byref(d), ptr(x), ptr(w9), ptr(out), ptr(stats), ptr(scratch))
     return out
 
@@ -204,11 +248,13 @@ def im2col(x, R, S, stride, pad, dil, kpad, nchw_f32):
 
 
 # ---------------------------------------------------------------- batch norm
-def bn_stats(x, stats=None):
+def bn_stats(x, stats=None, tickets=None):
     C = x.shape[-1]
     if stats is None:
-        stats = torch.zeros(2 * C, dtype=torch.float32, device=x.device)
-    call("seg_bn_stats", ptr(x), rows(x), C, ld(x), ptr(stats))
+        stats = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+    nr, nt = reduce_workspace(rows(x), C, 2)
+    fr, tickets = _fold_ws(nr, nt, tickets, x.device)
+    call("seg_bn_stats", ptr(x), rows(x), C, ld(x), ptr(stats), ptr(fr), ptr(tickets))
     return stats
 
 
@@ -229,12 +275,12 @@ def bn_eval_scale_shift(gamma, beta, rm, rv, eps, want_save=False):
     return (ss, save) if want_save else ss
 
 
-def bn_apply(x, scale_shift, res=None, out=None, relu=True, drop_p=0.0, seed=0, step_ctr=None):
+def bn_apply(x, scale_shift, res=None, out=None, relu=True, drop_p=0.0, seed=0, step_ctr=None, drop_hw=0):
     C = x.shape[-1]
     if out is None:
         out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     call("seg_bn_apply", ptr(x), ld(x), ptr(scale_shift), ptr(res), ld(res) if res is not None else 0, ptr(out), ld(out),
-         rows(x), C, int(relu), float(drop_p), int(seed), ptr(step_ctr))
+         rows(x), C, int(relu), float(drop_p), int(seed), ptr(step_ctr), int(drop_hw))
     return out
 
 
@@ -242,27 +288,25 @@ def counter_add(ctr, inc=1):
     call("seg_counter_add", ptr(ctr), int(inc))
 
 
-def bn_bwd_reduce_scratch_floats(C):
-    return int(lib.load().seg_bn_bwd_reduce_scratch_floats(0, C))
-
-
-def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, zero_scratch=None,
+def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, tickets=None,
                   gamma=None, beta=None):
-    """Returns sums [2C] = (sum dz, sum dz*xhat); optionally writes the parameter gradients from them.
-    zero_scratch: bn_bwd_reduce_scratch_floats(C) ZEROED floats -> one launch (the last block folds the slot rows).
+    """Returns sums [2C] = (sum dz, sum dz*xhat); optionally writes the parameter gradients from them.  One launch; the
+    cross-block sum is a fixed-order ticket tree (bit-reproducible).  tickets: reduce_workspace(M, C)[1] ZEROED words from
+    the caller's arena (allocated here if None).
     out=None (with relu, gamma, beta): the ReLU mask is recomputed from x instead of read from the stored activation."""
     C = x.shape[-1]
     M = rows(x)
     sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
-    scratch = zero_scratch if zero_scratch is not None else torch.empty(bn_bwd_reduce_scratch_floats(C), dtype=torch.float32, device=x.device)
+    nr, nt = reduce_workspace(M, C, 2)
+    fr, tickets = _fold_ws(nr, nt, tickets, x.device)
     call("seg_bn_bwd_reduce", ptr(dout), ld(dout), ptr(out), ld(out) if out is not None else 0, ptr(x), ld(x), ptr(save),
-         M, C, int(relu), float(drop_p), ptr(sums), ptr(scratch), ptr(dgamma), ptr(dbeta), int(accumulate),
-         int(zero_scratch is not None), ptr(gamma), ptr(beta), meta=_meta_rows(M, C, 3 if (relu and out is not None) else 2))
+         M, C, int(relu), float(drop_p), ptr(sums), ptr(fr), ptr(tickets), ptr(dgamma), ptr(dbeta), int(accumulate),
+         ptr(gamma), ptr(beta), meta=_meta_rows(M, C, 3 if (relu and out is not None) else 2))
     return sums
 
 
 def bn_apply_train(x, stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var, res=None, out=None,
-                   relu=True, drop_p=0.0, seed=0, step_ctr=None):
+                   relu=True, drop_p=0.0, seed=0, step_ctr=None, drop_hw=0):
     """Training-mode BN (+residual, ReLU, dropout) straight from the batch sums.  Returns (out, save[2C])."""
     C = x.shape[-1]
     if out is None:
@@ -270,7 +314,7 @@ def bn_apply_train(x, stats, count, gamma, beta, eps, momentum, clamp_eps, runni
     save = torch.empty(2 * C, dtype=torch.float32, device=x.device)
     call("seg_bn_apply_train", ptr(x), ld(x), ptr(stats), float(count), ptr(gamma), ptr(beta), float(eps), float(momentum),
          int(clamp_eps), ptr(running_mean), ptr(running_var), ptr(save), ptr(res), ld(res) if res is not None else 0,
-         ptr(out), ld(out), rows(x), C, int(relu), float(drop_p), int(seed), ptr(step_ctr),
+         ptr(out), ld(out), rows(x), C, int(relu), float(drop_p), int(seed), ptr(step_ctr), int(drop_hw),
          meta=_meta_rows(rows(x), C, 3 if res is not None else 2, res is not None))
     return out, save
 

@@ -69,6 +69,10 @@ class SGD(torch.optim.SGD):
                 t["hyper_val"] = hyper
             lib.call("seg_sgd_step_dev", t["p"].data_ptr(), t["g"].data_ptr(), t["m"].data_ptr(), t["n"].data_ptr(),
                      t["lr"].data_ptr(), len(params), t["hyper"].data_ptr(), 0, 1.0)
+            # the kernel writes through raw pointers: tell autograd (and every cache keyed on `_version`, e.g. the engine's
+            # packed bf16 weights, engine.ConvSpec.packed) that these tensors changed — exactly what the in-place ops of
+            # torch.optim.SGD.step do
+            torch.autograd.graph.increment_version(params)
         return loss
 
 

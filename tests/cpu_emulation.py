@@ -55,13 +55,21 @@ def unpack_wgrad(dwp, shape, beta=0.0, out=None):
     return out
 
 
+def conv_stats_workspace(*a, **k):
+    return (0, 1)
+
+
+def reduce_workspace(*a, **k):
+    return (0, 1)
+
+
 def conv2d_fwd(x, wp, K, R, S, stride=1, pad=0, dil=1, out=None, out_dtype=None, bias=None, beta=0.0, stats=None,
-               impl=0):
+               impl=0, tickets=None):
     y = F.conv2d(_nchw(x), _w_oihw(wp, R, S), bias, stride, pad, dil).permute(0, 2, 3, 1)
-    if stats is not None:
+    if stats is not None:  # written, not accumulated (the kernels' fixed-order reduction overwrites)
         C = y.shape[-1]
-        stats[:C] += y.reshape(-1, C).sum(0)
-        stats[C:] += (y * y).reshape(-1, C).sum(0)
+        stats[:C] = y.reshape(-1, C).sum(0)
+        stats[C:] = (y * y).reshape(-1, C).sum(0)
     if out is None:
         out = torch.empty(y.shape, dtype=out_dtype or ACT_DTYPE)
     return _store(out, y, beta)
@@ -147,13 +155,13 @@ def im2col(x, R, S, stride, pad, dil, kpad, nchw_f32):
     return out
 
 
-def bn_stats(x, stats=None):
+def bn_stats(x, stats=None, tickets=None):
     C = x.shape[-1]
     if stats is None:
         stats = torch.zeros(2 * C)
     f = x.float().reshape(-1, C)
-    stats[:C] += f.sum(0)
-    stats[C:] += (f * f).sum(0)
+    stats[:C] = f.sum(0)
+    stats[C:] = (f * f).sum(0)
     return stats
 
 
@@ -176,7 +184,7 @@ def bn_eval_scale_shift(gamma, beta, rm, rv, eps, want_save=False):
     return (ss, torch.cat([rm, istd])) if want_save else ss
 
 
-def bn_apply(x, ss, res=None, out=None, relu=True, drop_p=0.0, seed=0, step_ctr=None):
+def bn_apply(x, ss, res=None, out=None, relu=True, drop_p=0.0, seed=0, step_ctr=None, drop_hw=0):
     C = x.shape[-1]
     v = x.float() * ss[:C] + ss[C:]
     if res is not None:
@@ -190,13 +198,9 @@ def bn_apply(x, ss, res=None, out=None, relu=True, drop_p=0.0, seed=0, step_ctr=
 
 
 def bn_apply_train(x, stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var, res=None, out=None,
-                   relu=True, drop_p=0.0, seed=0, step_ctr=None):
+                   relu=True, drop_p=0.0, seed=0, step_ctr=None, drop_hw=0):
     ss, save = bn_finalize(stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var)
     return bn_apply(x, ss, res=res, out=out, relu=relu, drop_p=drop_p, seed=seed, step_ctr=step_ctr), save
-
-
-def bn_bwd_reduce_scratch_floats(C):
-    return 32 * C + 4
 
 
 def _dz(dout, out, relu, drop_p, x=None, save=None, gamma=None, beta=None):
@@ -210,7 +214,7 @@ def _dz(dout, out, relu, drop_p, x=None, save=None, gamma=None, beta=None):
     return dz
 
 
-def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, zero_scratch=None,
+def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, tickets=None,
                   gamma=None, beta=None):
     C = x.shape[-1]
     dz = _dz(dout, out, relu, drop_p, x, save, gamma, beta).reshape(-1, C)

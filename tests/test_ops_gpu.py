@@ -66,6 +66,7 @@ CONV_SHAPES = [
     (1, 129, 129, 64, 256, 1, 1, 0, 1),   # many M tiles, short K: epilogue-bound shape
     (4, 65, 65, 128, 1024, 1, 1, 0, 1),   # persistent kernel: 8 column blocks, several tiles per CTA
     (2, 65, 65, 192, 320, 3, 1, 1, 1),    # persistent kernel: column-block tail (320 = 2.5 x 128), C tail
+    (1, 129, 129, 64, 64, 3, 1, 1, 1),    # one-tile kernel with 131 row tiles: two-level statistics fold (layer1 conv2 shape)
 ]
 
 
@@ -88,17 +89,28 @@ def test_conv_fwd(shape, impl, gpu_out_dir):
     x, w = conv_inputs(shape)
     ref = F.conv2d(x, w, None, stride, pad, dil)
     wp = ops.pack_weight(w.to(DEV))
-    stats = torch.zeros(2 * K, device=DEV)
+    # fp32 output + statistics: tcgen05 path only (the CUDA-core path reduces the stored bf16 output)
+    stats = torch.full((2 * K,), float("nan"), device=DEV) if impl == IMPL_TC else None  # written, not accumulated
     y = ops.conv2d_fwd(to_nhwc_dev(x), wp, K, ks, ks, stride, pad, dil, out_dtype=torch.float32, stats=stats, impl=impl)
     torch.cuda.synchronize()
     check(f"conv_fwd[{impl}] {shape}", y.permute(0, 3, 1, 2), ref, 2e-3, gpu_out_dir)
     ref_s = torch.cat([ref.sum((0, 2, 3)), (ref * ref).sum((0, 2, 3))])
-    check(f"conv_fwd_stats[{impl}] {shape}", stats, ref_s, 2e-3, gpu_out_dir)
-    stats_b = torch.zeros(2 * K, device=DEV)
+    if stats is not None:
+        check(f"conv_fwd_stats[{impl}] {shape}", stats, ref_s, 2e-3, gpu_out_dir)
+    stats_b = torch.full((2 * K,), float("nan"), device=DEV)
     yb = ops.conv2d_fwd(to_nhwc_dev(x), wp, K, ks, ks, stride, pad, dil, stats=stats_b, impl=impl)
     torch.cuda.synchronize()
     check(f"conv_fwd_bf16[{impl}] {shape}", yb.permute(0, 3, 1, 2), ref, 1e-2, gpu_out_dir)
     check(f"conv_fwd_bf16_stats[{impl}] {shape}", stats_b, ref_s, 2e-3, gpu_out_dir)
+    # the statistics are the sums of the output AS STORED, reduced in a fixed order: exact against a float64 sum of the
+    # stored bf16 values up to fp32 rounding, and bit-identical from run to run
+    yd = yb.double().reshape(-1, K)
+    exact = torch.cat([yd.sum(0), (yd * yd).sum(0)]).float()
+    check(f"conv_fwd_bf16_stats_vs_stored[{impl}] {shape}", stats_b, exact, 2e-5, gpu_out_dir)
+    for _ in range(3):
+        again = torch.full((2 * K,), float("nan"), device=DEV)
+        ops.conv2d_fwd(to_nhwc_dev(x), wp, K, ks, ks, stride, pad, dil, stats=again, impl=impl)
+        assert torch.equal(again, stats_b), "BatchNorm statistics are not bit-reproducible"
 
 
 @pytest.mark.parametrize("impl", [IMPL_SIMT, IMPL_TC], ids=["simt", "tc"])

@@ -59,3 +59,43 @@ def test_refuses_cpu_parameters():
     p.grad = torch.ones(3)
     with pytest.raises(RuntimeError, match="no fallback"):
         SGD([p], lr=0.1, momentum=0.9).step()
+
+
+def test_fused_sgd_step_invalidates_packed_weight_caches():
+    """the kernel updates parameters through raw pointers; the eager plugin path caches packed bf16
+    weights keyed on `param._version`, so SGD.step must bump the versions — otherwise every forward after step 1 keeps
+    using the initial weights.  Two identical models, one stepped by torch.optim.SGD, one by seg_b200.optim.SGD: after
+    each step the logits must have moved and must agree between the two."""
+    import seg_b200
+    from oracle import synth, weights
+
+    sd = weights.deeplab_resnet_state_dict(19, "resnet14", seed=5)
+    x, y = synth.make_batch(2, 65, 65, 19, 255, seed=77)
+    x, y = x.cuda(), y.cuda()
+    crit = seg_b200.CrossEntropyLoss2d(ignore_index=255)
+    models, opts = [], []
+    for cls in (torch.optim.SGD, SGD):
+        m = seg_b200.DeepLab(19, backbone="resnet14", pretrained=False)
+        m.load_state_dict(sd, strict=True)
+        m.engine_dropout = False
+        m = m.cuda().train()
+        m.freeze_bn()  # a fixed, well-conditioned function: differences are the optimiser's, not BN chaos
+        models.append(m)
+        opts.append(cls([{"params": list(m.get_decoder_params())}, {"params": list(m.get_backbone_params()), "lr": 0.01}],
+                        lr=0.1, momentum=0.9, weight_decay=1e-4))
+    prev = None
+    for it in range(3):
+        outs = []
+        for m, o in zip(models, opts):
+            o.zero_grad(set_to_none=True)
+            out = m(x)
+            crit(out, y).backward()
+            o.step()
+            outs.append(out.detach().clone())
+        scale = outs[0].abs().max().item()
+        assert (outs[0] - outs[1]).abs().max().item() < 2e-2 * scale, it
+        if prev is not None:  # the step changed what the forward computes
+            assert (outs[1] - prev).abs().max().item() > 1e-3 * scale, "logits did not move: stale packed weights"
+        prev = outs[1]
+    for p in models[1].parameters():
+        assert p._version >= 3
