@@ -41,6 +41,20 @@ __device__ __forceinline__ FoldLane fold_lane(float* rows_ws, unsigned* tickets_
   return L;
 }
 
+// Sum of `n` (<= FOLD_G... any) floats spaced `stride` apart, added in index order in fp64.  The loads of a chunk of 32 are
+// all issued before the first add (a dependent-load chain here cost 20-50 us of kernel tail in the first version).
+__device__ __forceinline__ double fold_column(const float* base, int n, size_t stride) {
+  double s = 0.0;
+  for (int r0 = 0; r0 < n; r0 += 32) {
+    float v[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) v[r] = (r0 + r < n) ? __ldcg(base + (size_t)(r0 + r) * stride) : 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) s += (double)v[r];
+  }
+  return s;
+}
+
 // Called by the `nthr` cooperating threads of a block (tid 0..nthr-1; `sync()` is a barrier over exactly those threads)
 // AFTER they have written row `row` of L.rows1 with plain stores.  In exactly one block of the lane — the one that
 // completes the tree — it returns true after calling emit(column, total) for every column; everywhere else false.
@@ -59,31 +73,18 @@ __device__ __forceinline__ bool fold_arrive(const FoldLane& L, int row, int tid,
   if (!*sm_flag) return false;
   __threadfence();
   if (ngroups == 1) {
-    for (int c = tid; c < L.width; c += nthr) {
-      double s = 0.0;
-#pragma unroll 8
-      for (int r = 0; r < gn; ++r) s += (double)__ldcg(L.rows1 + (size_t)(g0 + r) * L.width + c);
-      emit(c, (float)s);
-    }
+    for (int c = tid; c < L.width; c += nthr) emit(c, (float)fold_column(L.rows1 + (size_t)g0 * L.width + c, gn, L.width));
     return true;
   }
-  for (int c = tid; c < L.width; c += nthr) {
-    double s = 0.0;
-    for (int r = 0; r < gn; ++r) s += (double)__ldcg(L.rows1 + (size_t)(g0 + r) * L.width + c);
-    L.rows2[(size_t)grp * L.width + c] = (float)s;
-  }
+  for (int c = tid; c < L.width; c += nthr)
+    L.rows2[(size_t)grp * L.width + c] = (float)fold_column(L.rows1 + (size_t)g0 * L.width + c, gn, L.width);
   __threadfence();
   sync();
   if (tid == 0) *sm_flag = (atomicAdd(L.tickets + ngroups, 1u) == (unsigned)(ngroups - 1));
   sync();
   if (!*sm_flag) return false;
   __threadfence();
-  for (int c = tid; c < L.width; c += nthr) {
-    double s = 0.0;
-#pragma unroll 8
-    for (int g = 0; g < ngroups; ++g) s += (double)__ldcg(L.rows2 + (size_t)g * L.width + c);
-    emit(c, (float)s);
-  }
+  for (int c = tid; c < L.width; c += nthr) emit(c, (float)fold_column(L.rows2 + c, ngroups, L.width));
   return true;
 }
 

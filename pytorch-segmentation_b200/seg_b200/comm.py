@@ -78,6 +78,24 @@ class LocalLoopbackGroup:
         return vec
 
 
+def dp_world(group=None):
+    """Number of data-parallel replicas (1 without an initialised process group)."""
+    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def dp_rank(group=None):
+    return dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
+
+
+def allreduce_mean_(flat, world):
+    """Gradient exchange of the data-parallel path (what nn.DataParallel's reduce-to-device-0 + next step's broadcast do
+    in the reference, base/base_trainer.py:33-38 / trainer.py:70-71): ONE NCCL all-reduce of the flat fp32 gradient
+    buffer, then the 1/world scale.  Identical result on every rank, so replicas stay bit-equal."""
+    dist.all_reduce(flat)
+    flat.mul_(1.0 / world)
+    return flat
+
+
 def init_distributed():
     """Initialise torch.distributed from the torchrun environment (no-op for a single process)."""
     import os

@@ -14,21 +14,39 @@ import torch.nn as nn
 from . import ops
 
 
+def _dp_world():
+    from .comm import dp_world
+    return dp_world()
+
+
 class _CEFn(torch.autograd.Function):
+    """mean over the non-ignored pixels (nn.CrossEntropyLoss(reduction='mean', ignore_index), utils/losses.py:24-31).  In the
+    reference nn.DataParallel gathers the logits and the loss is the mean over the GLOBAL batch; with one process per GPU
+    that is (sum over ranks of the loss sums) / (sum over ranks of the valid-pixel counts): the (sum, count) pair is
+    all-reduced — 16 bytes — so every rank reports the global loss and its gradient carries the global normalisation
+    (times world: the engine's gradient exchange averages over ranks).  `global_mean=False` keeps per-rank means."""
+
     @staticmethod
-    def forward(ctx, logits, target, ignore_index):
+    def forward(ctx, logits, target, ignore_index, global_mean=True):
         logits = logits.contiguous().float()
         target = target.contiguous()
-        loss, accum = ops.ce_nchw_fwd(logits, target, ignore_index)
+        world = _dp_world() if global_mean else 1
+        reduce_fn = None
+        if world > 1:
+            def reduce_fn(accum):
+                torch.distributed.all_reduce(accum)
+        loss, accum = ops.ce_nchw_fwd(logits, target, ignore_index, reduce_fn=reduce_fn)
         ctx.save_for_backward(logits, target, accum)
-        ctx.ignore_index = ignore_index
+        ctx.ignore_index, ctx.world = ignore_index, world
         return loss
 
     @staticmethod
     def backward(ctx, gout):
         logits, target, accum = ctx.saved_tensors
         g = gout.detach().reshape(1).float().contiguous()
-        return ops.ce_nchw_bwd(logits, target, ctx.ignore_index, accum, gscale=g), None, None
+        if ctx.world > 1:
+            g = g * float(ctx.world)
+        return (ops.ce_nchw_bwd(logits, target, ctx.ignore_index, accum, gscale=g),) + (None,) * (len(ctx.needs_input_grad) - 1)
 
 
 class CrossEntropyLoss2d(nn.Module):

@@ -193,12 +193,24 @@ def _check_pretrained(model, pretrained):
 
 # ----------------------------------------------------------------------------------------------- autograd bridge
 class _EngineFn(torch.autograd.Function):
-    """One autograd node for the whole model: forward = kernel tape, backward = tape replay."""
+    """One autograd node for the whole model: forward = kernel tape, backward = tape replay.  With an initialised process
+    group of more than one rank (one process per GPU) every parameter gradient is written into ONE flat fp32 buffer that is
+    all-reduced (mean) inside backward — the replicas of an unmodified train.py stay identical, which is what the
+    reference's nn.DataParallel wrapper guarantees (base/base_trainer.py:33-38)."""
 
     @staticmethod
     def forward(ctx, model, record, x, *params):
-        outs, tape, heads = model._run(x, training=model.training, record=record)
-        ctx.tape, ctx.heads, ctx.params = tape, heads, params
+        world = model._dp_world() if record else 1
+        views = flat = None
+        if world > 1:
+            flat = torch.zeros(sum(p.numel() for p in params if p.requires_grad), dtype=torch.float32, device=x.device)
+            views, off = {}, 0
+            for p in params:
+                if p.requires_grad:
+                    views[p] = flat[off:off + p.numel()].view(p.shape)
+                    off += p.numel()
+        outs, tape, heads = model._run(x, training=model.training, record=record, grads=views)
+        ctx.tape, ctx.heads, ctx.params, ctx.flat, ctx.world = tape, heads, params, flat, world
         return outs if len(outs) > 1 else outs[0]
 
     @staticmethod
@@ -215,8 +227,15 @@ class _EngineFn(torch.autograd.Function):
             lo_act.grad = g[..., :C]
         tape.backward()
         grads = tape.grads
+        if ctx.flat is not None:
+            from .comm import allreduce_mean_
+            allreduce_mean_(ctx.flat, ctx.world)
+            # pre-bound views hide which gradients the tape wrote: hand autograd only those (None otherwise, as at world 1)
+            out = tuple(grads.get(p) if p in tape.touched else None for p in ctx.params)
+        else:
+            out = tuple(grads.get(p) for p in ctx.params)
         ctx.tape = None
-        return (None, None, None) + tuple(grads.get(p) for p in ctx.params)
+        return (None, None, None) + out
 
 
 class _GraphEntry:
@@ -287,6 +306,9 @@ class _EngineModel(BaseModel):
         self.engine_dropout = True    # set False to run train-mode parity with p = 0
         self.engine_seed = None       # None: derived from torch.initial_seed() and the data-parallel rank at first use
         self.bn_sync = None           # seg_b200.comm.SyncBNGroup for multi-GPU SyncBN
+        self.use_sync_bn = False      # set by the overlay's convert_model (config "use_synch_bn"): attach a SyncBNGroup at the
+                                      # first forward under a multi-rank process group
+        self.dp_reduce = True         # all-reduce (mean) the gradients inside backward when world > 1
         self.syncbn_clamp_eps = True  # reproduce sync_batchnorm/batchnorm.py:145 when stats are synchronised
         self._step_ctr = None
         self._graphs_enabled = False
@@ -352,7 +374,8 @@ class _EngineModel(BaseModel):
     def _graph_lookup(self, x, record):
         _, tensors, bns = self._flat()
         bn_train = sum(1 for m in bns if m.training)
-        key = (tuple(x.shape), x.device.index, self.training, bool(record), bn_train, bool(self.engine_dropout), self.bn_sync is not None)
+        key = (tuple(x.shape), x.device.index, self.training, bool(record), bn_train, bool(self.engine_dropout), self.bn_sync is not None,
+               self._dp_world())
         ptrs = tuple(t.data_ptr() for t in tensors)
         e = self._graph_entries.get(key)
         if e is not None and e.ptrs != ptrs:  # a parameter / buffer was re-allocated (model.to(...), .half(), ...)
@@ -406,8 +429,8 @@ class _EngineModel(BaseModel):
         torch.cuda.synchronize()
         multi = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
         mode = "thread_local" if multi else "global"  # NCCL's watchdog thread polls events while we capture
-        if multi and self.bn_sync is not None:
-            torch.distributed.barrier()  # every rank has finished its eager SyncBN exchanges before anyone captures
+        if multi and (self.bn_sync is not None or self.dp_reduce):
+            torch.distributed.barrier()  # every rank has finished its eager exchanges before anyone captures
         fwd = torch.cuda.CUDAGraph()
         with torch.cuda.graph(fwd, pool=e.pool, capture_error_mode=mode):
             e.wt.pack()
@@ -426,6 +449,9 @@ class _EngineModel(BaseModel):
                     lo_act.grad = g[..., :C]
                 tape.backward()
                 e.wt.unpack()
+                if self._dp_world() > 1:  # the gradient exchange is part of the captured backward (NCCL kernels replay)
+                    from .comm import allreduce_mean_
+                    allreduce_mean_(e.flat_grad, self._dp_world())
             e.bwd = bwd
             # parameters the tape never wrote a gradient for get None, as on the eager path
             e.param_slices = [sl if (sl is not None and p in tape.touched) else None for p, sl in zip(params, slices)]
@@ -517,6 +543,21 @@ class _EngineModel(BaseModel):
         if tape.bn_modules:
             torch._foreach_add_([m.num_batches_tracked for m in tape.bn_modules], 1)
 
+    def _dp_world(self):
+        """Data-parallel replicas taking part in this model's backward (1 = no exchange)."""
+        if not self.dp_reduce:
+            return 1
+        from .comm import dp_world
+        return dp_world()
+
+    def _attach_sync_bn(self):
+        """config['use_synch_bn'] (base/base_trainer.py:33-35 -> the overlay's convert_model) under torchrun: BatchNorm
+        statistics are exchanged over NVLink peer memory (sync_batchnorm/batchnorm.py:105-145 semantics, clamp(var, eps))."""
+        from . import comm
+        if self.use_sync_bn and self.bn_sync is None and comm.dp_world() > 1:
+            self.bn_sync = comm.SyncBNGroup()
+            self.release_graphs()
+
     def _check_input(self, x):
         if not x.is_cuda:
             raise RuntimeError("seg_b200 models run on a B200 only; there is no CPU / eager fallback")
@@ -524,6 +565,8 @@ class _EngineModel(BaseModel):
 
     def forward(self, x):
         self._check_input(x)
+        if self.use_sync_bn and self.bn_sync is None:
+            self._attach_sync_bn()
         params = self._flat()[0]
         record = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if self._graphs_enabled:

@@ -406,11 +406,14 @@ def bilinear_logits_bwd(dy_nchw, Hi, Wi, align_corners, ldx):
 
 
 # ---------------------------------------------------------------- loss
-def ce_nchw_fwd(logits, target, ignore_index):
+def ce_nchw_fwd(logits, target, ignore_index, reduce_fn=None):
+    """reduce_fn(accum): optional in-place cross-rank sum of the fp64 (loss sum, valid-pixel count) pair before the mean."""
     N, C, H, W = logits.shape
     assert logits.is_contiguous() and logits.dtype == torch.float32 and target.dtype == torch.int64 and target.is_contiguous()
     accum = torch.zeros(2, dtype=torch.float64, device=logits.device)
     call("seg_ce_nchw_fwd", ptr(logits), ptr(target), N, C, H, W, int(ignore_index), ptr(accum))
+    if reduce_fn is not None:
+        reduce_fn(accum)
     loss = torch.empty((), dtype=torch.float32, device=logits.device)
     call("seg_ce_finalize", ptr(accum), ptr(loss))
     return loss, accum

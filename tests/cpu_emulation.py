@@ -66,10 +66,11 @@ def reduce_workspace(*a, **k):
 def conv2d_fwd(x, wp, K, R, S, stride=1, pad=0, dil=1, out=None, out_dtype=None, bias=None, beta=0.0, stats=None,
                impl=0, tickets=None):
     y = F.conv2d(_nchw(x), _w_oihw(wp, R, S), bias, stride, pad, dil).permute(0, 2, 3, 1)
-    if stats is not None:  # written, not accumulated (the kernels' fixed-order reduction overwrites)
-        C = y.shape[-1]
-        stats[:C] = y.reshape(-1, C).sum(0)
-        stats[C:] = (y * y).reshape(-1, C).sum(0)
+    if stats is not None:  # written, not accumulated (the kernels' fixed-order reduction overwrites); sums of the output
+        C = y.shape[-1]    # AS STORED (rounded to the output type), which is what bn_apply then normalises
+        ys = y.to(out.dtype if out is not None else (out_dtype or ACT_DTYPE)).float()
+        stats[:C] = ys.reshape(-1, C).sum(0)
+        stats[C:] = (ys * ys).reshape(-1, C).sum(0)
     if out is None:
         out = torch.empty(y.shape, dtype=out_dtype or ACT_DTYPE)
     return _store(out, y, beta)
@@ -308,18 +309,21 @@ def bilinear_logits_bwd(dy, Hi, Wi, align_corners, ldx):
     return out
 
 
-def ce_nchw_fwd(logits, target, ignore_index):
+def ce_nchw_fwd(logits, target, ignore_index, reduce_fn=None):
     valid = target != ignore_index
     loss_sum = F.cross_entropy(logits, target, ignore_index=ignore_index, reduction="sum")
     accum = torch.tensor([loss_sum.item(), float(valid.sum())], dtype=torch.float64)
-    return (loss_sum / valid.sum().clamp(min=1)).float(), accum
+    if reduce_fn is not None:
+        reduce_fn(accum)
+    return (accum[0] / accum[1].clamp(min=1)).float(), accum
 
 
 def ce_nchw_bwd(logits, target, ignore_index, accum, gscale=None):
+    """d(loss sum)/d(logits) / accum.count  (the count may be the cross-rank total)"""
     with torch.enable_grad():
         l = logits.detach().clone().requires_grad_(True)
-        F.cross_entropy(l, target, ignore_index=ignore_index, reduction="mean").backward()
-    return l.grad * (gscale.reshape(()) if gscale is not None else 1.0)
+        F.cross_entropy(l, target, ignore_index=ignore_index, reduction="sum").backward()
+    return (l.grad / accum[1].clamp(min=1)).float() * (gscale.reshape(()) if gscale is not None else 1.0)
 
 
 def relu_fwd(x):

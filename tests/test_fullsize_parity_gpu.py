@@ -1,0 +1,290 @@
+"""Model-level parity AT THE BASELINE SIZES, with the reference's own initialisers.
+
+For C3 (DeepLabV3+/ResNet-101, 513x513, 19 classes) and C2 (PSPNet/ResNet-50, 473x473, 21 classes + aux), batch 4,
+weights as `utils/helpers.py:12-22` / the trunk initialisers leave them (BN gamma = 1, beta = 1e-4 | 0, running statistics
+0 / 1 — `randomize_bn=False`), three modes are compared with the fp32 CPU oracle (pinned to the reference by tests/golden):
+
+  eval-init    model.eval() on the initialisers' running statistics (0 / 1: BatchNorm is the identity, the residual
+               trunk is un-normalised) — forward only
+  eval         model.eval() after the running statistics were set to one batch's statistics (a normalised network, as
+               after training): forward only                   (models/deeplabv3_plus.py:356-362, trainer.py:125-126)
+  frozen-BN    model.train() + freeze_bn(): forward + backward (config arch.args.freeze_bn, trainer.py:41-43)
+  train        batch statistics: forward + backward            (trainer.py:55-71) — the mode bench.py measures
+
+Every number is logged next to a CONTROL: the same oracle functions run on the GPU under torch.autocast(bfloat16), i.e.
+ATen's own bf16 implementation of the reference — the noise floor of bf16 storage with fp32 accumulation.  Asserted:
+logits max-norm relative error <= max(1e-2, 1.5 x control); arg-max identical on every pixel whose top-2 margin exceeds
+twice the max logit error (the fraction of such pixels is logged); loss within 1e-3 relative (eval / frozen) or within
+max(1e-3, 1.5 x control) (train); parameter gradients: median cosine > 0.99 and no worse than the control by more than
+the stated slack.  Two forward passes from the same state must be BIT-identical (deterministic statistics).
+"""
+import os
+import time
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import losses as ol
+from oracle import models as om
+from oracle import synth, weights
+
+if torch.cuda.is_available():
+    import seg_b200
+
+
+CONFIGS = {
+    "C3_deeplab_r101_513": dict(kind="deeplab", nc=19, backbone="resnet101", size=513, batch=4, seed=0, xseed=9001),
+    "C2_pspnet_r50_473": dict(kind="pspnet", nc=21, backbone="resnet50", size=473, batch=4, seed=1, xseed=9002),
+}
+
+
+def log(gpu_out_dir, msg):
+    print(msg)
+    with open(os.path.join(gpu_out_dir, "parity_fullsize.txt"), "a") as f:
+        f.write(msg + "\n")
+
+
+def relmax(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def relrms(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).pow(2).mean().sqrt() / (b.pow(2).mean().sqrt() + 1e-30)).item()
+
+
+def cosine(a, b):
+    return torch.nn.functional.cosine_similarity(a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten(), dim=0).item()
+
+
+def make(cfg):
+    if cfg["kind"] == "deeplab":
+        sd = weights.deeplab_resnet_state_dict(cfg["nc"], cfg["backbone"], seed=cfg["seed"], randomize_bn=False)
+        m = seg_b200.DeepLab(cfg["nc"], backbone=cfg["backbone"], pretrained=False, output_stride=16)
+    else:
+        sd = weights.pspnet_state_dict(cfg["nc"], cfg["backbone"], seed=cfg["seed"], randomize_bn=False)
+        m = seg_b200.PSPNet(cfg["nc"], backbone=cfg["backbone"], pretrained=False)
+    m.load_state_dict(sd, strict=True)
+    m.engine_dropout = False
+    return sd, m.cuda()
+
+
+def oracle_run(cfg, sd, x, y, train_bn, want_grad):
+    """Reference algorithm (fp32 when sd/x live on the CPU; ATen-bf16 control when called under autocast on the GPU).
+    Returns (out, aux|None, loss, {name: grad})."""
+    osd = om.clone_sd(sd, requires_grad=want_grad)
+    if cfg["kind"] == "deeplab":
+        out, aux = om.deeplab_forward(osd, x, backbone=cfg["backbone"], train=train_bn), None
+    else:
+        r = om.pspnet_forward(osd, x, backbone=cfg["backbone"], train=train_bn, use_aux=want_grad)
+        out, aux = r if isinstance(r, tuple) else (r, None)
+    loss = ol.cross_entropy2d(out.float(), y, 255)
+    if aux is not None:
+        loss = loss + 0.4 * ol.cross_entropy2d(aux.float(), y, 255)
+    grads = {}
+    if want_grad:
+        loss.backward()
+        grads = {k: osd[k].grad for k in om.param_names(osd) if osd[k].grad is not None}
+    running = {k: v.detach().float().cpu() for k, v in osd.items() if k.endswith("running_mean") or k.endswith("running_var")}
+    return out.detach().float(), None if aux is None else aux.detach().float(), float(loss.item()), grads, running
+
+
+def calibrated(cfg, sd, x):
+    csd = om.clone_sd(sd)
+    mom, om.MOM = om.MOM, 1.0
+    try:
+        with torch.no_grad():
+            if cfg["kind"] == "deeplab":
+                om.deeplab_forward(csd, x, backbone=cfg["backbone"], train=True)
+            else:
+                om.pspnet_forward(csd, x, backbone=cfg["backbone"], train=True, use_aux=True)
+    finally:
+        om.MOM = mom
+    for k in csd:
+        if k.endswith("num_batches_tracked"):
+            csd[k] = torch.zeros((), dtype=torch.int64)
+    return csd
+
+
+def control_run(cfg, sd, x, y, train_bn, want_grad):
+    """ATen's bf16: the oracle functions on cuda:0 under autocast(bfloat16) (cuDNN convolutions with bf16 operands, fp32
+    accumulation; batch norm on bf16 activations with fp32 statistics)."""
+    dsd = {k: v.cuda() for k, v in sd.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        r = oracle_run(cfg, dsd, x.cuda(), y.cuda(), train_bn, want_grad)
+    torch.cuda.synchronize()
+    return r[0].cpu(), None if r[1] is None else r[1].cpu(), r[2], {k: g.cpu() for k, g in r[3].items()}, r[4]
+
+
+def engine_run(cfg, m, x, y, mode, want_grad):
+    crit = seg_b200.CrossEntropyLoss2d(ignore_index=255)
+    if mode.startswith("eval"):
+        m.eval()
+    else:
+        m.train()
+        if mode == "frozen":
+            m.freeze_bn()
+    m.zero_grad(set_to_none=True)
+    xd, yd = x.cuda(), y.cuda()
+    with torch.set_grad_enabled(want_grad):
+        r = m(xd)
+        out, aux = r if isinstance(r, tuple) else (r, None)
+        if mode != "train":
+            aux = None  # the oracle's frozen-BN leg has no auxiliary head (its `train` flag is also the BN mode)
+        loss = crit(out, yd)
+        if aux is not None:
+            loss = loss + 0.4 * crit(aux, yd)
+        if want_grad:
+            loss.backward()
+    torch.cuda.synchronize()
+    grads = {n: p.grad.detach().cpu() for n, p in m.named_parameters() if p.grad is not None} if want_grad else {}
+    return out.detach().cpu(), None if aux is None else aux.detach().cpu(), float(loss.item()), grads
+
+
+def emulated_run(cfg, sd, x, y):
+    """The engine's own tape (same op order, same bf16 rounding points: conv output, BN output, every gradient buffer) with
+    every kernel replaced by its ATen-CPU restatement (tests/cpu_emulation.py, fp32 arithmetic between the rounding
+    points).  Engine-vs-emulation isolates the KERNELS' arithmetic in context from the effect of bf16 storage."""
+    import cpu_emulation as emu
+    from seg_b200 import engine, nets
+    from seg_b200 import losses as plosses
+    saved = [(mod, mod.ops) for mod in (engine, nets, plosses)]
+    check = nets._EngineModel._check_input
+    try:
+        for mod, _ in saved:
+            mod.ops = emu
+        nets._EngineModel._check_input = lambda self, x: None
+        if cfg["kind"] == "deeplab":
+            m = seg_b200.DeepLab(cfg["nc"], backbone=cfg["backbone"], pretrained=False, output_stride=16)
+        else:
+            m = seg_b200.PSPNet(cfg["nc"], backbone=cfg["backbone"], pretrained=False)
+        m.load_state_dict(sd, strict=True)
+        m.engine_dropout = False
+        m.train()
+        r = m(x)
+        out, aux = r if isinstance(r, tuple) else (r, None)
+        loss = plosses._CEFn.apply(out, y, 255, False)
+        if aux is not None:
+            loss = loss + 0.4 * plosses._CEFn.apply(aux, y, 255, False)
+        loss.backward()
+        grads = {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+        running = {k: v.detach().float().clone() for k, v in m.state_dict().items() if k.endswith("running_mean") or k.endswith("running_var")}
+        return out.detach().float(), None if aux is None else aux.detach().float(), float(loss.item()), grads, running
+    finally:
+        for mod, ops_ in saved:
+            mod.ops = ops_
+        nets._EngineModel._check_input = check
+
+
+def argmax_check(out, ref):
+    err = (out - ref).abs().max().item()
+    top2 = ref.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 2 * err
+    a, b = out.argmax(1), ref.argmax(1)
+    agree_all = (a == b).float().mean().item()
+    agree_safe = (a[safe] == b[safe]).float().mean().item() if safe.any() else 1.0
+    return agree_all, agree_safe, safe.float().mean().item()
+
+
+def grad_report(g, ref):
+    names = [k for k in ref if k in g and ref[k].abs().max() > 0]
+    cos = torch.tensor([cosine(g[k], ref[k]) for k in names])
+    rel = torch.tensor([relmax(g[k], ref[k]) for k in names])
+    worst = names[int(cos.argmin())]
+    return dict(n=len(names), cos_median=cos.median().item(), cos_min=cos.min().item(), cos_min_at=worst,
+                rel_median=rel.median().item(), rel_max=rel.max().item(), rel_max_at=names[int(rel.argmax())])
+
+
+@pytest.mark.parametrize("name", list(CONFIGS), ids=list(CONFIGS))
+def test_fullsize_parity(name, gpu_out_dir):
+    cfg = CONFIGS[name]
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    sd, m = make(cfg)
+    x, y = synth.make_batch(cfg["batch"], cfg["size"], cfg["size"], cfg["nc"], 255, seed=cfg["xseed"])
+    failures = []
+
+    def expect(cond, msg):
+        if not cond:
+            failures.append(msg)
+            log(gpu_out_dir, "  FAIL " + msg)
+
+    for mode, train_bn, want_grad in (("eval-init", False, False), ("eval", False, False), ("frozen", False, True), ("train", True, True)):
+        if mode == "eval":
+            # running statistics := the batch statistics of one reference forward (momentum 1): the eval / frozen-BN legs then
+            # run a NORMALISED network, as after training, instead of the exploding identity-BN network of the initialisers
+            sd = calibrated(cfg, sd, x)
+            m.load_state_dict(sd, strict=True)
+        t0 = time.time()
+        ref = oracle_run(cfg, sd, x, y, train_bn, want_grad)
+        t_ref = time.time() - t0
+        ctl = control_run(cfg, sd, x, y, train_bn, want_grad)
+        got = engine_run(cfg, m, x, y, mode, want_grad)
+        tag = f"[{name} {mode}]"
+        e_max, e_rms = relmax(got[0], ref[0]), relrms(got[0], ref[0])
+        c_max, c_rms = relmax(ctl[0], ref[0]), relrms(ctl[0], ref[0])
+        log(gpu_out_dir, f"{tag} logits vs fp32 oracle: engine max-norm {e_max:.3e} rms {e_rms:.3e} | ATen-bf16 control max-norm {c_max:.3e} rms {c_rms:.3e}"
+                         f" | oracle {t_ref:.1f} s")
+        chaotic = c_rms > 0.1  # ATen's own bf16 run is decorrelated from fp32: bf16 storage, not the implementation, decides
+        expect(e_max <= max(1e-2, 1.5 * c_max), f"{tag} logits max-norm error {e_max:.3e} > max(1e-2, 1.5 x control {c_max:.3e})")
+        expect(e_rms <= max(1e-2, 1.5 * c_rms), f"{tag} logits rms error {e_rms:.3e} > max(1e-2, 1.5 x control {c_rms:.3e})")
+        if got[1] is not None:
+            ea, ca = relmax(got[1], ref[1]), relmax(ctl[1], ref[1])
+            log(gpu_out_dir, f"{tag} aux logits: engine {ea:.3e} | control {ca:.3e}")
+            expect(ea <= max(1e-2, 1.5 * ca), f"{tag} aux logits {ea:.3e} vs control {ca:.3e}")
+        agree_all, agree_safe, frac = argmax_check(got[0], ref[0])
+        c_all, c_safe, c_frac = argmax_check(ctl[0], ref[0])
+        log(gpu_out_dir, f"{tag} arg-max: engine all-pixel agreement {agree_all:.6f}, margin-safe pixels ({frac:.4f} of the map) {agree_safe:.6f}"
+                         f" | control all {c_all:.6f}, safe ({c_frac:.4f}) {c_safe:.6f}")
+        expect(agree_safe == 1.0, f"{tag} arg-max differs on a margin-safe pixel")
+        l_e, l_c = abs(got[2] - ref[2]) / abs(ref[2]), abs(ctl[2] - ref[2]) / abs(ref[2])
+        log(gpu_out_dir, f"{tag} loss: engine {got[2]:.6f} oracle {ref[2]:.6f} (rel {l_e:.2e}) | control {ctl[2]:.6f} (rel {l_c:.2e})"
+                         + (" [logits decorrelated by bf16 storage: each loss is an independent sample]" if chaotic else ""))
+        expect(l_e <= (0.1 if chaotic else max(1e-3, 1.5 * l_c)), f"{tag} loss rel err {l_e:.2e} (control {l_c:.2e})")
+        if want_grad:
+            ge, gc = grad_report(got[3], ref[3]), grad_report(ctl[3], ref[3])
+            log(gpu_out_dir, f"{tag} param grads over {ge['n']} tensors: engine cosine median {ge['cos_median']:.5f} min {ge['cos_min']:.5f} ({ge['cos_min_at']}), "
+                             f"max-norm rel median {ge['rel_median']:.3e} worst {ge['rel_max']:.3e} ({ge['rel_max_at']})")
+            log(gpu_out_dir, f"{tag}                                  control cosine median {gc['cos_median']:.5f} min {gc['cos_min']:.5f} ({gc['cos_min_at']}), "
+                             f"max-norm rel median {gc['rel_median']:.3e} worst {gc['rel_max']:.3e} ({gc['rel_max_at']})")
+            expect(ge["n"] >= gc["n"], f"{tag} gradients missing: {ge['n']} of {gc['n']}")
+            expect(ge["cos_median"] >= min(0.99, gc["cos_median"] - 0.05), f"{tag} gradient cosine median {ge['cos_median']:.4f} (control {gc['cos_median']:.4f})")
+            expect(ge["rel_median"] <= max(2e-2, 1.5 * gc["rel_median"]), f"{tag} gradient rel median {ge['rel_median']:.3e} (control {gc['rel_median']:.3e})")
+        if mode == "train":
+            # determinism: the same forward again from the same state is bit-identical (fixed-order statistics)
+            esd0 = {k: v.clone() for k, v in m.state_dict().items()}
+            m.load_state_dict(sd, strict=True)
+            a = engine_run(cfg, m, x, y, "train", True)
+            m.load_state_dict(sd, strict=True)
+            b = engine_run(cfg, m, x, y, "train", True)
+            same_out = torch.equal(a[0], b[0])
+            n_diff = sum(0 if torch.equal(a[3][k], b[3][k]) else 1 for k in a[3])
+            worst = max(relmax(a[3][k], b[3][k]) for k in a[3])
+            log(gpu_out_dir, f"{tag} run-to-run: logits bit-identical {same_out}, loss {a[2]!r} vs {b[2]!r}, "
+                             f"{n_diff} of {len(a[3])} gradient tensors differ (worst rel {worst:.2e}; split-K wgrad atomics)")
+            expect(same_out and a[2] == b[2], f"{tag} forward is not bit-reproducible")
+            expect(worst < 1e-4, f"{tag} gradients differ run to run by {worst:.2e}")
+            # running statistics after one training forward (nn.BatchNorm2d: momentum 0.1, unbiased variance)
+            rs = {k: relmax(esd0[k], ref[4][k]) for k in ref[4]}
+            rc = {k: relmax(ctl[4][k], ref[4][k]) for k in ref[4]}
+            worst_k, worst_c = max(rs, key=rs.get), max(rc, key=rc.get)
+            med = sorted(rs.values())[len(rs) // 2]
+            log(gpu_out_dir, f"{tag} BN running statistics vs oracle: median max-norm rel {med:.3e}, worst {rs[worst_k]:.3e} at {worst_k}"
+                             f" | control worst {rc[worst_c]:.3e} at {worst_c}")
+            expect(rs[worst_k] <= max(1e-2, 1.5 * rc[worst_c]), f"{tag} running statistics off by {rs[worst_k]:.3e} at {worst_k} (control {rc[worst_c]:.3e})")
+            # ---- the engine against its own tape emulated with ATen on the CPU (same bf16 rounding points) ----
+            t0 = time.time()
+            emu = emulated_run(cfg, sd, x, y)
+            em, er = relmax(a[0], emu[0]), relrms(a[0], emu[0])
+            ge = grad_report(a[3], emu[3])
+            re_ = {k: relmax(esd0[k], emu[4][k]) for k in emu[4]}
+            wk = max(re_, key=re_.get)
+            log(gpu_out_dir, f"{tag} ENGINE vs bf16-faithful CPU emulation of the same tape ({time.time() - t0:.1f} s): logits max-norm {em:.3e} rms {er:.3e}; "
+                             f"loss {a[2]:.6f} vs {emu[2]:.6f}; grad cosine median {ge['cos_median']:.5f} min {ge['cos_min']:.5f} ({ge['cos_min_at']}); "
+                             f"running stats worst {re_[wk]:.3e} ({wk})")
+            expect(er <= 0.25 * c_rms + 1e-2, f"{tag} engine vs emulation logits rms {er:.3e}: not well below the bf16 noise floor {c_rms:.3e}")
+            expect(abs(a[2] - emu[2]) <= 2e-3 * abs(emu[2]), f"{tag} engine vs emulation loss {a[2]} vs {emu[2]}")
+            expect(ge["cos_median"] > 0.98, f"{tag} engine vs emulation gradient cosine median {ge['cos_median']:.4f}")
+    assert not failures, "\n".join(failures)

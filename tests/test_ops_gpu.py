@@ -223,9 +223,9 @@ def test_bn_train_fwd_bwd(C, M_shape, gpu_out_dir):
     check(f"bn_apply_train save C={C}", save2, save, 1e-5, gpu_out_dir)
     assert torch.allclose(rm2, rmd, rtol=1e-6, atol=1e-7) and torch.allclose(rv2, rvd, rtol=1e-6, atol=1e-7)
     dg2, db2 = torch.ones(C, device=DEV), torch.ones(C, device=DEV)
-    zs = torch.zeros(ops.bn_bwd_reduce_scratch_floats(C), device=DEV)
-    sums2 = ops.bn_bwd_reduce(dyd, out, xd, save, relu=True, dgamma=dg2, dbeta=db2, accumulate=True, zero_scratch=zs)
-    check(f"bn_bwd_reduce single-launch C={C}", sums2, sums, 1e-5, gpu_out_dir)
+    zs = torch.zeros(ops.reduce_workspace(count, C, 2)[1], device=DEV)  # tickets from a caller-zeroed arena
+    sums2 = ops.bn_bwd_reduce(dyd, out, xd, save, relu=True, dgamma=dg2, dbeta=db2, accumulate=True, tickets=zs)
+    assert torch.equal(sums2, sums), "the fixed-order reduction must be bit-reproducible"
     check(f"bn_dgamma accumulate C={C}", dg2 - 1.0, dgamma, 1e-4, gpu_out_dir)
     check(f"bn_dbeta accumulate C={C}", db2 - 1.0, dbeta, 1e-4, gpu_out_dir)
     # no residual: the ReLU mask recomputed from x (out=None) gives the same sums / dx as the mask read from the activation

@@ -79,10 +79,10 @@ def test_fused_sgd_step_invalidates_packed_weight_caches():
         m.load_state_dict(sd, strict=True)
         m.engine_dropout = False
         m = m.cuda().train()
-        m.freeze_bn()  # a fixed, well-conditioned function: differences are the optimiser's, not BN chaos
+        m.freeze_bn()  # a fixed function of the weights: differences are the optimiser's, not batch-statistics noise
         models.append(m)
-        opts.append(cls([{"params": list(m.get_decoder_params())}, {"params": list(m.get_backbone_params()), "lr": 0.01}],
-                        lr=0.1, momentum=0.9, weight_decay=1e-4))
+        opts.append(cls([{"params": list(m.get_decoder_params())}, {"params": list(m.get_backbone_params()), "lr": 1e-4}],
+                        lr=1e-3, momentum=0.9, weight_decay=1e-4))
     prev = None
     for it in range(3):
         outs = []
@@ -95,7 +95,7 @@ def test_fused_sgd_step_invalidates_packed_weight_caches():
         scale = outs[0].abs().max().item()
         assert (outs[0] - outs[1]).abs().max().item() < 2e-2 * scale, it
         if prev is not None:  # the step changed what the forward computes
-            assert (outs[1] - prev).abs().max().item() > 1e-3 * scale, "logits did not move: stale packed weights"
+            assert (outs[1] - prev).abs().max().item() > 1e-4 * scale, "logits did not move: stale packed weights"
         prev = outs[1]
     for p in models[1].parameters():
         assert p._version >= 3
