@@ -203,7 +203,7 @@ __device__ __forceinline__ void column_reduce(int64_t M, int C, float* fold_rows
   });
 }
 
-__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t M, int C, int ldx,
+__global__ void __launch_bounds__(256, 4) bn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t M, int C, int ldx,
                                                        float* __restrict__ stats, float* fold_rows, unsigned* fold_tickets) {
   column_reduce<2>(
       M, C, fold_rows, fold_tickets,
@@ -377,8 +377,9 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const __nv_bfloat16* _
   pdl_trigger();
 }
 
+// (256, 4): the streaming loop needs ~64 registers; the cold fold epilogue must not halve the occupancy of the whole kernel
 template <bool REMASK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ out, int ldo,
                          const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save, int64_t M, int C,
                          int relu, float drop_p, float* fold_rows, unsigned* fold_tickets, float* final_sums,

@@ -41,16 +41,16 @@ __device__ __forceinline__ FoldLane fold_lane(float* rows_ws, unsigned* tickets_
   return L;
 }
 
-// Sum of `n` (<= FOLD_G... any) floats spaced `stride` apart, added in index order in fp64.  The loads of a chunk of 32 are
+// Sum of `n` (<= FOLD_G... any) floats spaced `stride` apart, added in index order in fp64.  The loads of a chunk of 16 are
 // all issued before the first add (a dependent-load chain here cost 20-50 us of kernel tail in the first version).
 __device__ __forceinline__ double fold_column(const float* base, int n, size_t stride) {
   double s = 0.0;
-  for (int r0 = 0; r0 < n; r0 += 32) {
-    float v[32];
+  for (int r0 = 0; r0 < n; r0 += 16) {
+    float v[16];
 #pragma unroll
-    for (int r = 0; r < 32; ++r) v[r] = (r0 + r < n) ? __ldcg(base + (size_t)(r0 + r) * stride) : 0.f;
+    for (int r = 0; r < 16; ++r) v[r] = (r0 + r < n) ? __ldcg(base + (size_t)(r0 + r) * stride) : 0.f;
 #pragma unroll
-    for (int r = 0; r < 32; ++r) s += (double)v[r];
+    for (int r = 0; r < 16; ++r) s += (double)v[r];
   }
   return s;
 }

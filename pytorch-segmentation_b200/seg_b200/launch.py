@@ -6,8 +6,10 @@
 `python train.py` puts the script's own directory first on sys.path, ahead of PYTHONPATH, so the overlay packages
 (`overlay/models`, `overlay/utils`) could never win there; this launcher orders sys.path as
 [overlay, reference root, ...] and then executes the script as __main__ — the script's source is untouched.
-Under torchrun (one process per GPU) it also restricts each process to its own device so the reference's
-`n_gpu: 1` DataParallel-of-one path (base/base_trainer.py:33-38) runs one replica per GPU.
+Under torchrun (one process per GPU; `torchrun --nproc-per-node N -m seg_b200.launch train.py -c config.json` with
+`n_gpu: 1` in the config) every process becomes a data-parallel replica: its own GPU is device 0, the NCCL process group
+is up, gradients are all-reduced inside `loss.backward()`, the loss is the global-batch mean and `use_synch_bn` turns on
+the NVLink statistics exchange (`init_data_parallel`).
 """
 import os
 import runpy
@@ -38,14 +40,47 @@ def setup_paths(reference_root):
         sys.modules["skimage.filters"].gaussian = None
 
 
+def init_data_parallel():
+    """Under torchrun (one process per GPU) make this process a data-parallel replica of an UNMODIFIED train.py.
+
+    * The reference hard-codes `cuda:0` and `device_ids = range(n_gpu)` (base/base_trainer.py:176-187), so every process
+      must see ITS GPU as device 0 — but all GPUs have to stay visible for the NVLink peer-memory exchange (CUDA IPC) and
+      NCCL: CUDA_VISIBLE_DEVICES is rotated ([local, local+1, ..., local-1]) rather than restricted.  Run the config with
+      `n_gpu: 1`: its DataParallel-of-one wrapper (base/base_trainer.py:33-38) is then a pass-through.
+    * The NCCL process group is initialised here; from then on the engine's autograd nodes all-reduce (mean) the flat
+      gradient buffer inside `loss.backward()`, `CrossEntropyLoss2d` reports the global-batch mean, and — when the config
+      says `use_synch_bn` — the overlay's `convert_model` makes the engine exchange BatchNorm statistics over NVLink
+      (seg_b200/nets.py `_EngineFn`, seg_b200/losses.py `_CEFn`, overlay/utils/sync_batchnorm.py).  Identical replicas in,
+      identical replicas out: what nn.DataParallel guarantees in the reference.
+    Returns (rank, world)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1 or "LOCAL_RANK" not in os.environ:
+        return 0, 1
+    local = int(os.environ["LOCAL_RANK"])
+    if "CUDA_VISIBLE_DEVICES" in os.environ:
+        devs = [d for d in os.environ["CUDA_VISIBLE_DEVICES"].split(",") if d != ""]
+    else:
+        n = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        devs = [str(i) for i in range(n)]
+    if os.environ.get("SEG_DEVICES_ROTATED") != "1" and len(devs) > 1:
+        k = local % len(devs)
+        os.environ["CUDA_VISIBLE_DEVICES"] = ",".join(devs[k:] + devs[:k])
+        os.environ["SEG_DEVICES_ROTATED"] = "1"
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(0)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", 0))
+    return dist.get_rank(), dist.get_world_size()
+
+
 def main():
     if len(sys.argv) < 2:
         print(__doc__)
         sys.exit(2)
     script = os.path.abspath(sys.argv[1])
     setup_paths(os.path.dirname(script))
-    if "LOCAL_RANK" in os.environ and "CUDA_VISIBLE_DEVICES" not in os.environ:
-        os.environ["CUDA_VISIBLE_DEVICES"] = os.environ["LOCAL_RANK"]
+    init_data_parallel()
     if os.environ.get("SEG_FUSED_OPTIM", "1") != "0":
         # base/base_trainer.py:57 builds getattr(torch.optim, config['optimizer']['type']): "SGD" over CUDA fp32
         # parameters resolves to the torch.optim.SGD subclass whose step() is the multi-tensor kernel (same param_groups /

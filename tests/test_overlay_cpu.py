@@ -36,6 +36,14 @@ groups = [{'params': model.get_decoder_params()}, {'params': model.get_backbone_
 import torch
 opt = torch.optim.SGD(groups, lr=0.01, momentum=0.9, weight_decay=1e-4)
 assert sum(len(g['params']) for g in opt.param_groups) == len(list(model.parameters()))
+# base/base_trainer.py:11-12,33-35: config['use_synch_bn'] -> convert_model + DataParallelWithCallback from utils.sync_batchnorm
+from utils.sync_batchnorm import convert_model, DataParallelWithCallback, SynchronizedBatchNorm2d
+assert model.use_sync_bn is False and convert_model(model) is model and model.use_sync_bn is True   # engine model: marked, BN holders kept
+assert all(not isinstance(mm, SynchronizedBatchNorm2d) for mm in model.modules())
+import torch.nn as nn
+plain = convert_model(nn.Sequential(nn.Conv2d(3, 4, 1), nn.BatchNorm2d(4)))                         # anything else: the reference's conversion
+assert isinstance(plain[1], SynchronizedBatchNorm2d)
+assert issubclass(DataParallelWithCallback, nn.DataParallel)
 print(str(model).splitlines()[-1])
 print('OVERLAY_OK')
 """
