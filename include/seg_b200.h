@@ -45,6 +45,15 @@ typedef struct seg_conv_desc {
   int32_t ldy;          /* channel pitch of the output buffer (>= K)                 */
 } seg_conv_desc;
 
+/* SyncBN exchange handle (seg_comm_*): device array of every rank's symmetric-buffer pointer + this rank.  Passed to the
+ * kernels that produce / consume BatchNorm statistics so the cross-GPU exchange (utils/sync_batchnorm/batchnorm.py:105-126:
+ * ReduceAddCoalesced + Broadcast + thread pipes) rides inside them: no launch of its own (csrc/seg_sync.cuh). */
+typedef struct seg_sync_desc {
+  void* const* peers;        /* DEVICE array of `world` base pointers; peers[rank] is this rank's buffer */
+  int32_t rank, world, n_max;
+  int64_t timeout_clocks;    /* spin-wait bound in GPU clocks (<= 0: unbounded) */
+} seg_sync_desc;
+
 const char* seg_last_error(void);
 int seg_version(void);
 /* 0 if the current device is sm_100 and kernels can be launched */
@@ -63,8 +72,12 @@ void seg_launch_count_reset(void);
  * `stats_tickets` (uint32, must be ZERO at launch; not shareable). */
 int seg_conv_stats_workspace(const seg_conv_desc* d, int64_t* rows_floats, int64_t* tickets);
 int seg_conv2d_fwd(const seg_conv_desc* d, const void* x, const void* w_packed, void* y, int y_dtype,
-                   const float* bias, float beta, float* stats, float* stats_rows, void* stats_tickets, int impl,
-                   void* stream);
+                   const float* bias, float beta, float* stats, float* stats_rows, void* stats_tickets,
+                   const seg_sync_desc* sync, int impl, void* stream);
+/* 1 if seg_conv2d_fwd(d, ..., sync, impl) runs the tcgen05 path, whose epilogue pushes the statistics to the SyncBN peers
+ * (sync != NULL: the consumer, seg_bn_apply_train(..., sync, ...), then reads the world's sums itself); 0: CUDA-core path,
+ * no push (pass sync = NULL and exchange `stats` with seg_syncbn_exchange) */
+int seg_conv_fwd_pushes(const seg_conv_desc* d, int impl);
 /* dx[N,H,W,C] = beta*dx + conv_transpose(dy, w)   (autograd of the above w.r.t. x) */
 int seg_conv2d_dgrad(const seg_conv_desc* d, const void* dy, const void* w_packed, void* dx, float beta,
                      int impl, void* stream);
@@ -130,12 +143,15 @@ int seg_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const 
 int seg_bn_apply(const void* x, int ldx, const float* scale_shift, const void* res, int ldr, void* out, int ldo,
                  int64_t M, int C, int relu, float drop_p, uint64_t seed, const uint64_t* step_ctr, int drop_hw,
                  void* stream);
-/* seg_bn_finalize + seg_bn_apply in ONE launch (training mode): coefficients are derived from the batch sums inside the
+/* sync != NULL (SyncBN, the producer was seg_conv2d_fwd with the same handle): `stats` is ignored, the kernel waits for the
+ * world's flags and adds every rank's sums itself; `count` is then the WORLD's element count; sync_done = one zeroed uint32.
+ * seg_bn_finalize + seg_bn_apply in ONE launch (training mode): coefficients are derived from the batch sums inside the
  * kernel; save[2C] = (mean, 1/std) for the backward pass and the running statistics are written by one block row. */
 int seg_bn_apply_train(const void* x, int ldx, const float* stats, double count, const float* gamma, const float* beta,
                        float eps, float momentum, int clamp_eps, float* running_mean, float* running_var, float* save,
                        const void* res, int ldr, void* out, int ldo, int64_t M, int C, int relu, float drop_p,
-                       uint64_t seed, const uint64_t* step_ctr, int drop_hw, void* stream);
+                       uint64_t seed, const uint64_t* step_ctr, int drop_hw, const seg_sync_desc* sync,
+                       void* sync_done, void* stream);
 /* device-side step counter (*ctr += inc): mixed into dropout seeds and SyncBN epochs so a captured CUDA graph of the
  * train step stays correct on every replay */
 int seg_counter_add(uint64_t* ctr, uint64_t inc, void* stream);
@@ -156,6 +172,18 @@ int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const
                      const float* save_mean_istd, const float* gamma, const float* sums, double count, int64_t M,
                      int C, int relu, float drop_p, void* dx, int lddx, void* dres, int lddres, float beta_res,
                      const float* beta, void* stream);
+/* BatchNorm backward in ONE cooperative launch = seg_bn_bwd_reduce + (SyncBN exchange) + seg_bn_bwd_apply: partial sums per
+ * block -> grid barrier -> the cross-block sum spread over all blocks in fixed order (bit-reproducible) -> grid barrier ->
+ * dx / dres.  sums[2C] receives the LOCAL totals; dgamma / dbeta (optional) the parameter gradients from them.  count_total =
+ * rows summed over the world.  zero_sums != 0: frozen BatchNorm (BaseModel.freeze_bn): dx = gamma*istd*dz.  sync != NULL:
+ * the totals are exchanged with the SyncBN peers inside the kernel.  Workspace from seg_bn_bwd_fused_workspace: rows
+ * (uninitialised floats) and tickets (uint32, ZERO at launch).  The grid is sized to be co-resident. */
+int seg_bn_bwd_fused_workspace(int64_t M, int C, int64_t* rows_floats, int64_t* tickets);
+int seg_bn_bwd_fused(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx,
+                     const float* save_mean_istd, const float* gamma, const float* beta, double count_total, int64_t M,
+                     int C, int relu, float drop_p, float* sums, float* rows, void* tickets, float* dgamma, float* dbeta,
+                     int accumulate, void* dx, int lddx, void* dres, int lddres, float beta_res, int zero_sums,
+                     const seg_sync_desc* sync, void* stream);
 /* parameter grads from the LOCAL sums: dbeta (=|+=) sums[0:C], dgamma (=|+=) sums[C:2C] */
 int seg_bn_param_grad(const float* sums, int C, float* dgamma, float* dbeta, int accumulate, void* stream);
 

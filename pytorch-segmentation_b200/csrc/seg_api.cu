@@ -2,6 +2,7 @@
 // (tcgen05 path where the shape allows it, CUDA-core implicit GEMM otherwise).  No CPU fallback anywhere.
 #include <stdarg.h>
 #include "seg_common.cuh"
+#include "seg_sync.cuh"
 
 namespace seg {
 
@@ -19,7 +20,7 @@ namespace tc {
 bool supported(const seg_conv_desc* d);
 void stats_workspace(const seg_conv_desc* d, int64_t* rows_floats, int64_t* tickets);
 int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int y_dtype, const float* bias, float beta,
-             float* stats, float* stat_rows, unsigned* stat_tickets, cudaStream_t stream);
+             float* stats, float* stat_rows, unsigned* stat_tickets, const SyncDesc* sync, cudaStream_t stream);
 int conv_dgrad(const seg_conv_desc* d, const void* dy, const void* w, void* dx, float beta, cudaStream_t stream);
 int conv_wgrad(const seg_conv_desc* d, const void* dy, const void* x, float* dw, cudaStream_t stream);
 }  // namespace tc
@@ -81,14 +82,25 @@ int seg_conv_stats_workspace(const seg_conv_desc* d, int64_t* rows_floats, int64
   return 0;
 }
 
+int seg_conv_fwd_pushes(const seg_conv_desc* d, int impl) {
+  return (impl == SEG_IMPL_TC || (impl == SEG_IMPL_AUTO && tc::supported(d))) ? 1 : 0;
+}
+
 int seg_conv2d_fwd(const seg_conv_desc* d, const void* x, const void* w_packed, void* y, int y_dtype, const float* bias,
-                   float beta, float* stats, float* stats_rows, void* stats_tickets, int impl, void* stream) {
+                   float beta, float* stats, float* stats_rows, void* stats_tickets, const seg_sync_desc* sync, int impl,
+                   void* stream) {
   if (check_desc(d)) return 1;
   SEG_REQUIRE(!stats || (stats_rows && stats_tickets), "seg_conv2d_fwd: stats need the seg_conv_stats_workspace buffers");
   const bool tc_ok = tc::supported(d);
   unsigned* tk = reinterpret_cast<unsigned*>(stats_tickets);
-  if (impl == SEG_IMPL_TC || (impl == SEG_IMPL_AUTO && tc_ok))
-    return tc::conv_fwd(d, x, w_packed, y, y_dtype, bias, beta, stats, stats_rows, tk, ST(stream));
+  if (impl == SEG_IMPL_TC || (impl == SEG_IMPL_AUTO && tc_ok)) {
+    SyncDesc sd{nullptr, 0, 0, 0, 0};
+    if (sync) {
+      sd.peers = sync->peers; sd.rank = sync->rank; sd.world = sync->world; sd.n_max = sync->n_max; sd.timeout_clocks = sync->timeout_clocks;
+    }
+    return tc::conv_fwd(d, x, w_packed, y, y_dtype, bias, beta, stats, stats_rows, tk, sync ? &sd : nullptr, ST(stream));
+  }
+  SEG_REQUIRE(sync == nullptr, "seg_conv2d_fwd: the CUDA-core path does not push SyncBN statistics (see seg_conv_fwd_pushes)");
   return simt::conv_fwd(d, x, w_packed, y, y_dtype, bias, beta, stats, stats_rows, tk, ST(stream));
 }
 

@@ -30,6 +30,7 @@
 #include "seg_common.cuh"
 #include "seg_ptx.cuh"
 #include "seg_fold.cuh"
+#include "seg_sync.cuh"
 
 namespace seg {
 namespace tc {
@@ -65,7 +66,8 @@ struct TcParams {
   const float* bias;
   float* stats;      // [2*Ncols] or null: per-channel sum / sum of squares of the output (BatchNorm batch statistics)
   float* stat_rows;        // seg_fold.cuh workspace of the deterministic cross-CTA reduction (rows; uninitialised)
-  unsigned* stat_tickets;  //   "      (tickets; zero at launch)
+  unsigned* stat_tickets;  //   "      (tickets; zero at launch; one extra word after the lanes' tickets counts finished lanes)
+  SyncDesc sync;           // world > 0: SyncBN — the statistics are also pushed to every peer (seg_sync.cuh)
   // strided sub-grid output (stride>1 dgrad): row (n,i,j) -> pixel (n, i*osy+opy, j*osx+opx) of an out_H x out_W map
   int out_strided, out_H, out_W, osy, osx, opy, opx;
   // MM only
@@ -410,11 +412,22 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_tc(const __grid_constant__
           myrow[BN + c] = b;
         }
         volatile int* flag = reinterpret_cast<volatile int*>(smem_gen + C::STAGES * C::STAGE_BYTES + 128);
-        fold_arrive(L, blockIdx.x, e, 128, [] { asm volatile("bar.sync 1, 128;" ::: "memory"); }, flag,
-                    [&](int c, float v) {
-                      const int which = c / BN, col = c - which * BN;
-                      if (col < ncols_tile) p.stats[(size_t)which * p.Ncols + n0 + col] = v;
-                    });
+        auto bar = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+        const uint32_t epoch = p.sync.world > 0 ? sync_epoch(p.sync) : 0u;
+        const bool lane_done = fold_arrive(L, blockIdx.x, e, 128, bar, flag, [&](int c, float v) {
+          const int which = c / BN, col = c - which * BN;
+          if (col < ncols_tile) {
+            p.stats[(size_t)which * p.Ncols + n0 + col] = v;
+            if (p.sync.world > 0) sync_push_value(p.sync, epoch, which * p.Ncols + n0 + col, v);
+          }
+        });
+        if (lane_done && p.sync.world > 0) {  // the block finishing the layer's LAST column block raises the flags
+          __threadfence_system();
+          bar();
+          if (e == 0) *flag = (atomicAdd(p.stat_tickets + (size_t)gridDim.y * fold_lane_tickets(gridDim.x), 1u) == gridDim.y - 1u);
+          bar();
+          if (*flag) sync_publish(p.sync, epoch, e, bar);
+        }
       }
     }
     tc_fence_before();
@@ -589,11 +602,11 @@ void stats_workspace(const seg_conv_desc* d, int64_t* rows_floats, int64_t* tick
   // lanes x width: ceil(K/64) lanes of 128 floats, or ceil(K/128) of 256, or ceil(K/256) of 512 — all <= 2 * roundup(K, 256)
   const int64_t lane_floats_total = 2 * (int64_t)ceil_div(d->K, 256) * 256;
   *rows_floats = (int64_t)(rows + fold_groups(rows)) * lane_floats_total;
-  *tickets = (int64_t)ceil_div(d->K, 64) * fold_lane_tickets(rows);
+  *tickets = (int64_t)ceil_div(d->K, 64) * fold_lane_tickets(rows) + 1;  // + the finished-lanes counter (SyncBN publish)
 }
 
 int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int y_dtype, const float* bias, float beta,
-             float* stats, float* stat_rows, unsigned* stat_tickets, cudaStream_t stream) {
+             float* stats, float* stat_rows, unsigned* stat_tickets, const SyncDesc* sync, cudaStream_t stream) {
   SEG_REQUIRE(supported(d), "tcgen05 conv fwd: unsupported shape (C=%d ldx=%d R=%d pad=%d dil=%d)", d->C, d->ldx, d->R,
               d->pad, d->dil);
   TcParams p;
@@ -623,6 +636,10 @@ int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int 
   p.stat_rows = stat_rows;
   p.stat_tickets = stat_tickets;
   SEG_REQUIRE(!stats || (stat_rows && stat_tickets), "conv fwd: statistics need the reduction workspace");
+  if (sync && stats) {
+    SEG_REQUIRE(2 * d->K <= sync->n_max, "conv fwd: 2*K = %d statistics exceed the SyncBN buffer (%d floats)", 2 * d->K, sync->n_max);
+    p.sync = *sync;
+  }
   const int64_t m_tiles = ceil_div64(M, BM);
   // persistent double-buffered kernel for bf16 outputs wider than 64 channels; the one-tile-per-CTA kernel otherwise
   // (measured: with <= 2 tiles per SM and a long k-loop, two co-resident one-tile CTAs interleave better than one

@@ -213,10 +213,22 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_cons
         L.rows1[(size_t)myrow * (2 * BN) + which * BN + c] = val;
       }
       volatile int* flag = reinterpret_cast<volatile int*>(smem_gen + V2_STAGES * V2_STAGE_BYTES + V2_STAGING_BYTES + V2_STAT_BYTES + 128);
-      fold_arrive(L, myrow, etid, 256, [] { asm volatile("bar.sync 1, 256;" ::: "memory"); }, flag, [&](int c, float v) {
+      auto bar = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+      const uint32_t epoch = p.sync.world > 0 ? sync_epoch(p.sync) : 0u;
+      const bool lane_done = fold_arrive(L, myrow, etid, 256, bar, flag, [&](int c, float v) {
         const int which = c / BN, col = my_n * BN + (c - which * BN);
-        if (col < p.Ncols) p.stats[(size_t)which * p.Ncols + col] = v;
+        if (col < p.Ncols) {
+          p.stats[(size_t)which * p.Ncols + col] = v;
+          if (p.sync.world > 0) sync_push_value(p.sync, epoch, which * p.Ncols + col, v);  // SyncBN: to every peer
+        }
       });
+      if (lane_done && p.sync.world > 0) {  // the block finishing the layer's LAST column block raises the flags
+        __threadfence_system();
+        bar();
+        if (etid == 0) *flag = (atomicAdd(p.stat_tickets + (size_t)n_tiles * fold_lane_tickets(gridDim.x / n_tiles), 1u) == (unsigned)n_tiles - 1u);
+        bar();
+        if (*flag) sync_publish(p.sync, epoch, etid, bar);
+      }
     };
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
       const int b = i & 1;

@@ -5,6 +5,7 @@
 // Reference call sites are cited next to each entry point in include/seg_b200.h.
 #include "seg_common.cuh"
 #include "seg_fold.cuh"
+#include "seg_sync.cuh"
 
 namespace seg {
 
@@ -294,87 +295,102 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const __nv_bfloat16* _
                                                        const float* __restrict__ ss, const __nv_bfloat16* __restrict__ res,
                                                        int ldr, __nv_bfloat16* __restrict__ out, int ldo, int64_t M, int C,
                                                        int relu, float drop_p, uint64_t seed,
-                                                       const uint64_t* __restrict__ step_ctr, int drop_hw, const BnTrain tr) {
+                                                       const uint64_t* __restrict__ step_ctr, int drop_hw, const BnTrain tr,
+                                                       const SyncDesc sync, unsigned* sync_done) {
   pdl_wait();
   const RowMap rm = row_map(C);
-  if (!rm.active) return;
   if (step_ctr) seed += (*step_ctr) * 0x9E3779B97F4A7C15ull;  // device-side step counter keeps CUDA-graph replays fresh
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  float sc[8], sh[8];
-  if (tr.stats) {
-    float s1[8], s2[8], gm[8], bt[8];
-    ld8(tr.stats + rm.g * 8, s1);
-    ld8(tr.stats + C + rm.g * 8, s2);
-    ld8(tr.gamma + rm.g * 8, gm);
-    ld8(tr.beta + rm.g * 8, bt);
-    const bool writer = blockIdx.x == 0 && rm.rl == 0;
-    const double inv_count = 1.0 / tr.count;  // one division; the per-channel math below is multiply-add + fp32 rsqrt
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const double mean = (double)s1[j] * inv_count;
-      double var = fma((double)s2[j], inv_count, -mean * mean);
-      if (var < 0) var = 0;
-      const float vf = tr.clamp_eps ? fmaxf((float)var, tr.eps) : (float)(var + (double)tr.eps);
-      float istd = rsqrtf(vf);
-      istd = istd * (1.5f - 0.5f * vf * istd * istd);  // one Newton step: fp32-exact 1/sqrt
-      sc[j] = gm[j] * istd;
-      sh[j] = fmaf(-(float)mean, sc[j], bt[j]);
-      if (writer) {
-        const int c = rm.g * 8 + j;
-        tr.save[c] = (float)mean;
-        tr.save[C + c] = istd;
-        if (tr.running_mean) {
-          const double unbiased = tr.count > 1 ? var * tr.count / (tr.count - 1) : var;
-          tr.running_mean[c] = (float)((1.0 - tr.momentum) * tr.running_mean[c] + tr.momentum * mean);
-          tr.running_var[c] = (float)((1.0 - tr.momentum) * tr.running_var[c] + tr.momentum * unbiased);
-        }
-      }
-    }
-  } else {
-    ld8(ss + rm.g * 8, sc);
-    ld8(ss + C + rm.g * 8, sh);
+  // SyncBN (seg_sync.cuh): the producing conv pushed every rank's sums into this rank's symmetric buffer; wait for the
+  // world's flags, then add the world's sums in rank order
+  uint32_t epoch = 0u;
+  if (sync.world > 0) {
+    epoch = sync_epoch(sync);
+    sync_wait_world(sync, epoch);
   }
-  const int64_t step = (int64_t)gridDim.x * rm.rows_par;
-  const int co = rm.g * 8;
-  for (int64_t row = (int64_t)blockIdx.x * rm.rows_par + rm.rl; row < M; row += 2 * step) {
-    const int64_t row2 = row + step;
-    const bool has2 = row2 < M;
-    bf16x8 xa = *reinterpret_cast<const bf16x8*>(x + row * ldx + co), xb, ra, rb;
-    if (has2) xb = *reinterpret_cast<const bf16x8*>(x + row2 * ldx + co);
-    if (res) {
-      ra = *reinterpret_cast<const bf16x8*>(res + row * ldr + co);
-      if (has2) rb = *reinterpret_cast<const bf16x8*>(res + row2 * ldr + co);
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 1 && !has2) break;
-      const int64_t r = u ? row2 : row;
-      float f[8];
-      unpack8(u ? xb : xa, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
-      if (res) {
-        float q[8];
-        unpack8(u ? rb : ra, q);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] += q[j];
+  float sc[8], sh[8];
+  if (rm.active) {
+    if (tr.stats) {
+      float s1[8], s2[8], gm[8], bt[8];
+      if (sync.world > 0) {
+        sync_total8(sync, epoch, rm.g * 8, s1);
+        sync_total8(sync, epoch, C + rm.g * 8, s2);
+      } else {
+        ld8(tr.stats + rm.g * 8, s1);
+        ld8(tr.stats + C + rm.g * 8, s2);
       }
-      if (relu) {
+      ld8(tr.gamma + rm.g * 8, gm);
+      ld8(tr.beta + rm.g * 8, bt);
+      const bool writer = blockIdx.x == 0 && rm.rl == 0;
+      const double inv_count = 1.0 / tr.count;  // one division; the per-channel math below is multiply-add + fp32 rsqrt
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-      }
-      if (drop_p > 0.f) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          // nn.Dropout: one draw per element; nn.Dropout2d (drop_hw = H*W > 0): one draw per (image, channel)
-          const float uu = hash_uniform(seed, (uint64_t)((drop_hw > 0 ? r / drop_hw : r) * C + co + j));
-          f[j] = (uu >= drop_p) ? f[j] * keep_scale : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const double mean = (double)s1[j] * inv_count;
+        double var = fma((double)s2[j], inv_count, -mean * mean);
+        if (var < 0) var = 0;
+        const float vf = tr.clamp_eps ? fmaxf((float)var, tr.eps) : (float)(var + (double)tr.eps);
+        float istd = rsqrtf(vf);
+        istd = istd * (1.5f - 0.5f * vf * istd * istd);  // one Newton step: fp32-exact 1/sqrt
+        sc[j] = gm[j] * istd;
+        sh[j] = fmaf(-(float)mean, sc[j], bt[j]);
+        if (writer) {
+          const int c = rm.g * 8 + j;
+          tr.save[c] = (float)mean;
+          tr.save[C + c] = istd;
+          if (tr.running_mean) {
+            const double unbiased = tr.count > 1 ? var * tr.count / (tr.count - 1) : var;
+            tr.running_mean[c] = (float)((1.0 - tr.momentum) * tr.running_mean[c] + tr.momentum * mean);
+            tr.running_var[c] = (float)((1.0 - tr.momentum) * tr.running_var[c] + tr.momentum * unbiased);
+          }
         }
       }
-      *reinterpret_cast<bf16x8*>(out + r * ldo + co) = pack8(f);
+    } else {
+      ld8(ss + rm.g * 8, sc);
+      ld8(ss + C + rm.g * 8, sh);
+    }
+    const int64_t step = (int64_t)gridDim.x * rm.rows_par;
+    const int co = rm.g * 8;
+    for (int64_t row = (int64_t)blockIdx.x * rm.rows_par + rm.rl; row < M; row += 2 * step) {
+      const int64_t row2 = row + step;
+      const bool has2 = row2 < M;
+      bf16x8 xa = *reinterpret_cast<const bf16x8*>(x + row * ldx + co), xb, ra, rb;
+      if (has2) xb = *reinterpret_cast<const bf16x8*>(x + row2 * ldx + co);
+      if (res) {
+        ra = *reinterpret_cast<const bf16x8*>(res + row * ldr + co);
+        if (has2) rb = *reinterpret_cast<const bf16x8*>(res + row2 * ldr + co);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !has2) break;
+        const int64_t r = u ? row2 : row;
+        float f[8];
+        unpack8(u ? xb : xa, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+        if (res) {
+          float q[8];
+          unpack8(u ? rb : ra, q);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += q[j];
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (drop_p > 0.f) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            // nn.Dropout: one draw per element; nn.Dropout2d (drop_hw = H*W > 0): one draw per (image, channel)
+            const float uu = hash_uniform(seed, (uint64_t)((drop_hw > 0 ? r / drop_hw : r) * C + co + j));
+            f[j] = (uu >= drop_p) ? f[j] * keep_scale : 0.f;
+          }
+        }
+        *reinterpret_cast<bf16x8*>(out + r * ldo + co) = pack8(f);
+      }
     }
   }
   pdl_trigger();
+  if (sync.world > 0) sync_consumer_done(sync, epoch, sync_done, gridDim.x * gridDim.y);
 }
 
 // (256, 4): the streaming loop needs ~64 registers; the cold fold epilogue must not halve the occupancy of the whole kernel
@@ -509,6 +525,228 @@ __global__ void __launch_bounds__(256)
     *reinterpret_cast<bf16x8*>(dx + row * lddx + co) = pack8(o8);
   }
   pdl_trigger();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// BatchNorm backward in ONE cooperative launch (replaces bn_bwd_reduce + bn_bwd_apply on the engine's path; the two-launch
+// forms stay for callers that need the sums separately).
+//   phase 1   every block streams its rows once: per-channel partial sums (sum dz, sum dz*xhat) -> its own workspace row
+//   barrier   all blocks are co-resident (the host sizes the grid from the occupancy of THIS kernel), so a grid-wide
+//             barrier is an atomic counter + spin
+//   phase 1b  the cross-block sum is spread over ALL blocks: block b adds its few columns over every row, in row order ->
+//             bit-reproducible totals, no serial fold tail (the ticket tree of seg_fold.cuh cost 30-70 us here at C >= 1024);
+//             the same threads write dgamma / dbeta and, under SyncBN, push the totals to every peer (seg_sync.cuh)
+//   barrier   (+ SyncBN: block 0 raises this rank's flags, every block waits for the world's)
+//   phase 2   dx = A*dz + B*x + Cc (and the residual branch's gradient); the second read of dz / x hits L2 for the small maps
+// Same arithmetic as the two-launch path.
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(ctr) < target) {
+      if (clock64() - t0 > 8000000000ll) {  // ~4 s: the blocks were not co-resident; trap instead of hanging the box
+        printf("seg_b200: grid barrier timeout (block %d,%d target %u)\n", blockIdx.x, blockIdx.y, target);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct BnBwdFused {
+  const __nv_bfloat16 *dout, *out, *x;
+  int lddo, ldo, ldx;
+  const float *save, *gamma, *beta;
+  int64_t M;
+  int C, relu;
+  float drop_p, inv_count;  // inv_count = 1 / (rows summed over the WORLD)
+  float* rows;              // [gridDim.y][gridDim.x][2][W] partial sums (W = channels of a slab)
+  float* totals;            // [2C] LOCAL totals (always written)
+  unsigned* ctr;            // [0] grid-barrier counter, [1] SyncBN consumer ticket; zero at launch
+  float *dgamma, *dbeta;
+  int accumulate, zero_sums;  // zero_sums: frozen BatchNorm (eval statistics): dx = gamma*istd*dz
+  __nv_bfloat16 *dx, *dres;
+  int lddx, lddres;
+  float beta_res;
+  SyncDesc sync;
+};
+
+template <bool REMASK>
+__global__ void __launch_bounds__(256, 3) bn_bwd_fused_kernel(const BnBwdFused p) {
+  const RowMap rm = row_map(p.C);
+  const int C = p.C;
+  const int co = rm.g * 8;
+  const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  const int GB = min(C >> 3, 256);
+  const int W = GB * 8;
+  const unsigned nblocks = gridDim.x * gridDim.y;
+  __shared__ float red[256 * 8];
+  // forward coefficients of this thread's 8 channels (mask recomputation / xhat)
+  float mean[8], istd[8], gm[8], sh[REMASK ? 8 : 1];
+  if (rm.active) {
+    ld8(p.save + co, mean);
+    ld8(p.save + C + co, istd);
+    ld8(p.gamma + co, gm);
+    if constexpr (REMASK) {
+      float bt[8];
+      ld8(p.beta + co, bt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sh[j] = fmaf(-mean[j], gm[j] * istd[j], bt[j]);
+    }
+  }
+  const int64_t step = (int64_t)gridDim.x * rm.rows_par;
+  // ------------------------------------------------ phase 1: partial sums
+  {
+    float a0[8], a1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+    if (rm.active) {
+#pragma unroll 2
+      for (int64_t row = (int64_t)blockIdx.x * rm.rows_par + rm.rl; row < p.M; row += step) {
+        float dz[8], xv[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(p.dout + row * p.lddo + co), dz);
+        unpack8(*reinterpret_cast<const bf16x8*>(p.x + row * p.ldx + co), xv);
+        if constexpr (REMASK) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dz[j] = (fmaf(xv[j], gm[j] * istd[j], sh[j]) > 0.f) ? dz[j] : 0.f;
+        } else if (p.relu) {
+          float o[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(p.out + row * p.ldo + co), o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dz[j] = (o[j] > 0.f) ? dz[j] * keep_scale : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a0[j] += dz[j];
+          a1[j] += dz[j] * (xv[j] - mean[j]) * istd[j];
+        }
+      }
+    }
+    float* myrow = p.rows + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (2 * W);
+    const int gl = threadIdx.x % GB;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = a ? a1[j] : a0[j];
+      __syncthreads();
+      if (rm.rl == 0) {
+        float s[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = 0.f;
+        if (rm.g < (C >> 3)) {
+          for (int r = 0; r < rm.rows_par; ++r)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += red[(r * GB + gl) * 8 + j];
+        }
+        *reinterpret_cast<float4*>(myrow + a * W + gl * 8) = make_float4(s[0], s[1], s[2], s[3]);
+        *reinterpret_cast<float4*>(myrow + a * W + gl * 8 + 4) = make_float4(s[4], s[5], s[6], s[7]);
+      }
+    }
+  }
+  grid_barrier(p.ctr, nblocks);
+  // ------------------------------------------------ phase 1b: distributed fixed-order fold of this slab's 2W columns
+  const uint32_t epoch = p.sync.world > 0 ? sync_epoch(p.sync) : 0u;
+  {
+    const int nb = gridDim.x;
+    const int ncol = 2 * W;
+    const int cpb = (ncol + nb - 1) / nb;  // columns per block
+    const int c0 = blockIdx.x * cpb, c1 = min(c0 + cpb, ncol);
+    const int TC = min(cpb, 256), RL = 256 / TC;
+    const int tc = threadIdx.x % TC, rl = threadIdx.x / TC;
+    const float* base = p.rows + (size_t)blockIdx.y * nb * ncol;
+    for (int cb = c0; cb < c1; cb += TC) {  // uniform trip count over the block
+      const int col = cb + tc;
+      float part = 0.f;
+      if (col < c1 && rl < RL) {
+#pragma unroll 8
+        for (int r = rl; r < nb; r += RL) part += __ldcg(base + (size_t)r * ncol + col);
+      }
+      __syncthreads();
+      red[threadIdx.x] = part;
+      __syncthreads();
+      if (rl == 0 && col < c1) {
+        float tot = 0.f;
+        for (int q = 0; q < RL; ++q) tot += red[q * TC + tc];
+        const int a = col / W, ch = blockIdx.y * W + (col - a * W);
+        if (ch < C) {
+          p.totals[(size_t)a * C + ch] = tot;
+          float* pg = a == 0 ? p.dbeta : p.dgamma;
+          if (pg) pg[ch] = p.accumulate ? pg[ch] + tot : tot;
+          if (p.sync.world > 0) sync_push_value(p.sync, epoch, a * C + ch, tot);
+        }
+      }
+    }
+    if (p.sync.world > 0) __threadfence_system();
+  }
+  grid_barrier(p.ctr, 2u * nblocks);
+  // ------------------------------------------------ SyncBN: publish, wait for the world, totals from every rank
+  float s0[8], s1[8];
+  if (p.sync.world > 0) {
+    if (blockIdx.x == 0 && blockIdx.y == 0) sync_publish(p.sync, epoch, (int)threadIdx.x, [] { __syncthreads(); });
+    sync_wait_world(p.sync, epoch);
+    if (rm.active) {
+      sync_total8(p.sync, epoch, co, s0);
+      sync_total8(p.sync, epoch, C + co, s1);
+    }
+  } else if (rm.active) {
+    *reinterpret_cast<float4*>(s0) = __ldcg(reinterpret_cast<const float4*>(p.totals + co));
+    *reinterpret_cast<float4*>(s0 + 4) = __ldcg(reinterpret_cast<const float4*>(p.totals + co + 4));
+    *reinterpret_cast<float4*>(s1) = __ldcg(reinterpret_cast<const float4*>(p.totals + C + co));
+    *reinterpret_cast<float4*>(s1 + 4) = __ldcg(reinterpret_cast<const float4*>(p.totals + C + co + 4));
+  }
+  // ------------------------------------------------ phase 2: apply
+  if (rm.active) {
+    float cA[8], cB[8], cC[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = gm[j] * istd[j];
+      const float t0 = p.zero_sums ? 0.f : s0[j], t1 = p.zero_sums ? 0.f : s1[j];
+      cA[j] = a;
+      cB[j] = -a * istd[j] * t1 * p.inv_count;
+      cC[j] = -a * t0 * p.inv_count - cB[j] * mean[j];
+    }
+#pragma unroll 2
+    for (int64_t row = (int64_t)blockIdx.x * rm.rows_par + rm.rl; row < p.M; row += step) {
+      float dz[8], xv[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(p.dout + row * p.lddo + co), dz);
+      unpack8(*reinterpret_cast<const bf16x8*>(p.x + row * p.ldx + co), xv);
+      if constexpr (REMASK) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dz[j] = (fmaf(xv[j], cA[j], sh[j]) > 0.f) ? dz[j] : 0.f;
+      } else if (p.relu) {
+        float o[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(p.out + row * p.ldo + co), o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dz[j] = (o[j] > 0.f) ? dz[j] * keep_scale : 0.f;
+      }
+      if (p.dres) {
+        float r[8];
+        if (p.beta_res != 0.f) {
+          unpack8(*reinterpret_cast<const bf16x8*>(p.dres + row * p.lddres + co), r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = p.beta_res * r[j] + dz[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = dz[j];
+        }
+        *reinterpret_cast<bf16x8*>(p.dres + row * p.lddres + co) = pack8(r);
+      }
+      float o8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o8[j] = fmaf(cA[j], dz[j], fmaf(cB[j], xv[j], cC[j]));
+      *reinterpret_cast<bf16x8*>(p.dx + row * p.lddx + co) = pack8(o8);
+    }
+  }
+  if (p.sync.world > 0) sync_consumer_done(p.sync, epoch, p.ctr + 1, nblocks);
 }
 
 __global__ void bn_param_grad_kernel(const float* __restrict__ sums, int C, float* dgamma, float* dbeta, int accumulate) {
@@ -1153,18 +1391,24 @@ int seg_bn_apply(const void* x, int ldx, const float* ss, const void* res, int l
   BnTrain tr;
   memset(&tr, 0, sizeof(tr));
   launch_pdl(bn_apply_kernel, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(x), ldx, ss, CBF(res), ldr, BF(out), ldo, M, C, relu,
-             drop_p, seed, step_ctr, drop_hw, tr);
+             drop_p, seed, step_ctr, drop_hw, tr, SyncDesc{nullptr, 0, 0, 0, 0}, (unsigned*)nullptr);
   return check_launch("bn_apply");
 }
 int seg_bn_apply_train(const void* x, int ldx, const float* stats, double count, const float* gamma, const float* beta,
                        float eps, float momentum, int clamp_eps, float* running_mean, float* running_var, float* save,
                        const void* res, int ldr, void* out, int ldo, int64_t M, int C, int relu, float drop_p,
-                       uint64_t seed, const uint64_t* step_ctr, int drop_hw, void* stream) {
+                       uint64_t seed, const uint64_t* step_ctr, int drop_hw, const seg_sync_desc* sync, void* sync_done,
+                       void* stream) {
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldr % 8 == 0), "bn_apply_train: alignment");
   SEG_REQUIRE(stats && gamma && beta && save && count > 0, "bn_apply_train: stats, gamma, beta, save required");
+  SyncDesc sd{nullptr, 0, 0, 0, 0};
+  if (sync) {
+    SEG_REQUIRE(sync_done != nullptr && 2 * C <= sync->n_max, "bn_apply_train: SyncBN needs a zeroed ticket and 2*C <= n_max");
+    sd.peers = sync->peers; sd.rank = sync->rank; sd.world = sync->world; sd.n_max = sync->n_max; sd.timeout_clocks = sync->timeout_clocks;
+  }
   BnTrain tr = {stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var, save};
   launch_pdl(bn_apply_kernel, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(x), ldx, (const float*)nullptr, CBF(res), ldr, BF(out),
-             ldo, M, C, relu, drop_p, seed, step_ctr, drop_hw, tr);
+             ldo, M, C, relu, drop_p, seed, step_ctr, drop_hw, tr, sd, reinterpret_cast<unsigned*>(sync_done));
   return check_launch("bn_apply_train");
 }
 // reductions end with a block fold + a ticket: fewer, fatter blocks (>= 32 rows per thread)
@@ -1191,6 +1435,64 @@ int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const
              CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save,
              gamma, sums, (float)(1.0 / count), M, C, relu, drop_p, BF(dx), lddx, BF(dres), lddres, beta_res, beta);
   return check_launch("bn_bwd_apply");
+}
+}  // extern "C"
+// co-resident grid of the cooperative kernel: blocks per SM from the occupancy of the instantiation actually launched
+template <bool REMASK>
+static int fused_blocks_per_sm() {
+  static int v = 0;
+  if (v == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bn_bwd_fused_kernel<REMASK>, 256, 0) != cudaSuccess || n < 1) n = 1;
+    v = n;
+  }
+  return v;
+}
+extern "C" {
+static dim3 fused_grid(int64_t M, int C, int blocks_per_sm) {
+  dim3 g = rowmap_grid(M, C, 16);
+  const int64_t cap = (int64_t)num_sms() * blocks_per_sm / g.y;
+  if ((int64_t)g.x > cap) g.x = (unsigned)(cap < 1 ? 1 : cap);
+  return g;
+}
+int seg_bn_bwd_fused_workspace(int64_t M, int C, int64_t* rows_floats, int64_t* tickets) {
+  SEG_REQUIRE(C % 8 == 0 && rows_floats && tickets, "seg_bn_bwd_fused_workspace: bad arguments");
+  const int bps = fused_blocks_per_sm<true>() > fused_blocks_per_sm<false>() ? fused_blocks_per_sm<true>() : fused_blocks_per_sm<false>();
+  const dim3 g = fused_grid(M, C, bps);
+  const int G = C / 8, GB = G < 256 ? G : 256;
+  *rows_floats = (int64_t)g.y * g.x * 2 * GB * 8;
+  *tickets = 2;
+  return 0;
+}
+int seg_bn_bwd_fused(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,
+                     const float* gamma, const float* beta, double count_total, int64_t M, int C, int relu, float drop_p,
+                     float* sums, float* rows, void* tickets, float* dgamma, float* dbeta, int accumulate, void* dx, int lddx,
+                     void* dres, int lddres, float beta_res, int zero_sums, const seg_sync_desc* sync, void* stream) {
+  SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && (!out || ldo % 8 == 0) && (!dres || lddres % 8 == 0),
+              "bn_bwd_fused: alignment");
+  SEG_REQUIRE(!(relu && !out) || (beta && drop_p == 0.f), "bn_bwd_fused: out == NULL (mask recomputed from x) needs beta and no dropout");
+  SEG_REQUIRE(sums && rows && tickets && gamma && save && dx && count_total > 0, "bn_bwd_fused: missing buffer");
+  const bool remask = relu && !out;
+  BnBwdFused p;
+  memset(&p, 0, sizeof(p));
+  p.dout = CBF(dout); p.out = CBF(out); p.x = CBF(x);
+  p.lddo = lddo; p.ldo = ldo; p.ldx = ldx;
+  p.save = save; p.gamma = gamma; p.beta = beta;
+  p.M = M; p.C = C; p.relu = relu; p.drop_p = drop_p; p.inv_count = (float)(1.0 / count_total);
+  p.rows = rows; p.totals = sums; p.ctr = reinterpret_cast<unsigned*>(tickets);
+  p.dgamma = dgamma; p.dbeta = dbeta; p.accumulate = accumulate; p.zero_sums = zero_sums;
+  p.dx = BF(dx); p.dres = BF(dres); p.lddx = lddx; p.lddres = lddres; p.beta_res = beta_res;
+  if (sync) {
+    SEG_REQUIRE(2 * C <= sync->n_max, "bn_bwd_fused: 2*C = %d sums exceed the SyncBN buffer (%d floats)", 2 * C, sync->n_max);
+    p.sync.peers = sync->peers; p.sync.rank = sync->rank; p.sync.world = sync->world; p.sync.n_max = sync->n_max;
+    p.sync.timeout_clocks = sync->timeout_clocks;
+  }
+  const dim3 grid = fused_grid(M, C, remask ? fused_blocks_per_sm<true>() : fused_blocks_per_sm<false>());
+  if (remask)
+    bn_bwd_fused_kernel<true><<<grid, 256, 0, ST(stream)>>>(p);
+  else
+    bn_bwd_fused_kernel<false><<<grid, 256, 0, ST(stream)>>>(p);
+  return check_launch("bn_bwd_fused");
 }
 int seg_bn_param_grad(const float* sums, int C, float* dgamma, float* dbeta, int accumulate, void* stream) {
   bn_param_grad_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(sums, C, dgamma, dbeta, accumulate);

@@ -13,6 +13,17 @@ import torch.distributed as dist
 from . import lib
 
 
+def _sync_timeout_clocks():
+    """Spin-wait bound of the in-kernel exchange in GPU clocks (~2 GHz): SEG_SYNC_TIMEOUT_S seconds, default 120 — rank skew
+    from a slow data loader or a checkpoint write on one rank must not kill the job; 0 = wait forever."""
+    import os
+    return int(float(os.environ.get("SEG_SYNC_TIMEOUT_S", "120")) * 2e9)
+
+
+def _make_desc(peers, rank, world, n_max):
+    return lib.SyncDesc(peers.data_ptr(), rank, world, n_max, _sync_timeout_clocks())
+
+
 class SyncBNGroup:
     """Symmetric peer buffers for `seg_syncbn_exchange`.  `allreduce_(vec)` sums an fp32 vector
     (<= n_max floats) over all ranks in place, bit-identically on every rank."""
@@ -45,6 +56,8 @@ class SyncBNGroup:
             self._opened.append(p)
             ptrs.append(p.value)
         self.peers = torch.tensor(ptrs, dtype=torch.int64, device="cuda")
+        self.desc = _make_desc(self.peers, self.rank, self.world, n_max)
+        self.fused = True  # the kernels that produce / consume the statistics carry the exchange (csrc/seg_sync.cuh)
         dist.barrier(group=group)
 
     def allreduce_(self, vec):
@@ -72,6 +85,10 @@ class LocalLoopbackGroup:
             raise RuntimeError(lib.last_error())
         self._mine = mine
         self.peers = torch.tensor([mine.value], dtype=torch.int64, device="cuda")
+        self.desc = _make_desc(self.peers, 0, 1, n_max)
+        self.fused = True
+        self.force = False  # True: the engine runs the whole SyncBN protocol (push, flags, wait, sequence number) against
+                            # this one-rank buffer — the single-GPU test of the fused exchange
 
     def allreduce_(self, vec):
         lib.call("seg_syncbn_exchange", self.peers.data_ptr(), 0, 1, vec.data_ptr(), vec.numel(), self.n_max)

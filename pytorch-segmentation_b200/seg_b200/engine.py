@@ -132,6 +132,7 @@ class Tape:
         self.dw_buffers = {}
         self.clamp_eps = clamp_eps
         self._drop_ctr = 0
+        self._pushed = set()  # statistics vectors whose producing conv already pushed them to the SyncBN peers
         self.bn_modules = []
         # zero-initialised fp32 arena: BN-statistics accumulators and reduction slots of the whole step come out of ONE
         # zero fill instead of one fill per layer (arena_floats = what the previous step used; grows in 1M-float chunks)
@@ -142,6 +143,14 @@ class Tape:
         self.arena_used = 0
 
     # ------------------------------------------------------------------ helpers
+    def sync_active(self):
+        """SyncBN exchange on: more than one rank, or a loopback group forced on for the single-GPU protocol test."""
+        s = self.sync
+        return s is not None and (s.world > 1 or getattr(s, "force", False))
+
+    def sync_fused(self):
+        return self.sync_active() and getattr(self.sync, "fused", False)
+
     def zalloc(self, n, device):
         """n zeroed floats (128-byte aligned) from the step's arena."""
         n_al = (int(n) + 31) // 32 * 32
@@ -186,21 +195,29 @@ class Tape:
         want = want_stats and self.training
         if want:
             stats = self.zalloc(2 * spec.K, wp.device)
+        push = None  # SyncBN: the conv epilogue pushes the statistics to the peers (no exchange launch)
         if spec.explicit:
             nchw = not isinstance(x, Act)
             src = x if nchw else x.t
             col = ops.im2col(src, spec.R, spec.S, spec.stride, spec.pad, spec.dil, spec.kpad, nchw_f32=nchw)
             tk = self.zalloc(ops.conv_stats_workspace(*col.shape, spec.K, 1, 1)[1], wp.device) if want else None
+            if want and self.sync_fused() and ops.conv_fwd_pushes(col.shape, spec.K, 1, 1, 1, 0, 1, ops.ld(col), self.impl):
+                push = self.sync
             y = ops.conv2d_fwd(col, wp, spec.K, 1, 1, out=out, out_dtype=out_dtype,
-                               bias=bias.detach() if bias is not None else None, stats=stats, impl=self.impl, tickets=tk)
+                               bias=bias.detach() if bias is not None else None, stats=stats, impl=self.impl, tickets=tk, sync=push)
             xin, geo = col, (1, 1, 1, 0, 1)
         else:
             tk = self.zalloc(ops.conv_stats_workspace(*x.t.shape, spec.K, spec.R, spec.S, spec.stride, spec.pad, spec.dil)[1],
                              wp.device) if want else None
+            if want and self.sync_fused() and ops.conv_fwd_pushes(x.t.shape, spec.K, spec.R, spec.S, spec.stride, spec.pad, spec.dil,
+                                                                  ops.ld(x.t), self.impl):
+                push = self.sync
             y = ops.conv2d_fwd(x.t, wp, spec.K, spec.R, spec.S, spec.stride, spec.pad, spec.dil, out=out, out_dtype=out_dtype,
-                               bias=bias.detach() if bias is not None else None, stats=stats, impl=self.impl, tickets=tk)
+                               bias=bias.detach() if bias is not None else None, stats=stats, impl=self.impl, tickets=tk, sync=push)
             xin, geo = x.t, (spec.R, spec.S, spec.stride, spec.pad, spec.dil)
         ya = Act(y)
+        if push is not None:
+            self._pushed.add(stats.data_ptr())
         if self.record:
             def bwd():
                 dy = ya.grad
@@ -291,8 +308,12 @@ class Tape:
             if stats is None:
                 stats = ops.bn_stats(y.t)
             count = count_local
-            if self.sync is not None and self.sync.world > 1:
-                self.sync.allreduce_(stats)
+            in_kernel = None
+            if self.sync_active():
+                if stats.data_ptr() in self._pushed:
+                    in_kernel = self.sync      # bn_apply waits for the world's flags and adds every rank's sums itself
+                else:
+                    self.sync.allreduce_(stats)  # producer without the hook (depthwise conv, CUDA-core conv): stand-alone exchange
                 count = count_local * self.sync.world
             # finalize (coefficients, saved mean / 1/std, running statistics) happens inside the apply kernel
             a, save = ops.bn_apply_train(y.t, stats, count, bn.weight.detach(), bn.bias.detach(), bn.eps,
@@ -300,7 +321,8 @@ class Tape:
                                          1 if (self.clamp_eps and self.sync is not None and self.sync.world > 1) else 0,
                                          bn.running_mean, bn.running_var, res=res.t if res is not None else None, out=out,
                                          relu=relu, drop_p=drop_p, seed=seed, step_ctr=self.step_ctr if drop_p > 0.0 else None,
-                                         drop_hw=drop_hw)
+                                         drop_hw=drop_hw, sync=in_kernel,
+                                         sync_done=self.zalloc(1, y.t.device) if in_kernel is not None else None)
             self.bn_modules.append(bn)
         else:
             ss, save = ops.bn_eval_scale_shift(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps,
@@ -327,22 +349,29 @@ class Tape:
                     self.grads[bn.weight] = torch.empty(C, dtype=torch.float32, device=a.device)
                     self.grads[bn.bias] = torch.empty(C, dtype=torch.float32, device=a.device)
                 a_mask = None if remask else a
-                sums = ops.bn_bwd_reduce(da, a, y.t, save, relu=relu, drop_p=drop_p,
-                                         dgamma=self.grads[bn.weight] if want_pg else None,
-                                         dbeta=self.grads[bn.bias] if want_pg else None, accumulate=acc_pg,
-                                         tickets=self.zalloc(ops.reduce_workspace(count_local, C, 2)[1], a.device))
-                gsums = sums
-                if not use_batch_stats:
-                    gsums = torch.zeros_like(sums)  # frozen BN (freeze_bn): dx = gamma * inv_std * dz
-                elif self.sync is not None and self.sync.world > 1:
-                    gsums = sums.clone()
-                    self.sync.allreduce_(gsums)
                 dy = torch.empty(y.t.shape, dtype=ACT_DTYPE, device=a.device)
                 dres, beta_res = (None, 0.0)
                 if res is not None and res.needs_grad:
                     dres, beta_res = res.grad_target()
-                ops.bn_bwd_apply(da, a_mask, y.t, save, bn.weight.detach(), gsums, count, relu=relu, drop_p=drop_p, dx=dy, dres=dres,
-                                 beta_res=beta_res, beta=bn.bias.detach())
+                sync = self.sync if (use_batch_stats and self.sync_active()) else None
+                if sync is not None and not getattr(sync, "fused", False):
+                    # exchange object without the in-kernel protocol (e.g. the gloo stand-in of the CPU tests): two launches
+                    sums = ops.bn_bwd_reduce(da, a, y.t, save, relu=relu, drop_p=drop_p,
+                                             dgamma=self.grads[bn.weight] if want_pg else None,
+                                             dbeta=self.grads[bn.bias] if want_pg else None, accumulate=acc_pg,
+                                             tickets=self.zalloc(ops.reduce_workspace(count_local, C, 2)[1], a.device))
+                    gsums = sums.clone()
+                    sync.allreduce_(gsums)
+                    ops.bn_bwd_apply(da, a_mask, y.t, save, bn.weight.detach(), gsums, count, relu=relu, drop_p=drop_p, dx=dy,
+                                     dres=dres, beta_res=beta_res, beta=bn.bias.detach())
+                else:
+                    # reduce -> grid barrier -> fixed-order cross-block sum (-> SyncBN exchange) -> apply, ONE launch; frozen
+                    # BN (freeze_bn): dx = gamma * inv_std * dz, the sums only feed the parameter gradients
+                    ops.bn_bwd_fused(da, a_mask, y.t, save, bn.weight.detach(), count, relu=relu, drop_p=drop_p,
+                                     dgamma=self.grads[bn.weight] if want_pg else None,
+                                     dbeta=self.grads[bn.bias] if want_pg else None, accumulate=acc_pg, dx=dy, dres=dres,
+                                     beta_res=beta_res, beta=bn.bias.detach(), zero_sums=not use_batch_stats,
+                                     tickets=self.zalloc(2, a.device), sync=sync)
                 y.grad = dy
                 aa.grad = None
             self.back.append(bwd)

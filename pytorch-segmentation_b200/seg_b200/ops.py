@@ -134,9 +134,10 @@ def _fold_ws(rows_floats, n_tickets, tickets, device):
 
 
 def conv2d_fwd(x, w_packed, K, R, S, stride=1, pad=0, dil=1, out=None, out_dtype=torch.bfloat16, bias=None, beta=0.0,
-               stats=None, impl=IMPL_AUTO, tickets=None):
+               stats=None, impl=IMPL_AUTO, tickets=None, sync=None):
     """stats: fp32 [2K] written with the per-channel sum / sum of squares of the output (bit-reproducible).  tickets: zeroed
-    fp32/int32 words (conv_stats_workspace(...)[1] of them) from the caller's per-step arena; allocated here if None."""
+    fp32/int32 words (conv_stats_workspace(...)[1] of them) from the caller's per-step arena; allocated here if None.
+    sync: a comm.SyncBNGroup — the epilogue also pushes the statistics to every peer (check conv_fwd_pushes first)."""
     N, H, W, C = x.shape
     d = make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil, ldx=ld(x))
     if out is None:
@@ -148,10 +149,18 @@ def conv2d_fwd(x, w_packed, K, R, S, stride=1, pad=0, dil=1, out=None, out_dtype
         rows, tickets = _fold_ws(nr, nt, tickets, x.device)
     ev = _prof("fprop", d)
     call("seg_conv2d_fwd", ctypes.byref(d), ptr(x), ptr(w_packed), ptr(out), DT_BF16 if out.dtype == torch.bfloat16 else DT_F32,
-         ptr(bias), float(beta), ptr(stats), ptr(rows), ptr(tickets) if stats is not None else None, _impl(impl), meta=_meta(d))
+         ptr(bias), float(beta), ptr(stats), ptr(rows), ptr(tickets) if stats is not None else None,
+         ctypes.addressof(sync.desc) if (sync is not None and stats is not None) else None, _impl(impl), meta=_meta(d))
     if ev is not None:
         ev.record()
     return out
+
+
+def conv_fwd_pushes(x_shape, K, R, S, stride, pad, dil, ldx, impl=IMPL_AUTO):
+    """True if conv2d_fwd on this shape runs the tcgen05 path (whose epilogue can push SyncBN statistics)."""
+    N, H, W, C = x_shape
+    d = make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil, ldx=ldx)
+    return bool(lib.load().seg_conv_fwd_pushes(ctypes.byref(d), _impl(impl)))
 
 
 def conv2d_dgrad(dy, w_packed, x_shape, R, S, stride=1, pad=0, dil=1, out=None, beta=0.0, impl=IMPL_AUTO):
@@ -306,15 +315,20 @@ def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=
 
 
 def bn_apply_train(x, stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var, res=None, out=None,
-                   relu=True, drop_p=0.0, seed=0, step_ctr=None, drop_hw=0):
-    """Training-mode BN (+residual, ReLU, dropout) straight from the batch sums.  Returns (out, save[2C])."""
+                   relu=True, drop_p=0.0, seed=0, step_ctr=None, drop_hw=0, sync=None, sync_done=None):
+    """Training-mode BN (+residual, ReLU, dropout) straight from the batch sums.  Returns (out, save[2C]).
+    sync (comm.SyncBNGroup, with the producing conv2d_fwd(sync=...)): the kernel waits for the world's flags and adds every
+    rank's sums itself; `count` is the world's; sync_done: one zeroed word (allocated here if None)."""
     C = x.shape[-1]
     if out is None:
         out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     save = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+    if sync is not None and sync_done is None:
+        sync_done = torch.zeros(1, dtype=torch.float32, device=x.device)
     call("seg_bn_apply_train", ptr(x), ld(x), ptr(stats), float(count), ptr(gamma), ptr(beta), float(eps), float(momentum),
          int(clamp_eps), ptr(running_mean), ptr(running_var), ptr(save), ptr(res), ld(res) if res is not None else 0,
          ptr(out), ld(out), rows(x), C, int(relu), float(drop_p), int(seed), ptr(step_ctr), int(drop_hw),
+         ctypes.addressof(sync.desc) if sync is not None else None, ptr(sync_done) if sync is not None else None,
          meta=_meta_rows(rows(x), C, 3 if res is not None else 2, res is not None))
     return out, save
 
@@ -328,6 +342,36 @@ def bn_bwd_apply(dout, out, x, save, gamma, sums, count, relu=True, drop_p=0.0, 
          ld(dres) if dres is not None else 0, float(beta_res), ptr(beta),
          meta=_meta_rows(rows(x), C, (3 if (relu and out is not None) else 2) + 1 + (0 if dres is None else (2 if beta_res != 0.0 else 1)), dres is not None))
     return dx
+
+
+def bn_bwd_fused_workspace(M, C):
+    key = ("bnf", int(M), int(C))
+    v = _WS_CACHE.get(key)
+    if v is None:
+        r, t = ctypes.c_int64(), ctypes.c_int64()
+        if lib.load().seg_bn_bwd_fused_workspace(int(M), int(C), ctypes.byref(r), ctypes.byref(t)) != 0:
+            raise RuntimeError(lib.last_error())
+        v = _WS_CACHE[key] = (int(r.value), int(t.value))
+    return v
+
+
+def bn_bwd_fused(dout, out, x, save, gamma, count_total, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False,
+                 dx=None, dres=None, beta_res=0.0, beta=None, zero_sums=False, tickets=None, sync=None):
+    """BatchNorm backward in ONE cooperative launch (reduce -> grid barrier -> fixed-order cross-block sum [-> SyncBN exchange]
+    -> apply).  Returns (dx, local sums [2C]).  out=None: ReLU mask recomputed from x (needs beta).  tickets: 2 zeroed words."""
+    C = x.shape[-1]
+    M = rows(x)
+    if dx is None:
+        dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+    nr, nt = bn_bwd_fused_workspace(M, C)
+    fr, tickets = _fold_ws(nr, nt, tickets, x.device)
+    call("seg_bn_bwd_fused", ptr(dout), ld(dout), ptr(out), ld(out) if out is not None else 0, ptr(x), ld(x), ptr(save), ptr(gamma),
+         ptr(beta), float(count_total), M, C, int(relu), float(drop_p), ptr(sums), ptr(fr), ptr(tickets), ptr(dgamma), ptr(dbeta),
+         int(accumulate), ptr(dx), ld(dx), ptr(dres), ld(dres) if dres is not None else 0, float(beta_res), int(zero_sums),
+         ctypes.addressof(sync.desc) if sync is not None else None,
+         meta=_meta_rows(M, C, (3 if (relu and out is not None) else 2) * 2 + 1 + (0 if dres is None else (2 if beta_res != 0.0 else 1)), dres is not None))
+    return dx, sums
 
 
 def bn_param_grad(sums, dgamma, dbeta, accumulate=False):

@@ -63,8 +63,12 @@ def reduce_workspace(*a, **k):
     return (0, 1)
 
 
+def conv_fwd_pushes(*a, **k):
+    return False
+
+
 def conv2d_fwd(x, wp, K, R, S, stride=1, pad=0, dil=1, out=None, out_dtype=None, bias=None, beta=0.0, stats=None,
-               impl=0, tickets=None):
+               impl=0, tickets=None, sync=None):
     y = F.conv2d(_nchw(x), _w_oihw(wp, R, S), bias, stride, pad, dil).permute(0, 2, 3, 1)
     if stats is not None:  # written, not accumulated (the kernels' fixed-order reduction overwrites); sums of the output
         C = y.shape[-1]    # AS STORED (rounded to the output type), which is what bn_apply then normalises
@@ -199,7 +203,7 @@ def bn_apply(x, ss, res=None, out=None, relu=True, drop_p=0.0, seed=0, step_ctr=
 
 
 def bn_apply_train(x, stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var, res=None, out=None,
-                   relu=True, drop_p=0.0, seed=0, step_ctr=None, drop_hw=0):
+                   relu=True, drop_p=0.0, seed=0, step_ctr=None, drop_hw=0, sync=None, sync_done=None):
     ss, save = bn_finalize(stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var)
     return bn_apply(x, ss, res=res, out=out, relu=relu, drop_p=drop_p, seed=seed, step_ctr=step_ctr), save
 
@@ -236,6 +240,16 @@ def bn_bwd_apply(dout, out, x, save, gamma, sums, count, relu=True, drop_p=0.0, 
     if dx is None:
         dx = torch.empty(x.shape, dtype=ACT_DTYPE)
     return _store(dx, g)
+
+
+def bn_bwd_fused(dout, out, x, save, gamma, count_total, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False,
+                 dx=None, dres=None, beta_res=0.0, beta=None, zero_sums=False, tickets=None, sync=None):
+    assert sync is None
+    sums = bn_bwd_reduce(dout, out, x, save, relu=relu, drop_p=drop_p, dgamma=dgamma, dbeta=dbeta, accumulate=accumulate,
+                         gamma=gamma, beta=beta)
+    g = torch.zeros_like(sums) if zero_sums else sums
+    return bn_bwd_apply(dout, out, x, save, gamma, g, count_total, relu=relu, drop_p=drop_p, dx=dx, dres=dres, beta_res=beta_res,
+                        beta=beta), sums
 
 
 def bn_param_grad(sums, dgamma, dbeta, accumulate=False):

@@ -236,6 +236,22 @@ def test_bn_train_fwd_bwd(C, M_shape, gpu_out_dir):
     dx_read = ops.bn_bwd_apply(dyd, out3, xd, save3, gd, s_read, count, relu=True)
     dx_re = ops.bn_bwd_apply(dyd, None, xd, save3, gd, s_read, count, relu=True, beta=bd)
     assert torch.equal(dx_re, dx_read)
+    # ONE cooperative launch (reduce -> grid barrier -> distributed fixed-order sum -> apply) == the two-launch path
+    dg3, db3, dres3 = torch.ones(C, device=DEV), torch.ones(C, device=DEV), torch.empty_like(xd)
+    dx3, sums3 = ops.bn_bwd_fused(dyd, out, xd, save, gd, count, relu=True, dgamma=dg3, dbeta=db3, accumulate=True, dres=dres3)
+    check(f"bn_bwd_fused sums C={C}", sums3, sums, 1e-6, gpu_out_dir)
+    check(f"bn_bwd_fused dx C={C}", dx3.float(), dx.float(), 1e-2, gpu_out_dir)
+    assert torch.equal(dres3, dres)
+    check(f"bn_bwd_fused dgamma C={C}", dg3 - 1.0, dgamma, 1e-4, gpu_out_dir)
+    check(f"bn_bwd_fused dbeta C={C}", db3 - 1.0, dbeta, 1e-4, gpu_out_dir)
+    dx4, sums4 = ops.bn_bwd_fused(dyd, out, xd, save, gd, count, relu=True)
+    assert torch.equal(sums4, sums3) and torch.equal(dx4, dx3), "the cooperative BN backward must be bit-reproducible"
+    dx5, s5 = ops.bn_bwd_fused(dyd, None, xd, save3, gd, count, relu=True, beta=bd)  # mask recomputed from x
+    check(f"bn_bwd_fused remask sums C={C}", s5, s_read, 1e-6, gpu_out_dir)
+    check(f"bn_bwd_fused remask dx C={C}", dx5.float(), dx_read.float(), 1e-2, gpu_out_dir)
+    dx6, _ = ops.bn_bwd_fused(dyd, out, xd, save, gd, count, relu=True, zero_sums=True)  # frozen BN: dx = gamma*istd*dz
+    z = torch.zeros_like(sums)
+    check(f"bn_bwd_fused frozen dx C={C}", dx6.float(), ops.bn_bwd_apply(dyd, out, xd, save, gd, z, count, relu=True).float(), 1e-2, gpu_out_dir)
 
 
 def test_bn_clamp_eps_and_eval(gpu_out_dir):

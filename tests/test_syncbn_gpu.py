@@ -55,6 +55,38 @@ def test_two_simulated_ranks_on_one_gpu():
         L.seg_comm_free(b)
 
 
+def test_fused_exchange_protocol_on_a_one_rank_loopback():
+    """The SyncBN exchange now rides inside the conv epilogue (push + flags), bn_apply (wait + rank-ordered sum) and the
+    cooperative BN backward (both): run the WHOLE protocol — symmetric-buffer stores, release flags, acquire waits, device-side
+    sequence number, slot alternation — against a one-rank buffer.  With one rank the sums are unchanged, so three training
+    steps must be bit-identical to the same steps without an exchange, eagerly and replayed from a CUDA graph."""
+    import seg_b200
+    from seg_b200.train import FusedTrainStep
+    from oracle import synth, weights
+    sd = weights.deeplab_resnet_state_dict(7, "resnet14", seed=11)
+    x, y = synth.make_batch(4, 65, 65, 7, 255, seed=31)
+    xd, yd = x.cuda(), y.cuda()
+    results = []
+    for mode in ("plain", "loopback", "loopback-graph"):
+        m = seg_b200.DeepLab(7, backbone="resnet14", pretrained=False)
+        m.load_state_dict(sd)
+        m.engine_dropout = False
+        m = m.cuda().train()
+        if mode != "plain":
+            m.bn_sync = comm.LocalLoopbackGroup(n_max=8192)
+            m.bn_sync.force = True
+        st = FusedTrainStep(m, lr=0.01, cuda_graph=(mode == "loopback-graph"))
+        losses = [float(st.step(xd, yd)) for _ in range(3)]
+        torch.cuda.synchronize()
+        results.append((losses, torch.cat([p.detach().reshape(-1) for p in m.parameters()]).clone(),
+                        torch.cat([b.detach().float().reshape(-1) for n, b in m.named_buffers() if "running_" in n]).clone()))
+    for losses, params, stats in results[1:]:
+        assert losses == results[0][0], (losses, results[0][0])
+        assert torch.equal(stats, results[0][2])
+        # weight gradients go through split-K atomics (order varies): parameters agree to rounding, everything upstream is exact
+        assert (params - results[0][1]).abs().max().item() <= 1e-6 * results[0][1].abs().max().item()
+
+
 def _worker(rank, world, port, out_path, graph=False, nsteps=1):
     import torch.distributed as dist
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
