@@ -30,9 +30,30 @@ for p in (ROOT, PKG):
 
 import torch  # noqa: E402
 
-TRAIN_GFLOP_PER_IMG = 555.63  # conv fwd+dgrad+wgrad, DeepLabV3+/R101 513x513/19 (measured on the reference)
-NUM_CLASSES, SIZE, IGNORE = 19, 513, 255
-METRIC = "images/sec DeepLabV3+/ResNet101 513x513 train step (fwd+CE+bwd+SGD)"
+# BASELINE.json configs.  train GFLOP/img = conv fwd + dgrad + wgrad, measured on the reference with hooks
+# (BASELINE.md §3).  C3 is the headline (the metric string below is BASELINE.json's); the others are reported the same way.
+CONFIGS = {
+    "C3": dict(name="DeepLabV3+/ResNet101 513x513", arch="DeepLab", kw=dict(backbone="resnet101", output_stride=16), nc=19, size=513, batch=16,
+               loss="CE", ignore=255, gflop=555.63, sync_bn=True, recipe="CE, SGD m0.9 wd1e-4, lr .01/.001"),
+    "C2": dict(name="PSPNet/ResNet50 473x473", arch="PSPNet", kw=dict(backbone="resnet50"), nc=21, size=473, batch=16,
+               loss="CE", ignore=255, gflop=1071.78, sync_bn=False, recipe="CE + 0.4 CE(aux), SGD m0.9 wd1e-4, lr .01/.001"),
+    "C4": dict(name="DeepLabV3+/Xception 769x769", arch="DeepLab", kw=dict(backbone="xception", output_stride=16), nc=19, size=769, batch=8,
+               loss="CE", ignore=255, gflop=1150.90, sync_bn=False, recipe="CE, SGD m0.9 wd1e-4, lr .01/.001"),
+    "C5": dict(name="UperNet/ResNet101 512x512", arch="UperNet", kw=dict(backbone="resnet101"), nc=150, size=512, batch=8,
+               loss="LovaszSoftmax", ignore=-1, gflop=1123.96, sync_bn=False, recipe="Lovasz-softmax (ignore -1), SGD m0.9 wd1e-4, lr .01/.001"),
+}
+CFG = CONFIGS["C3"]  # replaced in main() by --config
+
+
+def metric_name():
+    if CFG is CONFIGS["C3"]:
+        return "images/sec DeepLabV3+/ResNet101 513x513 train step (fwd+CE+bwd+SGD)"
+    return f"images/sec {CFG['name']} train step (fwd+{CFG['loss']}+bwd+SGD)"
+
+
+def workload(backbone=None, world=1, sync_bn=False):
+    tag = [k for k, v in CONFIGS.items() if v is CFG][0]
+    return f"{CFG['name']} {CFG['nc']}cls train step ({tag}: {CFG['recipe']}" + (", SyncBN" if (world > 1 and sync_bn) else "") + ")"
 
 
 def measured_peaks():
@@ -89,7 +110,7 @@ class ClockSampler:
 
 def synthetic_batch(B, seed):
     from oracle import synth  # input recipe only; no oracle arithmetic
-    return synth.make_batch(B, SIZE, SIZE, NUM_CLASSES, IGNORE, seed=seed)
+    return synth.make_batch(B, CFG["size"], CFG["size"], CFG["nc"], CFG["ignore"], seed=seed)
 
 
 def host_threads():
@@ -101,24 +122,56 @@ def host_threads():
     return min(os.cpu_count() or 1, 32)
 
 
-def cpu_port_step_time(batch, steps, warmup, threads):
-    """Reference algorithm on the host cores: oracle model + CE + autograd backward + torch.optim.SGD (fp32)."""
-    from oracle import losses as ol
+def _oracle_model(device):
+    """(state_dict with requires_grad, forward fn, backbone-parameter predicate) of the oracle port of CFG's network."""
     from oracle import models as om
     from oracle import weights
-    torch.set_num_threads(threads)
-    sd = om.clone_sd(weights.deeplab_resnet_state_dict(NUM_CLASSES, "resnet101", seed=0), requires_grad=True)
+    a, kw, nc = CFG["arch"], CFG["kw"], CFG["nc"]
+    if a == "DeepLab" and kw["backbone"] == "xception":
+        sd0 = weights.deeplab_xception_state_dict(nc, seed=0)
+        fwd = lambda sd, x: (om.deeplab_forward(sd, x, backbone="xception", train=True, dropout=True),)
+    elif a == "DeepLab":
+        sd0 = weights.deeplab_resnet_state_dict(nc, kw["backbone"], seed=0)
+        fwd = lambda sd, x: (om.deeplab_forward(sd, x, backbone=kw["backbone"], train=True, dropout=True),)
+    elif a == "PSPNet":
+        sd0 = weights.pspnet_state_dict(nc, kw["backbone"], seed=0)
+        fwd = lambda sd, x: om.pspnet_forward(sd, x, backbone=kw["backbone"], train=True, dropout=True)
+    else:
+        sd0 = weights.upernet_state_dict(nc, kw["backbone"], seed=0)
+        fwd = lambda sd, x: (om.upernet_forward(sd, x, backbone=kw["backbone"], train=True, dropout=True),)
+    sd = om.clone_sd({k: v.to(device) for k, v in sd0.items()}, requires_grad=True)
     names = om.param_names(sd)
-    bb = [sd[n] for n in names if n.startswith("backbone.")]
-    dec = [sd[n] for n in names if not n.startswith("backbone.")]
+    is_bb = (lambda n: n.startswith("backbone.")) if a != "PSPNet" else (lambda n: n.startswith("initial.") or n.startswith("layer"))
+    seen, bb, dec = set(), [], []
+    for n in names:  # aliased tensors (UperNet's shared smooth conv) once
+        if id(sd[n]) in seen:
+            continue
+        seen.add(id(sd[n]))
+        (bb if is_bb(n) else dec).append(sd[n])
+    return sd, fwd, bb, dec
+
+
+def _oracle_loss(outs, y):
+    from oracle import losses as ol
+    if CFG["loss"] == "LovaszSoftmax":
+        return ol.lovasz_softmax(outs[0], y, CFG["ignore"])
+    loss = ol.cross_entropy2d(outs[0], y, CFG["ignore"])
+    if len(outs) > 1:
+        loss = loss + 0.4 * ol.cross_entropy2d(outs[1], y, CFG["ignore"])
+    return loss
+
+
+def cpu_port_step_time(batch, steps, warmup, threads):
+    """Reference algorithm on the host cores: oracle model + loss + autograd backward + torch.optim.SGD (fp32)."""
+    torch.set_num_threads(threads)
+    sd, fwd, bb, dec = _oracle_model("cpu")
     opt = torch.optim.SGD([{"params": dec}, {"params": bb, "lr": 0.001}], lr=0.01, momentum=0.9, weight_decay=1e-4)
     x, y = synthetic_batch(batch, 1234)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad()
-        out = om.deeplab_forward(sd, x, backbone="resnet101", train=True, dropout=True)
-        loss = ol.cross_entropy2d(out, y, IGNORE)
+        loss = _oracle_loss(fwd(sd, x), y)
         loss.backward()
         opt.step()
         dt = time.perf_counter() - t0
@@ -127,38 +180,114 @@ def cpu_port_step_time(batch, steps, warmup, threads):
     return sum(times) / len(times)
 
 
-def gpu_aten_step_time(batch, steps, warmup, device):
-    """The reference's OWN GPU path on this box: the oracle port (the same ATen modules/functions the reference calls —
-    cuDNN convolutions, ATen batch-norm, bilinear, CE, torch.optim.SGD; fp32, NCHW, cudnn.benchmark as trainer.py:35 sets)
-    on one B200.  Informational denominator for BASELINE.json's "x the reference's cuDNN-backed GPU images/sec"."""
-    from oracle import losses as ol
-    from oracle import models as om
-    from oracle import weights
+def _import_reference_tree():
+    """The UNMODIFIED reference tree, packed by baseline/install_ref.sh into baseline/_ref/reference.zip (git-ignored; built in
+    the build container where /root/reference exists, shipped to the GPU box like a built .so).  Returns its `models` package or
+    None.  Shims: SURVEY.md §8c (skimage stub; UperNet's undefined module globals)."""
+    z = os.path.join(ROOT, "baseline", "_ref", "reference.zip")
+    if not os.path.exists(z):
+        return None
+    import types
+    import warnings
+    warnings.filterwarnings("ignore")
+    for n in ("skimage", "skimage.filters"):
+        sys.modules.setdefault(n, types.ModuleType(n))
+    if not hasattr(sys.modules["skimage.filters"], "gaussian"):
+        sys.modules["skimage.filters"].gaussian = None
+    for name in list(sys.modules):  # this process may hold the overlay's / nothing's `models`, `utils`, `base`
+        if name.split(".")[0] in ("models", "utils", "base"):
+            del sys.modules[name]
+    sys.path.insert(0, z)
+    import models as ref_models
+    from utils import helpers
+    import models.upernet as up
+    up.freeze_backbone, up.set_trainable = False, helpers.set_trainable
+    return ref_models
+
+
+def reference_gpu_step_time(batch, steps, warmup, n_gpus):
+    """BASELINE.md §4 "Reference GPU path (cuDNN)" — the denominator of north_star's ">= 6x": the UNMODIFIED reference model,
+    wrapped exactly as BaseTrainer does it (base/base_trainer.py:33-38: convert_model + DataParallelWithCallback when
+    use_synch_bn, else nn.DataParallel; device_ids = range(n_gpu)), fp32 NCHW, cudnn.benchmark = True (trainer.py:35), the
+    reference's own loss class and torch.optim.SGD with the differential learning rates of base_trainer.py:46-57, the same
+    per-GPU batch, ONE process over n_gpus devices.  Falls back to the oracle port (single GPU) if the tree is not shipped."""
     torch.backends.cudnn.benchmark = True
-    sd0 = weights.deeplab_resnet_state_dict(NUM_CLASSES, "resnet101", seed=0)
-    sd = om.clone_sd({k: v.to(device) for k, v in sd0.items()}, requires_grad=True)
-    names = om.param_names(sd)
-    bb = [sd[n] for n in names if n.startswith("backbone.")]
-    dec = [sd[n] for n in names if not n.startswith("backbone.")]
-    opt = torch.optim.SGD([{"params": dec}, {"params": bb, "lr": 0.001}], lr=0.01, momentum=0.9, weight_decay=1e-4)
-    x, y = synthetic_batch(batch, 1234)
-    x, y = x.to(device), y.to(device)
+    dev = torch.device("cuda", 0)
+    x, y = synthetic_batch(batch * n_gpus, 1234)
+    ref_models = _import_reference_tree()
+    how = None
+    if ref_models is not None:
+        from utils import losses as ref_losses
+        from utils.sync_batchnorm import DataParallelWithCallback, convert_model
+        torch.manual_seed(0)
+        kw = dict(CFG["kw"])
+        model = getattr(ref_models, CFG["arch"])(CFG["nc"], pretrained=False, **kw)
+        ids = list(range(n_gpus))
+        if CFG["sync_bn"]:
+            model = DataParallelWithCallback(convert_model(model), device_ids=ids)
+        else:
+            model = torch.nn.DataParallel(model, device_ids=ids)
+        model.to(dev).train()
+        crit = getattr(ref_losses, CFG["loss"] if CFG["loss"] != "CE" else "CrossEntropyLoss2d")(ignore_index=CFG["ignore"])
+        opt = torch.optim.SGD([{"params": [p for p in model.module.get_decoder_params() if p.requires_grad]},
+                               {"params": [p for p in model.module.get_backbone_params() if p.requires_grad], "lr": 0.001}],
+                              lr=0.01, momentum=0.9, weight_decay=1e-4)
+
+        def step(xd, yd):
+            opt.zero_grad()
+            out = model(xd)
+            if isinstance(out, tuple):  # trainer.py:57-62: PSP* returns (out, aux)
+                loss = crit(out[0], yd) + 0.4 * crit(out[1], yd)
+            else:
+                loss = crit(out, yd)
+            if isinstance(model, torch.nn.DataParallel):
+                loss = loss.mean()
+            loss.backward()
+            opt.step()
+        how = (f"UNMODIFIED reference tree (baseline/_ref/reference.zip): models.{CFG['arch']} wrapped as base/base_trainer.py:33-38 "
+               f"({'convert_model + DataParallelWithCallback' if CFG['sync_bn'] else 'nn.DataParallel'}, device_ids=range({n_gpus})), fp32 NCHW, "
+               f"cudnn.benchmark, utils.losses.{'CrossEntropyLoss2d' if CFG['loss'] == 'CE' else CFG['loss']}, torch.optim.SGD; one process")
+    else:
+        if n_gpus > 1:
+            raise RuntimeError("reference tree not shipped (run baseline/install_ref.sh in the build container)")
+        sd, fwd, bb, dec = _oracle_model(dev)
+        opt = torch.optim.SGD([{"params": dec}, {"params": bb, "lr": 0.001}], lr=0.01, momentum=0.9, weight_decay=1e-4)
+
+        def step(xd, yd):
+            opt.zero_grad()
+            _oracle_loss(fwd(sd, xd), yd).backward()
+            opt.step()
+        how = "oracle port (same ATen/cuDNN calls as the reference; the reference tree was not shipped), fp32 NCHW, cudnn.benchmark"
+    xd, yd = x.to(dev), y.to(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(warmup + steps):
         if i == warmup:
-            torch.cuda.synchronize()
+            for d in range(n_gpus):
+                torch.cuda.synchronize(d)
             e0.record()
-        opt.zero_grad()
-        out = om.deeplab_forward(sd, x, backbone="resnet101", train=True, dropout=True)
-        loss = ol.cross_entropy2d(out, y, IGNORE)
-        loss.backward()
-        opt.step()
+        step(xd, yd)
     e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e-3 / steps
+    for d in range(n_gpus):
+        torch.cuda.synchronize(d)
+    return e0.elapsed_time(e1) * 1e-3 / steps, how
+
+
+def config_dict(args, world, use_graph=None, last_loss=None):
+    """`config` of the JSON line — the SAME dict for this engine's arm and for `--impl reference` (the driver compares them)."""
+    B = args.batch
+    c = {"workload": workload(world=world, sync_bn=CFG["sync_bn"]), "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+         "l2": "per-step working set (activations ~GBs) far exceeds the 126 MB L2; no explicit flush needed",
+         "dropout": "on (the reference's nn.Dropout / nn.Dropout2d sites)"}
+    if use_graph is not None:
+        c["cuda_graph"] = use_graph
+    if last_loss is not None:
+        c["last_loss"] = last_loss
+    return c
 
 
 def run_reference(args):
+    """Reference arm: the reference's algorithm for this path on the host cores (CPU oracle port, pinned bit-exactly to the
+    reference by tests/golden) on THIS arm's config; every timed step is a bounded sample of the configured step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -166,37 +295,43 @@ def run_reference(args):
     B = args.cpu_batch
     t = cpu_port_step_time(B, args.steps, args.warmup, threads)
     v = B / t
-    sample = f"{args.steps} timed steps of batch {B} (bounded sample of the {args.batch}-image step), fp32, {threads} threads"
+    sample = (f"{args.steps} timed steps (after {args.warmup} warm-up) of batch {B} — a bounded sample of the {args.batch}-image step of the same "
+              f"workload; the CPU path's images/sec does not depend on the batch at these sizes (conv-bound) — fp32, {threads} threads")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(), "value": v, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DeepLabV3+/ResNet101 513x513 19cls train step (C3)", "per_step_batch": B, "impl": "CPU oracle port of the reference path"},
+        "dtype": "f32", "data": "synthetic", "config": config_dict(args, max(args.gpus, 1)),
         "cpu_baseline": {"value": v, "unit": "images/sec", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 def main():
+    global CFG
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
-    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--config", default="C3", choices=list(CONFIGS), help="BASELINE.json config (C3 = the headline)")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (0 = the config's: 16 for C2/C3, 8 for C4/C5)")
+    ap.add_argument("--cpu-batch", type=int, default=4, help="per-step sample of the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-gpu-aten", action="store_true", help="skip the informational ATen/cuDNN timing of the oracle port on the GPU")
-    ap.add_argument("--backbone", default="resnet101")
+    ap.add_argument("--no-gpu-ref", "--no-gpu-aten", dest="no_gpu_ref", action="store_true",
+                    help="skip the reference-GPU leg (unmodified reference tree through ATen/cuDNN on the same GPUs)")
+    ap.add_argument("--gpu-ref-steps", type=int, default=int(os.environ.get("SEG_GPU_REF_STEPS", "30")),
+                    help="timed steps of the reference-GPU leg (BASELINE.md §4 asks 10 warm-up + 50; default 10 + 30 keeps the run short)")
     ap.add_argument("--graph", type=int, default=int(os.environ.get("SEG_CUDA_GRAPH", "1")), help="replay the fused step from a CUDA graph")
-    ap.add_argument("--plugin-graph", type=int, default=int(os.environ.get("SEG_PLUGIN_GRAPH", "-1")),
-                    help="e2e leg: replay model(x)/backward from CUDA graphs (seg_b200 model.cuda_graphs()); -1 = on at N=1, "
-                         "off at N>1 (the N>1 capture with SyncBN exchanges inside is built but was not measured this round)")
+    ap.add_argument("--plugin-graph", type=int, default=int(os.environ.get("SEG_PLUGIN_GRAPH", "1")),
+                    help="e2e leg: replay model(x)/backward from CUDA graphs (seg_b200 model.cuda_graphs())")
     ap.add_argument("--plugin-optim", default=os.environ.get("SEG_PLUGIN_OPTIM", "fused"), choices=["fused", "torch"],
                     help="e2e leg optimiser: seg_b200.optim.SGD (torch.optim.SGD subclass, one kernel per group) or stock torch.optim.SGD")
     ap.add_argument("--trace", default=None, help="after the timed runs, trace 2 steps per C-ABI call and write a table here")
     args = ap.parse_args()
+    CFG = CONFIGS[args.config]
+    if args.batch <= 0:
+        args.batch = CFG["batch"]
     if args.impl == "reference":
         return run_reference(args)
 
@@ -210,11 +345,13 @@ def main():
     lib.require_device()
     dev = torch.device("cuda", local)
     B, K, W = args.batch, args.steps, max(args.warmup, 0)
+    NC, IGNORE = CFG["nc"], CFG["ignore"]
 
     torch.manual_seed(0)
-    model = seg_b200.DeepLab(NUM_CLASSES, backbone=args.backbone, pretrained=False, output_stride=16).to(dev).train()
-    if world > 1:
-        model.bn_sync = comm.SyncBNGroup()
+    model = getattr(seg_b200, CFG["arch"])(NC, pretrained=False, **CFG["kw"]).to(dev).train()
+    if world > 1 and CFG["sync_bn"]:
+        model.use_sync_bn = True      # what the overlay's convert_model does for config["use_synch_bn"]
+        model._attach_sync_bn()
     x_cpu, y_cpu = synthetic_batch(B, 1234 + rank)
     x_pin, y_pin = x_cpu.pin_memory(), y_cpu.pin_memory()
     x_dev, y_dev = x_pin.to(dev), y_pin.to(dev)
@@ -231,17 +368,58 @@ def main():
             return float(t.item())
         return ms
 
-    # ------------------------------------------------------------ device-resident fused step  -> `value`
-    use_graph = bool(args.graph)  # the whole step (NCCL all-reduce and the SyncBN peer exchanges included) is one CUDA graph
-    stepper = FusedTrainStep(model, ignore_index=IGNORE, lr=0.01, backbone_lr_scale=0.1, momentum=0.9, weight_decay=1e-4, world=world,
-                             cuda_graph=use_graph)
-    for _ in range(W):
-        stepper.step(x_dev, y_dev)
+    crit_cls = seg_b200.CrossEntropyLoss2d if CFG["loss"] == "CE" else getattr(seg_b200, CFG["loss"])
+    from seg_b200.optim import SGD as FusedSGD
+
+    def plugin_objects():
+        """What train.py / BaseTrainer build: loss from the registry, SGD with differential learning rates."""
+        crit = crit_cls(ignore_index=IGNORE)
+        opt_cls = FusedSGD if args.plugin_optim == "fused" else torch.optim.SGD
+        opt = opt_cls([{"params": list(model.get_decoder_params())}, {"params": list(model.get_backbone_params()), "lr": 0.001}],
+                      lr=0.01, momentum=0.9, weight_decay=1e-4)
+        return crit, opt
+
+    def plugin_loss(crit, out, yd):
+        if isinstance(out, tuple):  # trainer.py:57-62: PSP* returns (out, aux)
+            return crit(out[0], yd) + 0.4 * crit(out[1], yd)
+        return crit(out, yd)
+
+    # ------------------------------------------------------------ device-resident step  -> `value`
+    # CE configs: the fused train step (fused upsample+CE, multi-tensor SGD, the whole step one CUDA graph).  Lovasz (C5): the
+    # plugin-surface step (model(x) -> LovaszSoftmax -> backward -> SGD) on device-resident inputs.
+    use_graph = bool(args.graph)
+    fused = CFG["loss"] == "CE"
+    if fused:
+        stepper = FusedTrainStep(model, ignore_index=IGNORE, lr=0.01, backbone_lr_scale=0.1, momentum=0.9, weight_decay=1e-4, world=world,
+                                 cuda_graph=use_graph)
+        dev_step = lambda: stepper.step(x_dev, y_dev)
+        eager_step = lambda: stepper._step_impl(x_dev, y_dev)
+    else:
+        stepper = None
+        crit_v, opt_v = plugin_objects()
+        if use_graph:
+            model.cuda_graphs(True, warmup=2)
+
+        def dev_step():
+            opt_v.zero_grad(set_to_none=True)
+            l = plugin_loss(crit_v, model(x_dev), y_dev)
+            l.backward()
+            opt_v.step()
+            return l
+        eager_step = dev_step
+    for _ in range(max(W, 4 if not fused else 0)):
+        dev_step()
     barrier()
     # kernel launches of ONE step (counted on an eager step; a graph replay issues the same kernels)
+    if not fused and use_graph:
+        model.cuda_graphs(False)
     lib.reset_launch_count()
-    stepper._step_impl(x_dev, y_dev)
+    eager_step()
     launches_per_step = lib.launch_count()
+    if not fused and use_graph:
+        model.cuda_graphs(True, warmup=0)
+        for _ in range(2):
+            dev_step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -250,16 +428,18 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
-        loss = stepper.step(x_dev, y_dev)
+        loss = dev_step()
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = launches_per_step * K
     prof, ops.PROFILE = ops.PROFILE, None
     if prof is None:  # graph replay: measure the conv launches on two extra eager steps (same kernels, same shapes)
+        if not fused:
+            model.cuda_graphs(False)
         ops.PROFILE = []
         for _ in range(2):
-            stepper._step_impl(x_dev, y_dev)
+            eager_step()
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         conv_steps = 2
@@ -282,33 +462,33 @@ def main():
     peak_tf, peak_hbm, peak_src = measured_peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic_r01.json")
-    if os.path.exists(tpath):  # dram__bytes_read+write per conv launch from the committed ncu launch list of this workload
-        with open(tpath) as f:
-            tj = json.load(f)
-        traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/roofline_traffic_r01.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over %d conv launches)" % tj.get("launches", 0)
+    for tname in ("roofline_traffic_r02.json", "roofline_traffic_r01.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if args.config == "C3" and os.path.exists(tpath):  # dram bytes per conv launch from the committed ncu launch list of this workload
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), f"profiles/{tname} (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over %d conv launches)" % tj.get("launches", 0)
+            break
     roofline = {
-        "bound": "tensor", "kernel": "conv_gemm_tc<BN,KIND> (tcgen05 implicit GEMM; fprop+dgrad+wgrad launches)",
+        "bound": "tensor", "kernel": "conv_gemm_tc<BN,KIND> / conv_gemm_tc2 (tcgen05 implicit GEMM; fprop+dgrad+wgrad launches)",
         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src,
         "traffic": traffic, "traffic_unit": "bytes/launch (DRAM)", "traffic_source": traffic_src,
         "algorithmic_bytes_per_launch": conv_bytes / max(len(prof), 1), "algorithmic_flops_per_launch": conv_flops / max(len(prof), 1),
         "launches": len(prof), "conv_share_of_step": (conv_ms / conv_steps) / (ms_total / K) if ms_total else None,
         "timed_on": "the timed steps" if not use_graph else "2 eager steps after the graph-replayed timed region (identical kernels)",
         "by_kind_tflops": {k: (v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0) for k, v in by_kind.items()},
-        "whole_step_frac_of_peak": value / world * TRAIN_GFLOP_PER_IMG / 1e3 / peak_tf,
+        "whole_step_frac_of_peak": value / world * CFG["gflop"] / 1e3 / peak_tf,
     }
 
     # ------------------------------------------------------------ plugin surface with host buffers -> `e2e`
+    # The repo's public API, nothing bench-local: model(x) -> loss -> backward -> optimizer.step().  At N > 1 the gradient
+    # all-reduce, the global-mean loss and the SyncBN exchange all happen INSIDE those calls (seg_b200/nets.py, losses.py).
     e2e = None
     if not args.no_e2e:
-        crit = seg_b200.CrossEntropyLoss2d(ignore_index=IGNORE)
-        # seg_b200.optim.SGD IS a torch.optim.SGD (param_groups / state_dict / schedulers unchanged) whose step() is one
-        # multi-tensor kernel per group; the launcher installs it as torch.optim.SGD for the unmodified train.py
-        from seg_b200.optim import SGD as FusedSGD
-        opt_cls = FusedSGD if args.plugin_optim == "fused" else torch.optim.SGD
-        opt = opt_cls([{"params": list(model.get_decoder_params())}, {"params": list(model.get_backbone_params()), "lr": 0.001}],
-                      lr=0.01, momentum=0.9, weight_decay=1e-4)
-        ddp_bufs = [p for p in model.parameters()]
+        if fused:
+            crit, opt = plugin_objects()
+        else:
+            crit, opt = crit_v, opt_v
 
         # the reference's DataPrefetcher (base/base_dataloader.py:49-85) copies the NEXT batch on a side stream while the
         # current step computes; same here: every step's batch still crosses PCIe once, inside the timed region
@@ -333,23 +513,14 @@ def main():
             torch.cuda.current_stream().wait_event(ev)
             prefetch(cur ^ 1)  # next step's batch, overlapped with this step's kernels
             opt.zero_grad(set_to_none=True)
-            out = model(xd)
-            l = crit(out, yd)
+            l = plugin_loss(crit, model(xd), yd)
             l.backward()
-            if world > 1:
-                flat = torch.cat([p.grad.reshape(-1) for p in ddp_bufs])
-                dist.all_reduce(flat)
-                flat.div_(world)
-                off = 0
-                for p in ddp_bufs:
-                    p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                    off += p.numel()
             opt.step()
             return l.item()  # device -> host read of the step's result (trainer.py:72)
 
         # graph replay of the plugin path: model(x) and loss.backward() replay captured forward / backward tapes (two
         # eager calls warm up, the third captures).  If the capture fails the leg is measured eagerly and says so.
-        plugin_graph, plugin_graph_err = (world == 1) if args.plugin_graph < 0 else bool(args.plugin_graph), None
+        plugin_graph, plugin_graph_err = bool(args.plugin_graph), None
         if plugin_graph:
             model.cuda_graphs(True, warmup=2)
             try:
@@ -362,6 +533,7 @@ def main():
                 state["i"] = 0
                 prefetch(0)
         if not plugin_graph:
+            model.cuda_graphs(False)
             for _ in range(min(W, 2)):
                 plugin_step()
         barrier()
@@ -375,13 +547,14 @@ def main():
         ms_e2e = max_over_ranks(t0.elapsed_time(t1))
         e2e = {"value": world * B * Ke / (ms_e2e * 1e-3), "unit": "images/sec",
                "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 8), "d2h_bytes_per_step": 4,
-               "api": "seg_b200.DeepLab.forward -> seg_b200.CrossEntropyLoss2d -> backward -> " + ("seg_b200.optim.SGD" if args.plugin_optim == "fused" else "torch.optim.SGD") + ".step (train.py plugin surface); batch prefetched on a side stream like the reference's DataPrefetcher",
+               "api": f"seg_b200.{CFG['arch']}.forward -> seg_b200.{crit_cls.__name__} -> backward -> " + ("seg_b200.optim.SGD" if args.plugin_optim == "fused" else "torch.optim.SGD") +
+                      ".step (train.py plugin surface; at N > 1 gradient all-reduce, global-mean loss and SyncBN exchange happen inside these calls); batch prefetched on a side stream like the reference's DataPrefetcher",
                "optimizer": args.plugin_optim,
                "ms_per_step": ms_e2e / Ke, "cuda_graph": plugin_graph, "cuda_graph_error": plugin_graph_err}
         if world > 1:
             model.release_graphs()
 
-    if args.trace and rank == 0:
+    if args.trace and rank == 0 and fused:
         lib.TRACE = []
         for _ in range(2):
             stepper._step_impl(x_dev, y_dev)  # eager: every C-ABI call is timed with its own event pair
@@ -407,36 +580,44 @@ def main():
                 tf = v[2] / (v[0] * 1e-3) / 1e12 if v[0] > 0 and v[2] > 0 else 0.0
                 f.write(f"{name:22s} {str(meta):48s} {v[0]:8.3f} {v[1]:4d} {tf:8.1f}\n")
 
+    # ------------------------------------------------------------ baselines: the reference's algorithm on this box
+    if stepper is not None and world > 1:
+        stepper.release_graph()  # a live graph holding NCCL kernels blocks the communicator's destruction
+    del stepper
+    model.release_graphs()
+    del model
+    torch.cuda.empty_cache()
+    barrier()
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = host_threads()
-        t = cpu_port_step_time(args.cpu_batch, 2, 1, threads)
-        cpu_baseline = {"value": args.cpu_batch / t, "unit": "images/sec", "cores": threads, "kind": "port",
-                        "sample": f"2 timed steps (after 1 warm-up) of batch {args.cpu_batch} of the same 513x513 train step, fp32 oracle port, {threads} threads"}
-        if not args.no_gpu_aten:
-            try:  # same leg, same port, on the GPU through ATen/cuDNN: what the reference itself would run on this B200
-                del stepper, model
-                torch.cuda.empty_cache()
-                tg = gpu_aten_step_time(B, 5, 3, dev)
-                cpu_baseline["reference_gpu_path"] = {"value": B / tg, "unit": "images/sec", "ms_per_step": tg * 1e3, "batch": B,
-                                                      "how": "oracle port on cuda:0 = the reference's ATen/cuDNN fp32 NCHW path (cudnn.benchmark), 5 timed steps after 3 warm-up, CUDA events"}
+    if rank == 0:
+        cpu_baseline = {}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = host_threads()
+            t = cpu_port_step_time(args.cpu_batch, 5, 1, threads)
+            cpu_baseline = {"value": args.cpu_batch / t, "unit": "images/sec", "cores": threads, "kind": "port",
+                            "sample": f"5 timed steps (after 1 warm-up) of batch {args.cpu_batch} of the same train step, fp32 oracle port, {threads} threads"}
+        if not args.no_gpu_ref:
+            try:  # the reference's OWN GPU path on the same GPUs: the denominator of north_star's ">= 6x" 
+                tg, how = reference_gpu_step_time(B, args.gpu_ref_steps, 10, world)
+                cpu_baseline["reference_gpu_path"] = {"value": B * world / tg, "unit": "images/sec", "ms_per_step": tg * 1e3, "per_gpu_batch": B,
+                                                      "n_gpus": world, "timed_steps": args.gpu_ref_steps, "warmup": 10, "how": how,
+                                                      "engine_over_reference_gpu": {"value": value / (B * world / tg), "e2e": (e2e["value"] / (B * world / tg)) if e2e else None}}
             except Exception as e:  # informational only
-                cpu_baseline["reference_gpu_path"] = {"unavailable": repr(e)[:200]}
+                cpu_baseline["reference_gpu_path"] = {"unavailable": repr(e)[:300]}
+        if not cpu_baseline:
+            cpu_baseline = None
+    if world > 1:
+        dist.barrier()  # the other ranks idle while rank 0 drives nn.DataParallel over all the GPUs
 
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": metric_name(), "value": value, "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic",
-            "config": {"workload": f"DeepLabV3+/{args.backbone} 513x513 19cls train step (C3: CE, SGD m0.9 wd1e-4, lr .01/.001" + (", SyncBN" if world > 1 else "") + ")",
-                       "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2": "per-step working set (activations ~GBs) far exceeds the 126 MB L2; no explicit flush needed",
-                       "dropout": "on (p=0.5 ASPP, p=0.1 decoder)", "cuda_graph": use_graph, "last_loss": last_loss},
+            "data": "synthetic", "config": config_dict(args, world, use_graph, last_loss),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }))
     sys.stdout.flush()
     if world > 1:
-        stepper.release_graph()  # a live graph holding NCCL kernels blocks the communicator's destruction
         dist.barrier()
         dist.destroy_process_group()
 

@@ -119,6 +119,7 @@ class Tape:
         self.training = training                                  # module.training semantics (batch stats, dropout)
         self.record = training if record is None else record      # record backward closures
         self.back = []
+        self.back_params = {}  # index into self.back -> parameters whose gradient that closure writes (bucketed all-reduce)
         self.grads = grads if grads is not None else {}  # Parameter -> fp32 grad tensor (param layout)
         self.touched = set()  # parameters whose gradient this tape's backward wrote (pre-bound `grads` hide that)
         self.impl = impl
@@ -175,9 +176,18 @@ class Tape:
             value_fn(g, 0.0)
             self.grads[p] = g
 
-    def backward(self):
-        for fn in reversed(self.back):
-            fn()
+    def _push_back(self, fn, params=()):
+        if params:
+            self.back_params[len(self.back)] = tuple(p for p in params if p is not None)
+        self.back.append(fn)
+
+    def backward(self, after=None):
+        """Replay the recorded closures in reverse.  after(i): called when closure i (and everything recorded after it) has
+        run — the fused train step uses it to launch a gradient bucket's all-reduce as soon as the bucket is complete."""
+        for i in range(len(self.back) - 1, -1, -1):
+            self.back[i]()
+            if after is not None:
+                after(i)
         if self.owner is not None and self.arena_used:
             self.owner._arena_floats = self.arena_used
         self.back = []
@@ -251,7 +261,7 @@ class Tape:
                     gx, beta = x.grad_target()
                     ops.conv2d_dgrad(dy, wp, tuple(x.t.shape), R, S, stride, pad, dil, out=gx, beta=beta, impl=self.impl)
                 ya.grad = None
-            self.back.append(bwd)
+            self._push_back(bwd, (spec.m.weight, bias))
         return ya, stats
 
     def dwconv(self, x, spec, want_stats=False):
@@ -272,7 +282,7 @@ class Tape:
                     gx, beta = x.grad_target()
                     ops.dwconv_bwd_data(dy, w9, tuple(x.t.shape), spec.stride, spec.pad, spec.dil, out=gx, beta=beta)
                 ya.grad = None
-            self.back.append(bwd)
+            self._push_back(bwd, (spec.m.weight,))
         return ya, stats
 
     def relu(self, x):
@@ -374,7 +384,7 @@ class Tape:
                                      tickets=self.zalloc(2, a.device), sync=sync)
                 y.grad = dy
                 aa.grad = None
-            self.back.append(bwd)
+            self._push_back(bwd, (bn.weight, bn.bias))
         return aa
 
     # ------------------------------------------------------------------ pooling / resize / concat

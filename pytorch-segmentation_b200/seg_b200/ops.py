@@ -517,7 +517,7 @@ def eval_metrics_nchw(logits, target, num_class):
     return out
 
 
-def upsample_ce_fwd(logits_lo, target, align_corners, ignore_index, want_argmax=False):
+def upsample_ce_fwd(logits_lo, target, align_corners, ignore_index, want_argmax=False, reduce_fn=None):
     N, Hi, Wi, C = logits_lo.shape
     _, Ho, Wo = target.shape
     assert logits_lo.is_contiguous() and logits_lo.dtype == torch.float32 and target.is_contiguous()
@@ -525,6 +525,8 @@ def upsample_ce_fwd(logits_lo, target, align_corners, ignore_index, want_argmax=
     am = torch.empty((N, Ho, Wo), dtype=torch.int32, device=logits_lo.device) if want_argmax else None
     call("seg_upsample_ce_fwd", ptr(logits_lo), ptr(target), N, Hi, Wi, Ho, Wo, C, int(align_corners), int(ignore_index),
          ptr(accum), ptr(am))
+    if reduce_fn is not None:  # cross-rank sum of the fp64 (loss sum, valid-pixel count) pair: global-batch mean
+        reduce_fn(accum)
     loss = torch.empty((), dtype=torch.float32, device=logits_lo.device)
     call("seg_ce_finalize", ptr(accum), ptr(loss))
     return loss, accum, am

@@ -52,7 +52,23 @@ class WeightTables:
         self.pack_table = torch.from_numpy(pack.view(np.uint8).copy()).to(dev)
         self.unpack_n = len(unp)
         self.unpack_table = torch.from_numpy(np.array(unp, dtype=dt).view(np.uint8).copy()).to(dev) if unp else None
+        self._unp, self._unp_params, self._dt, self._dev = unp, [s.m.weight for s in specs if (want_g and s.m.weight.requires_grad)], dt, dev
         self.param_ptrs = [s.m.weight.data_ptr() for s in specs]
+
+    def unpack_subtables(self, bucket_of):
+        """One unpack table per gradient bucket (bucket_of: Parameter -> bucket id): list of (device table, n, total) so a
+        bucket's packed weight gradients can be unpacked — and its all-reduce launched — as soon as its last wgrad retired."""
+        groups = {}
+        for entry, p in zip(self._unp, self._unp_params):
+            groups.setdefault(bucket_of[p], []).append(entry)
+        out = {}
+        for b, entries in groups.items():
+            start, fixed = 0, []
+            for e in entries:
+                fixed.append(e[:8] + (start,))
+                start += e[2] * e[3] * e[4] * e[5]  # K*C*R*S elements of the OIHW gradient
+            out[b] = (torch.from_numpy(np.array(fixed, dtype=self._dt).view(np.uint8).copy()).to(self._dev), len(fixed), start)
+        return out
 
     def stale(self):
         """True when a parameter was re-allocated (e.g. model.to(...), load_state_dict on a fresh module): the tables
@@ -72,7 +88,7 @@ class WeightTables:
 
 class FusedTrainStep:
     def __init__(self, model, ignore_index=255, lr=0.01, backbone_lr_scale=0.1, momentum=0.9, weight_decay=1e-4,
-                 aux_weight=0.4, world=1, cuda_graph=False):
+                 aux_weight=0.4, world=1, cuda_graph=False, bucket_mb=25.0):
         self.model = model
         self.ignore_index = ignore_index
         self._momentum, self.wd = float(momentum), float(weight_decay)
@@ -103,6 +119,26 @@ class FusedTrainStep:
         self.steps = 0
         self.wt = WeightTables(model, self.grad_views, dev)
         self.specs = self.wt.specs
+        # gradient buckets (world > 1): contiguous ranges of the flat gradient buffer of ~bucket_mb each, in parameter order;
+        # the backward produces them from the last to the first, and each bucket's all-reduce is launched on a side stream as
+        # soon as its last gradient is written — the exchange hides behind the rest of the backward
+        self.bucket_mb = float(bucket_mb)
+        self.buckets, self.bucket_of = [], {}
+        if world > 1 and bucket_mb > 0:
+            lo, acc = 0, 0
+            limit = int(self.bucket_mb * (1 << 20) / 4)
+            off = 0
+            for p in self.params:
+                self.bucket_of[p] = len(self.buckets)
+                off += p.numel()
+                acc += p.numel()
+                if acc >= limit:
+                    self.buckets.append((lo, off))
+                    lo, acc = off, 0
+            if acc > 0:
+                self.buckets.append((lo, off))
+            self.sub_unpack = self.wt.unpack_subtables(self.bucket_of)
+            self.side = torch.cuda.Stream()
         # CUDA graph of the whole step (forward, loss, backward, all-reduce, SGD): ~1 200 kernel launches per step are
         # replayed by the driver instead of being re-issued from Python.  Dropout seeds and SyncBN epochs come from a
         # device-side step counter, so every replay is a fresh step.
@@ -178,6 +214,44 @@ class FusedTrainStep:
         self.steps -= 1  # the capture pass itself executed nothing
         self._graph, self._static = g, (xs, ys, loss)
 
+    def _backward_bucketed(self, tape):
+        """tape.backward() with the gradient exchange overlapped: after the closure that completes a bucket, the bucket's
+        packed weight gradients are unpacked (one batched launch) and its slice of the flat buffer is all-reduced on the side
+        stream while the main stream carries on with the backward.  Captured as-is by the CUDA graph of the step."""
+        last = {}  # bucket -> smallest closure index writing into it (the backward runs indices downwards)
+        for i, ps in tape.back_params.items():
+            for p in ps:
+                b = self.bucket_of.get(p)
+                if b is not None and (b not in last or i < last[b]):
+                    last[b] = i
+        fire = {}
+        for b, i in last.items():
+            fire.setdefault(i, []).append(b)
+        cur = torch.cuda.current_stream()
+        done = set()
+
+        def launch(b):
+            done.add(b)
+            tab = self.sub_unpack.get(b)
+            if tab is not None:
+                lib.call("seg_unpack_wgrads_batched", tab[0].data_ptr(), tab[1], tab[2], 0.0)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            lo, hi = self.buckets[b]
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(ev)
+                dist.all_reduce(self.flat_grad[lo:hi])
+
+        def after(i):
+            for b in sorted(fire.get(i, ()), reverse=True):
+                launch(b)
+
+        tape.backward(after=after)
+        for b in range(len(self.buckets) - 1, -1, -1):  # buckets no closure wrote into (frozen parameters): zeros, still exchanged
+            if b not in done:
+                launch(b)
+        cur.wait_stream(self.side)
+
     def _step_impl(self, x, target):
         m = self.model
         self.flat_grad.zero_()
@@ -188,19 +262,27 @@ class FusedTrainStep:
         tape.packed_override, tape.dw_buffers = self.wt.packed_bufs, self.wt.dw_bufs
         heads = m._forward_heads(tape, x.contiguous().float())
         total = None
+        # mean over the valid pixels of the GLOBAL batch, as nn.DataParallel's gathered logits give the reference
+        # (trainer.py:60-66): the (loss sum, valid count) pair is all-reduced — 16 bytes — and the gradient is scaled by
+        # world because the exchanged gradients are averaged over ranks below
+        rf = (lambda acc: dist.all_reduce(acc)) if self.world > 1 else None
         for i, (lo, ac) in enumerate(heads):
             C = lo.t.shape[-1]
-            loss, accum, _ = ops.upsample_ce_fwd(lo.t, target, ac, self.ignore_index)
+            loss, accum, _ = ops.upsample_ce_fwd(lo.t, target, ac, self.ignore_index, reduce_fn=rf)
             w = 1.0 if i == 0 else self.aux_weight
-            g = None if w == 1.0 else torch.full((1,), w, dtype=torch.float32, device=lo.t.device)
+            wg = w * self.world
+            g = None if wg == 1.0 else torch.full((1,), wg, dtype=torch.float32, device=lo.t.device)
             dx, _ = ops.upsample_ce_bwd(lo.t, target, ac, self.ignore_index, accum, (C + 7) // 8 * 8, gscale=g)
             lo.grad = dx[..., :C]
             total = loss if total is None else total + w * loss
         m._finish(tape)
-        tape.backward()
-        self.wt.unpack()
-        if self.world > 1:
-            dist.all_reduce(self.flat_grad)
+        if self.world > 1 and self.buckets:
+            self._backward_bucketed(tape)
+        else:
+            tape.backward()
+            self.wt.unpack()
+            if self.world > 1:
+                dist.all_reduce(self.flat_grad)
         lib.call("seg_sgd_step_dev", self.p_ptrs.data_ptr(), self.g_ptrs.data_ptr(), self.m_ptrs.data_ptr(), self.sizes.data_ptr(),
                  self.lrs.data_ptr(), len(self.params), self.hyper.data_ptr(), 0, 1.0 / self.world)
         # (momentum buffers start at zero, so "first step: buf = d" of torch.optim.SGD is the general formula)

@@ -51,8 +51,20 @@ def run(M, C, res, iters):
     t_red = timeit(red, iters)
     t_bapply = timeit(lambda i: ops.bn_bwd_apply(dys[i % nbuf], outs[i % nbuf], xs[i % nbuf], save, gamma, sums, M, relu=True, dx=dxs[i % nbuf],
                                                  dres=rs[i % nbuf] if res else None, beta_res=0.0), iters)
+    zf = torch.zeros(32 * (iters + 16), device="cuda")
+    kf = [0]
+
+    def fused(i, remask=False):
+        ops.bn_bwd_fused(dys[i % nbuf], None if remask else outs[i % nbuf], xs[i % nbuf], save, gamma, M, relu=True, dx=dxs[i % nbuf],
+                         dres=rs[i % nbuf] if (res and not remask) else None, beta_res=0.0, beta=beta, tickets=zf[kf[0] * 32:kf[0] * 32 + 2])
+        kf[0] += 1
+    t_fused = timeit(fused, iters)
+    zf.zero_()
+    kf[0] = 0
+    t_fused_rm = timeit(lambda i: fused(i, True), iters)
     b = 2.0 * M * C
-    for name, t, passes in (("bn_apply_train", t_apply, 3 if res else 2), ("bn_bwd_reduce", t_red, 3), ("bn_bwd_apply", t_bapply, 5 if res else 4)):
+    for name, t, passes in (("bn_apply_train", t_apply, 3 if res else 2), ("bn_bwd_reduce", t_red, 3), ("bn_bwd_apply", t_bapply, 5 if res else 4),
+                            ("bn_bwd_fused", t_fused, 5 if res else 4), ("bn_bwd_fused(remask,nores)", t_fused_rm, 3)):
         print(f"{name:16s} M={M} C={C} res={res}: {t:7.2f} us  {b * passes / t / 1e6:6.2f} TB/s")
 
 
