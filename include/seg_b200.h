@@ -65,19 +65,16 @@ void seg_launch_count_reset(void);
 /* ---- convolution: replaces nn.Conv2d (models/deeplabv3_plus.py:21,256,268,306,312-319; torchvision
  *      Bottleneck conv1/2/3 + downsample.0 mutated at deeplabv3_plus.py:35-53; models/resnet.py:43-48,80-86) ---- */
 /* y[N,P,Q,K] = conv(x, w) (+bias[K]);  y = beta*y + result.  y_dtype in {bf16, fp32}.
- * stats (optional, fp32 [2*K], written): per-channel sum and sum of squares of the result as stored — the reduction half
- * of nn.BatchNorm2d, produced by the conv epilogue.  The cross-CTA sum is a fixed-order ticket tree (no atomics on the
- * data): the statistics are bit-reproducible from run to run.  It needs two workspaces sized by
- * seg_conv_stats_workspace: `stats_rows` (floats, uninitialised; may be shared by consecutive calls on one stream) and
- * `stats_tickets` (uint32, must be ZERO at launch; not shareable). */
-int seg_conv_stats_workspace(const seg_conv_desc* d, int64_t* rows_floats, int64_t* tickets);
+ * stats (optional): fp64 [2*K], ZERO at launch: per-channel sum and sum of squares of the result as stored — the reduction
+ * half of nn.BatchNorm2d, produced by the conv epilogue.  Every CTA adds its (fixed-order) fp32 column sums with one fp64
+ * atomic per channel: a sum of fp32 values in fp64 is exact while their exponents span < 2^17, so the order of the atomics
+ * cannot change the result — the statistics are bit-reproducible (round 1's fp32 atomics were not).
+ * sync (optional, with stats): SyncBN — the last CTA to finish also pushes the totals (as fp32) to every peer's symmetric
+ * buffer and raises the flags (csrc/seg_sync.cuh); sync_ticket = one zeroed uint32.  The consumer is
+ * seg_bn_apply_train(..., sync, ...). */
 int seg_conv2d_fwd(const seg_conv_desc* d, const void* x, const void* w_packed, void* y, int y_dtype,
-                   const float* bias, float beta, float* stats, float* stats_rows, void* stats_tickets,
-                   const seg_sync_desc* sync, int impl, void* stream);
-/* 1 if seg_conv2d_fwd(d, ..., sync, impl) runs the tcgen05 path, whose epilogue pushes the statistics to the SyncBN peers
- * (sync != NULL: the consumer, seg_bn_apply_train(..., sync, ...), then reads the world's sums itself); 0: CUDA-core path,
- * no push (pass sync = NULL and exchange `stats` with seg_syncbn_exchange) */
-int seg_conv_fwd_pushes(const seg_conv_desc* d, int impl);
+                   const float* bias, float beta, double* stats, const seg_sync_desc* sync, void* sync_ticket,
+                   int impl, void* stream);
 /* dx[N,H,W,C] = beta*dx + conv_transpose(dy, w)   (autograd of the above w.r.t. x) */
 int seg_conv2d_dgrad(const seg_conv_desc* d, const void* dy, const void* w_packed, void* dx, float beta,
                      int impl, void* stream);
@@ -88,10 +85,10 @@ int seg_conv2d_wgrad(const seg_conv_desc* d, const void* dy, const void* x, floa
 /* ---- depthwise 3x3 (atrous) convolution: SeparableConv2d.conv1 of the Aligned-Xception backbone
  *      (models/deeplabv3_plus.py:77-78, groups = C).  desc: K == C, R = S = 3.  Packed weights: fp32 [9][C]. ---- */
 int64_t seg_dwconv_scratch_floats(int C);
-/* y = dw(x); stats (optional, fp32 [2C], written) = per-channel sum / sum of squares of y (fixed-order cross-block sum);
- * scratch: seg_dwconv_scratch_floats(C) floats */
-int seg_dwconv3x3_fwd(const seg_conv_desc* d, const void* x, const float* w9, void* y, float* stats, float* scratch,
-                      void* stream);
+/* y = dw(x); stats (optional, fp64 [2C], zero at launch) += per-channel sum / sum of squares of y (exact fp64 accumulation);
+ * sync / sync_ticket: as seg_conv2d_fwd */
+int seg_dwconv3x3_fwd(const seg_conv_desc* d, const void* x, const float* w9, void* y, double* stats,
+                      const seg_sync_desc* sync, void* sync_ticket, void* stream);
 /* dx = beta*dx + dw^T(dy) */
 int seg_dwconv3x3_bwd_data(const seg_conv_desc* d, const void* dy, const float* w9, void* dx, float beta, void* stream);
 /* dw9 (fp32 [9][C]) = beta*dw9 + sum_pixels dy * x_shifted; scratch: seg_dwconv_scratch_floats(C) floats */
@@ -119,17 +116,15 @@ int seg_im2col(const seg_conv_desc* d, const void* x, int x_nchw_f32, void* col,
 
 /* ---- batch norm (nn.BatchNorm2d everywhere on the path; sync_batchnorm/batchnorm.py:128-145 for the multi-GPU
  *      variant): statistics, finalize, apply(+residual+ReLU+dropout), backward ---- */
-/* workspace of a deterministic column reduction (seg_bn_stats: nacc = 2, seg_bn_bwd_reduce: nacc = 2) over M rows x C
- * channels: `rows_floats` floats of uninitialised scratch (shareable between consecutive calls on one stream) and
- * `tickets` uint32 that must be ZERO at launch */
-int seg_reduce_workspace(int64_t M, int C, int nacc, int64_t* rows_floats, int64_t* tickets);
-/* stats[0:C] = sum_x, stats[C:2C] = sum_x^2 over M rows of x[M][ldx] (bf16); fixed-order cross-block sum */
-int seg_bn_stats(const void* x, int64_t M, int C, int ldx, float* stats, float* fold_rows, void* fold_tickets, void* stream);
+/* stats[0:C] += sum_x, stats[C:2C] += sum_x^2 over M rows of x[M][ldx] (bf16); stats fp64, zero at launch (exact, order-
+ * independent accumulation); sync / sync_ticket as seg_conv2d_fwd */
+int seg_bn_stats(const void* x, int64_t M, int C, int ldx, double* stats, const seg_sync_desc* sync, void* sync_ticket,
+                 void* stream);
 /* mean/var from (possibly all-reduced) sums over `count` elements; writes scale_shift[0:C]=gamma*inv_std,
  * [C:2C]=beta-mean*scale, save_mean_istd[0:C]=mean,[C:2C]=inv_std; updates running stats with momentum and the
  * unbiased variance.  clamp_eps=0: inv_std=(var+eps)^-1/2 (F.batch_norm); 1: clamp(var,eps)^-1/2
  * (sync_batchnorm/batchnorm.py:145). */
-int seg_bn_finalize(const float* stats, double count, int C, const float* gamma, const float* beta, float eps,
+int seg_bn_finalize(const double* stats, double count, int C, const float* gamma, const float* beta, float eps,
                     float momentum, int clamp_eps, float* running_mean, float* running_var, float* scale_shift,
                     float* save_mean_istd, void* stream);
 /* eval-mode (or frozen, BaseModel.freeze_bn): scale/shift from running stats; optionally also (mean, inv_std) */
@@ -143,11 +138,12 @@ int seg_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const 
 int seg_bn_apply(const void* x, int ldx, const float* scale_shift, const void* res, int ldr, void* out, int ldo,
                  int64_t M, int C, int relu, float drop_p, uint64_t seed, const uint64_t* step_ctr, int drop_hw,
                  void* stream);
-/* sync != NULL (SyncBN, the producer was seg_conv2d_fwd with the same handle): `stats` is ignored, the kernel waits for the
+/* stats: fp64 [2C] from seg_conv2d_fwd / seg_dwconv3x3_fwd / seg_bn_stats.
+ * sync != NULL (SyncBN, the producer was called with the same handle): `stats` is ignored, the kernel waits for the
  * world's flags and adds every rank's sums itself; `count` is then the WORLD's element count; sync_done = one zeroed uint32.
  * seg_bn_finalize + seg_bn_apply in ONE launch (training mode): coefficients are derived from the batch sums inside the
  * kernel; save[2C] = (mean, 1/std) for the backward pass and the running statistics are written by one block row. */
-int seg_bn_apply_train(const void* x, int ldx, const float* stats, double count, const float* gamma, const float* beta,
+int seg_bn_apply_train(const void* x, int ldx, const double* stats, double count, const float* gamma, const float* beta,
                        float eps, float momentum, int clamp_eps, float* running_mean, float* running_var, float* save,
                        const void* res, int ldr, void* out, int ldo, int64_t M, int C, int relu, float drop_p,
                        uint64_t seed, const uint64_t* step_ctr, int drop_hw, const seg_sync_desc* sync,
@@ -156,22 +152,24 @@ int seg_bn_apply_train(const void* x, int ldx, const float* stats, double count,
  * train step stays correct on every replay */
 int seg_counter_add(uint64_t* ctr, uint64_t inc, void* stream);
 /* backward, pass 1: sums[0:C] = sum(dz), sums[C:2C] = sum(dz*xhat), dz = dout * (out>0) * 1/(1-drop_p) if relu.  ONE
- * launch: every block writes its partial sums to its own workspace row, the last block of each ticket group adds the rows
- * in fixed order (bit-reproducible; workspace from seg_reduce_workspace(M, C, 2): fold_rows uninitialised, fold_tickets
- * zero).  If given, dbeta (=|+=) sums[0:C] and dgamma (=|+=) sums[C:2C] — the parameter gradients from the LOCAL sums.
+ * launch: every block adds its partial sums to `acc` (fp64 [2C], ZERO at launch; exact, order-independent accumulation); the
+ * last block (ticket: one zeroed uint32) rounds them into sums[] and, if given, dbeta (=|+=) sums[0:C] and dgamma (=|+=)
+ * sums[C:2C] — the parameter gradients from the LOCAL sums.  sync: SyncBN — that block also pushes the sums to every peer;
+ * the consumer is seg_bn_bwd_apply(..., sync, sync_done, ...).
  * out == NULL with relu (both backward passes): the ReLU mask is recomputed from x with the forward's own coefficients
  * (sc = gamma/std, sh = fma(-mean, sc, beta)) instead of being read from the stored activation — valid for
  * conv -> BN(batch statistics) -> ReLU with no residual and no dropout; needs gamma and beta. */
 int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx,
-                      const float* save_mean_istd, int64_t M, int C, int relu, float drop_p, float* sums,
-                      float* fold_rows, void* fold_tickets, float* dgamma, float* dbeta, int accumulate,
-                      const float* gamma, const float* beta, void* stream);
+                      const float* save_mean_istd, int64_t M, int C, int relu, float drop_p, float* sums, double* acc,
+                      void* ticket, float* dgamma, float* dbeta, int accumulate, const float* gamma, const float* beta,
+                      const seg_sync_desc* sync, void* stream);
 /* backward, pass 2: dx = gamma*istd*(dz - sums0/count - xhat*sums1/count); dres = beta_res*dres + dz (optional).
- * `sums` are the (possibly all-reduced) sums, `count` the matching element count. */
+ * `sums` are the sums over `count` elements; sync != NULL: `sums` is ignored, the kernel waits for the world's flags and adds
+ * every rank's sums itself (count = the world's); sync_done = one zeroed uint32. */
 int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx,
                      const float* save_mean_istd, const float* gamma, const float* sums, double count, int64_t M,
                      int C, int relu, float drop_p, void* dx, int lddx, void* dres, int lddres, float beta_res,
-                     const float* beta, void* stream);
+                     const float* beta, const seg_sync_desc* sync, void* sync_done, void* stream);
 /* BatchNorm backward in ONE cooperative launch = seg_bn_bwd_reduce + (SyncBN exchange) + seg_bn_bwd_apply: partial sums per
  * block -> grid barrier -> the cross-block sum spread over all blocks in fixed order (bit-reproducible) -> grid barrier ->
  * dx / dres.  sums[2C] receives the LOCAL totals; dgamma / dbeta (optional) the parameter gradients from them.  count_total =

@@ -18,15 +18,14 @@ void set_error(const char* fmt, ...) {
 
 namespace tc {
 bool supported(const seg_conv_desc* d);
-void stats_workspace(const seg_conv_desc* d, int64_t* rows_floats, int64_t* tickets);
 int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int y_dtype, const float* bias, float beta,
-             float* stats, float* stat_rows, unsigned* stat_tickets, const SyncDesc* sync, cudaStream_t stream);
+             double* stats, unsigned* stat_ticket, const SyncDesc* sync, cudaStream_t stream);
 int conv_dgrad(const seg_conv_desc* d, const void* dy, const void* w, void* dx, float beta, cudaStream_t stream);
 int conv_wgrad(const seg_conv_desc* d, const void* dy, const void* x, float* dw, cudaStream_t stream);
 }  // namespace tc
 namespace simt {
 int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int y_dtype, const float* bias, float beta,
-             float* stats, float* stat_rows, unsigned* stat_tickets, cudaStream_t stream);
+             double* stats, unsigned* stat_ticket, const seg_sync_desc* sync, cudaStream_t stream);
 int conv_dgrad(const seg_conv_desc* d, const void* dy, const void* w, void* dx, float beta, cudaStream_t stream);
 int conv_wgrad(const seg_conv_desc* d, const void* dy, const void* x, float* dw, cudaStream_t stream);
 }  // namespace simt
@@ -71,37 +70,20 @@ int seg_device_ok(void) {
   return 0;
 }
 
-int seg_conv_stats_workspace(const seg_conv_desc* d, int64_t* rows_floats, int64_t* tickets) {
-  if (check_desc(d)) return 1;
-  SEG_REQUIRE(rows_floats && tickets, "seg_conv_stats_workspace: null output");
-  int64_t r1 = 0, t1 = 0, r2 = 0, t2 = 0;
-  tc::stats_workspace(d, &r1, &t1);
-  if (d->K % 8 == 0 && seg_reduce_workspace((int64_t)d->N * d->P * d->Q, d->K, 2, &r2, &t2)) return 1;  // CUDA-core path
-  *rows_floats = r1 > r2 ? r1 : r2;
-  *tickets = t1 > t2 ? t1 : t2;
-  return 0;
-}
-
-int seg_conv_fwd_pushes(const seg_conv_desc* d, int impl) {
-  return (impl == SEG_IMPL_TC || (impl == SEG_IMPL_AUTO && tc::supported(d))) ? 1 : 0;
-}
-
 int seg_conv2d_fwd(const seg_conv_desc* d, const void* x, const void* w_packed, void* y, int y_dtype, const float* bias,
-                   float beta, float* stats, float* stats_rows, void* stats_tickets, const seg_sync_desc* sync, int impl,
-                   void* stream) {
+                   float beta, double* stats, const seg_sync_desc* sync, void* sync_ticket, int impl, void* stream) {
   if (check_desc(d)) return 1;
-  SEG_REQUIRE(!stats || (stats_rows && stats_tickets), "seg_conv2d_fwd: stats need the seg_conv_stats_workspace buffers");
+  SEG_REQUIRE(!sync || (stats && sync_ticket), "seg_conv2d_fwd: SyncBN needs stats and a zeroed ticket word");
   const bool tc_ok = tc::supported(d);
-  unsigned* tk = reinterpret_cast<unsigned*>(stats_tickets);
+  unsigned* tk = reinterpret_cast<unsigned*>(sync_ticket);
   if (impl == SEG_IMPL_TC || (impl == SEG_IMPL_AUTO && tc_ok)) {
     SyncDesc sd{nullptr, 0, 0, 0, 0};
     if (sync) {
       sd.peers = sync->peers; sd.rank = sync->rank; sd.world = sync->world; sd.n_max = sync->n_max; sd.timeout_clocks = sync->timeout_clocks;
     }
-    return tc::conv_fwd(d, x, w_packed, y, y_dtype, bias, beta, stats, stats_rows, tk, sync ? &sd : nullptr, ST(stream));
+    return tc::conv_fwd(d, x, w_packed, y, y_dtype, bias, beta, stats, tk, sync ? &sd : nullptr, ST(stream));
   }
-  SEG_REQUIRE(sync == nullptr, "seg_conv2d_fwd: the CUDA-core path does not push SyncBN statistics (see seg_conv_fwd_pushes)");
-  return simt::conv_fwd(d, x, w_packed, y, y_dtype, bias, beta, stats, stats_rows, tk, ST(stream));
+  return simt::conv_fwd(d, x, w_packed, y, y_dtype, bias, beta, stats, tk, sync, ST(stream));
 }
 
 int seg_conv2d_dgrad(const seg_conv_desc* d, const void* dy, const void* w_packed, void* dx, float beta, int impl,

@@ -5,7 +5,7 @@
 #include "seg_common.cuh"
 
 namespace seg {
-int bn_stats_launch(const void* x, int64_t M, int C, int ldx, float* stats, float* fold_rows, unsigned* fold_tickets,
+int bn_stats_launch(const void* x, int64_t M, int C, int ldx, double* stats, const seg_sync_desc* sync, unsigned* ticket,
                     cudaStream_t stream);  // seg_elementwise.cu
 namespace simt {
 
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) igemm_simt(const P p) {
 }
 
 int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int y_dtype, const float* bias, float beta,
-             float* stats, float* stat_rows, unsigned* stat_tickets, cudaStream_t stream) {
+             double* stats, unsigned* stat_ticket, const seg_sync_desc* sync, cudaStream_t stream) {
   SEG_REQUIRE(!stats || (y_dtype == SEG_DT_BF16 && d->K % 8 == 0 && d->ldy % 8 == 0),
               "CUDA-core conv: BatchNorm statistics need a bf16 output with K, ldy multiples of 8");
   P p;
@@ -189,7 +189,7 @@ int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int 
   igemm_simt<FWD><<<grid, 256, 0, stream>>>(p);
   if (check_launch("igemm_simt<FWD>")) return 1;
   // statistics of the output AS STORED, by the deterministic column reduction (same workspace contract as the tcgen05 path)
-  if (stats) return bn_stats_launch(y, p.M, d->K, d->ldy, stats, stat_rows, stat_tickets, stream);
+  if (stats) return bn_stats_launch(y, p.M, d->K, d->ldy, stats, sync, stat_ticket, stream);
   return 0;
 }
 

@@ -29,7 +29,6 @@
 #include <stdlib.h>
 #include "seg_common.cuh"
 #include "seg_ptx.cuh"
-#include "seg_fold.cuh"
 #include "seg_sync.cuh"
 
 namespace seg {
@@ -64,10 +63,10 @@ struct TcParams {
   int out_dtype;
   float beta;
   const float* bias;
-  float* stats;      // [2*Ncols] or null: per-channel sum / sum of squares of the output (BatchNorm batch statistics)
-  float* stat_rows;        // seg_fold.cuh workspace of the deterministic cross-CTA reduction (rows; uninitialised)
-  unsigned* stat_tickets;  //   "      (tickets; zero at launch; one extra word after the lanes' tickets counts finished lanes)
-  SyncDesc sync;           // world > 0: SyncBN — the statistics are also pushed to every peer (seg_sync.cuh)
+  double* stats;     // [2*Ncols] or null, ZERO at launch: per-channel sum / sum of squares of the output (BatchNorm batch
+                     // statistics), accumulated with fp64 atomics (see the epilogue)
+  unsigned* stat_ticket;   // SyncBN only: one zeroed word counting finished CTAs
+  SyncDesc sync;           // world > 0: SyncBN — the last CTA pushes the finished totals to every peer (seg_sync.cuh)
   // strided sub-grid output (stride>1 dgrad): row (n,i,j) -> pixel (n, i*osy+opy, j*osx+opx) of an out_H x out_W map
   int out_strided, out_H, out_W, osy, osx, opy, opx;
   // MM only
@@ -391,42 +390,29 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_tc(const __grid_constant__
           }
         }
       }
-      // -------- phase 3: BN statistics: this CTA's column sums -> its own row of the column block's fold lane; the last
-      //          CTA of the column block adds the rows in fixed order (seg_fold.cuh) and writes stats[] — no atomics on
-      //          the data, so the statistics are bit-reproducible --------
+      // -------- phase 3: BN statistics: this CTA's column sums (fixed order inside the CTA) are added to the layer's totals
+      //          with fp64 atomics.  Each contribution is an fp32 value, so the fp64 sum of the <= few thousand partials of a
+      //          channel is EXACT (no rounding at all) whenever their exponents span less than 2^17 — then the order of the
+      //          atomics cannot matter and the statistics are bit-reproducible; round 1's fp32 atomics were not, and the
+      //          batch-2 image-pooling BatchNorm amplified that into 3-5 % logit differences between runs.  (Beyond that
+      //          span the order can move the fp64 sum by one fp64 ulp — invisible after the rounding to fp32 below.) --------
       if (p.stats) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int e = (warp - 2) * 32 + lane;
-        const FoldLane L = fold_lane(p.stat_rows, p.stat_tickets, blockIdx.y, gridDim.x, 2 * BN);
-        float* myrow = L.rows1 + (size_t)blockIdx.x * (2 * BN);
-        for (int c = e; c < BN; c += 128) {
+        for (int c = e; c < ncols_tile; c += 128) {
           float a = 0.f, b = 0.f;
-          if (c < ncols_tile) {
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              a += stat_sm[(w * 2 + 0) * BN + c];
-              b += stat_sm[(w * 2 + 1) * BN + c];
-            }
+          for (int w = 0; w < 4; ++w) {
+            a += stat_sm[(w * 2 + 0) * BN + c];
+            b += stat_sm[(w * 2 + 1) * BN + c];
           }
-          myrow[c] = a;
-          myrow[BN + c] = b;
+          atomicAdd(p.stats + n0 + c, (double)a);
+          atomicAdd(p.stats + p.Ncols + n0 + c, (double)b);
         }
-        volatile int* flag = reinterpret_cast<volatile int*>(smem_gen + C::STAGES * C::STAGE_BYTES + 128);
-        auto bar = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
-        const uint32_t epoch = p.sync.world > 0 ? sync_epoch(p.sync) : 0u;
-        const bool lane_done = fold_arrive(L, blockIdx.x, e, 128, bar, flag, [&](int c, float v) {
-          const int which = c / BN, col = c - which * BN;
-          if (col < ncols_tile) {
-            p.stats[(size_t)which * p.Ncols + n0 + col] = v;
-            if (p.sync.world > 0) sync_push_value(p.sync, epoch, which * p.Ncols + n0 + col, v);
-          }
-        });
-        if (lane_done && p.sync.world > 0) {  // the block finishing the layer's LAST column block raises the flags
-          __threadfence_system();
-          bar();
-          if (e == 0) *flag = (atomicAdd(p.stat_tickets + (size_t)gridDim.y * fold_lane_tickets(gridDim.x), 1u) == gridDim.y - 1u);
-          bar();
-          if (*flag) sync_publish(p.sync, epoch, e, bar);
+        if (p.sync.world > 0) {
+          volatile int* flag = reinterpret_cast<volatile int*>(smem_gen + C::STAGES * C::STAGE_BYTES + 128);
+          sync_push_when_last(p.sync, p.stats, 2 * p.Ncols, p.stat_ticket, gridDim.x * gridDim.y, e, 128,
+                              [] { asm volatile("bar.sync 1, 128;" ::: "memory"); }, flag);
         }
       }
     }
@@ -593,20 +579,8 @@ bool supported(const seg_conv_desc* d) {
 
 static bool is_pointwise(const seg_conv_desc* d) { return d->R == 1 && d->S == 1 && d->stride == 1 && d->pad == 0; }
 
-// Upper bound of the statistics-reduction workspace of conv_fwd for this shape (either schedule, any tile width): one
-// fold lane per column block, one row per contributing CTA (seg_fold.cuh).
-void stats_workspace(const seg_conv_desc* d, int64_t* rows_floats, int64_t* tickets) {
-  const int64_t M = (int64_t)d->N * d->P * d->Q;
-  const int64_t m_tiles = ceil_div64(M, BM);
-  const int rows = (int)(m_tiles > num_sms() ? m_tiles : num_sms());
-  // lanes x width: ceil(K/64) lanes of 128 floats, or ceil(K/128) of 256, or ceil(K/256) of 512 — all <= 2 * roundup(K, 256)
-  const int64_t lane_floats_total = 2 * (int64_t)ceil_div(d->K, 256) * 256;
-  *rows_floats = (int64_t)(rows + fold_groups(rows)) * lane_floats_total;
-  *tickets = (int64_t)ceil_div(d->K, 64) * fold_lane_tickets(rows) + 1;  // + the finished-lanes counter (SyncBN publish)
-}
-
 int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int y_dtype, const float* bias, float beta,
-             float* stats, float* stat_rows, unsigned* stat_tickets, const SyncDesc* sync, cudaStream_t stream) {
+             double* stats, unsigned* stat_ticket, const SyncDesc* sync, cudaStream_t stream) {
   SEG_REQUIRE(supported(d), "tcgen05 conv fwd: unsupported shape (C=%d ldx=%d R=%d pad=%d dil=%d)", d->C, d->ldx, d->R,
               d->pad, d->dil);
   TcParams p;
@@ -633,10 +607,9 @@ int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int 
   p.beta = beta;
   p.bias = bias;
   p.stats = stats;
-  p.stat_rows = stat_rows;
-  p.stat_tickets = stat_tickets;
-  SEG_REQUIRE(!stats || (stat_rows && stat_tickets), "conv fwd: statistics need the reduction workspace");
+  p.stat_ticket = stat_ticket;
   if (sync && stats) {
+    SEG_REQUIRE(stat_ticket != nullptr, "conv fwd: SyncBN needs a zeroed ticket word");
     SEG_REQUIRE(2 * d->K <= sync->n_max, "conv fwd: 2*K = %d statistics exceed the SyncBN buffer (%d floats)", 2 * d->K, sync->n_max);
     p.sync = *sync;
   }

@@ -196,38 +196,24 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_cons
     int i = 0;
     float v[32];
     // BN statistics: the host sizes the grid as a multiple of the number of column blocks, so this CTA stays on column
-    // block blockIdx.x % n_tiles for all of its tiles and its shared-memory accumulators are written out ONCE, at the end,
-    // as row blockIdx.x / n_tiles of that column block's fold lane (seg_fold.cuh: fixed-order cross-CTA sum, no atomics
-    // on the data -> bit-reproducible statistics)
+    // block blockIdx.x % n_tiles for all of its tiles and its shared-memory accumulators are flushed ONCE, at the end, with
+    // one fp64 atomic per channel (exact accumulation of fp32 partials: see conv_gemm_tc's epilogue — bit-reproducible)
     auto finish_stats = [&]() {
       // called by all 256 epilogue threads
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int my_n = blockIdx.x % n_tiles;
-      const FoldLane L = fold_lane(p.stat_rows, p.stat_tickets, my_n, gridDim.x / n_tiles, 2 * BN);
-      const int myrow = blockIdx.x / n_tiles;
       {
         const int c = etid & 127, which = etid >> 7;
+        const int col = my_n * BN + c;
         float val = 0.f;
 #pragma unroll
         for (int g = 0; g < 4; ++g) val += stat_sm[(g * 2 + which) * BN + c];
-        L.rows1[(size_t)myrow * (2 * BN) + which * BN + c] = val;
+        if (col < p.Ncols) atomicAdd(p.stats + (size_t)which * p.Ncols + col, (double)val);
       }
-      volatile int* flag = reinterpret_cast<volatile int*>(smem_gen + V2_STAGES * V2_STAGE_BYTES + V2_STAGING_BYTES + V2_STAT_BYTES + 128);
-      auto bar = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
-      const uint32_t epoch = p.sync.world > 0 ? sync_epoch(p.sync) : 0u;
-      const bool lane_done = fold_arrive(L, myrow, etid, 256, bar, flag, [&](int c, float v) {
-        const int which = c / BN, col = my_n * BN + (c - which * BN);
-        if (col < p.Ncols) {
-          p.stats[(size_t)which * p.Ncols + col] = v;
-          if (p.sync.world > 0) sync_push_value(p.sync, epoch, which * p.Ncols + col, v);  // SyncBN: to every peer
-        }
-      });
-      if (lane_done && p.sync.world > 0) {  // the block finishing the layer's LAST column block raises the flags
-        __threadfence_system();
-        bar();
-        if (etid == 0) *flag = (atomicAdd(p.stat_tickets + (size_t)n_tiles * fold_lane_tickets(gridDim.x / n_tiles), 1u) == (unsigned)n_tiles - 1u);
-        bar();
-        if (*flag) sync_publish(p.sync, epoch, etid, bar);
+      if (p.sync.world > 0) {  // SyncBN: the last CTA pushes the finished totals to every peer and raises the flags
+        volatile int* flag = reinterpret_cast<volatile int*>(smem_gen + V2_STAGES * V2_STAGE_BYTES + V2_STAGING_BYTES + V2_STAT_BYTES + 128);
+        sync_push_when_last(p.sync, p.stats, 2 * p.Ncols, p.stat_ticket, gridDim.x, etid, 256,
+                            [] { asm volatile("bar.sync 1, 256;" ::: "memory"); }, flag);
       }
     };
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {

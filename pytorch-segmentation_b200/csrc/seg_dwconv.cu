@@ -8,7 +8,7 @@
 //   bwd_weight: dw[9][C] += sum_pixels dy * x_shifted   (72 register accumulators per thread, slotted atomics)
 // Packed depthwise weights: fp32 [9][C] (tap-major).
 #include "seg_common.cuh"
-#include "seg_fold.cuh"
+#include "seg_sync.cuh"
 
 namespace seg {
 
@@ -36,50 +36,35 @@ __device__ __forceinline__ void load_taps(const float* __restrict__ w9, int C, i
   }
 }
 
-// block-level reduction of NACC x 8 per-thread sums over the row lanes; the block's sums become its row of the channel
-// slab's fold lane (seg_fold.cuh: fixed-order cross-block sum, bit-reproducible); the block that completes the tree writes
-// out[a][c] = beta*out[a][c] + total
+// block-level reduction of NACC x 8 per-thread sums over the row lanes (fixed order), then ONE fp64 atomic per channel into
+// acc[NACC][C] (zero at launch): exact accumulation of fp32 partials -> order-independent, bit-reproducible totals
 template <int NACC>
-__device__ __forceinline__ void dw_block_reduce(const DwMap& m, int C, float (*acc)[8], float* fold_rows, unsigned* fold_tickets,
-                                                float* __restrict__ out, float beta) {
+__device__ __forceinline__ void dw_block_reduce(const DwMap& m, int C, float (*acc)[8], double* __restrict__ acc_out) {
   __shared__ float red[256 * 8];
-  __shared__ int fold_flag;
   const int GB = min(C >> 3, 256);
   const int gl = threadIdx.x % GB;
-  const int W = GB * 8;
-  const FoldLane L = fold_lane(fold_rows, fold_tickets, blockIdx.y, gridDim.x, NACC * W);
-  float* myrow = L.rows1 + (size_t)blockIdx.x * (NACC * W);
   for (int a = 0; a < NACC; ++a) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = m.active ? acc[a][i] : 0.f;
     __syncthreads();
-    if (m.rl == 0) {
+    if (m.rl == 0 && m.g < (C >> 3)) {
       float s[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) s[i] = 0.f;
-      if (m.g < (C >> 3)) {
-        for (int r = 0; r < m.rows_par; ++r)
+      for (int r = 0; r < m.rows_par; ++r)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) s[i] += red[(r * GB + gl) * 8 + i];
-      }
-      *reinterpret_cast<float4*>(myrow + a * W + gl * 8) = make_float4(s[0], s[1], s[2], s[3]);
-      *reinterpret_cast<float4*>(myrow + a * W + gl * 8 + 4) = make_float4(s[4], s[5], s[6], s[7]);
+        for (int i = 0; i < 8; ++i) s[i] += red[(r * GB + gl) * 8 + i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(acc_out + (size_t)a * C + m.g * 8 + i, (double)s[i]);
     }
   }
-  fold_arrive(L, blockIdx.x, threadIdx.x, 256, [] { __syncthreads(); }, &fold_flag, [&](int c, float v) {
-    const int a = c / W, ch = blockIdx.y * W + (c - a * W);
-    if (ch < C) {
-      float* o = out + (size_t)a * C + ch;
-      *o = (beta != 0.f) ? beta * *o + v : v;
-    }
-  });
 }
 
 __global__ void __launch_bounds__(256)
     dwconv_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ w9, __nv_bfloat16* __restrict__ y,
                       int ldy, int N, int H, int W, int C, int P, int Q, int stride, int pad, int dil,
-                      float* __restrict__ stats, float* fold_rows, unsigned* fold_tickets) {
+                      double* __restrict__ stats, const SyncDesc sync, unsigned* sync_ticket) {
   const DwMap m = dw_map(C);
   float w[9][8];
   float acc[2][8];
@@ -121,7 +106,13 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
-  if (stats) dw_block_reduce<2>(m, C, acc, fold_rows, fold_tickets, stats, 0.f);
+  if (stats) {
+    dw_block_reduce<2>(m, C, acc, stats);
+    if (sync.world > 0) {  // SyncBN: the last block pushes the finished totals to the peers
+      __shared__ int sm_flag;
+      sync_push_when_last(sync, stats, 2 * C, sync_ticket, gridDim.x * gridDim.y, (int)threadIdx.x, 256, [] { __syncthreads(); }, &sm_flag);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -174,7 +165,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     dwconv_bwd_weight_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ x, int ldx,
                              int N, int H, int W, int C, int P, int Q, int stride, int pad, int dil,
-                             float* fold_rows, unsigned* fold_tickets, float* __restrict__ dw9, float beta) {
+                             double* acc9 /*[9][C] fp64, zero at launch*/, unsigned* ticket, float* __restrict__ dw9, float beta) {
   const DwMap m = dw_map(C);
   float acc[9][8];
 #pragma unroll
@@ -207,7 +198,19 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
-  dw_block_reduce<9>(m, C, acc, fold_rows, fold_tickets, dw9, beta);
+  dw_block_reduce<9>(m, C, acc, acc9);
+  // the last block rounds the fp64 totals: dw9 = beta*dw9 + total
+  __shared__ int last_flag;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last_flag = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1u);
+  __syncthreads();
+  if (!last_flag) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+    const float v = (float)__ldcg(acc9 + i);
+    dw9[i] = (beta != 0.f) ? beta * dw9[i] + v : v;
+  }
 }
 
 // depthwise master weight [C][1][3][3] fp32 <-> packed [9][C] fp32
@@ -225,6 +228,7 @@ __global__ void dw_unpack_kernel(const float* __restrict__ g9, float* __restrict
   g[i] = (beta != 0.f) ? beta * g[i] + v : v;
 }
 
+constexpr int DW_WGRAD_BLOCKS_PER_SM = 4;  // every block ends with 72*C/8 fp64 atomics: fewer, fatter blocks
 static dim3 dw_grid(int64_t M, int C, int blocks_per_sm = 6) {
   const int G = C / 8;
   const int GB = G < 256 ? G : 256;
@@ -236,15 +240,6 @@ static dim3 dw_grid(int64_t M, int C, int blocks_per_sm = 6) {
   if (gx < 1) gx = 1;
   return dim3((unsigned)gx, (unsigned)gy, 1);
 }
-// reduction workspace of a dwconv launch: fold rows (floats), then the tickets, in ONE scratch buffer
-static int64_t dw_ws_rows(dim3 grid, int C, int nacc) {
-  const int G = C / 8;
-  const int GB = G < 256 ? G : 256;
-  return (int64_t)grid.y * fold_lane_floats((int)grid.x, nacc * GB * 8);
-}
-static int64_t dw_ws_tickets(dim3 grid) { return (int64_t)grid.y * fold_lane_tickets((int)grid.x); }
-constexpr int DW_WGRAD_BLOCKS_PER_SM = 2;  // every block writes a [9][C] row of partial sums: keep the rows few
-
 }  // namespace seg
 
 using namespace seg;
@@ -254,13 +249,8 @@ using namespace seg;
 
 extern "C" {
 
-// upper bound (any M) of the scratch a dwconv call needs: fold rows + tickets (seg_fold.cuh)
-int64_t seg_dwconv_scratch_floats(int C) {
-  const int64_t big = (int64_t)1 << 40;
-  const dim3 gf = dw_grid(big, C), gw = dw_grid(big, C, DW_WGRAD_BLOCKS_PER_SM);
-  const int64_t f = dw_ws_rows(gf, C, 2) + dw_ws_tickets(gf), w = dw_ws_rows(gw, C, 9) + dw_ws_tickets(gw);
-  return (f > w ? f : w) + 64;
-}
+// scratch of seg_dwconv3x3_bwd_weight: fp64 accumulators [9][C] + a ticket, as floats
+int64_t seg_dwconv_scratch_floats(int C) { return (int64_t)2 * 9 * C + 32; }
 
 static int dw_check(const seg_conv_desc* d) {
   SEG_REQUIRE(d && d->R == 3 && d->S == 3 && d->K == d->C, "dwconv: 3x3 depthwise (K == C) only");
@@ -270,21 +260,17 @@ static int dw_check(const seg_conv_desc* d) {
   return 0;
 }
 
-int seg_dwconv3x3_fwd(const seg_conv_desc* d, const void* x, const float* w9, void* y, float* stats, float* scratch,
-                      void* stream) {
+int seg_dwconv3x3_fwd(const seg_conv_desc* d, const void* x, const float* w9, void* y, double* stats,
+                      const seg_sync_desc* sync, void* sync_ticket, void* stream) {
   if (dw_check(d)) return 1;
-  SEG_REQUIRE(!stats || scratch, "dwconv fwd: stats need a scratch of seg_dwconv_scratch_floats(C) floats");
+  SEG_REQUIRE(!sync || (stats && sync_ticket && 2 * d->C <= sync->n_max), "dwconv fwd: SyncBN needs stats, a zeroed ticket and 2*C <= n_max");
   const int64_t M = (int64_t)d->N * d->P * d->Q;
-  const dim3 grid = dw_grid(M, d->C);
-  float* rows = scratch;
-  unsigned* tickets = nullptr;
-  if (stats) {
-    const int64_t nr = (dw_ws_rows(grid, d->C, 2) + 31) / 32 * 32;
-    tickets = reinterpret_cast<unsigned*>(scratch + nr);
-    cudaMemsetAsync(tickets, 0, (size_t)dw_ws_tickets(grid) * sizeof(unsigned), ST(stream));
+  SyncDesc sd{nullptr, 0, 0, 0, 0};
+  if (sync) {
+    sd.peers = sync->peers; sd.rank = sync->rank; sd.world = sync->world; sd.n_max = sync->n_max; sd.timeout_clocks = sync->timeout_clocks;
   }
-  dwconv_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(x), d->ldx, w9, BF(y), d->ldy, d->N, d->H, d->W, d->C, d->P, d->Q,
-                                                  d->stride, d->pad, d->dil, stats, rows, tickets);
+  dwconv_fwd_kernel<<<dw_grid(M, d->C), 256, 0, ST(stream)>>>(CBF(x), d->ldx, w9, BF(y), d->ldy, d->N, d->H, d->W, d->C, d->P, d->Q,
+                                                              d->stride, d->pad, d->dil, stats, sd, reinterpret_cast<unsigned*>(sync_ticket));
   return check_launch("dwconv_fwd");
 }
 
@@ -299,14 +285,15 @@ int seg_dwconv3x3_bwd_data(const seg_conv_desc* d, const void* dy, const float* 
 int seg_dwconv3x3_bwd_weight(const seg_conv_desc* d, const void* dy, const void* x, float* dw9, float beta, float* scratch,
                              void* stream) {
   if (dw_check(d)) return 1;
-  SEG_REQUIRE(scratch != nullptr, "dwconv bwd_weight: scratch of seg_dwconv_scratch_floats(C) floats required");
+  SEG_REQUIRE(scratch != nullptr && (reinterpret_cast<uintptr_t>(scratch) & 7) == 0,
+              "dwconv bwd_weight: 8-byte aligned scratch of seg_dwconv_scratch_floats(C) floats required");
   const int64_t M = (int64_t)d->N * d->P * d->Q;
-  const dim3 grid = dw_grid(M, d->C, DW_WGRAD_BLOCKS_PER_SM);
-  const int64_t nr = (dw_ws_rows(grid, d->C, 9) + 31) / 32 * 32;
-  unsigned* tickets = reinterpret_cast<unsigned*>(scratch + nr);
-  cudaMemsetAsync(tickets, 0, (size_t)dw_ws_tickets(grid) * sizeof(unsigned), ST(stream));
-  dwconv_bwd_weight_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(dy), d->ldy, CBF(x), d->ldx, d->N, d->H, d->W, d->C, d->P, d->Q,
-                                                         d->stride, d->pad, d->dil, scratch, tickets, dw9, beta);
+  const size_t acc_bytes = (size_t)9 * d->C * sizeof(double);
+  cudaMemsetAsync(scratch, 0, acc_bytes + 64, ST(stream));
+  double* acc9 = reinterpret_cast<double*>(scratch);
+  unsigned* ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(scratch) + acc_bytes);
+  dwconv_bwd_weight_kernel<<<dw_grid(M, d->C, DW_WGRAD_BLOCKS_PER_SM), 256, 0, ST(stream)>>>(
+      CBF(dy), d->ldy, CBF(x), d->ldx, d->N, d->H, d->W, d->C, d->P, d->Q, d->stride, d->pad, d->dil, acc9, ticket, dw9, beta);
   return check_launch("dwconv_bwd_weight");
 }
 

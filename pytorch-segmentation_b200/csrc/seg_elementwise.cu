@@ -4,7 +4,6 @@
 // 16-byte (8-channel) vectors per thread; reductions use warp shuffles + one atomic per block-column.
 // Reference call sites are cited next to each entry point in include/seg_b200.h.
 #include "seg_common.cuh"
-#include "seg_fold.cuh"
 #include "seg_sync.cuh"
 
 namespace seg {
@@ -154,11 +153,11 @@ __global__ void __launch_bounds__(256) im2col_kernel(seg_conv_desc d, const void
 
 // ------------------------------------------------------------------ BatchNorm
 // Column-reduction skeleton shared by bn_stats and bn_bwd_reduce: a 256-thread block owns GB = min(G,256) channel
-// groups (8 channels each) and 256/GB row lanes; rows are grid-strided.  The block's sums become ITS row of the channel
-// slab's fold lane (seg_fold.cuh): the cross-block sum is a fixed-order ticket tree, not atomics — bit-reproducible.
-// emit(a, channel, total) is called once per (accumulator, channel) by the block that completes the tree.
-template <int NACC, class F, class E>
-__device__ __forceinline__ void column_reduce(int64_t M, int C, float* fold_rows, unsigned* fold_tickets, F f, E emit) {
+// groups (8 channels each) and 256/GB row lanes; rows are grid-strided.  The block's sums (fixed order inside the block)
+// are added to acc[NACC][C] (fp64, ZERO at launch) with one fp64 atomic per channel: exact accumulation of fp32 partials,
+// hence order-independent and bit-reproducible (see conv_gemm_tc's statistics epilogue for the argument).
+template <int NACC, class F>
+__device__ __forceinline__ void column_reduce(int64_t M, int C, double* acc_out, F f) {
   const int G = C >> 3;
   const int GB = min(G, 256);
   const int rows_par = 256 / GB;
@@ -176,59 +175,62 @@ __device__ __forceinline__ void column_reduce(int64_t M, int C, float* fold_rows
       f(row, g, acc);
   }
   __shared__ float red[256 * 8];
-  __shared__ int fold_flag;
-  const int W = GB * 8;  // channels of this slab
-  const FoldLane L = fold_lane(fold_rows, fold_tickets, blockIdx.y, gridDim.x, NACC * W);
-  float* myrow = L.rows1 + (size_t)blockIdx.x * (NACC * W);
   for (int a = 0; a < NACC; ++a) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[a][i];
     __syncthreads();
-    if (rl == 0) {
+    if (rl == 0 && g < G) {
       float s[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) s[i] = 0.f;
-      if (g < G) {
-        for (int r = 0; r < rows_par; ++r)
+      for (int r = 0; r < rows_par; ++r)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) s[i] += red[(r * GB + gl) * 8 + i];
-      }
-      *reinterpret_cast<float4*>(myrow + a * W + gl * 8) = make_float4(s[0], s[1], s[2], s[3]);
-      *reinterpret_cast<float4*>(myrow + a * W + gl * 8 + 4) = make_float4(s[4], s[5], s[6], s[7]);
+        for (int i = 0; i < 8; ++i) s[i] += red[(r * GB + gl) * 8 + i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(acc_out + (size_t)a * C + g * 8 + i, (double)s[i]);
     }
   }
-  fold_arrive(L, blockIdx.x, threadIdx.x, 256, [] { __syncthreads(); }, &fold_flag, [&](int c, float v) {
-    const int a = c / W, ch = blockIdx.y * W + (c - a * W);
-    if (ch < C) emit(a, ch, v);
-  });
 }
 
+// `ticket` pattern shared by the reductions: true in every thread of the LAST of gridDim.x*gridDim.y blocks to arrive
+__device__ __forceinline__ bool last_block_arrived(unsigned* ticket) {
+  __shared__ int last_flag;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last_flag = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1u);
+  __syncthreads();
+  if (last_flag) __threadfence();
+  return last_flag != 0;
+}
+
+// stats[2C] fp64 (zero at launch) += (sum x, sum x^2); SyncBN: the last block pushes the totals to the peers
 __global__ void __launch_bounds__(256, 4) bn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t M, int C, int ldx,
-                                                       float* __restrict__ stats, float* fold_rows, unsigned* fold_tickets) {
-  column_reduce<2>(
-      M, C, fold_rows, fold_tickets,
-      [&](int64_t row, int g, float(*acc)[8]) {
-        const bf16x8 v = *reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8);
-        float f[8];
-        unpack8(v, f);
+                                                          double* __restrict__ stats, const SyncDesc sync, unsigned* ticket) {
+  column_reduce<2>(M, C, stats, [&](int64_t row, int g, float(*acc)[8]) {
+    const bf16x8 v = *reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8);
+    float f[8];
+    unpack8(v, f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc[0][i] += f[i];
-          acc[1][i] += f[i] * f[i];
-        }
-      },
-      [&](int a, int ch, float v) { stats[(size_t)a * C + ch] = v; });
+    for (int i = 0; i < 8; ++i) {
+      acc[0][i] += f[i];
+      acc[1][i] += f[i] * f[i];
+    }
+  });
+  if (sync.world > 0) {
+    __shared__ int sm_flag;
+    sync_push_when_last(sync, stats, 2 * C, ticket, gridDim.x * gridDim.y, (int)threadIdx.x, 256, [] { __syncthreads(); }, &sm_flag);
+  }
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, double count, int C, const float* __restrict__ gamma,
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, int C, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum, int clamp_eps,
                                    float* running_mean, float* running_var, float* __restrict__ scale_shift,
                                    float* __restrict__ save) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double mean = (double)stats[c] / count;
-  double var = (double)stats[C + c] / count - mean * mean;
+  const double mean = stats[c] / count;
+  double var = stats[C + c] / count - mean * mean;
   if (var < 0) var = 0;
   const double istd = clamp_eps ? 1.0 / sqrt(var < (double)eps ? (double)eps : var) : 1.0 / sqrt(var + (double)eps);
   if (running_mean) {
@@ -283,7 +285,7 @@ __device__ __forceinline__ void ld8(const float* p, float* v) {
 // its 8 channels from the batch sums; the threads of block row 0 also record (mean, 1/std) for the backward pass and
 // update the running statistics (nn.BatchNorm2d semantics: momentum, unbiased variance).
 struct BnTrain {
-  const float* stats;  // [2C] sum, sum of squares over `count` elements (null: use the precomputed scale_shift)
+  const double* stats;  // [2C] fp64 sum, sum of squares over `count` elements (null: use the precomputed scale_shift)
   double count;
   const float *gamma, *beta;
   float eps, momentum;
@@ -311,13 +313,23 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const __nv_bfloat16* _
   float sc[8], sh[8];
   if (rm.active) {
     if (tr.stats) {
-      float s1[8], s2[8], gm[8], bt[8];
+      double s1[8], s2[8];
+      float gm[8], bt[8];
       if (sync.world > 0) {
-        sync_total8(sync, epoch, rm.g * 8, s1);
-        sync_total8(sync, epoch, C + rm.g * 8, s2);
+        float t1[8], t2[8];
+        sync_total8(sync, epoch, rm.g * 8, t1);
+        sync_total8(sync, epoch, C + rm.g * 8, t2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] = t1[j];
+          s2[j] = t2[j];
+        }
       } else {
-        ld8(tr.stats + rm.g * 8, s1);
-        ld8(tr.stats + C + rm.g * 8, s2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] = __ldg(tr.stats + rm.g * 8 + j);
+          s2[j] = __ldg(tr.stats + C + rm.g * 8 + j);
+        }
       }
       ld8(tr.gamma + rm.g * 8, gm);
       ld8(tr.beta + rm.g * 8, bt);
@@ -325,8 +337,8 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const __nv_bfloat16* _
       const double inv_count = 1.0 / tr.count;  // one division; the per-channel math below is multiply-add + fp32 rsqrt
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const double mean = (double)s1[j] * inv_count;
-        double var = fma((double)s2[j], inv_count, -mean * mean);
+        const double mean = s1[j] * inv_count;
+        double var = fma(s2[j], inv_count, -mean * mean);
         if (var < 0) var = 0;
         const float vf = tr.clamp_eps ? fmaxf((float)var, tr.eps) : (float)(var + (double)tr.eps);
         float istd = rsqrtf(vf);
@@ -393,14 +405,13 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const __nv_bfloat16* _
   if (sync.world > 0) sync_consumer_done(sync, epoch, sync_done, gridDim.x * gridDim.y);
 }
 
-// (256, 4): the streaming loop needs ~64 registers; the cold fold epilogue must not halve the occupancy of the whole kernel
 template <bool REMASK>
 __global__ void __launch_bounds__(256, 4)
     bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ out, int ldo,
                          const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save, int64_t M, int C,
-                         int relu, float drop_p, float* fold_rows, unsigned* fold_tickets, float* final_sums,
+                         int relu, float drop_p, double* acc /*[2C] fp64, zero at launch*/, unsigned* ticket, float* final_sums,
                          float* dgamma, float* dbeta, int accumulate, const float* __restrict__ gamma,
-                         const float* __restrict__ beta) {
+                         const float* __restrict__ beta, const SyncDesc sync) {
   pdl_wait();
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const RowMap rm = row_map(C);
@@ -422,37 +433,41 @@ __global__ void __launch_bounds__(256, 4)
       }
     }
   }
-  // cross-block sum: fixed-order ticket tree (seg_fold.cuh); the block that completes it writes the sums and, if asked,
-  // the parameter gradients (dbeta = sum dz, dgamma = sum dz*xhat)
-  column_reduce<2>(
-      M, C, fold_rows, fold_tickets,
-      [&](int64_t row, int g, float(*acc)[8]) {
-        float dz[8], xv[8];
-        const bf16x8 dv = *reinterpret_cast<const bf16x8*>(dout + row * lddo + g * 8);
-        const bf16x8 xx = *reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8);
-        unpack8(dv, dz);
-        unpack8(xx, xv);
-        if constexpr (REMASK) {
+  column_reduce<2>(M, C, acc, [&](int64_t row, int g, float(*a)[8]) {
+    float dz[8], xv[8];
+    const bf16x8 dv = *reinterpret_cast<const bf16x8*>(dout + row * lddo + g * 8);
+    const bf16x8 xx = *reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8);
+    unpack8(dv, dz);
+    unpack8(xx, xv);
+    if constexpr (REMASK) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dz[i] = (fmaf(xv[i], sc[i], sh[i]) > 0.f) ? dz[i] : 0.f;
-        } else if (relu) {
-          float o[8];
-          unpack8(*reinterpret_cast<const bf16x8*>(out + row * ldo + g * 8), o);
+      for (int i = 0; i < 8; ++i) dz[i] = (fmaf(xv[i], sc[i], sh[i]) > 0.f) ? dz[i] : 0.f;
+    } else if (relu) {
+      float o[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(out + row * ldo + g * 8), o);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dz[i] = (o[i] > 0.f) ? dz[i] * keep_scale : 0.f;
-        }
+      for (int i = 0; i < 8; ++i) dz[i] = (o[i] > 0.f) ? dz[i] * keep_scale : 0.f;
+    }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc[0][i] += dz[i];
-          acc[1][i] += dz[i] * (xv[i] - mean[i]) * wi[i];
-        }
-      },
-      [&](int a, int ch, float v) {
-        final_sums[(size_t)a * C + ch] = v;
-        float* pg = a == 0 ? dbeta : dgamma;
-        if (pg) pg[ch] = accumulate ? pg[ch] + v : v;
-      });
+    for (int i = 0; i < 8; ++i) {
+      a[0][i] += dz[i];
+      a[1][i] += dz[i] * (xv[i] - mean[i]) * wi[i];
+    }
+  });
   pdl_trigger();
+  // the last block to finish rounds the fp64 totals to fp32, writes the parameter gradients (dbeta = sum dz, dgamma = sum
+  // dz*xhat) and, under SyncBN, pushes the totals to every peer (consumer: bn_bwd_apply with the same handle)
+  if (!last_block_arrived(ticket)) return;
+  const uint32_t epoch = sync.world > 0 ? sync_epoch(sync) : 0u;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    const float v = (float)__ldcg(acc + c);
+    final_sums[c] = v;
+    float* pg = c < C ? dbeta : dgamma;
+    const int ch = c < C ? c : c - C;
+    if (pg) pg[ch] = accumulate ? pg[ch] + v : v;
+    if (sync.world > 0) sync_push_value(sync, epoch, c, v);
+  }
+  if (sync.world > 0) sync_publish(sync, epoch, (int)threadIdx.x, [] { __syncthreads(); });
 }
 
 // dx = A*dz + B*x + Cc with A = gamma*istd, B = -gamma*istd^2*s1/count, Cc = -gamma*istd*s0/count + gamma*istd^2*mean*s1/count
@@ -462,21 +477,29 @@ __global__ void __launch_bounds__(256)
                         const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save,
                         const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count, int64_t M, int C,
                         int relu, float drop_p, __nv_bfloat16* __restrict__ dx, int lddx, __nv_bfloat16* dres, int lddres,
-                        float beta_res, const float* __restrict__ beta) {
+                        float beta_res, const float* __restrict__ beta, const SyncDesc sync, unsigned* sync_done) {
   pdl_wait();
   const RowMap rm = row_map(C);
-  if (!rm.active) return;
+  uint32_t epoch = 0u;
+  if (sync.world > 0) {  // SyncBN: bn_bwd_reduce pushed every rank's sums; wait for the world, add in rank order
+    epoch = sync_epoch(sync);
+    sync_wait_world(sync, epoch);
+  }
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const int co = rm.g * 8;
-  constexpr bool remask = REMASK;  // see bn_bwd_reduce_kernel
   float cA[8], cB[8], cC[8], sh[REMASK ? 8 : 1];
-  {
+  if (rm.active) {
     float mean[8], istd[8], gm[8], s0[8], s1[8];
     ld8(save + co, mean);
     ld8(save + C + co, istd);
     ld8(gamma + co, gm);
-    ld8(sums + co, s0);
-    ld8(sums + C + co, s1);
+    if (sync.world > 0) {
+      sync_total8(sync, epoch, co, s0);
+      sync_total8(sync, epoch, C + co, s1);
+    } else {
+      ld8(sums + co, s0);
+      ld8(sums + C + co, s1);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float a = gm[j] * istd[j];
@@ -492,7 +515,7 @@ __global__ void __launch_bounds__(256)
     }
   }
   const int64_t step = (int64_t)gridDim.x * rm.rows_par;
-  for (int64_t row = (int64_t)blockIdx.x * rm.rows_par + rm.rl; row < M; row += step) {
+  for (int64_t row = (int64_t)blockIdx.x * rm.rows_par + rm.rl; rm.active && row < M; row += step) {
     float dz[8], xv[8];
     const bf16x8 dv = *reinterpret_cast<const bf16x8*>(dout + row * lddo + co);
     const bf16x8 xx = *reinterpret_cast<const bf16x8*>(x + row * ldx + co);
@@ -525,6 +548,7 @@ __global__ void __launch_bounds__(256)
     *reinterpret_cast<bf16x8*>(dx + row * lddx + co) = pack8(o8);
   }
   pdl_trigger();
+  if (sync.world > 0) sync_consumer_done(sync, epoch, sync_done, gridDim.x * gridDim.y);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -534,7 +558,7 @@ __global__ void __launch_bounds__(256)
 //   barrier   all blocks are co-resident (the host sizes the grid from the occupancy of THIS kernel), so a grid-wide
 //             barrier is an atomic counter + spin
 //   phase 1b  the cross-block sum is spread over ALL blocks: block b adds its few columns over every row, in row order ->
-//             bit-reproducible totals, no serial fold tail (the ticket tree of seg_fold.cuh cost 30-70 us here at C >= 1024);
+//             bit-reproducible totals with no atomics at all;
 //             the same threads write dgamma / dbeta and, under SyncBN, push the totals to every peer (seg_sync.cuh)
 //   barrier   (+ SyncBN: block 0 raises this rank's flags, every block waits for the world's)
 //   phase 2   dx = A*dz + B*x + Cc (and the residual branch's gradient); the second read of dz / x hits L2 for the small maps
@@ -1341,39 +1365,29 @@ static dim3 colreduce_grid(int64_t M, int C) {
   return dim3((unsigned)gx, (unsigned)gy, 1);
 }
 
-// workspace of column_reduce for a given launch grid: per channel slab (grid.y) one fold lane of grid.x rows
-static void reduce_ws(dim3 grid, int C, int nacc, int64_t* rows_floats, int64_t* tickets) {
-  const int G = C / 8;
-  const int GB = G < 256 ? G : 256;
-  *rows_floats = (int64_t)grid.y * fold_lane_floats((int)grid.x, nacc * GB * 8);
-  *tickets = (int64_t)grid.y * fold_lane_tickets((int)grid.x);
+static SyncDesc to_sync(const seg_sync_desc* sync) {
+  SyncDesc sd{nullptr, 0, 0, 0, 0};
+  if (sync) {
+    sd.peers = sync->peers; sd.rank = sync->rank; sd.world = sync->world; sd.n_max = sync->n_max; sd.timeout_clocks = sync->timeout_clocks;
+  }
+  return sd;
 }
-static dim3 reduce2_grid(int64_t M, int C);
 }  // extern "C"
 namespace seg {
 // also used by the CUDA-core conv path (seg_conv_simt.cu) for its BatchNorm statistics
-int bn_stats_launch(const void* x, int64_t M, int C, int ldx, float* stats, float* fold_rows, unsigned* fold_tickets,
+int bn_stats_launch(const void* x, int64_t M, int C, int ldx, double* stats, const seg_sync_desc* sync, unsigned* ticket,
                     cudaStream_t stream) {
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0, "bn_stats: C/ldx must be multiples of 8 (C=%d ldx=%d)", C, ldx);
-  SEG_REQUIRE(fold_rows && fold_tickets, "bn_stats: reduction workspace (seg_reduce_workspace) required");
-  bn_stats_kernel<<<colreduce_grid(M, C), 256, 0, stream>>>(CBF(x), M, C, ldx, stats, fold_rows, fold_tickets);
+  SEG_REQUIRE(!sync || (ticket && 2 * C <= sync->n_max), "bn_stats: SyncBN needs a zeroed ticket and 2*C <= n_max");
+  bn_stats_kernel<<<colreduce_grid(M, C), 256, 0, stream>>>(CBF(x), M, C, ldx, stats, to_sync(sync), ticket);
   return check_launch("bn_stats");
 }
 }  // namespace seg
 extern "C" {
-int seg_reduce_workspace(int64_t M, int C, int nacc, int64_t* rows_floats, int64_t* tickets) {
-  SEG_REQUIRE(C % 8 == 0 && nacc >= 1 && rows_floats && tickets, "seg_reduce_workspace: bad arguments");
-  int64_t r1, t1, r2, t2;
-  reduce_ws(colreduce_grid(M, C), C, nacc, &r1, &t1);
-  reduce_ws(reduce2_grid(M, C), C, nacc, &r2, &t2);
-  *rows_floats = r1 > r2 ? r1 : r2;
-  *tickets = t1 > t2 ? t1 : t2;
-  return 0;
+int seg_bn_stats(const void* x, int64_t M, int C, int ldx, double* stats, const seg_sync_desc* sync, void* sync_ticket, void* stream) {
+  return bn_stats_launch(x, M, C, ldx, stats, sync, reinterpret_cast<unsigned*>(sync_ticket), ST(stream));
 }
-int seg_bn_stats(const void* x, int64_t M, int C, int ldx, float* stats, float* fold_rows, void* fold_tickets, void* stream) {
-  return bn_stats_launch(x, M, C, ldx, stats, fold_rows, reinterpret_cast<unsigned*>(fold_tickets), ST(stream));
-}
-int seg_bn_finalize(const float* stats, double count, int C, const float* gamma, const float* beta, float eps,
+int seg_bn_finalize(const double* stats, double count, int C, const float* gamma, const float* beta, float eps,
                     float momentum, int clamp_eps, float* running_mean, float* running_var, float* scale_shift,
                     float* save, void* stream) {
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(stats, count, C, gamma, beta, eps, momentum, clamp_eps,
@@ -1394,46 +1408,48 @@ int seg_bn_apply(const void* x, int ldx, const float* ss, const void* res, int l
              drop_p, seed, step_ctr, drop_hw, tr, SyncDesc{nullptr, 0, 0, 0, 0}, (unsigned*)nullptr);
   return check_launch("bn_apply");
 }
-int seg_bn_apply_train(const void* x, int ldx, const float* stats, double count, const float* gamma, const float* beta,
+int seg_bn_apply_train(const void* x, int ldx, const double* stats, double count, const float* gamma, const float* beta,
                        float eps, float momentum, int clamp_eps, float* running_mean, float* running_var, float* save,
                        const void* res, int ldr, void* out, int ldo, int64_t M, int C, int relu, float drop_p,
                        uint64_t seed, const uint64_t* step_ctr, int drop_hw, const seg_sync_desc* sync, void* sync_done,
                        void* stream) {
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldr % 8 == 0), "bn_apply_train: alignment");
   SEG_REQUIRE(stats && gamma && beta && save && count > 0, "bn_apply_train: stats, gamma, beta, save required");
-  SyncDesc sd{nullptr, 0, 0, 0, 0};
-  if (sync) {
-    SEG_REQUIRE(sync_done != nullptr && 2 * C <= sync->n_max, "bn_apply_train: SyncBN needs a zeroed ticket and 2*C <= n_max");
-    sd.peers = sync->peers; sd.rank = sync->rank; sd.world = sync->world; sd.n_max = sync->n_max; sd.timeout_clocks = sync->timeout_clocks;
-  }
+  SEG_REQUIRE(!sync || (sync_done != nullptr && 2 * C <= sync->n_max), "bn_apply_train: SyncBN needs a zeroed ticket and 2*C <= n_max");
+  const SyncDesc sd = to_sync(sync);
   BnTrain tr = {stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var, save};
   launch_pdl(bn_apply_kernel, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(x), ldx, (const float*)nullptr, CBF(res), ldr, BF(out),
              ldo, M, C, relu, drop_p, seed, step_ctr, drop_hw, tr, sd, reinterpret_cast<unsigned*>(sync_done));
   return check_launch("bn_apply_train");
 }
-// reductions end with a block fold + a ticket: fewer, fatter blocks (>= 32 rows per thread)
+// reductions end with a block fold + 2C atomics per block: fewer, fatter blocks (>= 32 rows per thread)
 static dim3 reduce2_grid(int64_t M, int C) { return rowmap_grid(M, C, 32); }
 
 int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,
-                      int64_t M, int C, int relu, float drop_p, float* sums, float* fold_rows, void* fold_tickets,
-                      float* dgamma, float* dbeta, int accumulate, const float* gamma, const float* beta, void* stream) {
+                      int64_t M, int C, int relu, float drop_p, float* sums, double* acc, void* ticket, float* dgamma,
+                      float* dbeta, int accumulate, const float* gamma, const float* beta, const seg_sync_desc* sync,
+                      void* stream) {
   SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && (!relu || !out || ldo % 8 == 0), "bn_bwd_reduce: alignment");
   SEG_REQUIRE(!(relu && !out) || (gamma && beta && drop_p == 0.f), "bn_bwd_reduce: out == NULL (mask recomputed from x) needs gamma, beta and no dropout");
-  SEG_REQUIRE(fold_rows && fold_tickets, "bn_bwd_reduce: reduction workspace (seg_reduce_workspace(M, C, 2)) required");
+  SEG_REQUIRE(acc && ticket, "bn_bwd_reduce: zeroed fp64 accumulator [2C] and ticket word required");
+  SEG_REQUIRE(!sync || 2 * C <= sync->n_max, "bn_bwd_reduce: 2*C exceeds the SyncBN buffer");
   const dim3 grid = reduce2_grid(M, C);
   launch_pdl((relu && !out) ? bn_bwd_reduce_kernel<true> : bn_bwd_reduce_kernel<false>, grid, dim3(256), 0, ST(stream), CBF(dout),
-             lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p, fold_rows, reinterpret_cast<unsigned*>(fold_tickets), sums,
-             dgamma, dbeta, accumulate, gamma, beta);
+             lddo, CBF(out), ldo, CBF(x), ldx, save, M, C, relu, drop_p, acc, reinterpret_cast<unsigned*>(ticket), sums, dgamma, dbeta,
+             accumulate, gamma, beta, to_sync(sync));
   return check_launch("bn_bwd_reduce");
 }
 int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,
                      const float* gamma, const float* sums, double count, int64_t M, int C, int relu, float drop_p,
-                     void* dx, int lddx, void* dres, int lddres, float beta_res, const float* beta, void* stream) {
+                     void* dx, int lddx, void* dres, int lddres, float beta_res, const float* beta, const seg_sync_desc* sync,
+                     void* sync_done, void* stream) {
   SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0, "bn_bwd_apply: alignment");
   SEG_REQUIRE(!(relu && !out) || (beta && drop_p == 0.f), "bn_bwd_apply: out == NULL (mask recomputed from x) needs beta and no dropout");
+  SEG_REQUIRE(!sync || (sync_done && 2 * C <= sync->n_max), "bn_bwd_apply: SyncBN needs a zeroed ticket and 2*C <= n_max");
   launch_pdl((relu && !out) ? bn_bwd_apply_kernel<true> : bn_bwd_apply_kernel<false>, rowmap_grid(M, C), dim3(256), 0, ST(stream),
              CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save,
-             gamma, sums, (float)(1.0 / count), M, C, relu, drop_p, BF(dx), lddx, BF(dres), lddres, beta_res, beta);
+             gamma, sums, (float)(1.0 / count), M, C, relu, drop_p, BF(dx), lddx, BF(dres), lddres, beta_res, beta, to_sync(sync),
+             reinterpret_cast<unsigned*>(sync_done));
   return check_launch("bn_bwd_apply");
 }
 }  // extern "C"

@@ -82,6 +82,23 @@ __device__ __forceinline__ void sync_publish(const SyncDesc& s, uint32_t epoch, 
   }
 }
 
+// producer epilogue for kernels that accumulate their per-channel totals with fp64 atomics into `acc` (n doubles): every
+// contributing block calls this with its `nthr` cooperating threads after issuing its atomics; the LAST of `nblocks` blocks to
+// arrive (ticket) reads the finished totals and pushes them (as fp32) to every peer, then raises the flags.
+template <class Sync>
+__device__ __forceinline__ void sync_push_when_last(const SyncDesc& s, const double* acc, int n, unsigned* ticket, unsigned nblocks,
+                                                    int tid, int nthr, Sync sync, volatile int* sm_flag) {
+  __threadfence();
+  sync();
+  if (tid == 0) *sm_flag = (atomicAdd(ticket, 1u) == nblocks - 1u);
+  sync();
+  if (!*sm_flag) return;
+  __threadfence();
+  const uint32_t epoch = sync_epoch(s);
+  for (int i = tid; i < n; i += nthr) sync_push_value(s, epoch, i, (float)__ldcg(acc + i));
+  sync_publish(s, epoch, tid, sync);
+}
+
 // consumer: all threads of the block call this; returns after every rank's flag shows `epoch`
 __device__ __forceinline__ void sync_wait_world(const SyncDesc& s, uint32_t epoch) {
   if ((int)threadIdx.x < s.world) {

@@ -18,6 +18,7 @@ from .lib import IMPL_AUTO
 
 BN_EPS = 1e-5
 BN_MOM = 0.1
+FUSED_BWD_MAX_BYTES = 40 << 20  # BN backward: one cooperative launch up to this activation size (bf16 bytes), two above
 ACT_DTYPE = torch.bfloat16  # storage type of activations / activation gradients (the kernels are bf16-only;
                             # tests/test_engine_cpu_emulated.py flips this to fp32 together with the ATen emulation)
 
@@ -164,6 +165,10 @@ class Tape:
         self.arena_used += n_al
         return v
 
+    def zalloc64(self, n, device):
+        """n zeroed fp64 words from the step's arena (the arena hands out 128-byte aligned float ranges)."""
+        return self.zalloc(2 * int(n), device).view(torch.float64)
+
     def _param_grad(self, p, value_fn):
         """Write (or accumulate into) the fp32 gradient of parameter p.  value_fn(out, beta) fills it."""
         if not p.requires_grad:
@@ -203,30 +208,24 @@ class Tape:
         if out_dtype is None:
             out_dtype = ACT_DTYPE
         want = want_stats and self.training
+        sync = tk = None
         if want:
-            stats = self.zalloc(2 * spec.K, wp.device)
-        push = None  # SyncBN: the conv epilogue pushes the statistics to the peers (no exchange launch)
+            stats = self.zalloc64(2 * spec.K, wp.device)  # fp64 accumulators: the conv epilogue adds its column sums
+            if self.sync_fused():  # SyncBN: the last CTA pushes the totals to the peers (no exchange launch)
+                sync, tk = self.sync, self.zalloc(1, wp.device)
         if spec.explicit:
             nchw = not isinstance(x, Act)
             src = x if nchw else x.t
             col = ops.im2col(src, spec.R, spec.S, spec.stride, spec.pad, spec.dil, spec.kpad, nchw_f32=nchw)
-            tk = self.zalloc(ops.conv_stats_workspace(*col.shape, spec.K, 1, 1)[1], wp.device) if want else None
-            if want and self.sync_fused() and ops.conv_fwd_pushes(col.shape, spec.K, 1, 1, 1, 0, 1, ops.ld(col), self.impl):
-                push = self.sync
-            y = ops.conv2d_fwd(col, wp, spec.K, 1, 1, out=out, out_dtype=out_dtype,
-                               bias=bias.detach() if bias is not None else None, stats=stats, impl=self.impl, tickets=tk, sync=push)
+            y = ops.conv2d_fwd(col, wp, spec.K, 1, 1, out=out, out_dtype=out_dtype, bias=bias.detach() if bias is not None else None,
+                               stats=stats, impl=self.impl, sync=sync, sync_ticket=tk)
             xin, geo = col, (1, 1, 1, 0, 1)
         else:
-            tk = self.zalloc(ops.conv_stats_workspace(*x.t.shape, spec.K, spec.R, spec.S, spec.stride, spec.pad, spec.dil)[1],
-                             wp.device) if want else None
-            if want and self.sync_fused() and ops.conv_fwd_pushes(x.t.shape, spec.K, spec.R, spec.S, spec.stride, spec.pad, spec.dil,
-                                                                  ops.ld(x.t), self.impl):
-                push = self.sync
             y = ops.conv2d_fwd(x.t, wp, spec.K, spec.R, spec.S, spec.stride, spec.pad, spec.dil, out=out, out_dtype=out_dtype,
-                               bias=bias.detach() if bias is not None else None, stats=stats, impl=self.impl, tickets=tk, sync=push)
+                               bias=bias.detach() if bias is not None else None, stats=stats, impl=self.impl, sync=sync, sync_ticket=tk)
             xin, geo = x.t, (spec.R, spec.S, spec.stride, spec.pad, spec.dil)
         ya = Act(y)
-        if push is not None:
+        if sync is not None:
             self._pushed.add(stats.data_ptr())
         if self.record:
             def bwd():
@@ -255,8 +254,8 @@ class Tape:
                 if bias is not None and bias.requires_grad:
                     cpad = ops.ld(dy)
                     wide = dy if dy.shape[-1] % 8 == 0 else dy.as_strided(dy.shape[:-1] + (cpad,), dy.stride(), dy.storage_offset())
-                    s = ops.bn_stats(wide)
-                    self._param_grad(bias, lambda g, beta: g.add_(s[: spec.K]) if beta else g.copy_(s[: spec.K]))
+                    s = ops.bn_stats(wide)[: spec.K].float()  # column sums of dY (fp64 accumulation)
+                    self._param_grad(bias, lambda g, beta: g.add_(s) if beta else g.copy_(s))
                 if (not spec.explicit) and isinstance(x, Act) and x.needs_grad:
                     gx, beta = x.grad_target()
                     ops.conv2d_dgrad(dy, wp, tuple(x.t.shape), R, S, stride, pad, dil, out=gx, beta=beta, impl=self.impl)
@@ -267,8 +266,12 @@ class Tape:
     def dwconv(self, x, spec, want_stats=False):
         """Depthwise 3x3 (SeparableConv2d.conv1).  Returns (raw output Act, BN statistics or None)."""
         w9 = spec.packed()
-        stats = self.zalloc(2 * spec.C, w9.device) if (want_stats and self.training) else None
-        y = ops.dwconv_fwd(x.t, w9, spec.stride, spec.pad, spec.dil, stats=stats)
+        stats = self.zalloc64(2 * spec.C, w9.device) if (want_stats and self.training) else None
+        sync = self.sync if (stats is not None and self.sync_fused()) else None
+        y = ops.dwconv_fwd(x.t, w9, spec.stride, spec.pad, spec.dil, stats=stats, sync=sync,
+                           sync_ticket=self.zalloc(1, w9.device) if sync is not None else None)
+        if sync is not None:
+            self._pushed.add(stats.data_ptr())
         ya = Act(y)
         if self.record:
             def bwd():
@@ -316,14 +319,17 @@ class Tape:
             seed = (self.seed * 1000003 + self._drop_ctr * 7919) & 0x7FFFFFFFFFFFFFFF  # + step counter on the device
         if use_batch_stats:
             if stats is None:
-                stats = ops.bn_stats(y.t)
+                sync0 = self.sync if self.sync_fused() else None
+                stats = ops.bn_stats(y.t, sync=sync0)
+                if sync0 is not None:
+                    self._pushed.add(stats.data_ptr())
             count = count_local
             in_kernel = None
             if self.sync_active():
                 if stats.data_ptr() in self._pushed:
                     in_kernel = self.sync      # bn_apply waits for the world's flags and adds every rank's sums itself
-                else:
-                    self.sync.allreduce_(stats)  # producer without the hook (depthwise conv, CUDA-core conv): stand-alone exchange
+                else:  # exchange object without the in-kernel protocol (the gloo stand-in of the CPU tests): sums over ranks
+                    self.sync.allreduce_(stats)
                 count = count_local * self.sync.world
             # finalize (coefficients, saved mean / 1/std, running statistics) happens inside the apply kernel
             a, save = ops.bn_apply_train(y.t, stats, count, bn.weight.detach(), bn.bias.detach(), bn.eps,
@@ -364,24 +370,32 @@ class Tape:
                 if res is not None and res.needs_grad:
                     dres, beta_res = res.grad_target()
                 sync = self.sync if (use_batch_stats and self.sync_active()) else None
+                dg = self.grads[bn.weight] if want_pg else None
+                db = self.grads[bn.bias] if want_pg else None
                 if sync is not None and not getattr(sync, "fused", False):
-                    # exchange object without the in-kernel protocol (e.g. the gloo stand-in of the CPU tests): two launches
-                    sums = ops.bn_bwd_reduce(da, a, y.t, save, relu=relu, drop_p=drop_p,
-                                             dgamma=self.grads[bn.weight] if want_pg else None,
-                                             dbeta=self.grads[bn.bias] if want_pg else None, accumulate=acc_pg,
-                                             tickets=self.zalloc(ops.reduce_workspace(count_local, C, 2)[1], a.device))
+                    # exchange object without the in-kernel protocol (the gloo stand-in of the CPU tests)
+                    sums = ops.bn_bwd_reduce(da, a, y.t, save, relu=relu, drop_p=drop_p, dgamma=dg, dbeta=db, accumulate=acc_pg,
+                                             acc=self.zalloc64(2 * C + 1, a.device))
                     gsums = sums.clone()
                     sync.allreduce_(gsums)
                     ops.bn_bwd_apply(da, a_mask, y.t, save, bn.weight.detach(), gsums, count, relu=relu, drop_p=drop_p, dx=dy,
                                      dres=dres, beta_res=beta_res, beta=bn.bias.detach())
+                elif count_local * C * 2 <= FUSED_BWD_MAX_BYTES:
+                    # small maps (the operands stay in L2 between the phases): reduce -> grid barrier -> fixed-order cross-block
+                    # sum (-> SyncBN exchange) -> apply in ONE cooperative launch.  Frozen BN (freeze_bn): dx = gamma*inv_std*dz,
+                    # the sums only feed the parameter gradients
+                    ops.bn_bwd_fused(da, a_mask, y.t, save, bn.weight.detach(), count, relu=relu, drop_p=drop_p, dgamma=dg, dbeta=db,
+                                     accumulate=acc_pg, dx=dy, dres=dres, beta_res=beta_res, beta=bn.bias.detach(),
+                                     zero_sums=not use_batch_stats, tickets=self.zalloc(2, a.device), sync=sync)
                 else:
-                    # reduce -> grid barrier -> fixed-order cross-block sum (-> SyncBN exchange) -> apply, ONE launch; frozen
-                    # BN (freeze_bn): dx = gamma * inv_std * dz, the sums only feed the parameter gradients
-                    ops.bn_bwd_fused(da, a_mask, y.t, save, bn.weight.detach(), count, relu=relu, drop_p=drop_p,
-                                     dgamma=self.grads[bn.weight] if want_pg else None,
-                                     dbeta=self.grads[bn.bias] if want_pg else None, accumulate=acc_pg, dx=dy, dres=dres,
-                                     beta_res=beta_res, beta=bn.bias.detach(), zero_sums=not use_batch_stats,
-                                     tickets=self.zalloc(2, a.device), sync=sync)
+                    # large maps stream from HBM in both passes anyway: two launches at full occupancy; under SyncBN the
+                    # reduction's last block pushes the sums and the apply pass waits for the world's
+                    sums = ops.bn_bwd_reduce(da, a, y.t, save, relu=relu, drop_p=drop_p, dgamma=dg, dbeta=db, accumulate=acc_pg,
+                                             acc=self.zalloc64(2 * C + 1, a.device), sync=sync)
+                    gsums = sums if use_batch_stats else torch.zeros_like(sums)
+                    ops.bn_bwd_apply(da, a_mask, y.t, save, bn.weight.detach(), gsums, count, relu=relu, drop_p=drop_p, dx=dy,
+                                     dres=dres, beta_res=beta_res, beta=bn.bias.detach(), sync=sync,
+                                     sync_done=self.zalloc(1, a.device) if sync is not None else None)
                 y.grad = dy
                 aa.grad = None
             self._push_back(bwd, (bn.weight, bn.bias))

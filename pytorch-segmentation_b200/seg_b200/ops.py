@@ -98,69 +98,38 @@ def conv_desc_for(x, K, R, S, stride, pad, dil, ldy=None):
 _WS_CACHE = {}
 
 
-def conv_stats_workspace(N, H, W, C, K, R, S, stride=1, pad=0, dil=1):
-    """(rows_floats, tickets) of the deterministic statistics reduction of conv2d_fwd for this shape (cached)."""
-    key = ("conv", N, H, W, C, K, R, S, stride, pad, dil)
-    v = _WS_CACHE.get(key)
-    if v is None:
-        d = make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil)
-        r, t = ctypes.c_int64(), ctypes.c_int64()
-        if lib.load().seg_conv_stats_workspace(ctypes.byref(d), ctypes.byref(r), ctypes.byref(t)) != 0:
-            raise RuntimeError(lib.last_error())
-        v = _WS_CACHE[key] = (int(r.value), int(t.value))
-    return v
+def new_stats(C, device):
+    """Zeroed fp64 [2C] accumulator for BatchNorm batch statistics (sum, sum of squares) — the producers ADD into it."""
+    return torch.zeros(2 * C, dtype=torch.float64, device=device)
 
 
-def reduce_workspace(M, C, nacc=2):
-    """(rows_floats, tickets) of a deterministic column reduction over M rows x C channels (cached)."""
-    key = ("red", int(M), int(C), int(nacc))
-    v = _WS_CACHE.get(key)
-    if v is None:
-        r, t = ctypes.c_int64(), ctypes.c_int64()
-        if lib.load().seg_reduce_workspace(int(M), int(C), int(nacc), ctypes.byref(r), ctypes.byref(t)) != 0:
-            raise RuntimeError(lib.last_error())
-        v = _WS_CACHE[key] = (int(r.value), int(t.value))
-    return v
-
-
-def _fold_ws(rows_floats, n_tickets, tickets, device):
-    """Workspace pair of a fixed-order cross-block reduction: uninitialised rows + ZERO tickets (from the caller's zeroed
-    arena when given)."""
-    rows = torch.empty(max(rows_floats, 1), dtype=torch.float32, device=device)
-    if tickets is None:
-        tickets = torch.zeros(max(n_tickets, 1), dtype=torch.float32, device=device)
-    assert tickets.numel() >= n_tickets
-    return rows, tickets
+def _sync_args(sync, ticket, device):
+    """(desc pointer, ticket pointer, ticket tensor kept alive) for a SyncBN producer / consumer call."""
+    if sync is None:
+        return None, None, None
+    if ticket is None:
+        ticket = torch.zeros(1, dtype=torch.float32, device=device)
+    return ctypes.addressof(sync.desc), ptr(ticket), ticket
 
 
 def conv2d_fwd(x, w_packed, K, R, S, stride=1, pad=0, dil=1, out=None, out_dtype=torch.bfloat16, bias=None, beta=0.0,
-               stats=None, impl=IMPL_AUTO, tickets=None, sync=None):
-    """stats: fp32 [2K] written with the per-channel sum / sum of squares of the output (bit-reproducible).  tickets: zeroed
-    fp32/int32 words (conv_stats_workspace(...)[1] of them) from the caller's per-step arena; allocated here if None.
-    sync: a comm.SyncBNGroup — the epilogue also pushes the statistics to every peer (check conv_fwd_pushes first)."""
+               stats=None, impl=IMPL_AUTO, sync=None, sync_ticket=None):
+    """stats: fp64 [2K], ZERO on entry (new_stats): the per-channel sum / sum of squares of the output are added to it
+    (exact fp64 accumulation: bit-reproducible).  sync: a comm.SyncBNGroup — the last CTA also pushes the totals to every
+    peer; sync_ticket: one zeroed word from the caller's arena (allocated here if None)."""
     N, H, W, C = x.shape
     d = make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil, ldx=ld(x))
     if out is None:
         out = torch.empty((N, d.P, d.Q, K), dtype=out_dtype, device=x.device)
     d.ldy = ld(out)
-    rows = None
-    if stats is not None:
-        nr, nt = conv_stats_workspace(N, H, W, C, K, R, S, stride, pad, dil)
-        rows, tickets = _fold_ws(nr, nt, tickets, x.device)
+    assert stats is None or stats.dtype == torch.float64
+    sp, tp, _keep = _sync_args(sync if stats is not None else None, sync_ticket, x.device)
     ev = _prof("fprop", d)
     call("seg_conv2d_fwd", ctypes.byref(d), ptr(x), ptr(w_packed), ptr(out), DT_BF16 if out.dtype == torch.bfloat16 else DT_F32,
-         ptr(bias), float(beta), ptr(stats), ptr(rows), ptr(tickets) if stats is not None else None,
-         ctypes.addressof(sync.desc) if (sync is not None and stats is not None) else None, _impl(impl), meta=_meta(d))
+         ptr(bias), float(beta), ptr(stats), sp, tp, _impl(impl), meta=_meta(d))
     if ev is not None:
         ev.record()
     return out
-
-
-def conv_fwd_pushes(x_shape, K, R, S, stride, pad, dil, ldx, impl=IMPL_AUTO):
-    """True if conv2d_fwd on this shape runs the tcgen05 path (whose epilogue can push SyncBN statistics)."""
-    N, H, W, C = x_shape
-    d = make_conv_desc(N, H, W, C, K, R, S, stride, pad, dil, ldx=ldx)
-    return bool(lib.load().seg_conv_fwd_pushes(ctypes.byref(d), _impl(impl)))
 
 
 def conv2d_dgrad(dy, w_packed, x_shape, R, S, stride=1, pad=0, dil=1, out=None, beta=0.0, impl=IMPL_AUTO):
@@ -211,14 +180,15 @@ def _dw_desc(x_shape, stride, pad, dil, ldx, ldy):
     return make_conv_desc(N, H, W, C, C, 3, 3, stride, pad, dil, ldx=ldx, ldy=ldy)
 
 
-def dwconv_fwd(x, w9, stride=1, pad=1, dil=1, out=None, stats=None):
+def dwconv_fwd(x, w9, stride=1, pad=1, dil=1, out=None, stats=None, sync=None, sync_ticket=None):
     N, H, W, C = x.shape
     d = _dw_desc(x.shape, stride, pad, dil, ld(x), C)
     if out is None:
         out = torch.empty((N, d.P, d.Q, C), dtype=torch.bfloat16, device=x.device)
     d.ldy = ld(out)
-    scratch = torch.empty(int(lib.load().seg_dwconv_scratch_floats(C)), dtype=torch.float32, device=x.device) if stats is not None else None
-    call("seg_dwconv3x3_fwd", ctypes.byref(d), ptr(x), ptr(w9), ptr(out), ptr(stats), ptr(scratch))
+    assert stats is None or stats.dtype == torch.float64
+    sp, tp, _keep = _sync_args(sync if stats is not None else None, sync_ticket, x.device)
+    call("seg_dwconv3x3_fwd", ctypes.byref(d), ptr(x), ptr(w9), ptr(out), ptr(stats), sp, tp)
     return out
 
 
@@ -238,7 +208,7 @@ def dwconv_bwd_weight(dy, x, stride=1, pad=1, dil=1, out=None, beta=0.0):
         out = torch.empty((9, C), dtype=torch.float32, device=x.device)
         beta = 0.0
     d = _dw_desc(x.shape, stride, pad, dil, ld(x), ld(dy))
-    scratch = torch.empty(int(lib.load().seg_dwconv_scratch_floats(C)), dtype=torch.float32, device=x.device)
+    scratch = torch.empty(int(lib.load().seg_dwconv_scratch_floats(C)) // 2 + 1, dtype=torch.float64, device=x.device)
     call("seg_dwconv3x3_bwd_weight", ctypes.byref(d), ptr(dy), ptr(x), ptr(out), float(beta), ptr(scratch))
     return out
 
@@ -257,13 +227,13 @@ def im2col(x, R, S, stride, pad, dil, kpad, nchw_f32):
 
 
 # ---------------------------------------------------------------- batch norm
-def bn_stats(x, stats=None, tickets=None):
+def bn_stats(x, stats=None, sync=None, sync_ticket=None):
+    """fp64 [2C] (sum, sum of squares) over the rows of x (added to `stats`, which must be zero on entry if given)."""
     C = x.shape[-1]
     if stats is None:
-        stats = torch.empty(2 * C, dtype=torch.float32, device=x.device)
-    nr, nt = reduce_workspace(rows(x), C, 2)
-    fr, tickets = _fold_ws(nr, nt, tickets, x.device)
-    call("seg_bn_stats", ptr(x), rows(x), C, ld(x), ptr(stats), ptr(fr), ptr(tickets))
+        stats = new_stats(C, x.device)
+    sp, tp, _keep = _sync_args(sync, sync_ticket, x.device)
+    call("seg_bn_stats", ptr(x), rows(x), C, ld(x), ptr(stats), sp, tp)
     return stats
 
 
@@ -297,20 +267,23 @@ def counter_add(ctr, inc=1):
     call("seg_counter_add", ptr(ctr), int(inc))
 
 
-def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, tickets=None,
-                  gamma=None, beta=None):
-    """Returns sums [2C] = (sum dz, sum dz*xhat); optionally writes the parameter gradients from them.  One launch; the
-    cross-block sum is a fixed-order ticket tree (bit-reproducible).  tickets: reduce_workspace(M, C)[1] ZEROED words from
-    the caller's arena (allocated here if None).
+def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, acc=None,
+                  gamma=None, beta=None, sync=None):
+    """Returns sums fp32 [2C] = (sum dz, sum dz*xhat); optionally writes the parameter gradients from them.  One launch: fp64
+    atomics into `acc` (exact, bit-reproducible), the last block rounds / writes.  acc: zeroed fp64 [2C + 1] (accumulators +
+    ticket) from the caller's arena, allocated here if None.  sync: SyncBN — the last block pushes the sums to the peers (the
+    consumer is bn_bwd_apply(sync=...)).
     out=None (with relu, gamma, beta): the ReLU mask is recomputed from x instead of read from the stored activation."""
     C = x.shape[-1]
     M = rows(x)
     sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
-    nr, nt = reduce_workspace(M, C, 2)
-    fr, tickets = _fold_ws(nr, nt, tickets, x.device)
+    if acc is None:
+        acc = torch.zeros(2 * C + 1, dtype=torch.float64, device=x.device)
+    assert acc.dtype == torch.float64 and acc.numel() >= 2 * C + 1
     call("seg_bn_bwd_reduce", ptr(dout), ld(dout), ptr(out), ld(out) if out is not None else 0, ptr(x), ld(x), ptr(save),
-         M, C, int(relu), float(drop_p), ptr(sums), ptr(fr), ptr(tickets), ptr(dgamma), ptr(dbeta), int(accumulate),
-         ptr(gamma), ptr(beta), meta=_meta_rows(M, C, 3 if (relu and out is not None) else 2))
+         M, C, int(relu), float(drop_p), ptr(sums), ptr(acc), acc.data_ptr() + 16 * C, ptr(dgamma), ptr(dbeta), int(accumulate),
+         ptr(gamma), ptr(beta), ctypes.addressof(sync.desc) if sync is not None else None,
+         meta=_meta_rows(M, C, 3 if (relu and out is not None) else 2))
     return sums
 
 
@@ -323,6 +296,7 @@ def bn_apply_train(x, stats, count, gamma, beta, eps, momentum, clamp_eps, runni
     if out is None:
         out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     save = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+    assert stats.dtype == torch.float64
     if sync is not None and sync_done is None:
         sync_done = torch.zeros(1, dtype=torch.float32, device=x.device)
     call("seg_bn_apply_train", ptr(x), ld(x), ptr(stats), float(count), ptr(gamma), ptr(beta), float(eps), float(momentum),
@@ -333,13 +307,15 @@ def bn_apply_train(x, stats, count, gamma, beta, eps, momentum, clamp_eps, runni
     return out, save
 
 
-def bn_bwd_apply(dout, out, x, save, gamma, sums, count, relu=True, drop_p=0.0, dx=None, dres=None, beta_res=0.0, beta=None):
+def bn_bwd_apply(dout, out, x, save, gamma, sums, count, relu=True, drop_p=0.0, dx=None, dres=None, beta_res=0.0, beta=None,
+                 sync=None, sync_done=None):
     C = x.shape[-1]
     if dx is None:
         dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    sp, tp, _keep = _sync_args(sync, sync_done, x.device)
     call("seg_bn_bwd_apply", ptr(dout), ld(dout), ptr(out), ld(out) if out is not None else 0, ptr(x), ld(x), ptr(save),
          ptr(gamma), ptr(sums), float(count), rows(x), C, int(relu), float(drop_p), ptr(dx), ld(dx), ptr(dres),
-         ld(dres) if dres is not None else 0, float(beta_res), ptr(beta),
+         ld(dres) if dres is not None else 0, float(beta_res), ptr(beta), sp, tp,
          meta=_meta_rows(rows(x), C, (3 if (relu and out is not None) else 2) + 1 + (0 if dres is None else (2 if beta_res != 0.0 else 1)), dres is not None))
     return dx
 
@@ -365,7 +341,9 @@ def bn_bwd_fused(dout, out, x, save, gamma, count_total, relu=True, drop_p=0.0, 
         dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
     nr, nt = bn_bwd_fused_workspace(M, C)
-    fr, tickets = _fold_ws(nr, nt, tickets, x.device)
+    fr = torch.empty(max(nr, 1), dtype=torch.float32, device=x.device)
+    if tickets is None:
+        tickets = torch.zeros(max(nt, 1), dtype=torch.float32, device=x.device)
     call("seg_bn_bwd_fused", ptr(dout), ld(dout), ptr(out), ld(out) if out is not None else 0, ptr(x), ld(x), ptr(save), ptr(gamma),
          ptr(beta), float(count_total), M, C, int(relu), float(drop_p), ptr(sums), ptr(fr), ptr(tickets), ptr(dgamma), ptr(dbeta),
          int(accumulate), ptr(dx), ld(dx), ptr(dres), ld(dres) if dres is not None else 0, float(beta_res), int(zero_sums),

@@ -55,26 +55,18 @@ def unpack_wgrad(dwp, shape, beta=0.0, out=None):
     return out
 
 
-def conv_stats_workspace(*a, **k):
-    return (0, 1)
-
-
-def reduce_workspace(*a, **k):
-    return (0, 1)
-
-
-def conv_fwd_pushes(*a, **k):
-    return False
+def new_stats(C, device=None):
+    return torch.zeros(2 * C, dtype=torch.float64)
 
 
 def conv2d_fwd(x, wp, K, R, S, stride=1, pad=0, dil=1, out=None, out_dtype=None, bias=None, beta=0.0, stats=None,
-               impl=0, tickets=None, sync=None):
+               impl=0, sync=None, sync_ticket=None):
     y = F.conv2d(_nchw(x), _w_oihw(wp, R, S), bias, stride, pad, dil).permute(0, 2, 3, 1)
-    if stats is not None:  # written, not accumulated (the kernels' fixed-order reduction overwrites); sums of the output
-        C = y.shape[-1]    # AS STORED (rounded to the output type), which is what bn_apply then normalises
-        ys = y.to(out.dtype if out is not None else (out_dtype or ACT_DTYPE)).float()
-        stats[:C] = ys.reshape(-1, C).sum(0)
-        stats[C:] = (ys * ys).reshape(-1, C).sum(0)
+    if stats is not None:  # fp64 accumulators (zero on entry); sums of the output AS STORED (rounded to the output type),
+        C = y.shape[-1]    # which is what bn_apply then normalises
+        ys = y.to(out.dtype if out is not None else (out_dtype or ACT_DTYPE)).double()
+        stats[:C] += ys.reshape(-1, C).sum(0)
+        stats[C:] += (ys * ys).reshape(-1, C).sum(0)
     if out is None:
         out = torch.empty(y.shape, dtype=out_dtype or ACT_DTYPE)
     return _store(out, y, beta)
@@ -115,7 +107,7 @@ def _dw_w(w9):
     return w9.t().reshape(C, 1, 3, 3).float()
 
 
-def dwconv_fwd(x, w9, stride=1, pad=1, dil=1, out=None, stats=None):
+def dwconv_fwd(x, w9, stride=1, pad=1, dil=1, out=None, stats=None, sync=None, sync_ticket=None):
     C = x.shape[-1]
     y = F.conv2d(_nchw(x), _w_round(_dw_w(w9)), None, stride, pad, dil, groups=C).permute(0, 2, 3, 1)
     if stats is not None:
@@ -160,13 +152,13 @@ def im2col(x, R, S, stride, pad, dil, kpad, nchw_f32):
     return out
 
 
-def bn_stats(x, stats=None, tickets=None):
+def bn_stats(x, stats=None, sync=None, sync_ticket=None):
     C = x.shape[-1]
     if stats is None:
-        stats = torch.zeros(2 * C)
-    f = x.float().reshape(-1, C)
-    stats[:C] = f.sum(0)
-    stats[C:] = (f * f).sum(0)
+        stats = torch.zeros(2 * C, dtype=torch.float64)
+    f = x.double().reshape(-1, C)
+    stats[:C] += f.sum(0)
+    stats[C:] += (f * f).sum(0)
     return stats
 
 
@@ -219,8 +211,8 @@ def _dz(dout, out, relu, drop_p, x=None, save=None, gamma=None, beta=None):
     return dz
 
 
-def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, tickets=None,
-                  gamma=None, beta=None):
+def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, acc=None,
+                  gamma=None, beta=None, sync=None):
     C = x.shape[-1]
     dz = _dz(dout, out, relu, drop_p, x, save, gamma, beta).reshape(-1, C)
     xhat = ((x.float() - save[:C]) * save[C:]).reshape(-1, C)
@@ -230,7 +222,8 @@ def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=
     return sums
 
 
-def bn_bwd_apply(dout, out, x, save, gamma, sums, count, relu=True, drop_p=0.0, dx=None, dres=None, beta_res=0.0, beta=None):
+def bn_bwd_apply(dout, out, x, save, gamma, sums, count, relu=True, drop_p=0.0, dx=None, dres=None, beta_res=0.0, beta=None,
+                 sync=None, sync_done=None):
     C = x.shape[-1]
     dz = _dz(dout, out, relu, drop_p, x, save, gamma, beta)
     xhat = (x.float() - save[:C]) * save[C:]

@@ -90,25 +90,25 @@ def test_conv_fwd(shape, impl, gpu_out_dir):
     ref = F.conv2d(x, w, None, stride, pad, dil)
     wp = ops.pack_weight(w.to(DEV))
     # fp32 output + statistics: tcgen05 path only (the CUDA-core path reduces the stored bf16 output)
-    stats = torch.full((2 * K,), float("nan"), device=DEV) if impl == IMPL_TC else None  # written, not accumulated
+    stats = ops.new_stats(K, DEV) if impl == IMPL_TC else None  # zeroed fp64 accumulators
     y = ops.conv2d_fwd(to_nhwc_dev(x), wp, K, ks, ks, stride, pad, dil, out_dtype=torch.float32, stats=stats, impl=impl)
     torch.cuda.synchronize()
     check(f"conv_fwd[{impl}] {shape}", y.permute(0, 3, 1, 2), ref, 2e-3, gpu_out_dir)
     ref_s = torch.cat([ref.sum((0, 2, 3)), (ref * ref).sum((0, 2, 3))])
     if stats is not None:
         check(f"conv_fwd_stats[{impl}] {shape}", stats, ref_s, 2e-3, gpu_out_dir)
-    stats_b = torch.full((2 * K,), float("nan"), device=DEV)
+    stats_b = ops.new_stats(K, DEV)
     yb = ops.conv2d_fwd(to_nhwc_dev(x), wp, K, ks, ks, stride, pad, dil, stats=stats_b, impl=impl)
     torch.cuda.synchronize()
     check(f"conv_fwd_bf16[{impl}] {shape}", yb.permute(0, 3, 1, 2), ref, 1e-2, gpu_out_dir)
     check(f"conv_fwd_bf16_stats[{impl}] {shape}", stats_b, ref_s, 2e-3, gpu_out_dir)
-    # the statistics are the sums of the output AS STORED, reduced in a fixed order: exact against a float64 sum of the
-    # stored bf16 values up to fp32 rounding, and bit-identical from run to run
+    # the statistics are the sums of the output AS STORED, accumulated exactly in fp64: equal to a float64 sum of the stored
+    # bf16 values up to the fp32 rounding of the per-CTA partial sums, and bit-identical from run to run
     yd = yb.double().reshape(-1, K)
-    exact = torch.cat([yd.sum(0), (yd * yd).sum(0)]).float()
+    exact = torch.cat([yd.sum(0), (yd * yd).sum(0)])
     check(f"conv_fwd_bf16_stats_vs_stored[{impl}] {shape}", stats_b, exact, 2e-5, gpu_out_dir)
     for _ in range(3):
-        again = torch.full((2 * K,), float("nan"), device=DEV)
+        again = ops.new_stats(K, DEV)
         ops.conv2d_fwd(to_nhwc_dev(x), wp, K, ks, ks, stride, pad, dil, stats=again, impl=impl)
         assert torch.equal(again, stats_b), "BatchNorm statistics are not bit-reproducible"
 
@@ -223,9 +223,9 @@ def test_bn_train_fwd_bwd(C, M_shape, gpu_out_dir):
     check(f"bn_apply_train save C={C}", save2, save, 1e-5, gpu_out_dir)
     assert torch.allclose(rm2, rmd, rtol=1e-6, atol=1e-7) and torch.allclose(rv2, rvd, rtol=1e-6, atol=1e-7)
     dg2, db2 = torch.ones(C, device=DEV), torch.ones(C, device=DEV)
-    zs = torch.zeros(ops.reduce_workspace(count, C, 2)[1], device=DEV)  # tickets from a caller-zeroed arena
-    sums2 = ops.bn_bwd_reduce(dyd, out, xd, save, relu=True, dgamma=dg2, dbeta=db2, accumulate=True, tickets=zs)
-    assert torch.equal(sums2, sums), "the fixed-order reduction must be bit-reproducible"
+    zs = torch.zeros(2 * C + 1, dtype=torch.float64, device=DEV)  # fp64 accumulators + ticket from a caller-zeroed arena
+    sums2 = ops.bn_bwd_reduce(dyd, out, xd, save, relu=True, dgamma=dg2, dbeta=db2, accumulate=True, acc=zs)
+    assert torch.equal(sums2, sums), "the exact fp64 accumulation must be bit-reproducible"
     check(f"bn_dgamma accumulate C={C}", dg2 - 1.0, dgamma, 1e-4, gpu_out_dir)
     check(f"bn_dbeta accumulate C={C}", db2 - 1.0, dbeta, 1e-4, gpu_out_dir)
     # no residual: the ReLU mask recomputed from x (out=None) gives the same sums / dx as the mask read from the activation
@@ -252,6 +252,26 @@ def test_bn_train_fwd_bwd(C, M_shape, gpu_out_dir):
     dx6, _ = ops.bn_bwd_fused(dyd, out, xd, save, gd, count, relu=True, zero_sums=True)  # frozen BN: dx = gamma*istd*dz
     z = torch.zeros_like(sums)
     check(f"bn_bwd_fused frozen dx C={C}", dx6.float(), ops.bn_bwd_apply(dyd, out, xd, save, gd, z, count, relu=True).float(), 1e-2, gpu_out_dir)
+
+
+def test_dropout2d_is_channelwise():
+    """nn.Dropout2d (models/pspnet.py:22,68, upernet.py:22) zeroes WHOLE channels per image; nn.Dropout draws per element
+    (deeplabv3_plus.py:282,318).  bn_apply's dropout epilogue does both (drop_hw = H*W selects the channel-wise draw)."""
+    N, H, W, C, p = 4, 9, 7, 256, 0.3
+    x = torch.ones(N, H, W, C, device=DEV, dtype=torch.bfloat16)
+    ss = torch.cat([torch.ones(C), torch.zeros(C)]).to(DEV)  # identity BatchNorm
+    ctr = torch.zeros(1, dtype=torch.int64, device=DEV)
+    y2 = ops.bn_apply(x, ss, relu=True, drop_p=p, seed=123, step_ctr=ctr, drop_hw=H * W).float().reshape(N, H * W, C)
+    kept = y2[:, 0, :] > 0
+    assert torch.equal(y2 > 0, kept[:, None, :].expand_as(y2)), "Dropout2d mask must be constant over a channel's pixels"
+    assert abs(kept.float().mean().item() - (1 - p)) < 0.06
+    vals = y2[y2 > 0]
+    assert torch.allclose(vals, torch.full_like(vals, 1 / (1 - p)), rtol=1e-2)
+    assert not torch.equal(kept[0], kept[1]), "different images draw different channels"
+    y1 = ops.bn_apply(x, ss, relu=True, drop_p=p, seed=123, step_ctr=ctr, drop_hw=0).float().reshape(N, H * W, C)
+    per_pixel = (y1 > 0)
+    assert not torch.equal(per_pixel, per_pixel[:, :1, :].expand_as(per_pixel)), "nn.Dropout draws per element"
+    assert abs(per_pixel.float().mean().item() - (1 - p)) < 0.02
 
 
 def test_bn_clamp_eps_and_eval(gpu_out_dir):
@@ -425,7 +445,7 @@ def test_depthwise_conv(shape, gpu_out_dir):
     dy = bf(torch.randn(y.shape, generator=g))
     y.backward(dy)
     w9 = ops.dw_pack_weight(w.detach().to(DEV))
-    stats = torch.zeros(2 * C, device=DEV)
+    stats = ops.new_stats(C, DEV)
     yd = ops.dwconv_fwd(to_nhwc_dev(x.detach()), w9, stride, dil, dil, stats=stats)
     torch.cuda.synchronize()
     check(f"dwconv_fwd {shape}", yd.permute(0, 3, 1, 2), y, 1e-2, gpu_out_dir)

@@ -36,8 +36,8 @@ def run(M, C, res, iters):
     gamma, beta = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
     rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
     stats = ops.bn_stats(xs[0])
-    n = (ops.reduce_workspace(M, C, 2)[1] + 31) // 32 * 32
-    zs = torch.zeros(n * (iters + 16), device="cuda")
+    n = 2 * C + 2
+    zs = torch.zeros(n * (iters + 16), dtype=torch.float64, device="cuda")
     _, save = ops.bn_apply_train(xs[0], stats, M, gamma, beta, 1e-5, 0.1, 0, rm, rv, out=outs[0])
     sums = ops.bn_bwd_reduce(dys[0], outs[0], xs[0], save, relu=True)
     t_apply = timeit(lambda i: ops.bn_apply_train(xs[i % nbuf], stats, M, gamma, beta, 1e-5, 0.1, 0, rm, rv,
@@ -45,7 +45,7 @@ def run(M, C, res, iters):
     k = [0]
 
     def red(i):
-        ops.bn_bwd_reduce(dys[i % nbuf], outs[i % nbuf], xs[i % nbuf], save, relu=True, tickets=zs[k[0] * n:(k[0] + 1) * n])
+        ops.bn_bwd_reduce(dys[i % nbuf], outs[i % nbuf], xs[i % nbuf], save, relu=True, acc=zs[k[0] * n:(k[0] + 1) * n])
         k[0] += 1
     zs.zero_()
     t_red = timeit(red, iters)

@@ -29,7 +29,7 @@ def run(shape, kind, iters, stats, impl, beta=0.0):
     out_ys = [torch.empty(N, P, Q, K, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
     out_dxs = [torch.zeros(N, H, W, C, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]  # rotated: cold in L2
     dwp = torch.zeros(ks * ks, K, C, device="cuda")
-    st = torch.zeros(2 * K, device="cuda") if stats else None
+    st = torch.zeros(2 * K, dtype=torch.float64, device="cuda") if stats else None
     flops = 2.0 * N * P * Q * K * C * ks * ks
     byt = {"fwd": (N * H * W * C + N * P * Q * K) * 2, "dgrad": (N * H * W * C + N * P * Q * K) * 2, "wgrad": (N * H * W * C + N * P * Q * K) * 2}
 
