@@ -560,6 +560,23 @@ static int env_bn() {
   return v;
 }
 
+static int env_v2bn() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SEG_TC_V2BN");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+// tile width of the persistent kernel for an output of `ncols` columns and `m_tiles` row tiles
+static int pick_v2_bn(int ncols, int64_t m_tiles, bool tma_ok) {
+  if (!tma_ok || ncols < 256) return V2_BN;
+  const int forced = env_v2bn();
+  if (forced == 128 || forced == 256) return forced;
+  return (m_tiles * ceil_div(ncols, 256) >= num_sms()) ? 256 : V2_BN;
+}
+
 static int pick_bn(int ncols, int out_dtype) {
   if (ncols <= 64) return 64;
   if (out_dtype == SEG_DT_F32) return 64;  // fp32 staging tile: 128 x 64 x 4 B
@@ -610,7 +627,7 @@ int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int 
   p.stat_ticket = stat_ticket;
   if (sync && stats) {
     SEG_REQUIRE(stat_ticket != nullptr, "conv fwd: SyncBN needs a zeroed ticket word");
-    SEG_REQUIRE(2 * d->K <= sync->n_max, "conv fwd: 2*K = %d statistics exceed the SyncBN buffer (%d floats)", 2 * d->K, sync->n_max);
+    SEG_REQUIRE(4 * d->K <= sync->n_max, "conv fwd: 2*K = %d fp64 statistics exceed the SyncBN buffer (%d floats)", 2 * d->K, sync->n_max);
     p.sync = *sync;
   }
   const int64_t m_tiles = ceil_div64(M, BM);
@@ -620,7 +637,10 @@ int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int 
   const int64_t tiles128 = m_tiles * ceil_div(d->K, 128);
   const bool long_k_few_tiles = tiles128 <= 2 * num_sms() && (int64_t)d->R * d->S * ceil_div(d->C, BK) >= 32;
   const bool v2 = use_v2() && y_dtype == SEG_DT_BF16 && bias == nullptr && d->K > 64 && !long_k_few_tiles;
-  const int bn = v2 ? V2_BN : pick_bn(d->K, y_dtype);
+  // 256-wide persistent tiles (0.75x the operand bytes per flop) where the layer has >= 256 output channels, the output can
+  // go through the TMA epilogue and there are enough 128 x 256 tiles to fill the SMs (env SEG_TC_V2BN = 128 | 256 forces)
+  const int v2bn = v2 ? pick_v2_bn(d->K, m_tiles, v2_tma_epilogue_ok(y, d->ldy, beta, false)) : V2_BN;
+  const int bn = v2 ? v2bn : pick_bn(d->K, y_dtype);
   if (is_pointwise(d)) {
     p.x_im2col = 0;
     if (make_map_2d(&p.mapA, x, M, d->C, d->ldx, BM)) return 1;
@@ -630,7 +650,7 @@ int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int 
     if (make_map_im2col(&p.mapA, x, d->N, d->H, d->W, d->C, d->ldx, -d->pad, -d->pad, upper, upper, d->stride, BM)) return 1;
   }
   if (make_map_2d(&p.mapB, w, (int64_t)p.taps * d->K, d->C, d->C, bn)) return 1;
-  if (v2) return launch_v2<KIND_KK>(p, stream);
+  if (v2) return launch_v2<KIND_KK>(p, stream, v2bn);
   dim3 grid((unsigned)m_tiles, (unsigned)ceil_div(d->K, bn), 1);
   return launch_bn<KIND_KK>(bn, p, grid, stream);
 }
@@ -716,7 +736,8 @@ int conv_dgrad(const seg_conv_desc* d, const void* dy, const void* w, void* dx, 
         if (make_map_2d(&p.mapB, w, (int64_t)d->R * d->S * d->K, d->C, d->C, 64)) return 1;
       }
       if (v2 && p.taps > 0) {
-        if (launch_v2<KIND_KM>(p, stream)) return 1;
+        const int v2bn = pick_v2_bn(d->C, m_tiles, v2_tma_epilogue_ok(dx, d->ldx, beta, s > 1));
+        if (launch_v2<KIND_KM>(p, stream, v2bn)) return 1;
         continue;
       }
       dim3 grid((unsigned)m_tiles, (unsigned)ceil_div(d->C, v2 ? 128 : bn), 1);
@@ -748,7 +769,12 @@ int conv_wgrad(const seg_conv_desc* d, const void* dy, const void* x, float* dw,
   p.dw_K = d->K;
   p.dw_C = d->C;
   p.kblocks_total = (int)ceil_div64(npix, BK);
-  const int bn = (d->C <= 64) ? 64 : 128;
+  static int wgrad_bn_env = -1;
+  if (wgrad_bn_env < 0) {
+    const char* e = getenv("SEG_TC_WGRAD_BN");
+    wgrad_bn_env = e ? atoi(e) : 0;
+  }
+  const int bn = (d->C <= 64) ? 64 : ((wgrad_bn_env == 256 && d->C >= 256) ? 256 : 128);
   const int tiles = ceil_div(d->K, BM) * ceil_div(d->C, bn) * p.taps;
   // one wave: tiles * splits <= resident CTA slots (2 per SM), so no CTA waits for a second wave
   int splits = max(1, (2 * num_sms()) / tiles);

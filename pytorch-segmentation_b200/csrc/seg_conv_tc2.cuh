@@ -19,13 +19,19 @@
 namespace seg {
 namespace tc {
 
-constexpr int V2_BN = 128;
-constexpr int V2_STAGES = 5;
-constexpr int V2_STAGE_BYTES = A_BYTES + V2_BN * 128;  // 32 KB
+constexpr int V2_BN = 128;     // default tile width
 constexpr int V2_THREADS = 320;
-constexpr int V2_STAGING_BYTES = BM * V2_BN * 2;       // 32 KB
-constexpr int V2_STAT_BYTES = 4 * 2 * V2_BN * 4;         // [lane group][sum, sum of squares][column] fp32
-constexpr int V2_SMEM = V2_STAGES * V2_STAGE_BYTES + V2_STAGING_BYTES + V2_STAT_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+// Tile-width dependent layout.  BNT = 128: 5 stages of 32 KB.  BNT = 256 (TMA epilogue only): 3 stages of 48 KB, both TMEM
+// accumulators = all 512 columns; a 128 x 256 tile moves 48 KB of operands per 64-deep k-step for twice the MACs of a
+// 128 x 128 tile's 32 KB — 0.75x the L2->SM bytes per flop, which is what bounds these kernels.
+template <int BNT>
+struct V2Cfg {
+  static constexpr int STAGES = (BNT == 128) ? 5 : 3;
+  static constexpr int STAGE_BYTES = A_BYTES + BNT * 128;
+  static constexpr int STAGING_BYTES = BM * 128 * 2;      // 32 KB: eight [32 rows][64 columns] boxes (one pass of 128 columns)
+  static constexpr int STAT_BYTES = 4 * 2 * BNT * 4;      // [lane group][sum, sum of squares][column] fp32
+  static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + STAT_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+};
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -70,9 +76,13 @@ __device__ __forceinline__ void warp_column_stats(const uint8_t* base, uint32_t 
   *reinterpret_cast<float2*>(slot + slot_stride) = s2;
 }
 
-template <int KIND, int EPI>
+template <int KIND, int EPI, int BNT = V2_BN>
 __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_constant__ TcParams p) {
-  constexpr int BN = V2_BN;
+  constexpr int BN = BNT;
+  static_assert(BNT == 128 || (BNT == 256 && EPI == EPI_TMA), "256-wide tiles use the TMA epilogue");
+  using VC = V2Cfg<BNT>;
+  constexpr int V2_STAGES = VC::STAGES, V2_STAGE_BYTES = VC::STAGE_BYTES, V2_STAGING_BYTES = VC::STAGING_BYTES, V2_STAT_BYTES = VC::STAT_BYTES;
+  constexpr int NPASS = BNT / 128;  // epilogue passes of 128 columns over a tile
   constexpr bool BETA = (EPI == EPI_MANUAL_BETA);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -202,8 +212,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_cons
       // called by all 256 epilogue threads
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int my_n = blockIdx.x % n_tiles;
-      {
-        const int c = etid & 127, which = etid >> 7;
+      for (int idx = etid; idx < 2 * BN; idx += 256) {
+        const int which = idx / BN, c = idx - which * BN;
         const int col = my_n * BN + c;
         float val = 0.f;
 #pragma unroll
@@ -221,39 +231,45 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_cons
       const int n_tile = t % n_tiles;
       const int m0 = (t / n_tiles) * BM, n0 = n_tile * BN;
       if constexpr (EPI == EPI_TMA) {
-        // ---- TMA epilogue: this warp owns rows 32*lg.. and columns 64*h.. of the tile = one [32][64] box whose
+        // ---- TMA epilogue: per pass of 128 columns this warp owns rows 32*lg.. and columns 64*h.. = one [32][64] box whose
         //      staging region (4 KB, 128-byte rows, SWIZZLE_128B pattern) only this warp touches ----
         uint8_t* region = stage + h * 16384 + lg * 4096;
-        if (lane == 0) bulk_wait_group_read0();  // my previous box has been read out of shared memory
-        __syncwarp();
         mbar_wait(tfull_bar(b), ((uint32_t)i >> 1) & 1u);
         tc_fence_after();
-        float v1[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * BN + h * 64), v);
-        tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * BN + h * 64 + 32), v1);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(b));  // accumulator drained: the MMA warp may reuse it
-        if (!(p.dbg & 4)) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            *reinterpret_cast<bf16x8*>(region + lane * 128 + ((g ^ (lane & 7)) << 4)) = pack8(v + g * 8);
-            *reinterpret_cast<bf16x8*>(region + lane * 128 + (((4 + g) ^ (lane & 7)) << 4)) = pack8(v1 + g * 8);
+        for (int ps = 0; ps < NPASS; ++ps) {
+          const int cbase = ps * 128 + h * 64;  // first column of this warp's box inside the tile
+          if (lane == 0) bulk_wait_group_read0();  // my previous box has been read out of shared memory
+          __syncwarp();
+          float v1[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * BN + cbase), v);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * BN + cbase + 32), v1);
+          tmem_ld_wait();
+          if (ps == NPASS - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(b));  // accumulator drained: the MMA warp may reuse it
           }
-        }
-        __syncwarp();
-        if (p.stats && !(p.dbg & 2))
-          warp_column_stats<128, 7>(region + (lane & 3) * 4, (uint32_t)(lane >> 2) << 4, min(32, p.M - m0 - lg * 32),
-                                    stat_sm + (size_t)(lg * 2) * BN + h * 64 + (lane >> 2) * 8 + (lane & 3) * 2, BN);
-        fence_proxy_async();  // generic-proxy writes -> visible to the TMA engine
-        __syncwarp();
-        if (lane == 0 && !(p.dbg & 1) && m0 + lg * 32 < p.M && n0 + h * 64 < p.Ncols) {
-          if (p.beta != 0.f)
-            tma_reduce_add_2d(&p.mapC, smem_u32(region), n0 + h * 64, m0 + lg * 32);  // dst += tile, bf16 add in L2
-          else
-            tma_store_2d(&p.mapC, smem_u32(region), n0 + h * 64, m0 + lg * 32);
-          bulk_commit_group();
+          if (!(p.dbg & 4)) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              *reinterpret_cast<bf16x8*>(region + lane * 128 + ((g ^ (lane & 7)) << 4)) = pack8(v + g * 8);
+              *reinterpret_cast<bf16x8*>(region + lane * 128 + (((4 + g) ^ (lane & 7)) << 4)) = pack8(v1 + g * 8);
+            }
+          }
+          __syncwarp();
+          if (p.stats && !(p.dbg & 2))
+            warp_column_stats<128, 7>(region + (lane & 3) * 4, (uint32_t)(lane >> 2) << 4, min(32, p.M - m0 - lg * 32),
+                                      stat_sm + (size_t)(lg * 2) * BN + cbase + (lane >> 2) * 8 + (lane & 3) * 2, BN);
+          fence_proxy_async();  // generic-proxy writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0 && !(p.dbg & 1) && m0 + lg * 32 < p.M && n0 + cbase < p.Ncols) {
+            if (p.beta != 0.f)
+              tma_reduce_add_2d(&p.mapC, smem_u32(region), n0 + cbase, m0 + lg * 32);  // dst += tile, bf16 add in L2
+            else
+              tma_store_2d(&p.mapC, smem_u32(region), n0 + cbase, m0 + lg * 32);
+            bulk_commit_group();
+          }
         }
         continue;
       }
@@ -350,16 +366,17 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_gemm_tc2(const __grid_cons
   }
 }
 
-template <int KIND, int EPI>
+template <int KIND, int EPI, int BNT = V2_BN>
 static int launch_v2_impl(const TcParams& p, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kfn = conv_gemm_tc2<KIND, EPI>;
+  auto kfn = conv_gemm_tc2<KIND, EPI, BNT>;
+  constexpr int SMEM = V2Cfg<BNT>::SMEM;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM);
-    SEG_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(v2 smem=%d): %s", V2_SMEM, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    SEG_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(v2 smem=%d): %s", SMEM, cudaGetErrorString(e));
     attr_set = true;
   }
-  const int n_tiles = ceil_div(p.Ncols, V2_BN);
+  const int n_tiles = ceil_div(p.Ncols, BNT);
   const int64_t num_tiles = ceil_div64(p.M, BM) * n_tiles;
   int grid = num_sms();
   // a grid that is a multiple of the number of column blocks pins every CTA to one column block: the weight tile stays
@@ -367,25 +384,32 @@ static int launch_v2_impl(const TcParams& p, cudaStream_t stream) {
   if (n_tiles <= grid) grid = (grid / n_tiles) * n_tiles;
   if ((int64_t)grid > num_tiles) grid = (int)num_tiles;
   SEG_REQUIRE(p.stats == nullptr || grid % n_tiles == 0, "conv_gemm_tc2: statistics need a grid that pins every CTA to one column block");
-  launch_pdl(kfn, dim3(grid), dim3(V2_THREADS), (size_t)V2_SMEM, stream, p);
+  launch_pdl(kfn, dim3(grid), dim3(V2_THREADS), (size_t)SMEM, stream, p);
   return check_launch("conv_gemm_tc2");
 }
 
 // `p` by value: the destination map and the experiment flags are filled in here
 template <int KIND>
-static int launch_v2(TcParams p, cudaStream_t stream) {
+static int launch_v2(TcParams p, cudaStream_t stream, int bnt = V2_BN) {
   p.dbg = env_dbg();
   const bool tma_ok = !p.out_strided && p.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
                       (p.beta == 0.f || p.beta == 1.f) && !(p.dbg & 16);
   if (tma_ok) {
     if (make_map_2d(&p.mapC, p.out, p.M, p.Ncols, p.ldo, 32)) return 1;
+    if (bnt == 256) return launch_v2_impl<KIND, EPI_TMA, 256>(p, stream);
     return launch_v2_impl<KIND, EPI_TMA>(p, stream);
   }
+  SEG_REQUIRE(bnt == V2_BN, "conv_gemm_tc2: 256-wide tiles need the TMA epilogue");
   if (p.beta != 0.f) {
     SEG_REQUIRE(p.stats == nullptr, "conv_gemm_tc2: beta-accumulate and BN statistics are not combined on this path");
     return launch_v2_impl<KIND, EPI_MANUAL_BETA>(p, stream);
   }
   return launch_v2_impl<KIND, EPI_MANUAL>(p, stream);
+}
+
+// can the persistent kernel take this output through its TMA epilogue (the only epilogue of the 256-wide tiles)?
+static bool v2_tma_epilogue_ok(const void* out, long long ldo, float beta, bool strided) {
+  return !strided && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (beta == 0.f || beta == 1.f) && !(env_dbg() & 16);
 }
 
 }  // namespace tc

@@ -263,7 +263,7 @@ static int dw_check(const seg_conv_desc* d) {
 int seg_dwconv3x3_fwd(const seg_conv_desc* d, const void* x, const float* w9, void* y, double* stats,
                       const seg_sync_desc* sync, void* sync_ticket, void* stream) {
   if (dw_check(d)) return 1;
-  SEG_REQUIRE(!sync || (stats && sync_ticket && 2 * d->C <= sync->n_max), "dwconv fwd: SyncBN needs stats, a zeroed ticket and 2*C <= n_max");
+  SEG_REQUIRE(!sync || (stats && sync_ticket && 4 * d->C <= sync->n_max), "dwconv fwd: SyncBN needs stats, a zeroed ticket and 4*C <= n_max");
   const int64_t M = (int64_t)d->N * d->P * d->Q;
   SyncDesc sd{nullptr, 0, 0, 0, 0};
   if (sync) {

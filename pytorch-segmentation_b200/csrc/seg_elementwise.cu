@@ -313,32 +313,17 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const __nv_bfloat16* _
   float sc[8], sh[8];
   if (rm.active) {
     if (tr.stats) {
-      double s1[8], s2[8];
       float gm[8], bt[8];
-      if (sync.world > 0) {
-        float t1[8], t2[8];
-        sync_total8(sync, epoch, rm.g * 8, t1);
-        sync_total8(sync, epoch, C + rm.g * 8, t2);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s1[j] = t1[j];
-          s2[j] = t2[j];
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s1[j] = __ldg(tr.stats + rm.g * 8 + j);
-          s2[j] = __ldg(tr.stats + C + rm.g * 8 + j);
-        }
-      }
-      ld8(tr.gamma + rm.g * 8, gm);
-      ld8(tr.beta + rm.g * 8, bt);
       const bool writer = blockIdx.x == 0 && rm.rl == 0;
       const double inv_count = 1.0 / tr.count;  // one division; the per-channel math below is multiply-add + fp32 rsqrt
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const double mean = s1[j] * inv_count;
-        double var = fma(s2[j], inv_count, -mean * mean);
+        // fp64 totals, one channel at a time (no register arrays of doubles): local accumulators, or the world's (SyncBN)
+        const int cj = rm.g * 8 + j;
+        const double s1 = sync.world > 0 ? sync_total_d(sync, epoch, cj) : __ldg(tr.stats + cj);
+        const double s2 = sync.world > 0 ? sync_total_d(sync, epoch, C + cj) : __ldg(tr.stats + C + cj);
+        const double mean = s1 * inv_count;
+        double var = fma(s2, inv_count, -mean * mean);
         if (var < 0) var = 0;
         const float vf = tr.clamp_eps ? fmaxf((float)var, tr.eps) : (float)(var + (double)tr.eps);
         float istd = rsqrtf(vf);
@@ -472,7 +457,7 @@ __global__ void __launch_bounds__(256, 4)
 
 // dx = A*dz + B*x + Cc with A = gamma*istd, B = -gamma*istd^2*s1/count, Cc = -gamma*istd*s0/count + gamma*istd^2*mean*s1/count
 template <bool REMASK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ out, int ldo,
                         const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save,
                         const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count, int64_t M, int C,
@@ -515,7 +500,8 @@ __global__ void __launch_bounds__(256)
     }
   }
   const int64_t step = (int64_t)gridDim.x * rm.rows_par;
-  for (int64_t row = (int64_t)blockIdx.x * rm.rows_par + rm.rl; rm.active && row < M; row += step) {
+  const int64_t row_end = rm.active ? M : 0;
+  for (int64_t row = (int64_t)blockIdx.x * rm.rows_par + rm.rl; row < row_end; row += step) {
     float dz[8], xv[8];
     const bf16x8 dv = *reinterpret_cast<const bf16x8*>(dout + row * lddo + co);
     const bf16x8 xx = *reinterpret_cast<const bf16x8*>(x + row * ldx + co);
@@ -1378,7 +1364,7 @@ namespace seg {
 int bn_stats_launch(const void* x, int64_t M, int C, int ldx, double* stats, const seg_sync_desc* sync, unsigned* ticket,
                     cudaStream_t stream) {
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0, "bn_stats: C/ldx must be multiples of 8 (C=%d ldx=%d)", C, ldx);
-  SEG_REQUIRE(!sync || (ticket && 2 * C <= sync->n_max), "bn_stats: SyncBN needs a zeroed ticket and 2*C <= n_max");
+  SEG_REQUIRE(!sync || (ticket && 4 * C <= sync->n_max), "bn_stats: SyncBN needs a zeroed ticket and 4*C <= n_max (fp64 totals)");
   bn_stats_kernel<<<colreduce_grid(M, C), 256, 0, stream>>>(CBF(x), M, C, ldx, stats, to_sync(sync), ticket);
   return check_launch("bn_stats");
 }
@@ -1415,7 +1401,7 @@ int seg_bn_apply_train(const void* x, int ldx, const double* stats, double count
                        void* stream) {
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldr % 8 == 0), "bn_apply_train: alignment");
   SEG_REQUIRE(stats && gamma && beta && save && count > 0, "bn_apply_train: stats, gamma, beta, save required");
-  SEG_REQUIRE(!sync || (sync_done != nullptr && 2 * C <= sync->n_max), "bn_apply_train: SyncBN needs a zeroed ticket and 2*C <= n_max");
+  SEG_REQUIRE(!sync || (sync_done != nullptr && 4 * C <= sync->n_max), "bn_apply_train: SyncBN needs a zeroed ticket and 4*C <= n_max (fp64 totals)");
   const SyncDesc sd = to_sync(sync);
   BnTrain tr = {stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var, save};
   launch_pdl(bn_apply_kernel, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(x), ldx, (const float*)nullptr, CBF(res), ldr, BF(out),

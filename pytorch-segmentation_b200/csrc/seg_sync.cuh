@@ -4,17 +4,17 @@
 // world-wide flag barrier sitting alone between a conv epilogue and bn_apply; at 8 GPUs that cost ~33 us per exchange —
 // the limiter of the 1 -> 8 scaling curve.  Now the exchange has no launch of its own:
 //
-//   producer  = the block that completes the fixed-order statistics fold (seg_fold.cuh) of a conv epilogue / of
-//               bn_bwd_reduce.  While emitting the local totals it also stores them into slot[rank] of EVERY peer's
-//               symmetric buffer (P2P stores through NVSwitch); the block that finishes the LAST column block / channel
-//               slab of the layer raises this rank's flag on every peer (st.release.sys).  The NVLink latency overlaps the
-//               kernel's tail and the next launch.
+//   producer  = a kernel that ends with per-channel totals: the conv epilogues / the depthwise conv / bn_stats (fp64 atomics
+//               into the layer's accumulators) and bn_bwd_reduce / the cooperative BN backward.  The LAST block to finish
+//               (one ticket per launch) reads the finished totals and stores them into slot[rank] of EVERY peer's symmetric
+//               buffer (P2P stores through NVSwitch), then raises this rank's flag on every peer (st.release.sys).  The NVLink
+//               latency overlaps the kernel's tail and the next launch.
 //   consumer  = the prologue of bn_apply / bn_bwd_apply: every block waits for the world's flags (ld.acquire.sys), then each
 //               thread adds, in rank order (-> bit-identical totals on every rank, no broadcast), the world's sums for its own
 //               channels from the LOCAL symmetric buffer.  The last consumer block to finish advances the sequence number.
 //
-// Protocol state is the same as seg_comm.cu's stand-alone exchange (still used where the producer is a kernel without the
-// hook, e.g. the depthwise convolution): per rank a symmetric buffer
+// Protocol state is the same as seg_comm.cu's stand-alone exchange kernel (kept for tests and callers outside the engine): per
+// rank a symmetric buffer
 //     float data[2][world][n_max] | uint32 flags[2][world] | uint32 seq
 // `seq` = number of exchanges this rank has COMPLETED, kept on the device (all ranks issue the same exchanges in the same
 // order) so a captured CUDA graph replays correctly; epoch = seq + 1 is the flag value and its parity picks the slot.  A rank
@@ -69,6 +69,19 @@ __device__ __forceinline__ void sync_push_value(const SyncDesc& s, uint32_t epoc
   for (int p = 0; p < s.world; ++p) reinterpret_cast<float*>(s.peers[p])[off] = v;
 }
 
+// the forward statistics travel as fp64 (the slot is addressed as doubles: 2 * n values need 4 * n <= n_max floats), so the
+// world total is the exact sum of the ranks' exact totals and a one-rank "world" reproduces the local result bit for bit
+__device__ __forceinline__ void sync_push_value_d(const SyncDesc& s, uint32_t epoch, int idx, double v) {
+  const size_t off = ((size_t)(epoch & 1u) * s.world + s.rank) * s.n_max;
+  for (int p = 0; p < s.world; ++p) reinterpret_cast<double*>(reinterpret_cast<float*>(s.peers[p]) + off)[idx] = v;
+}
+__device__ __forceinline__ double sync_total_d(const SyncDesc& s, uint32_t epoch, int idx) {
+  const float* my = reinterpret_cast<const float*>(s.peers[s.rank]) + (size_t)(epoch & 1u) * s.world * s.n_max;
+  double t = 0.0;
+  for (int p = 0; p < s.world; ++p) t += __ldcv(reinterpret_cast<const double*>(my + (size_t)p * s.n_max) + idx);
+  return t;
+}
+
 // producer, once per layer, by the `nthr` cooperating threads of the block that completed the layer's LAST lane (every
 // pushing block executed __threadfence_system() before taking the lane ticket): raise this rank's flag on every peer
 template <class Sync>
@@ -84,7 +97,7 @@ __device__ __forceinline__ void sync_publish(const SyncDesc& s, uint32_t epoch, 
 
 // producer epilogue for kernels that accumulate their per-channel totals with fp64 atomics into `acc` (n doubles): every
 // contributing block calls this with its `nthr` cooperating threads after issuing its atomics; the LAST of `nblocks` blocks to
-// arrive (ticket) reads the finished totals and pushes them (as fp32) to every peer, then raises the flags.
+// arrive (ticket) reads the finished totals and pushes them (as fp64) to every peer, then raises the flags.
 template <class Sync>
 __device__ __forceinline__ void sync_push_when_last(const SyncDesc& s, const double* acc, int n, unsigned* ticket, unsigned nblocks,
                                                     int tid, int nthr, Sync sync, volatile int* sm_flag) {
@@ -95,7 +108,7 @@ __device__ __forceinline__ void sync_push_when_last(const SyncDesc& s, const dou
   if (!*sm_flag) return;
   __threadfence();
   const uint32_t epoch = sync_epoch(s);
-  for (int i = tid; i < n; i += nthr) sync_push_value(s, epoch, i, (float)__ldcg(acc + i));
+  for (int i = tid; i < n; i += nthr) sync_push_value_d(s, epoch, i, __ldcg(acc + i));
   sync_publish(s, epoch, tid, sync);
 }
 

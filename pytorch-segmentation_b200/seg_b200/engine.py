@@ -18,7 +18,7 @@ from .lib import IMPL_AUTO
 
 BN_EPS = 1e-5
 BN_MOM = 0.1
-FUSED_BWD_MAX_BYTES = 40 << 20  # BN backward: one cooperative launch up to this activation size (bf16 bytes), two above
+FUSED_BWD_MAX_BYTES = 24 << 20  # BN backward: one cooperative launch up to this activation size (bf16 bytes), two above
 ACT_DTYPE = torch.bfloat16  # storage type of activations / activation gradients (the kernels are bf16-only;
                             # tests/test_engine_cpu_emulated.py flips this to fp32 together with the ATen emulation)
 
