@@ -152,13 +152,15 @@ int seg_bn_apply_train(const void* x, int ldx, const double* stats, double count
  * train step stays correct on every replay */
 int seg_counter_add(uint64_t* ctr, uint64_t inc, void* stream);
 /* backward, pass 1: sums[0:C] = sum(dz), sums[C:2C] = sum(dz*xhat), dz = dout * (out>0) * 1/(1-drop_p) if relu.  ONE
- * launch: every block adds its partial sums to `acc` (fp64 [2C], ZERO at launch; exact, order-independent accumulation); the
+ * launch: every block adds its partial sums to one of seg_bn_bwd_reduce_slots() copies of `acc` (fp64 [slots][2C], ZERO at
+ * launch; exact, order-independent accumulation; the copies spread the atomics); the
  * last block (ticket: one zeroed uint32) rounds them into sums[] and, if given, dbeta (=|+=) sums[0:C] and dgamma (=|+=)
  * sums[C:2C] — the parameter gradients from the LOCAL sums.  sync: SyncBN — that block also pushes the sums to every peer;
  * the consumer is seg_bn_bwd_apply(..., sync, sync_done, ...).
  * out == NULL with relu (both backward passes): the ReLU mask is recomputed from x with the forward's own coefficients
  * (sc = gamma/std, sh = fma(-mean, sc, beta)) instead of being read from the stored activation — valid for
  * conv -> BN(batch statistics) -> ReLU with no residual and no dropout; needs gamma and beta. */
+int seg_bn_bwd_reduce_slots(void);
 int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx,
                       const float* save_mean_istd, int64_t M, int C, int relu, float drop_p, float* sums, double* acc,
                       void* ticket, float* dgamma, float* dbeta, int accumulate, const float* gamma, const float* beta,

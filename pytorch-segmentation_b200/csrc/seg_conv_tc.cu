@@ -542,6 +542,15 @@ static int env_dbg() {
 namespace seg {
 namespace tc {
 
+static bool long_k_rule() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SEG_TC_LONGK");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 static bool use_v2() {
   static int v = -1;
   if (v < 0) {
@@ -570,11 +579,15 @@ static int env_v2bn() {
 }
 
 // tile width of the persistent kernel for an output of `ncols` columns and `m_tiles` row tiles
+// (profiles/conv_sweep_r02.txt: 256-wide tiles win or tie on every C3 shape with >= 256 output columns — 3x3 512->512 d2 @33^2
+//  937 -> 1336 TFLOP/s, 1x1 512->2048 722 -> 875, decoder 3x3 256->256 @129^2 1067 -> 1366 — except where the last column
+//  block would be mostly padding: dgrad of the 304-channel decoder input, 846 -> 812)
 static int pick_v2_bn(int ncols, int64_t m_tiles, bool tma_ok) {
   if (!tma_ok || ncols < 256) return V2_BN;
   const int forced = env_v2bn();
   if (forced == 128 || forced == 256) return forced;
-  return (m_tiles * ceil_div(ncols, 256) >= num_sms()) ? 256 : V2_BN;
+  const int waste = ceil_div(ncols, 256) * 256 - ncols;
+  return waste < 128 ? 256 : V2_BN;
 }
 
 static int pick_bn(int ncols, int out_dtype) {
@@ -635,7 +648,11 @@ int conv_fwd(const seg_conv_desc* d, const void* x, const void* w, void* y, int 
   // (measured: with <= 2 tiles per SM and a long k-loop, two co-resident one-tile CTAs interleave better than one
   //  persistent CTA; everywhere else — short k-loops, many tiles — the persistent kernel wins by 1.3-1.8x)
   const int64_t tiles128 = m_tiles * ceil_div(d->K, 128);
-  const bool long_k_few_tiles = tiles128 <= 2 * num_sms() && (int64_t)d->R * d->S * ceil_div(d->C, BK) >= 32;
+  // (measured, profiles/conv_longk_r02.txt: with few tiles and a long k-loop the two co-resident one-tile CTAs still win for
+  //  the 3x3s — 256->256 @33^2: 751 vs 704 TFLOP/s — but not for a 1x1 with >= 256 outputs: 2048->256 612 vs 687 on 256-wide tiles)
+  const bool wide_ok = d->K >= 256 && v2_tma_epilogue_ok(y, d->ldy, beta, false);
+  const bool long_k_few_tiles = long_k_rule() && tiles128 <= 2 * num_sms() && (int64_t)d->R * d->S * ceil_div(d->C, BK) >= 32 &&
+                                !(wide_ok && d->R * d->S == 1);
   const bool v2 = use_v2() && y_dtype == SEG_DT_BF16 && bias == nullptr && d->K > 64 && !long_k_few_tiles;
   // 256-wide persistent tiles (0.75x the operand bytes per flop) where the layer has >= 256 output channels, the output can
   // go through the TMA epilogue and there are enough 128 x 256 tiles to fill the SMs (env SEG_TC_V2BN = 128 | 256 forces)
@@ -662,7 +679,10 @@ int conv_dgrad(const seg_conv_desc* d, const void* dy, const void* w, void* dx, 
               d->K, d->ldy);
   const int s = d->stride;
   const int64_t tiles128 = ceil_div64((int64_t)d->N * d->H * d->W, BM) * ceil_div(d->C, 128) / (s * s);
-  const bool long_k_few_tiles = tiles128 <= 2 * num_sms() && (int64_t)d->R * d->S * ceil_div(d->K, BK) / (s * s) >= 32;
+  // (measured: dgrad 256<-256 3x3 @33^2 647 TFLOP/s on the one-tile kernel, 966 on 256-wide persistent tiles)
+  const bool wide_ok = s == 1 && pick_v2_bn(d->C, 1 << 20, v2_tma_epilogue_ok(dx, d->ldx, beta, false)) == 256;
+  const bool long_k_few_tiles = long_k_rule() && !wide_ok && tiles128 <= 2 * num_sms() &&
+                                (int64_t)d->R * d->S * ceil_div(d->K, BK) / (s * s) >= 32;
   const bool v2 = use_v2() && d->C > 64 && !long_k_few_tiles;
   const int bn = v2 ? V2_BN : pick_bn(d->C, SEG_DT_BF16);
   // One launch per parity class (py, px) of the input pixels; stride 1 has the single class (0, 0).
@@ -774,7 +794,10 @@ int conv_wgrad(const seg_conv_desc* d, const void* dy, const void* x, float* dw,
     const char* e = getenv("SEG_TC_WGRAD_BN");
     wgrad_bn_env = e ? atoi(e) : 0;
   }
-  const int bn = (d->C <= 64) ? 64 : ((wgrad_bn_env == 256 && d->C >= 256) ? 256 : 128);
+  // 256-wide wgrad tiles pay on the 3x3 convs with C a multiple of 256 (measured: 2048->256 d12 1231 -> 1376 TFLOP/s, decoder
+  // 256->256 @129^2 1182 -> 1332) and lose on the 1x1s (478 -> 363: half as many tiles for the one-wave split-K); env forces
+  const bool wide = wgrad_bn_env == 256 ? d->C >= 256 : (wgrad_bn_env == 128 ? false : (d->R * d->S >= 9 && d->C >= 256 && d->C % 256 == 0));
+  const int bn = (d->C <= 64) ? 64 : (wide ? 256 : 128);
   const int tiles = ceil_div(d->K, BM) * ceil_div(d->C, bn) * p.taps;
   // one wave: tiles * splits <= resident CTA slots (2 per SM), so no CTA waits for a second wave
   int splits = max(1, (2 * num_sms()) / tiles);

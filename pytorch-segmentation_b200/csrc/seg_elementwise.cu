@@ -156,8 +156,9 @@ __global__ void __launch_bounds__(256) im2col_kernel(seg_conv_desc d, const void
 // groups (8 channels each) and 256/GB row lanes; rows are grid-strided.  The block's sums (fixed order inside the block)
 // are added to acc[NACC][C] (fp64, ZERO at launch) with one fp64 atomic per channel: exact accumulation of fp32 partials,
 // hence order-independent and bit-reproducible (see conv_gemm_tc's statistics epilogue for the argument).
-template <int NACC, class F>
-__device__ __forceinline__ void column_reduce(int64_t M, int C, double* acc_out, F f) {
+constexpr int RED_SLOTS = 8;  // accumulator copies the blocks spread their atomics over (contention: blocks / 8 per address)
+template <int NACC, int SLOTS = 1, class F>
+__device__ __forceinline__ void column_reduce(int64_t M, int C, double* acc_out /*[SLOTS][NACC][C]*/, F f) {
   const int G = C >> 3;
   const int GB = min(G, 256);
   const int rows_par = 256 / GB;
@@ -187,8 +188,9 @@ __device__ __forceinline__ void column_reduce(int64_t M, int C, double* acc_out,
       for (int r = 0; r < rows_par; ++r)
 #pragma unroll
         for (int i = 0; i < 8; ++i) s[i] += red[(r * GB + gl) * 8 + i];
+      double* o = acc_out + ((size_t)(blockIdx.x % SLOTS) * NACC + a) * C + g * 8;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(acc_out + (size_t)a * C + g * 8 + i, (double)s[i]);
+      for (int i = 0; i < 8; ++i) atomicAdd(o + i, (double)s[i]);
     }
   }
 }
@@ -293,6 +295,7 @@ struct BnTrain {
   float *running_mean, *running_var, *save;
 };
 
+template <bool SYNC>
 __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                        const float* __restrict__ ss, const __nv_bfloat16* __restrict__ res,
                                                        int ldr, __nv_bfloat16* __restrict__ out, int ldo, int64_t M, int C,
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const __nv_bfloat16* _
   // SyncBN (seg_sync.cuh): the producing conv pushed every rank's sums into this rank's symmetric buffer; wait for the
   // world's flags, then add the world's sums in rank order
   uint32_t epoch = 0u;
-  if (sync.world > 0) {
+  if constexpr (SYNC) {
     epoch = sync_epoch(sync);
     sync_wait_world(sync, epoch);
   }
@@ -314,14 +317,16 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const __nv_bfloat16* _
   if (rm.active) {
     if (tr.stats) {
       float gm[8], bt[8];
+      ld8(tr.gamma + rm.g * 8, gm);
+      ld8(tr.beta + rm.g * 8, bt);
       const bool writer = blockIdx.x == 0 && rm.rl == 0;
       const double inv_count = 1.0 / tr.count;  // one division; the per-channel math below is multiply-add + fp32 rsqrt
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         // fp64 totals, one channel at a time (no register arrays of doubles): local accumulators, or the world's (SyncBN)
         const int cj = rm.g * 8 + j;
-        const double s1 = sync.world > 0 ? sync_total_d(sync, epoch, cj) : __ldg(tr.stats + cj);
-        const double s2 = sync.world > 0 ? sync_total_d(sync, epoch, C + cj) : __ldg(tr.stats + C + cj);
+        const double s1 = SYNC ? sync_total_d(sync, epoch, cj) : __ldg(tr.stats + cj);
+        const double s2 = SYNC ? sync_total_d(sync, epoch, C + cj) : __ldg(tr.stats + C + cj);
         const double mean = s1 * inv_count;
         double var = fma(s2, inv_count, -mean * mean);
         if (var < 0) var = 0;
@@ -387,14 +392,14 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const __nv_bfloat16* _
     }
   }
   pdl_trigger();
-  if (sync.world > 0) sync_consumer_done(sync, epoch, sync_done, gridDim.x * gridDim.y);
+  if constexpr (SYNC) sync_consumer_done(sync, epoch, sync_done, gridDim.x * gridDim.y);
 }
 
 template <bool REMASK>
 __global__ void __launch_bounds__(256, 4)
     bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ out, int ldo,
                          const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save, int64_t M, int C,
-                         int relu, float drop_p, double* acc /*[2C] fp64, zero at launch*/, unsigned* ticket, float* final_sums,
+                         int relu, float drop_p, double* acc /*[RED_SLOTS][2C] fp64, zero at launch*/, unsigned* ticket, float* final_sums,
                          float* dgamma, float* dbeta, int accumulate, const float* __restrict__ gamma,
                          const float* __restrict__ beta, const SyncDesc sync) {
   pdl_wait();
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(256, 4)
       }
     }
   }
-  column_reduce<2>(M, C, acc, [&](int64_t row, int g, float(*a)[8]) {
+  column_reduce<2, RED_SLOTS>(M, C, acc, [&](int64_t row, int g, float(*a)[8]) {
     float dz[8], xv[8];
     const bf16x8 dv = *reinterpret_cast<const bf16x8*>(dout + row * lddo + g * 8);
     const bf16x8 xx = *reinterpret_cast<const bf16x8*>(x + row * ldx + g * 8);
@@ -445,7 +450,10 @@ __global__ void __launch_bounds__(256, 4)
   if (!last_block_arrived(ticket)) return;
   const uint32_t epoch = sync.world > 0 ? sync_epoch(sync) : 0u;
   for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
-    const float v = (float)__ldcg(acc + c);
+    double t = 0.0;  // the slots' totals are exact sums; so is their sum
+#pragma unroll
+    for (int sl = 0; sl < RED_SLOTS; ++sl) t += __ldcg(acc + (size_t)sl * 2 * C + c);
+    const float v = (float)t;
     final_sums[c] = v;
     float* pg = c < C ? dbeta : dgamma;
     const int ch = c < C ? c : c - C;
@@ -456,7 +464,7 @@ __global__ void __launch_bounds__(256, 4)
 }
 
 // dx = A*dz + B*x + Cc with A = gamma*istd, B = -gamma*istd^2*s1/count, Cc = -gamma*istd*s0/count + gamma*istd^2*mean*s1/count
-template <bool REMASK>
+template <bool REMASK, bool SYNC>
 __global__ void __launch_bounds__(256, 4)
     bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ out, int ldo,
                         const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ save,
@@ -466,7 +474,7 @@ __global__ void __launch_bounds__(256, 4)
   pdl_wait();
   const RowMap rm = row_map(C);
   uint32_t epoch = 0u;
-  if (sync.world > 0) {  // SyncBN: bn_bwd_reduce pushed every rank's sums; wait for the world, add in rank order
+  if constexpr (SYNC) {  // SyncBN: bn_bwd_reduce pushed every rank's sums; wait for the world, add in rank order
     epoch = sync_epoch(sync);
     sync_wait_world(sync, epoch);
   }
@@ -478,7 +486,7 @@ __global__ void __launch_bounds__(256, 4)
     ld8(save + co, mean);
     ld8(save + C + co, istd);
     ld8(gamma + co, gm);
-    if (sync.world > 0) {
+    if constexpr (SYNC) {
       sync_total8(sync, epoch, co, s0);
       sync_total8(sync, epoch, C + co, s1);
     } else {
@@ -534,7 +542,7 @@ __global__ void __launch_bounds__(256, 4)
     *reinterpret_cast<bf16x8*>(dx + row * lddx + co) = pack8(o8);
   }
   pdl_trigger();
-  if (sync.world > 0) sync_consumer_done(sync, epoch, sync_done, gridDim.x * gridDim.y);
+  if constexpr (SYNC) sync_consumer_done(sync, epoch, sync_done, gridDim.x * gridDim.y);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1390,7 +1398,7 @@ int seg_bn_apply(const void* x, int ldx, const float* ss, const void* res, int l
   SEG_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && (!res || ldr % 8 == 0), "bn_apply: alignment");
   BnTrain tr;
   memset(&tr, 0, sizeof(tr));
-  launch_pdl(bn_apply_kernel, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(x), ldx, ss, CBF(res), ldr, BF(out), ldo, M, C, relu,
+  launch_pdl(bn_apply_kernel<false>, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(x), ldx, ss, CBF(res), ldr, BF(out), ldo, M, C, relu,
              drop_p, seed, step_ctr, drop_hw, tr, SyncDesc{nullptr, 0, 0, 0, 0}, (unsigned*)nullptr);
   return check_launch("bn_apply");
 }
@@ -1404,20 +1412,22 @@ int seg_bn_apply_train(const void* x, int ldx, const double* stats, double count
   SEG_REQUIRE(!sync || (sync_done != nullptr && 4 * C <= sync->n_max), "bn_apply_train: SyncBN needs a zeroed ticket and 4*C <= n_max (fp64 totals)");
   const SyncDesc sd = to_sync(sync);
   BnTrain tr = {stats, count, gamma, beta, eps, momentum, clamp_eps, running_mean, running_var, save};
-  launch_pdl(bn_apply_kernel, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(x), ldx, (const float*)nullptr, CBF(res), ldr, BF(out),
-             ldo, M, C, relu, drop_p, seed, step_ctr, drop_hw, tr, sd, reinterpret_cast<unsigned*>(sync_done));
+  launch_pdl(sync ? bn_apply_kernel<true> : bn_apply_kernel<false>, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(x), ldx,
+             (const float*)nullptr, CBF(res), ldr, BF(out), ldo, M, C, relu, drop_p, seed, step_ctr, drop_hw, tr, sd,
+             reinterpret_cast<unsigned*>(sync_done));
   return check_launch("bn_apply_train");
 }
 // reductions end with a block fold + 2C atomics per block: fewer, fatter blocks (>= 32 rows per thread)
 static dim3 reduce2_grid(int64_t M, int C) { return rowmap_grid(M, C, 32); }
 
+int seg_bn_bwd_reduce_slots(void) { return RED_SLOTS; }
 int seg_bn_bwd_reduce(const void* dout, int lddo, const void* out, int ldo, const void* x, int ldx, const float* save,
                       int64_t M, int C, int relu, float drop_p, float* sums, double* acc, void* ticket, float* dgamma,
                       float* dbeta, int accumulate, const float* gamma, const float* beta, const seg_sync_desc* sync,
                       void* stream) {
   SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && (!relu || !out || ldo % 8 == 0), "bn_bwd_reduce: alignment");
   SEG_REQUIRE(!(relu && !out) || (gamma && beta && drop_p == 0.f), "bn_bwd_reduce: out == NULL (mask recomputed from x) needs gamma, beta and no dropout");
-  SEG_REQUIRE(acc && ticket, "bn_bwd_reduce: zeroed fp64 accumulator [2C] and ticket word required");
+  SEG_REQUIRE(acc && ticket, "bn_bwd_reduce: zeroed fp64 accumulators [seg_bn_bwd_reduce_slots()][2C] and ticket word required");
   SEG_REQUIRE(!sync || 2 * C <= sync->n_max, "bn_bwd_reduce: 2*C exceeds the SyncBN buffer");
   const dim3 grid = reduce2_grid(M, C);
   launch_pdl((relu && !out) ? bn_bwd_reduce_kernel<true> : bn_bwd_reduce_kernel<false>, grid, dim3(256), 0, ST(stream), CBF(dout),
@@ -1432,7 +1442,9 @@ int seg_bn_bwd_apply(const void* dout, int lddo, const void* out, int ldo, const
   SEG_REQUIRE(C % 8 == 0 && lddo % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0, "bn_bwd_apply: alignment");
   SEG_REQUIRE(!(relu && !out) || (beta && drop_p == 0.f), "bn_bwd_apply: out == NULL (mask recomputed from x) needs beta and no dropout");
   SEG_REQUIRE(!sync || (sync_done && 2 * C <= sync->n_max), "bn_bwd_apply: SyncBN needs a zeroed ticket and 2*C <= n_max");
-  launch_pdl((relu && !out) ? bn_bwd_apply_kernel<true> : bn_bwd_apply_kernel<false>, rowmap_grid(M, C), dim3(256), 0, ST(stream),
+  auto kfn = sync ? ((relu && !out) ? bn_bwd_apply_kernel<true, true> : bn_bwd_apply_kernel<false, true>)
+                  : ((relu && !out) ? bn_bwd_apply_kernel<true, false> : bn_bwd_apply_kernel<false, false>);
+  launch_pdl(kfn, rowmap_grid(M, C), dim3(256), 0, ST(stream),
              CBF(dout), lddo, CBF(out), ldo, CBF(x), ldx, save,
              gamma, sums, (float)(1.0 / count), M, C, relu, drop_p, BF(dx), lddx, BF(dres), lddres, beta_res, beta, to_sync(sync),
              reinterpret_cast<unsigned*>(sync_done));

@@ -375,7 +375,7 @@ class Tape:
                 if sync is not None and not getattr(sync, "fused", False):
                     # exchange object without the in-kernel protocol (the gloo stand-in of the CPU tests)
                     sums = ops.bn_bwd_reduce(da, a, y.t, save, relu=relu, drop_p=drop_p, dgamma=dg, dbeta=db, accumulate=acc_pg,
-                                             acc=self.zalloc64(2 * C + 1, a.device))
+                                             acc=self.zalloc64(ops.bn_bwd_reduce_acc_words(C), a.device))
                     gsums = sums.clone()
                     sync.allreduce_(gsums)
                     ops.bn_bwd_apply(da, a_mask, y.t, save, bn.weight.detach(), gsums, count, relu=relu, drop_p=drop_p, dx=dy,
@@ -391,7 +391,7 @@ class Tape:
                     # large maps stream from HBM in both passes anyway: two launches at full occupancy; under SyncBN the
                     # reduction's last block pushes the sums and the apply pass waits for the world's
                     sums = ops.bn_bwd_reduce(da, a, y.t, save, relu=relu, drop_p=drop_p, dgamma=dg, dbeta=db, accumulate=acc_pg,
-                                             acc=self.zalloc64(2 * C + 1, a.device), sync=sync)
+                                             acc=self.zalloc64(ops.bn_bwd_reduce_acc_words(C), a.device), sync=sync)
                     gsums = sums if use_batch_stats else torch.zeros_like(sums)
                     ops.bn_bwd_apply(da, a_mask, y.t, save, bn.weight.detach(), gsums, count, relu=relu, drop_p=drop_p, dx=dy,
                                      dres=dres, beta_res=beta_res, beta=bn.bias.detach(), sync=sync,

@@ -267,21 +267,27 @@ def counter_add(ctr, inc=1):
     call("seg_counter_add", ptr(ctr), int(inc))
 
 
+def bn_bwd_reduce_acc_words(C):
+    """fp64 words of the zeroed accumulator block of bn_bwd_reduce: [slots][2C] sums + one ticket word."""
+    return int(lib.load().seg_bn_bwd_reduce_slots()) * 2 * C + 1
+
+
 def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, acc=None,
                   gamma=None, beta=None, sync=None):
     """Returns sums fp32 [2C] = (sum dz, sum dz*xhat); optionally writes the parameter gradients from them.  One launch: fp64
-    atomics into `acc` (exact, bit-reproducible), the last block rounds / writes.  acc: zeroed fp64 [2C + 1] (accumulators +
-    ticket) from the caller's arena, allocated here if None.  sync: SyncBN — the last block pushes the sums to the peers (the
+    atomics into `acc` (exact, bit-reproducible), the last block rounds / writes.  acc: zeroed fp64 [bn_bwd_reduce_acc_words(C)]
+    (accumulator copies + ticket) from the caller's arena, allocated here if None.  sync: SyncBN — the last block pushes the sums to the peers (the
     consumer is bn_bwd_apply(sync=...)).
     out=None (with relu, gamma, beta): the ReLU mask is recomputed from x instead of read from the stored activation."""
     C = x.shape[-1]
     M = rows(x)
     sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+    nw = bn_bwd_reduce_acc_words(C)
     if acc is None:
-        acc = torch.zeros(2 * C + 1, dtype=torch.float64, device=x.device)
-    assert acc.dtype == torch.float64 and acc.numel() >= 2 * C + 1
+        acc = torch.zeros(nw, dtype=torch.float64, device=x.device)
+    assert acc.dtype == torch.float64 and acc.numel() >= nw
     call("seg_bn_bwd_reduce", ptr(dout), ld(dout), ptr(out), ld(out) if out is not None else 0, ptr(x), ld(x), ptr(save),
-         M, C, int(relu), float(drop_p), ptr(sums), ptr(acc), acc.data_ptr() + 16 * C, ptr(dgamma), ptr(dbeta), int(accumulate),
+         M, C, int(relu), float(drop_p), ptr(sums), ptr(acc), acc.data_ptr() + 8 * (nw - 1), ptr(dgamma), ptr(dbeta), int(accumulate),
          ptr(gamma), ptr(beta), ctypes.addressof(sync.desc) if sync is not None else None,
          meta=_meta_rows(M, C, 3 if (relu and out is not None) else 2))
     return sums

@@ -211,6 +211,10 @@ def _dz(dout, out, relu, drop_p, x=None, save=None, gamma=None, beta=None):
     return dz
 
 
+def bn_bwd_reduce_acc_words(C):
+    return 2 * C + 1
+
+
 def bn_bwd_reduce(dout, out, x, save, relu=True, drop_p=0.0, dgamma=None, dbeta=None, accumulate=False, acc=None,
                   gamma=None, beta=None, sync=None):
     C = x.shape[-1]

@@ -223,7 +223,7 @@ def test_bn_train_fwd_bwd(C, M_shape, gpu_out_dir):
     check(f"bn_apply_train save C={C}", save2, save, 1e-5, gpu_out_dir)
     assert torch.allclose(rm2, rmd, rtol=1e-6, atol=1e-7) and torch.allclose(rv2, rvd, rtol=1e-6, atol=1e-7)
     dg2, db2 = torch.ones(C, device=DEV), torch.ones(C, device=DEV)
-    zs = torch.zeros(2 * C + 1, dtype=torch.float64, device=DEV)  # fp64 accumulators + ticket from a caller-zeroed arena
+    zs = torch.zeros(ops.bn_bwd_reduce_acc_words(C), dtype=torch.float64, device=DEV)  # accumulators + ticket from a zeroed arena
     sums2 = ops.bn_bwd_reduce(dyd, out, xd, save, relu=True, dgamma=dg2, dbeta=db2, accumulate=True, acc=zs)
     assert torch.equal(sums2, sums), "the exact fp64 accumulation must be bit-reproducible"
     check(f"bn_dgamma accumulate C={C}", dg2 - 1.0, dgamma, 1e-4, gpu_out_dir)

@@ -36,7 +36,7 @@ def run(M, C, res, iters):
     gamma, beta = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
     rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
     stats = ops.bn_stats(xs[0])
-    n = 2 * C + 2
+    n = ops.bn_bwd_reduce_acc_words(C) + 1
     zs = torch.zeros(n * (iters + 16), dtype=torch.float64, device="cuda")
     _, save = ops.bn_apply_train(xs[0], stats, M, gamma, beta, 1e-5, 0.1, 0, rm, rv, out=outs[0])
     sums = ops.bn_bwd_reduce(dys[0], outs[0], xs[0], save, relu=True)
