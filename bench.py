@@ -327,6 +327,8 @@ def main():
                     help="e2e leg: replay model(x)/backward from CUDA graphs (seg_b200 model.cuda_graphs())")
     ap.add_argument("--plugin-optim", default=os.environ.get("SEG_PLUGIN_OPTIM", "fused"), choices=["fused", "torch"],
                     help="e2e leg optimiser: seg_b200.optim.SGD (torch.optim.SGD subclass, one kernel per group) or stock torch.optim.SGD")
+    ap.add_argument("--bucket-mb", type=float, default=float(os.environ.get("SEG_BUCKET_MB", "25")),
+                    help="N > 1: gradient all-reduce bucket size of the fused step (0 = one all-reduce after the backward)")
     ap.add_argument("--trace", default=None, help="after the timed runs, trace 2 steps per C-ABI call and write a table here")
     args = ap.parse_args()
     CFG = CONFIGS[args.config]
@@ -391,7 +393,7 @@ def main():
     fused = CFG["loss"] == "CE"
     if fused:
         stepper = FusedTrainStep(model, ignore_index=IGNORE, lr=0.01, backbone_lr_scale=0.1, momentum=0.9, weight_decay=1e-4, world=world,
-                                 cuda_graph=use_graph)
+                                 cuda_graph=use_graph, bucket_mb=args.bucket_mb)
         dev_step = lambda: stepper.step(x_dev, y_dev)
         eager_step = lambda: stepper._step_impl(x_dev, y_dev)
     else:
@@ -554,7 +556,7 @@ def main():
         if world > 1:
             model.release_graphs()
 
-    if args.trace and rank == 0 and fused:
+    if args.trace and fused:  # every rank runs the traced steps (they contain the exchanges); rank 0 writes the table
         lib.TRACE = []
         for _ in range(2):
             stepper._step_impl(x_dev, y_dev)  # eager: every C-ABI call is timed with its own event pair
@@ -571,8 +573,8 @@ def main():
         by_name = {}
         for (name, _), v in agg.items():
             by_name[name] = by_name.get(name, 0.0) + v[0]
-        with open(args.trace, "w") as f:
-            f.write(f"# per-step totals over 2 traced steps; sum of call times {tot:.2f} ms\n")
+        with open(args.trace if rank == 0 else os.devnull, "w") as f:
+            f.write(f"# per-step totals over 2 traced steps (eager, every C-ABI call timed with its own CUDA-event pair), {world} rank(s); sum of call times {tot:.2f} ms\n")
             for name, ms in sorted(by_name.items(), key=lambda kv: -kv[1]):
                 f.write(f"{name:28s} {ms:9.3f} ms  {100 * ms / tot:5.1f}%\n")
             f.write("\n# name (N,H,W,C,K,R,stride,dil | rows,C,flag) ms/step calls/2steps TFLOP/s (conv) or TB/s algorithmic (streaming)\n")
@@ -607,7 +609,13 @@ def main():
         if not cpu_baseline:
             cpu_baseline = None
     if world > 1:
-        dist.barrier()  # the other ranks idle while rank 0 drives nn.DataParallel over all the GPUs
+        # the other ranks wait on the HOST (TCPStore key) while rank 0 drives nn.DataParallel over all the GPUs: an NCCL barrier
+        # would park a spinning kernel on every GPU the reference is about to use
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("seg_bench_reference_leg_done", "1")
+        else:
+            store.wait(["seg_bench_reference_leg_done"])
 
     if rank == 0:
         print(json.dumps({

@@ -52,6 +52,9 @@ typedef struct seg_sync_desc {
   void* const* peers;        /* DEVICE array of `world` base pointers; peers[rank] is this rank's buffer */
   int32_t rank, world, n_max;
   int64_t timeout_clocks;    /* spin-wait bound in GPU clocks (<= 0: unbounded) */
+  int32_t mode;              /* 0: producers push, the CONSUMER kernels (seg_bn_apply_train / seg_bn_bwd_apply with the same handle)
+                              *    wait for the world and add; 1: the producer's last block performs the whole exchange and leaves
+                              *    the world's totals in its output (stats / sums): call the consumers with sync = NULL */
 } seg_sync_desc;
 
 const char* seg_last_error(void);

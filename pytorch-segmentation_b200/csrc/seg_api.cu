@@ -77,9 +77,9 @@ int seg_conv2d_fwd(const seg_conv_desc* d, const void* x, const void* w_packed, 
   const bool tc_ok = tc::supported(d);
   unsigned* tk = reinterpret_cast<unsigned*>(sync_ticket);
   if (impl == SEG_IMPL_TC || (impl == SEG_IMPL_AUTO && tc_ok)) {
-    SyncDesc sd{nullptr, 0, 0, 0, 0};
+    SyncDesc sd{nullptr, 0, 0, 0, 0, 0};
     if (sync) {
-      sd.peers = sync->peers; sd.rank = sync->rank; sd.world = sync->world; sd.n_max = sync->n_max; sd.timeout_clocks = sync->timeout_clocks;
+      sd.peers = sync->peers; sd.rank = sync->rank; sd.world = sync->world; sd.n_max = sync->n_max; sd.timeout_clocks = sync->timeout_clocks; sd.mode = sync->mode;
     }
     return tc::conv_fwd(d, x, w_packed, y, y_dtype, bias, beta, stats, tk, sync ? &sd : nullptr, ST(stream));
   }

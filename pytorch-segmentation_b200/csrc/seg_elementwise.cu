@@ -458,9 +458,17 @@ __global__ void __launch_bounds__(256, 4)
     float* pg = c < C ? dbeta : dgamma;
     const int ch = c < C ? c : c - C;
     if (pg) pg[ch] = accumulate ? pg[ch] + v : v;
-    if (sync.world > 0) sync_push_value(sync, epoch, c, v);
+    if (sync.world > 0 && sync.mode == 0) sync_push_value(sync, epoch, c, v);
   }
-  if (sync.world > 0) sync_publish(sync, epoch, (int)threadIdx.x, [] { __syncthreads(); });
+  if (sync.world > 0) {
+    if (sync.mode == 1) {  // whole exchange here: final_sums becomes the world's sums (bn_bwd_apply then needs no SyncBN logic)
+      __threadfence();
+      __syncthreads();
+      sync_exchange_block_f(sync, final_sums, 2 * C, (int)threadIdx.x, (int)blockDim.x, [] { __syncthreads(); });
+    } else {
+      sync_publish(sync, epoch, (int)threadIdx.x, [] { __syncthreads(); });
+    }
+  }
 }
 
 // dx = A*dz + B*x + Cc with A = gamma*istd, B = -gamma*istd^2*s1/count, Cc = -gamma*istd*s0/count + gamma*istd^2*mean*s1/count
@@ -699,7 +707,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_fused_kernel(const BnBwdFused p
           p.totals[(size_t)a * C + ch] = tot;
           float* pg = a == 0 ? p.dbeta : p.dgamma;
           if (pg) pg[ch] = p.accumulate ? pg[ch] + tot : tot;
-          if (p.sync.world > 0) sync_push_value(p.sync, epoch, a * C + ch, tot);
+          if (p.sync.world > 0 && p.sync.mode == 0) sync_push_value(p.sync, epoch, a * C + ch, tot);
         }
       }
     }
@@ -708,7 +716,13 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_fused_kernel(const BnBwdFused p
   grid_barrier(p.ctr, 2u * nblocks);
   // ------------------------------------------------ SyncBN: publish, wait for the world, totals from every rank
   float s0[8], s1[8];
-  if (p.sync.world > 0) {
+  if (p.sync.world > 0 && p.sync.mode == 1) {
+    // mode 1: ONE block exchanges the finished local totals with the world and leaves the world's in p.totals
+    if (blockIdx.x == 0 && blockIdx.y == 0)
+      sync_exchange_block_f(p.sync, p.totals, 2 * C, (int)threadIdx.x, 256, [] { __syncthreads(); });
+    grid_barrier(p.ctr, 3u * nblocks);
+  }
+  if (p.sync.world > 0 && p.sync.mode == 0) {
     if (blockIdx.x == 0 && blockIdx.y == 0) sync_publish(p.sync, epoch, (int)threadIdx.x, [] { __syncthreads(); });
     sync_wait_world(p.sync, epoch);
     if (rm.active) {
@@ -764,7 +778,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_fused_kernel(const BnBwdFused p
       *reinterpret_cast<bf16x8*>(p.dx + row * p.lddx + co) = pack8(o8);
     }
   }
-  if (p.sync.world > 0) sync_consumer_done(p.sync, epoch, p.ctr + 1, nblocks);
+  if (p.sync.world > 0 && p.sync.mode == 0) sync_consumer_done(p.sync, epoch, p.ctr + 1, nblocks);
 }
 
 __global__ void bn_param_grad_kernel(const float* __restrict__ sums, int C, float* dgamma, float* dbeta, int accumulate) {
@@ -1360,9 +1374,10 @@ static dim3 colreduce_grid(int64_t M, int C) {
 }
 
 static SyncDesc to_sync(const seg_sync_desc* sync) {
-  SyncDesc sd{nullptr, 0, 0, 0, 0};
+  SyncDesc sd{nullptr, 0, 0, 0, 0, 0};
   if (sync) {
     sd.peers = sync->peers; sd.rank = sync->rank; sd.world = sync->world; sd.n_max = sync->n_max; sd.timeout_clocks = sync->timeout_clocks;
+    sd.mode = sync->mode;
   }
   return sd;
 }
@@ -1399,7 +1414,7 @@ int seg_bn_apply(const void* x, int ldx, const float* ss, const void* res, int l
   BnTrain tr;
   memset(&tr, 0, sizeof(tr));
   launch_pdl(bn_apply_kernel<false>, rowmap_grid(M, C), dim3(256), 0, ST(stream), CBF(x), ldx, ss, CBF(res), ldr, BF(out), ldo, M, C, relu,
-             drop_p, seed, step_ctr, drop_hw, tr, SyncDesc{nullptr, 0, 0, 0, 0}, (unsigned*)nullptr);
+             drop_p, seed, step_ctr, drop_hw, tr, SyncDesc{nullptr, 0, 0, 0, 0, 0}, (unsigned*)nullptr);
   return check_launch("bn_apply");
 }
 int seg_bn_apply_train(const void* x, int ldx, const double* stats, double count, const float* gamma, const float* beta,
@@ -1498,8 +1513,7 @@ int seg_bn_bwd_fused(const void* dout, int lddo, const void* out, int ldo, const
   p.dx = BF(dx); p.dres = BF(dres); p.lddx = lddx; p.lddres = lddres; p.beta_res = beta_res;
   if (sync) {
     SEG_REQUIRE(2 * C <= sync->n_max, "bn_bwd_fused: 2*C = %d sums exceed the SyncBN buffer (%d floats)", 2 * C, sync->n_max);
-    p.sync.peers = sync->peers; p.sync.rank = sync->rank; p.sync.world = sync->world; p.sync.n_max = sync->n_max;
-    p.sync.timeout_clocks = sync->timeout_clocks;
+    p.sync = to_sync(sync);
   }
   const dim3 grid = fused_grid(M, C, remask ? fused_blocks_per_sm<true>() : fused_blocks_per_sm<false>());
   if (remask)

@@ -30,6 +30,8 @@ struct SyncDesc {  // mirror of seg_sync_desc (include/seg_b200.h)
   void* const* peers;        // device array of `world` symmetric-buffer base pointers (peers[rank] = mine)
   int rank, world, n_max;
   long long timeout_clocks;  // spin-wait bound (<= 0: 2^62)
+  int mode;                  // 0: the CONSUMER kernel waits for the world and sums (every block polls the flags);
+                             // 1: the PRODUCER's last block does the whole exchange and leaves the world totals in the local buffer
 };
 
 __host__ __device__ inline size_t sync_flags_offset(int world, int n_max) {
@@ -107,27 +109,13 @@ __device__ __forceinline__ void sync_push_when_last(const SyncDesc& s, const dou
   sync();
   if (!*sm_flag) return;
   __threadfence();
+  if (s.mode == 1) {  // the whole exchange here: acc becomes the world's totals, the consumer needs no SyncBN logic
+    sync_exchange_block_d(s, const_cast<double*>(acc), n, tid, nthr, sync);
+    return;
+  }
   const uint32_t epoch = sync_epoch(s);
   for (int i = tid; i < n; i += nthr) sync_push_value_d(s, epoch, i, __ldcg(acc + i));
   sync_publish(s, epoch, tid, sync);
-}
-
-// consumer: all threads of the block call this; returns after every rank's flag shows `epoch`
-__device__ __forceinline__ void sync_wait_world(const SyncDesc& s, uint32_t epoch) {
-  if ((int)threadIdx.x < s.world) {
-    const uint32_t* mine = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(s.peers[s.rank]) + sync_flags_offset(s.world, s.n_max)) +
-                           (size_t)(epoch & 1u) * s.world + threadIdx.x;
-    const long long limit = s.timeout_clocks > 0 ? s.timeout_clocks : (1ll << 62);
-    const long long t0 = clock64();
-    while (sync_ld_acquire_sys(mine) != epoch) {
-      if (clock64() - t0 > limit) {
-        printf("seg_b200: SyncBN exchange timeout (rank %d waiting for rank %d, epoch %u; raise SEG_SYNC_TIMEOUT_S)\n", s.rank,
-               (int)threadIdx.x, epoch);
-        __trap();
-      }
-    }
-  }
-  __syncthreads();
 }
 
 // consumer: world total of element idx, added in rank order (bit-identical on every rank)
@@ -147,6 +135,72 @@ __device__ __forceinline__ void sync_total8(const SyncDesc& s, uint32_t epoch, i
     out8[0] += a.x; out8[1] += a.y; out8[2] += a.z; out8[3] += a.w;
     out8[4] += b.x; out8[5] += b.y; out8[6] += b.z; out8[7] += b.w;
   }
+}
+
+// ---- mode 1: the whole exchange inside the producer's last block -----------------------------------------------------------------
+// wait for the world's flags with the `nthr` cooperating threads of ONE block (tid 0..nthr-1, `sync()` their barrier)
+template <class Sync>
+__device__ __forceinline__ void sync_wait_world_block(const SyncDesc& s, uint32_t epoch, int tid, Sync sync) {
+  if (tid < s.world) {
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(s.peers[s.rank]) + sync_flags_offset(s.world, s.n_max)) +
+                           (size_t)(epoch & 1u) * s.world + tid;
+    const long long limit = s.timeout_clocks > 0 ? s.timeout_clocks : (1ll << 62);
+    const long long t0 = clock64();
+    while (sync_ld_acquire_sys(mine) != epoch) {
+      if (clock64() - t0 > limit) {
+        printf("seg_b200: SyncBN exchange timeout (rank %d waiting for rank %d, epoch %u; raise SEG_SYNC_TIMEOUT_S)\n", s.rank, tid, epoch);
+        __trap();
+      }
+    }
+  }
+  sync();
+}
+__device__ __forceinline__ void sync_advance(const SyncDesc& s, uint32_t epoch) {
+  uint32_t* seq = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(s.peers[s.rank]) + sync_seq_offset(s.world, s.n_max));
+  *seq = epoch;
+  __threadfence();
+}
+// fp64 totals acc[0..n) (this rank's, final) -> world totals, in place; called by the cooperating threads of ONE block
+template <class Sync>
+__device__ __forceinline__ void sync_exchange_block_d(const SyncDesc& s, double* acc, int n, int tid, int nthr, Sync sync) {
+  const uint32_t epoch = sync_epoch(s);
+  for (int i = tid; i < n; i += nthr) sync_push_value_d(s, epoch, i, __ldcg(acc + i));
+  sync_publish(s, epoch, tid, sync);
+  sync_wait_world_block(s, epoch, tid, sync);
+  for (int i = tid; i < n; i += nthr) acc[i] = sync_total_d(s, epoch, i);
+  __threadfence();
+  sync();
+  if (tid == 0) sync_advance(s, epoch);
+}
+// fp32 variant (BatchNorm backward sums)
+template <class Sync>
+__device__ __forceinline__ void sync_exchange_block_f(const SyncDesc& s, float* vals, int n, int tid, int nthr, Sync sync) {
+  const uint32_t epoch = sync_epoch(s);
+  for (int i = tid; i < n; i += nthr) sync_push_value(s, epoch, i, __ldcg(vals + i));
+  sync_publish(s, epoch, tid, sync);
+  sync_wait_world_block(s, epoch, tid, sync);
+  for (int i = tid; i < n; i += nthr) vals[i] = sync_total(s, epoch, i);
+  __threadfence();
+  sync();
+  if (tid == 0) sync_advance(s, epoch);
+}
+
+// consumer: all threads of the block call this; returns after every rank's flag shows `epoch`
+__device__ __forceinline__ void sync_wait_world(const SyncDesc& s, uint32_t epoch) {
+  if ((int)threadIdx.x < s.world) {
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(s.peers[s.rank]) + sync_flags_offset(s.world, s.n_max)) +
+                           (size_t)(epoch & 1u) * s.world + threadIdx.x;
+    const long long limit = s.timeout_clocks > 0 ? s.timeout_clocks : (1ll << 62);
+    const long long t0 = clock64();
+    while (sync_ld_acquire_sys(mine) != epoch) {
+      if (clock64() - t0 > limit) {
+        printf("seg_b200: SyncBN exchange timeout (rank %d waiting for rank %d, epoch %u; raise SEG_SYNC_TIMEOUT_S)\n", s.rank,
+               (int)threadIdx.x, epoch);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
 }
 
 // consumer, at the very end of the kernel (every thread of every block calls it): the last block to get here advances seq.

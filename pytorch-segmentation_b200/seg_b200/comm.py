@@ -20,8 +20,16 @@ def _sync_timeout_clocks():
     return int(float(os.environ.get("SEG_SYNC_TIMEOUT_S", "120")) * 2e9)
 
 
+def _sync_mode():
+    """1 (default): the producer kernel's last block performs the whole exchange (push, flags, wait, rank-ordered sum) and
+    leaves the world's totals in its output — ONE block polls the flags.  0: producers push, every block of the consumer kernel
+    (bn_apply / bn_bwd_apply) waits for the world and adds.  SEG_SYNC_MODE overrides (A/B measurements)."""
+    import os
+    return int(os.environ.get("SEG_SYNC_MODE", "1"))
+
+
 def _make_desc(peers, rank, world, n_max):
-    return lib.SyncDesc(peers.data_ptr(), rank, world, n_max, _sync_timeout_clocks())
+    return lib.SyncDesc(peers.data_ptr(), rank, world, n_max, _sync_timeout_clocks(), _sync_mode())
 
 
 class SyncBNGroup:
@@ -57,6 +65,7 @@ class SyncBNGroup:
             ptrs.append(p.value)
         self.peers = torch.tensor(ptrs, dtype=torch.int64, device="cuda")
         self.desc = _make_desc(self.peers, self.rank, self.world, n_max)
+        self.mode = self.desc.mode
         self.fused = True  # the kernels that produce / consume the statistics carry the exchange (csrc/seg_sync.cuh)
         dist.barrier(group=group)
 
@@ -86,6 +95,7 @@ class LocalLoopbackGroup:
         self._mine = mine
         self.peers = torch.tensor([mine.value], dtype=torch.int64, device="cuda")
         self.desc = _make_desc(self.peers, 0, 1, n_max)
+        self.mode = self.desc.mode
         self.fused = True
         self.force = False  # True: the engine runs the whole SyncBN protocol (push, flags, wait, sequence number) against
                             # this one-rank buffer — the single-GPU test of the fused exchange

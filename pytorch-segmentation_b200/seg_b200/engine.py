@@ -327,7 +327,9 @@ class Tape:
             in_kernel = None
             if self.sync_active():
                 if stats.data_ptr() in self._pushed:
-                    in_kernel = self.sync      # bn_apply waits for the world's flags and adds every rank's sums itself
+                    if getattr(self.sync, "mode", 0) == 0:
+                        in_kernel = self.sync  # bn_apply waits for the world's flags and adds every rank's sums itself
+                    # mode 1: the producer's last block already did the exchange; `stats` holds the world's totals
                 else:  # exchange object without the in-kernel protocol (the gloo stand-in of the CPU tests): sums over ranks
                     self.sync.allreduce_(stats)
                 count = count_local * self.sync.world
@@ -393,9 +395,10 @@ class Tape:
                     sums = ops.bn_bwd_reduce(da, a, y.t, save, relu=relu, drop_p=drop_p, dgamma=dg, dbeta=db, accumulate=acc_pg,
                                              acc=self.zalloc64(ops.bn_bwd_reduce_acc_words(C), a.device), sync=sync)
                     gsums = sums if use_batch_stats else torch.zeros_like(sums)
+                    csync = sync if (sync is not None and getattr(sync, "mode", 0) == 0) else None  # mode 1: sums are the world's
                     ops.bn_bwd_apply(da, a_mask, y.t, save, bn.weight.detach(), gsums, count, relu=relu, drop_p=drop_p, dx=dy,
-                                     dres=dres, beta_res=beta_res, beta=bn.bias.detach(), sync=sync,
-                                     sync_done=self.zalloc(1, a.device) if sync is not None else None)
+                                     dres=dres, beta_res=beta_res, beta=bn.bias.detach(), sync=csync,
+                                     sync_done=self.zalloc(1, a.device) if csync is not None else None)
                 y.grad = dy
                 aa.grad = None
             self._push_back(bwd, (bn.weight, bn.bias))

@@ -20,7 +20,8 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
 class SyncDesc(Structure):
     """Mirror of ``seg_sync_desc`` (include/seg_b200.h)."""
 
-    _fields_ = [("peers", c_void_p), ("rank", c_int32), ("world", c_int32), ("n_max", c_int32), ("timeout_clocks", c_int64)]
+    _fields_ = [("peers", c_void_p), ("rank", c_int32), ("world", c_int32), ("n_max", c_int32), ("timeout_clocks", c_int64),
+                ("mode", c_int32)]
 
 
 class ConvDesc(Structure):

@@ -1,90 +1,30 @@
-"""The plugin surface as a multi-GPU drop-in: what `torchrun --nproc-per-node 2 -m seg_b200.launch train.py`
-sets up — rotated device list (own GPU = cuda:0), NCCL process group, `use_synch_bn` -> SyncBN over NVLink — and then ONLY the
-calls an unmodified trainer makes: model(x) -> CrossEntropyLoss2d -> loss.backward() -> optimizer.step().  Needs 2 GPUs."""
+"""The plugin surface as a multi-GPU drop-in: see tests/dp_worker.py (one process per GPU under torchrun,
+exactly as `torchrun --nproc-per-node 2 -m seg_b200.launch train.py` would set things up).  Needs 2 GPUs."""
 import os
+import subprocess
 import sys
 
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-
-
-def _worker(rank, world, port, out_path, graphs):
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for p in (root, os.path.join(root, "pytorch-segmentation_b200")):
-        if p not in sys.path:
-            sys.path.insert(0, p)
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
-                      LOCAL_WORLD_SIZE=str(world))
-    from seg_b200 import launch
-    r, w = launch.init_data_parallel()  # before any CUDA call of this process
-    assert (r, w) == (rank, world) and torch.cuda.current_device() == 0
-    import torch.distributed as dist
-    import seg_b200
-    from seg_b200.optim import SGD
-    from oracle import synth, weights
-    sd = weights.deeplab_resnet_state_dict(7, "resnet14", seed=11)
-    x, y = synth.make_batch(8, 65, 65, 7, 255, seed=31)
-    y[0, 8:40, :] = 255  # unequal valid-pixel counts on the two ranks
-    m = seg_b200.DeepLab(7, backbone="resnet14", pretrained=False)
-    m.load_state_dict(sd)
-    m.engine_dropout = False
-    m.use_sync_bn = True  # overlay/utils/sync_batchnorm.convert_model does this for config["use_synch_bn"]
-    m = m.cuda().train()
-    if graphs:
-        m.cuda_graphs(True, warmup=1)
-    crit = seg_b200.CrossEntropyLoss2d(ignore_index=255)
-    opt = SGD([{"params": list(m.get_decoder_params())}, {"params": list(m.get_backbone_params()), "lr": 0.001}], lr=0.01, momentum=0.9, weight_decay=1e-4)
-    half = slice(rank * 4, rank * 4 + 4)
-    xd, yd = x[half].cuda(), y[half].cuda()
-    losses = []
-    for _ in range(4):
-        opt.zero_grad(set_to_none=True)
-        loss = crit(m(xd), yd)
-        loss.backward()
-        opt.step()
-        losses.append(loss.item())
-    assert m.bn_sync is not None and m.bn_sync.world == world
-    flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()] + [b.detach().float().reshape(-1) for n, b in m.named_buffers() if "running_" in n])
-    gathered = [torch.empty_like(flat) for _ in range(world)]
-    dist.all_gather(gathered, flat)
-    lt = torch.tensor(losses, device="cuda", dtype=torch.float64)
-    lg = [torch.empty_like(lt) for _ in range(world)]
-    dist.all_gather(lg, lt)
-    m.release_graphs()
-    if rank == 0:
-        # single-GPU control on the concatenated batch (no process group involvement: dp_reduce off, local loss)
-        m1 = seg_b200.DeepLab(7, backbone="resnet14", pretrained=False)
-        m1.load_state_dict(sd)
-        m1.engine_dropout = False
-        m1.dp_reduce = False
-        m1 = m1.cuda().train()
-        from seg_b200.losses import _CEFn
-        opt1 = SGD([{"params": list(m1.get_decoder_params())}, {"params": list(m1.get_backbone_params()), "lr": 0.001}], lr=0.01, momentum=0.9, weight_decay=1e-4)
-        l1 = []
-        for _ in range(4):
-            opt1.zero_grad(set_to_none=True)
-            loss = _CEFn.apply(m1(x.cuda()), y.cuda(), 255, False)
-            loss.backward()
-            opt1.step()
-            l1.append(loss.item())
-        torch.save({"replicas_equal": all(torch.equal(gathered[0], g) for g in gathered[1:]),
-                    "losses_equal": all(torch.equal(lg[0], g) for g in lg[1:]), "losses2": losses, "losses1": l1}, out_path)
-    dist.barrier()
-    dist.destroy_process_group()
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("graphs", [False, True], ids=["eager", "graph-replay"])
 def test_plugin_surface_two_gpus_replicas_stay_identical(tmp_path, graphs):
-    import torch.multiprocessing as mp
     out = str(tmp_path / "r.pt")
-    mp.spawn(_worker, args=(2, 29900 + (os.getpid() + int(graphs) * 13) % 1000, out, graphs), nprocs=2, join=True)
-    r = torch.load(out)
-    print(r)
-    assert r["replicas_equal"], "replicas diverged (parameters / running statistics differ between the two ranks)"
-    assert r["losses_equal"], "the ranks report different losses: the loss is not the global-batch mean"
+    port = 29900 + (os.getpid() + int(graphs) * 13) % 1000
+    env = {k: v for k, v in os.environ.items() if k not in ("CUDA_VISIBLE_DEVICES", "SEG_DEVICES_ROTATED")}
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(HERE, "dp_worker.py"), out, "1" if graphs else "0"],
+                       env=env, capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0 and os.path.exists(out), r.stdout[-2000:] + r.stderr[-4000:]
+    res = torch.load(out)
+    print(res)
+    assert res["replicas_equal"], "replicas diverged (parameters / running statistics differ between the two ranks)"
+    assert res["losses_equal"], "the ranks report different losses: the loss is not the global-batch mean"
     # same training as one GPU on the concatenated batch (SyncBN + global mean + gradient mean), up to bf16 / clamp(var, eps) noise
-    assert abs(r["losses2"][0] - r["losses1"][0]) < 2e-2 * abs(r["losses1"][0]), r
-    assert r["losses2"][-1] < r["losses2"][0] and abs(r["losses2"][-1] - r["losses1"][-1]) < 0.1 * abs(r["losses1"][-1]), r
+    assert abs(res["losses2"][0] - res["losses1"][0]) < 2e-2 * abs(res["losses1"][0]), res
+    assert res["losses2"][-1] < res["losses2"][0] and abs(res["losses2"][-1] - res["losses1"][-1]) < 0.1 * abs(res["losses1"][-1]), res
