@@ -327,6 +327,9 @@ def main():
                     help="e2e leg: replay model(x)/backward from CUDA graphs (seg_b200 model.cuda_graphs())")
     ap.add_argument("--plugin-optim", default=os.environ.get("SEG_PLUGIN_OPTIM", "fused"), choices=["fused", "torch"],
                     help="e2e leg optimiser: seg_b200.optim.SGD (torch.optim.SGD subclass, one kernel per group) or stock torch.optim.SGD")
+    ap.add_argument("--ref-only", action="store_true", help="run ONLY the reference-GPU leg (single process, nn.DataParallel over --ref-gpus devices) and print its JSON")
+    ap.add_argument("--ref-gpus", type=int, default=1)
+    ap.add_argument("--ref-sync-bn", type=int, default=-1, help="reference-GPU leg: 1 = convert_model + DataParallelWithCallback, 0 = nn.DataParallel, -1 = the config's")
     ap.add_argument("--bucket-mb", type=float, default=float(os.environ.get("SEG_BUCKET_MB", "25")),
                     help="N > 1: gradient all-reduce bucket size of the fused step (0 = one all-reduce after the backward)")
     ap.add_argument("--trace", default=None, help="after the timed runs, trace 2 steps per C-ABI call and write a table here")
@@ -336,6 +339,14 @@ def main():
         args.batch = CFG["batch"]
     if args.impl == "reference":
         return run_reference(args)
+    if args.ref_only:
+        if args.ref_sync_bn >= 0:
+            CFG = dict(CFG, sync_bn=bool(args.ref_sync_bn))
+        tg, how = reference_gpu_step_time(args.batch, args.steps, args.warmup, args.ref_gpus)
+        print(json.dumps({"impl": "reference-gpu", "metric": metric_name(), "value": args.batch * args.ref_gpus / tg, "unit": "images/sec",
+                          "n_gpus": args.ref_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tg * 1e3, "per_gpu_batch": args.batch,
+                          "sync_bn": CFG["sync_bn"], "how": how}))
+        return
 
     import torch.distributed as dist
     import seg_b200

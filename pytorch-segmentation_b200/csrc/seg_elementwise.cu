@@ -1515,7 +1515,11 @@ int seg_bn_bwd_fused(const void* dout, int lddo, const void* out, int ldo, const
     SEG_REQUIRE(2 * C <= sync->n_max, "bn_bwd_fused: 2*C = %d sums exceed the SyncBN buffer (%d floats)", 2 * C, sync->n_max);
     p.sync = to_sync(sync);
   }
-  const dim3 grid = fused_grid(M, C, remask ? fused_blocks_per_sm<true>() : fused_blocks_per_sm<false>());
+  // multi-GPU: leave one block slot per SM free — a concurrently running NCCL kernel (bucketed gradient all-reduce on the side
+  // stream) must not keep part of this grid from becoming resident, or every block would sit at the barrier until it finishes
+  int bps = remask ? fused_blocks_per_sm<true>() : fused_blocks_per_sm<false>();
+  if (sync && bps > 1) bps -= 1;
+  const dim3 grid = fused_grid(M, C, bps);
   if (remask)
     bn_bwd_fused_kernel<true><<<grid, 256, 0, ST(stream)>>>(p);
   else
