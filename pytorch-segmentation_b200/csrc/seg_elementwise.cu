@@ -395,6 +395,31 @@ __global__ void __launch_bounds__(256, 4) bn_apply_kernel(const __nv_bfloat16* _
   if constexpr (SYNC) sync_consumer_done(sync, epoch, sync_done, gridDim.x * gridDim.y);
 }
 
+__device__ __noinline__ void bn_bwd_reduce_finalize(const double* acc, float* final_sums, float* dgamma, float* dbeta, int accumulate,
+                                                    int C, const SyncDesc sync) {
+  const uint32_t epoch = (sync.world > 0 && sync.mode == 0) ? sync_epoch(sync) : 0u;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    double t = 0.0;  // the copies' totals are exact sums; so is their sum
+#pragma unroll
+    for (int sl = 0; sl < RED_SLOTS; ++sl) t += __ldcg(acc + (size_t)sl * 2 * C + c);
+    const float v = (float)t;
+    final_sums[c] = v;
+    float* pg = c < C ? dbeta : dgamma;
+    const int ch = c < C ? c : c - C;
+    if (pg) pg[ch] = accumulate ? pg[ch] + v : v;
+    if (sync.world > 0 && sync.mode == 0) sync_push_value(sync, epoch, c, v);
+  }
+  if (sync.world > 0) {
+    if (sync.mode == 1) {  // whole exchange here: final_sums becomes the world's sums (bn_bwd_apply then needs no SyncBN logic)
+      __threadfence();
+      __syncthreads();
+      sync_exchange_block_f(sync, final_sums, 2 * C, (int)threadIdx.x, (int)blockDim.x, [] { __syncthreads(); });
+    } else {
+      sync_publish(sync, epoch, (int)threadIdx.x, [] { __syncthreads(); });
+    }
+  }
+}
+
 template <bool REMASK>
 __global__ void __launch_bounds__(256, 4)
     bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int lddo, const __nv_bfloat16* __restrict__ out, int ldo,
@@ -446,29 +471,10 @@ __global__ void __launch_bounds__(256, 4)
   });
   pdl_trigger();
   // the last block to finish rounds the fp64 totals to fp32, writes the parameter gradients (dbeta = sum dz, dgamma = sum
-  // dz*xhat) and, under SyncBN, pushes the totals to every peer (consumer: bn_bwd_apply with the same handle)
+  // dz*xhat) and, under SyncBN, exchanges the sums with the peers — a cold path kept out of line so that its registers do not
+  // push the streaming loop above 64 (4 blocks per SM)
   if (!last_block_arrived(ticket)) return;
-  const uint32_t epoch = sync.world > 0 ? sync_epoch(sync) : 0u;
-  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
-    double t = 0.0;  // the slots' totals are exact sums; so is their sum
-#pragma unroll
-    for (int sl = 0; sl < RED_SLOTS; ++sl) t += __ldcg(acc + (size_t)sl * 2 * C + c);
-    const float v = (float)t;
-    final_sums[c] = v;
-    float* pg = c < C ? dbeta : dgamma;
-    const int ch = c < C ? c : c - C;
-    if (pg) pg[ch] = accumulate ? pg[ch] + v : v;
-    if (sync.world > 0 && sync.mode == 0) sync_push_value(sync, epoch, c, v);
-  }
-  if (sync.world > 0) {
-    if (sync.mode == 1) {  // whole exchange here: final_sums becomes the world's sums (bn_bwd_apply then needs no SyncBN logic)
-      __threadfence();
-      __syncthreads();
-      sync_exchange_block_f(sync, final_sums, 2 * C, (int)threadIdx.x, (int)blockDim.x, [] { __syncthreads(); });
-    } else {
-      sync_publish(sync, epoch, (int)threadIdx.x, [] { __syncthreads(); });
-    }
-  }
+  bn_bwd_reduce_finalize(acc, final_sums, dgamma, dbeta, accumulate, C, sync);
 }
 
 // dx = A*dz + B*x + Cc with A = gamma*istd, B = -gamma*istd^2*s1/count, Cc = -gamma*istd*s0/count + gamma*istd^2*mean*s1/count
