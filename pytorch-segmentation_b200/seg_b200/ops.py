@@ -611,7 +611,8 @@ def augment_scale_batch_u8(arena, table, B, crop_h, crop_w, mean, std, want_labe
 
 
 def augment_full_batch_u8(arena, table, B, crop_h, crop_w, mean, std, want_labels=True):
-    """EXPERIMENTAL (not yet run on a GPU): augment_scale_batch_u8 with the rotation fused in; table = B seg_aug_full_entry records."""
+    """augment_scale_batch_u8 with the rotation (cv2.getRotationMatrix2D + warpAffine arithmetic) fused in; table = B
+    seg_aug_full_entry records."""
     assert arena.dtype == torch.uint8 and table.dtype == torch.uint8 and table.numel() == B * lib.load().seg_aug_full_entry_bytes()
     out = torch.empty((B, 3, crop_h, crop_w), dtype=torch.float32, device=arena.device)
     labels = torch.empty((B, crop_h, crop_w), dtype=torch.int64, device=arena.device) if want_labels else None

@@ -108,9 +108,7 @@ def test_device_scaled_tail_is_bit_exact_against_oracle_and_within_one_level_of_
         assert torch.equal(x2[i].cpu(), rx), (i, (x2[i].cpu() - rx).abs().max().item())
 
 
-@pytest.mark.skipif(os.environ.get("SEG_EXPERIMENTAL") != "1",
-                    reason="seg_augment_full_batch_u8 was written after round 1's GPU budget was spent: compiled, CPU-transcription-checked, not yet run")
-def test_device_scale_rotate_tail_experimental():
+def test_device_scale_rotate_tail():
     """scale -> rotate -> pad -> crop -> flip -> normalise in one kernel: bit-exact against the staged oracle (which equals
     cv2's resize / warpAffine arithmetic), labels exact and images within one level of the reference's as-run goldens."""
     g = np.load(GOLD)
