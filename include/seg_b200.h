@@ -314,7 +314,7 @@ typedef struct seg_aug_scale_entry {
 int seg_aug_scale_entry_bytes(void);
 int seg_augment_scale_batch_u8(const uint8_t* arena, const seg_aug_scale_entry* table, int B, int crop_h, int crop_w,
                                const float* mean3, const float* std3, float* out_nchw, int64_t* out_labels, void* stream);
-/* EXPERIMENTAL (compiled and exported, not yet run on a GPU): the same with the rotation of base/base_dataset.py:77-83
+/* the same with the rotation of base/base_dataset.py:77-83
  * between the resize and the tail.  (a11 a12 b1; a21 a22 b2) = the INVERSE of cv2.getRotationMatrix2D((w/2, h/2), angle, 1)
  * computed by the host in float64 exactly as cv::warpAffine does (oracle/data.py::cv_warp_affine); identity = no rotation. */
 typedef struct seg_aug_full_entry {

@@ -12,6 +12,9 @@ for p in (ROOT, os.path.join(ROOT, "pytorch-segmentation_b200")):
 
 def main():
     out_path, graphs = sys.argv[1], sys.argv[2] == "1"
+    if os.environ.get("SEG_DP_WORKER_DUMP_S"):  # diagnostics: dump every thread's stack if the worker is still alive after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["SEG_DP_WORKER_DUMP_S"]), exit=True)
     from seg_b200 import launch
     rank, world = launch.init_data_parallel()  # before any CUDA call of this process
     import torch
@@ -29,14 +32,14 @@ def main():
     m.use_sync_bn = True  # overlay/utils/sync_batchnorm.convert_model does this for config["use_synch_bn"]
     m = m.cuda().train()
     if graphs:
-        m.cuda_graphs(True, warmup=1)
+        m.cuda_graphs(True, warmup=int(os.environ.get("SEG_DP_WORKER_WARMUP", "2")))
     crit = seg_b200.CrossEntropyLoss2d(ignore_index=255)
     opt = SGD([{"params": list(m.get_decoder_params())}, {"params": list(m.get_backbone_params()), "lr": 0.001}], lr=0.01, momentum=0.9, weight_decay=1e-4)
     n = 8 // world
     half = slice(rank * n, rank * n + n)
     xd, yd = x[half].cuda(), y[half].cuda()
     losses = []
-    for _ in range(4):
+    for _ in range(5):
         opt.zero_grad(set_to_none=True)
         loss = crit(m(xd), yd)
         loss.backward()
@@ -61,7 +64,7 @@ def main():
         from seg_b200.losses import _CEFn
         opt1 = SGD([{"params": list(m1.get_decoder_params())}, {"params": list(m1.get_backbone_params()), "lr": 0.001}], lr=0.01, momentum=0.9, weight_decay=1e-4)
         l1 = []
-        for _ in range(4):
+        for _ in range(5):
             opt1.zero_grad(set_to_none=True)
             loss = _CEFn.apply(m1(x.cuda()), y.cuda(), 255, False)
             loss.backward()
