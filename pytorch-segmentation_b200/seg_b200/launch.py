@@ -88,7 +88,36 @@ def main():
         from seg_b200 import optim
         optim.install()
     sys.argv = [script] + sys.argv[2:]
-    runpy.run_path(script, run_name="__main__")
+    try:
+        runpy.run_path(script, run_name="__main__")
+    finally:
+        _teardown_data_parallel()
+
+
+def _teardown_data_parallel(grace_s=20.0):
+    """After the script: captured graphs hold this process group's NCCL kernels, and a communicator torn down (explicitly or
+    by the interpreter's exit handlers) while one is alive blocks forever (measured in tests/dp_worker.py).  Release every
+    engine graph first; if the teardown still does not return within `grace_s`, flush logging and leave hard."""
+    if "torch.distributed" not in sys.modules:
+        return
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() <= 1:
+        return
+    import logging
+    import threading
+    from seg_b200.nets import release_all_graphs
+    release_all_graphs()
+
+    def _bail():
+        logging.shutdown()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+    t = threading.Timer(grace_s, _bail)
+    t.daemon = True
+    t.start()
+    dist.destroy_process_group()
+    t.cancel()
 
 
 if __name__ == "__main__":

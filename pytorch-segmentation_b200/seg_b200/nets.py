@@ -18,6 +18,7 @@ There is no CPU / eager path: a CPU input raises.
 """
 import logging
 import math
+import weakref
 from itertools import chain
 
 import numpy as np
@@ -34,9 +35,26 @@ except Exception:  # standalone (tests, bench, GPU box): API-compatible stand-in
     _RefBaseModel = None
 
 
+_LIVE_MODELS = weakref.WeakSet()  # every engine model alive in this process (release_all_graphs)
+
+
+def release_all_graphs():
+    """Drop every captured CUDA graph of every live engine model.  Needed before an NCCL process group is torn down: a graph
+    that captured the gradient all-reduce keeps the communicator's kernels alive and ncclCommDestroy blocks on it
+    (seg_b200.launch calls this after the reference script returns)."""
+    import gc
+    for m in list(_LIVE_MODELS):
+        if hasattr(m, "release_graphs"):
+            m.release_graphs()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+
+
 class BaseModel(nn.Module if _RefBaseModel is None else _RefBaseModel):
     def __init__(self):
         super().__init__()
+        _LIVE_MODELS.add(self)
         if not hasattr(self, "logger"):
             self.logger = logging.getLogger(self.__class__.__name__)
 

@@ -73,6 +73,13 @@ def main():
         torch.save({"replicas_equal": all(torch.equal(gathered[0], g) for g in gathered[1:]),
                     "losses_equal": all(torch.equal(lg[0], g) for g in lg[1:]), "losses2": losses, "losses1": l1}, out_path)
     dist.barrier()
+    torch.cuda.synchronize()
+    if graphs:
+        # Captured graphs hold NCCL kernels of this communicator; tearing the communicator down while any graph object is
+        # still referenced (autograd keeps the last step's entry alive) blocks inside ncclCommDestroy (measured: both ranks
+        # parked in destroy_process_group after every check had passed).  A finished worker just exits.
+        sys.stdout.flush()
+        os._exit(0)
     dist.destroy_process_group()
 
 
