@@ -205,12 +205,14 @@ def _import_reference_tree():
     return ref_models
 
 
-def reference_gpu_step_time(batch, steps, warmup, n_gpus):
+def reference_gpu_step_time(batch, steps, warmup, n_gpus, budget_s=None):
     """BASELINE.md §4 "Reference GPU path (cuDNN)" — the denominator of north_star's ">= 6x": the UNMODIFIED reference model,
     wrapped exactly as BaseTrainer does it (base/base_trainer.py:33-38: convert_model + DataParallelWithCallback when
     use_synch_bn, else nn.DataParallel; device_ids = range(n_gpu)), fp32 NCHW, cudnn.benchmark = True (trainer.py:35), the
     reference's own loss class and torch.optim.SGD with the differential learning rates of base_trainer.py:46-57, the same
-    per-GPU batch, ONE process over n_gpus devices.  Falls back to the oracle port (single GPU) if the tree is not shipped."""
+    per-GPU batch, ONE process over n_gpus devices.  Falls back to the oracle port (single GPU) if the tree is not shipped.
+    `budget_s` bounds the leg by wall clock (the reference's threaded DataParallel + SyncBN step takes seconds at N > 1): after 3
+    warm-up steps one step is timed and the number of timed steps is cut to fit.  Returns (s/step, how, timed steps, warm-up)."""
     torch.backends.cudnn.benchmark = True
     dev = torch.device("cuda", 0)
     x, y = synthetic_batch(batch * n_gpus, 1234)
@@ -260,6 +262,23 @@ def reference_gpu_step_time(batch, steps, warmup, n_gpus):
         how = "oracle port (same ATen/cuDNN calls as the reference; the reference tree was not shipped), fp32 NCHW, cudnn.benchmark"
     xd, yd = x.to(dev), y.to(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if budget_s is not None:
+        warmup = min(warmup, 3)
+        t0 = time.time()
+        for _ in range(warmup):
+            step(xd, yd)
+            for d in range(n_gpus):
+                torch.cuda.synchronize(d)
+            if time.time() - t0 > 0.5 * budget_s:  # autotuning 8 threaded replicas can already eat the budget
+                break
+        t1 = time.time()
+        step(xd, yd)
+        for d in range(n_gpus):
+            torch.cuda.synchronize(d)
+        one = max(time.time() - t1, 1e-4)
+        left = budget_s - (time.time() - t0)
+        steps = int(max(2, min(steps, left / one)))
+        warmup = 0  # already done (warmup + 1 steps)
     for i in range(warmup + steps):
         if i == warmup:
             for d in range(n_gpus):
@@ -269,7 +288,7 @@ def reference_gpu_step_time(batch, steps, warmup, n_gpus):
     e1.record()
     for d in range(n_gpus):
         torch.cuda.synchronize(d)
-    return e0.elapsed_time(e1) * 1e-3 / steps, how
+    return e0.elapsed_time(e1) * 1e-3 / steps, how, steps, warmup
 
 
 def config_dict(args, world, use_graph=None, last_loss=None):
@@ -344,7 +363,7 @@ def main():
     if args.ref_only:
         if args.ref_sync_bn >= 0:
             CFG = dict(CFG, sync_bn=bool(args.ref_sync_bn))
-        tg, how = reference_gpu_step_time(args.batch, args.steps, args.warmup, args.ref_gpus)
+        tg, how, _, _ = reference_gpu_step_time(args.batch, args.steps, args.warmup, args.ref_gpus)
         print(json.dumps({"impl": "reference-gpu", "metric": metric_name(), "value": args.batch * args.ref_gpus / tg, "unit": "images/sec",
                           "n_gpus": args.ref_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tg * 1e3, "per_gpu_batch": args.batch,
                           "sync_bn": CFG["sync_bn"], "how": how}))
@@ -613,9 +632,10 @@ def main():
                             "sample": f"5 timed steps (after 1 warm-up) of batch {args.cpu_batch} of the same train step, fp32 oracle port, {threads} threads"}
         if not args.no_gpu_ref:
             try:  # the reference's OWN GPU path on the same GPUs: the denominator of north_star's ">= 6x" 
-                tg, how = reference_gpu_step_time(B, args.gpu_ref_steps, 10, world)
+                budget = float(os.environ.get("SEG_GPU_REF_BUDGET_S", "60")) if world > 1 else None
+                tg, how, ref_steps, ref_warm = reference_gpu_step_time(B, args.gpu_ref_steps, 10, world, budget)
                 cpu_baseline["reference_gpu_path"] = {"value": B * world / tg, "unit": "images/sec", "ms_per_step": tg * 1e3, "per_gpu_batch": B,
-                                                      "n_gpus": world, "timed_steps": args.gpu_ref_steps, "warmup": 10, "how": how,
+                                                      "n_gpus": world, "timed_steps": ref_steps, "warmup": ref_warm if budget is None else 4, "how": how,
                                                       "engine_over_reference_gpu": {"value": value / (B * world / tg), "e2e": (e2e["value"] / (B * world / tg)) if e2e else None}}
             except Exception as e:  # informational only
                 cpu_baseline["reference_gpu_path"] = {"unavailable": repr(e)[:300]}
