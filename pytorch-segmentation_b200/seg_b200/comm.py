@@ -1,9 +1,11 @@
-"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed/NCCL for the gradient all-reduce, and the
-one-shot NVLink peer-memory exchange (`seg_syncbn_exchange`) for SyncBN statistics.
+"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed/NCCL for the gradient all-reduce, and the symmetric
+NVLink peer buffers of the SyncBN statistics exchange.
 
 Replaces the reference's single-process nn.DataParallel + threaded SyncBN (base/base_trainer.py:33-38,
-utils/sync_batchnorm/batchnorm.py:105-126, comm.py): batch-dim sharding stays, the per-step parameter broadcast and
-logit gather disappear, and the two small collectives per BN layer become one kernel.
+utils/sync_batchnorm/batchnorm.py:105-126, comm.py): batch-dim sharding stays, the per-step parameter broadcast and logit gather
+disappear, and the two small collectives per BN layer ride inside the kernels that produce the statistics (csrc/seg_sync.cuh;
+`SyncBNGroup.desc` is the descriptor those kernels take).  The stand-alone exchange kernel (`allreduce_`, `seg_syncbn_exchange`)
+shares the buffers and the device-side sequence number, for callers outside the engine and for tests.
 """
 import ctypes
 
