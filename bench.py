@@ -630,7 +630,9 @@ def main():
             t = cpu_port_step_time(args.cpu_batch, 5, 1, threads)
             cpu_baseline = {"value": args.cpu_batch / t, "unit": "images/sec", "cores": threads, "kind": "port",
                             "sample": f"5 timed steps (after 1 warm-up) of batch {args.cpu_batch} of the same train step, fp32 oracle port, {threads} threads"}
-        if not args.no_gpu_ref:
+        # at N > 1 the reference's one-process DataParallelWithCallback + threaded SyncBN step takes SECONDS (measured: 4.9 s at
+        # N = 2, profiles/bench_r02_n2.json) — informational, so opt-in there (SEG_GPU_REF_MULTI=1) to keep scaling runs short
+        if not args.no_gpu_ref and (world == 1 or os.environ.get("SEG_GPU_REF_MULTI", "0") == "1"):
             try:  # the reference's OWN GPU path on the same GPUs: the denominator of north_star's ">= 6x" 
                 budget = float(os.environ.get("SEG_GPU_REF_BUDGET_S", "60")) if world > 1 else None
                 tg, how, ref_steps, ref_warm = reference_gpu_step_time(B, args.gpu_ref_steps, 10, world, budget)
