@@ -29,11 +29,12 @@ def main(path):
             cnt[name] += 1
     tot = sum(a["gpu__time_duration.sum"] for a in agg.values())
     print(f"# {path}: {sum(cnt.values())} launches, total device time {tot / 1e3:.2f} ms (cold-cache, serialised: compare SHARES)")
-    print(f"# {'share':>6} {'time_us':>10} {'launches':>8} {'avg_us':>8} {'dram_MB/launch':>14}  kernel")
+    print(f"# {'share':>6} {'time_us':>10} {'launches':>8} {'avg_us':>8} {'dram_MB/launch':>14} {'dram_GB/s':>9}  kernel")
     for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["gpu__time_duration.sum"]):
         t = a["gpu__time_duration.sum"]
         dram = (a.get("dram__bytes_read.sum", 0.0) + a.get("dram__bytes_write.sum", 0.0)) / max(cnt[name], 1) / 1e6
-        print(f"  {100 * t / tot:5.1f}% {t:10.1f} {cnt[name]:8d} {t / max(cnt[name], 1):8.1f} {dram:14.2f}  {name}")
+        gbs = dram * 1e6 * max(cnt[name], 1) / (t * 1e-6) / 1e9 if t > 0 else 0.0  # DRAM bytes / device time of the kernel's launches
+        print(f"  {100 * t / tot:5.1f}% {t:10.1f} {cnt[name]:8d} {t / max(cnt[name], 1):8.1f} {dram:14.2f} {gbs:9.0f}  {name}")
 
 
 if __name__ == "__main__":
