@@ -109,8 +109,16 @@ class ClockSampler:
 
 
 def synthetic_batch(B, seed):
-    from oracle import synth  # input recipe only; no oracle arithmetic
-    return synth.make_batch(B, CFG["size"], CFG["size"], CFG["nc"], CFG["ignore"], seed=seed)
+    """Synthetic inputs of SURVEY.md §8(d): randn images; 16x16-block-constant labels with a 4-pixel ignore border.  Stated here
+    (not imported from oracle/, which only the CPU legs may touch); tests/test_bench_contract_cpu.py pins it to the oracle's."""
+    H = W = CFG["size"]
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 3, H, W, generator=g)
+    blocks = torch.randint(0, CFG["nc"], (B, (H + 15) // 16, (W + 15) // 16), generator=g)
+    y = blocks.repeat_interleave(16, 1).repeat_interleave(16, 2)[:, :H, :W].contiguous()
+    for sl in ((slice(None), slice(0, 4)), (slice(None), slice(-4, None)), (slice(None), slice(None), slice(0, 4)), (slice(None), slice(None), slice(-4, None))):
+        y[sl] = CFG["ignore"]
+    return x, y
 
 
 def host_threads():

@@ -80,3 +80,15 @@ def test_both_arms_describe_the_same_workload():
         assert tag in mine["workload"] and b.CFG["name"] in b.metric_name()
     b.CFG = b.CONFIGS["C3"]
     assert b.metric_name() == "images/sec DeepLabV3+/ResNet101 513x513 train step (fwd+CE+bwd+SGD)"  # BASELINE.json's metric
+
+
+def test_bench_input_recipe_is_the_oracles():
+    from oracle import synth
+    b = _bench()
+    for tag in ("C3", "C5"):
+        b.CFG = b.CONFIGS[tag]
+        cfg = b.CFG
+        x, y = b.synthetic_batch(2, 1234)
+        xr, yr = synth.make_batch(2, cfg["size"], cfg["size"], cfg["nc"], cfg["ignore"], seed=1234)
+        assert torch.equal(x, xr) and torch.equal(y, yr)
+    b.CFG = b.CONFIGS["C3"]
